@@ -1,0 +1,165 @@
+/*
+ * nafgpu.h — C ABI of libnafgpu.so, the B200 (sm_100a) implementation of the NAF encode/decode
+ * hot path.  Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ *
+ * The reference (KirillKryukov/naf v1.3.0) has no plugin/FFI interface: ennaf and unnaf are two
+ * single-translation-unit C programs.  The seams this library replaces are the in-process ones the
+ * reference already has (all paths relative to /root/reference):
+ *
+ *   encode   process()                       ennaf/src/process.c:586   text  -> name/comment/seq/qual chunks
+ *            seq_writer_masked_4bit          ennaf/src/process.c:24    chunk -> extract_mask + encode_dna
+ *            compress()/compressor_end_stream ennaf/src/compressor.c:120,64   stream bytes -> zstd frame
+ *            container writer                ennaf/src/ennaf.c:538-589 header + VLE + magic-stripped frames
+ *   decode   read_header / load_*            unnaf/src/input.c:31,145-246     container -> streams
+ *            ZSTD_decompress / ZSTD_decompressStream loops  unnaf/src/input.c:155, output.c:640-650
+ *            write_4bit_as_fasta + print_dna_buffer_as_fasta unnaf/src/output.c:445,369
+ *            print_fastq                     unnaf/src/output-fastq.c:100
+ *
+ * nafgpu_encode() / nafgpu_decode() are what ennaf's main() (ennaf.c:433) and unnaf's main()
+ * (unnaf.c:356) call once the command line is parsed and the input is mapped; INTEGRATION.md
+ * shows the binding.  Stage entry points below exist for parity tests and profiling.
+ *
+ * Conventions: every call returns 0 on success or a negative NAFGPU_E_* code; the message that the
+ * reference would have passed to die() (without its "ennaf error: " / "unnaf error: " prefix) is
+ * available from nafgpu_last_error().  A context owns one CUDA stream, a device arena and pinned
+ * host staging; it is not thread-safe — use one context per host thread / GPU.  Output pointers
+ * returned by a call stay valid until the next call on the same context.
+ * There is NO CPU fallback: every entry point fails with NAFGPU_E_CUDA if no sm_100 device is usable.
+ */
+#ifndef NAFGPU_H
+#define NAFGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAFGPU_VERSION "0.1.0"
+
+enum {
+    NAFGPU_OK          =  0,
+    NAFGPU_E_CUDA      = -1,   /* CUDA runtime / no device */
+    NAFGPU_E_INPUT     = -2,   /* the reference would die() on this input; see nafgpu_last_error */
+    NAFGPU_E_FORMAT    = -3,   /* corrupt .naf container or zstd stream */
+    NAFGPU_E_UNSUPPORTED = -4, /* valid, but outside what this build handles (stated in the message) */
+    NAFGPU_E_ARG       = -5
+};
+
+/* sequence types: ennaf --dna/--rna/--protein/--text (ennaf.c:54), NAF v2 type byte (input.c:44) */
+enum { NAFGPU_DNA = 0, NAFGPU_RNA = 1, NAFGPU_PROTEIN = 2, NAFGPU_TEXT = 3 };
+enum { NAFGPU_FMT_AUTO = 0, NAFGPU_FMT_FASTA = 1, NAFGPU_FMT_FASTQ = 2 };
+
+/* output views of unnaf (unnaf.c:16-23).  Views that only read the header or tiny sections are
+ * produced on the host by the CLI; the ones listed here run on the GPU. */
+enum {
+    NAFGPU_OUT_DEFAULT = 0,     /* FASTQ if the file has qualities, else FASTA (unnaf.c:372) */
+    NAFGPU_OUT_FASTA   = 1,     /* print_fasta            output.c:608 */
+    NAFGPU_OUT_FASTQ   = 2,     /* print_fastq            output-fastq.c:100 */
+    NAFGPU_OUT_SEQ     = 3,     /* print_dna (--seq)      output.c:457 */
+    NAFGPU_OUT_SEQUENCES = 4,   /* print_sequences        output-sequences.c:61 */
+    NAFGPU_OUT_4BIT    = 5,     /* print_4bit             output.c:266 */
+    NAFGPU_OUT_IDS     = 6,     /* the decompressed id stream, '\0' -> '\n'      output.c:95 */
+    NAFGPU_OUT_NAMES   = 7,     /* id[ sep comment]\n per record                 output.c:143 */
+    NAFGPU_OUT_LENGTHS = 8,     /* raw u32 LE length units (CLI formats them)    output.c:180 */
+    NAFGPU_OUT_MASK    = 9,     /* raw u8 mask units (CLI formats them)          output.c:222 */
+    NAFGPU_OUT_CHARCOUNT = 10   /* 256 x u64 LE counts (CLI formats them)        output.c:544 */
+};
+
+typedef struct nafgpu_ctx nafgpu_ctx;
+
+typedef struct {
+    int32_t  seq_type;          /* NAFGPU_DNA.. */
+    int32_t  input_format;      /* NAFGPU_FMT_AUTO: detect like confirm_input_format (process.c:547) */
+    int32_t  no_mask;           /* ennaf --no-mask */
+    int32_t  strict;            /* ennaf --strict: fail on the first unexpected character */
+    int32_t  well_formed;       /* ennaf --well-formed */
+    int32_t  have_line_length;  /* ennaf --line-length N */
+    uint64_t line_length;
+    int32_t  level;             /* ennaf -#: accepted for CLI compatibility; the GPU encoder has one parse */
+    int32_t  window_log;        /* ennaf --long N: declared window of the SEQ frame (0 = default) */
+    const char *title;          /* ennaf --title, NULL = none */
+} nafgpu_enc_opts;
+
+typedef struct {
+    int32_t  out_type;          /* NAFGPU_OUT_* */
+    int32_t  no_mask;           /* unnaf --no-mask */
+    int32_t  have_line_length;  /* unnaf --line-length N */
+    uint64_t line_length;
+} nafgpu_dec_opts;
+
+/* Facts ennaf prints or needs after encoding (ennaf.c:556,594-596). */
+typedef struct {
+    uint64_t n_sequences;
+    uint64_t longest_line;
+    uint64_t n_bases;                 /* seq_size_original */
+    int32_t  format;                  /* NAFGPU_FMT_FASTA/FASTQ, 0 for empty input */
+    int32_t  reserved;
+    uint64_t stream_raw[6];           /* ids, comments, lengths, mask, sequence, quality: uncompressed bytes */
+    uint64_t stream_comp[6];          /* compressed bytes as stored (frame minus 4-byte magic) */
+    uint64_t unexpected[4][257];      /* id, comment, sequence, quality (process.c:75 report) */
+} nafgpu_enc_info;
+
+/* Timing of the last call, CUDA events on the context's stream (milliseconds). */
+typedef struct {
+    float h2d_ms, kernels_ms, d2h_ms, total_ms;
+    uint32_t kernel_launches;         /* launches of this library's own kernels in the last call */
+    uint32_t reserved;
+} nafgpu_timing;
+
+/* ---- context ---- */
+int  nafgpu_create(int device, nafgpu_ctx **ctx);     /* -1 = current device */
+void nafgpu_destroy(nafgpu_ctx *ctx);
+const char *nafgpu_last_error(const nafgpu_ctx *ctx); /* ctx may be NULL: error of a failed nafgpu_create */
+const char *nafgpu_version(void);
+int  nafgpu_get_timing(const nafgpu_ctx *ctx, nafgpu_timing *t);
+void *nafgpu_stream(nafgpu_ctx *ctx);                 /* the cudaStream_t all work is launched on */
+
+/* Pinned host memory for zero-staging transfers (optional; pageable pointers are accepted too). */
+int  nafgpu_host_alloc(size_t n, void **p);
+void nafgpu_host_free(void *p);
+
+/* ---- the hot path, host buffers (what ennaf / unnaf call) ---- */
+
+/* FASTA/FASTQ text -> .naf bytes.  Replaces process() + compress() + the container writer.
+ * *naf points into pinned memory owned by ctx. */
+int nafgpu_encode(nafgpu_ctx *ctx, const uint8_t *text, size_t n, const nafgpu_enc_opts *opts,
+                  const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info);
+
+/* .naf bytes -> text of the requested view.  Replaces load_*(), the ZSTD_decompress* loops and
+ * print_fasta()/print_fastq()/print_dna()/print_sequences()/print_4bit(). */
+int nafgpu_decode(nafgpu_ctx *ctx, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts,
+                  const uint8_t **text, size_t *text_size);
+
+/* ---- the hot path, device-resident (bench `value`, pipelines that keep data in HBM) ----
+ * d_text / d_naf are device pointers on ctx's device; outputs are device pointers into ctx's arena.
+ * `host_copy` (may be NULL) is a host mirror of the compressed input used only to walk zstd block
+ * headers without a device round trip; if NULL the headers are fetched from the device. */
+int nafgpu_encode_device(nafgpu_ctx *ctx, const uint8_t *d_text, size_t n, const nafgpu_enc_opts *opts,
+                         const uint8_t **d_naf, size_t *naf_size, nafgpu_enc_info *info);
+int nafgpu_decode_device(nafgpu_ctx *ctx, const uint8_t *d_naf, size_t n, const uint8_t *host_copy,
+                         const nafgpu_dec_opts *opts, const uint8_t **d_text, size_t *text_size);
+
+/* ---- stage entry points (parity tests, ncu) — host buffers in, pinned ctx-owned buffers out ---- */
+
+/* zstd frame(s) -> bytes.  Replaces ZSTD_decompress (input.c:155; multi-frame) when one_frame = 0 and
+ * the single-frame ZSTD_decompressStream loop (output.c:640) when one_frame = 1.  `src` starts with
+ * the 4-byte zstd magic.  expected_size = regenerated size if known, else 0 (then it is derived). */
+int nafgpu_zstd_decompress(nafgpu_ctx *ctx, const uint8_t *src, size_t n, size_t expected_size, int one_frame,
+                           const uint8_t **out, size_t *out_size);
+
+/* bytes -> one zstd frame (with magic).  Replaces ZSTD_initCStream/compressStream/endStream
+ * (compressor.c:7-20,120,64). */
+int nafgpu_zstd_compress(nafgpu_ctx *ctx, const uint8_t *src, size_t n, int window_log,
+                         const uint8_t **out, size_t *out_size);
+
+/* text -> the six uncompressed streams (no zstd).  streams[k]/sizes[k] in container order
+ * ids, comments, lengths, mask, sequence, quality.  Replaces process() + encoders.c. */
+int nafgpu_split(nafgpu_ctx *ctx, const uint8_t *text, size_t n, const nafgpu_enc_opts *opts,
+                 const uint8_t *streams[6], size_t sizes[6], nafgpu_enc_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,407 @@
+// zstd_hd.cuh — zstd *format* building blocks as __host__ __device__ functions.
+//
+// Everything here is thread-serial logic executed by ONE GPU thread per work item (a block header,
+// a Huffman table, a Huffman stream, the sequences of one block).  The parallelism of the decoder
+// comes from running tens of thousands of those items at once (zstd_dec.cuh), not from inside them.
+// Because the functions are HD, tests/emu runs the very same code on the CPU against the oracle
+// before any GPU time is spent; the shipped library only ever instantiates them in kernels.
+//
+// Written from zstd/doc/zstd_compression_format.md (v1.5.0 as vendored by the reference).  The
+// reference functions whose behaviour each piece replaces are cited per function
+// (paths relative to /root/reference/zstd/lib).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __CUDACC__
+#define HD __host__ __device__ __forceinline__
+#define HDN __host__ __device__
+#else
+#define HD inline
+#define HDN
+#endif
+
+namespace nafz {
+
+typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
+typedef int32_t i32; typedef int64_t i64;
+
+enum : int {
+    Z_OK = 0,
+    Z_ERR_TRUNCATED = 1, Z_ERR_LIT_HEADER = 2, Z_ERR_HUF_TREE = 3, Z_ERR_HUF_STREAM = 4, Z_ERR_FSE_HEADER = 5,
+    Z_ERR_SEQ_HEADER = 6, Z_ERR_SEQ_STREAM = 7, Z_ERR_NO_TABLE = 8, Z_ERR_OFFSET = 9, Z_ERR_SIZE = 10,
+    Z_ERR_RESERVED = 11, Z_ERR_TOO_LARGE = 12
+};
+
+HD int hibit(u32 v)
+{
+#ifdef __CUDA_ARCH__
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
+
+// ------------------------------------------------------------------ backward bit reader
+// Huffman and FSE bitstreams are written forward and read from their last byte (spec "Huffman
+// Coding" / "FSE").  `cont` holds the next unread bits left-aligned; bytes are pulled from
+// decreasing addresses.  Reading past the start of the stream yields zero bits and is detected by
+// `consumed() > total`.  Replaces common/bitstream.h BIT_initDStream/BIT_reloadDStream.
+struct BackBits {
+    const u8 *p;      // stream start
+    i64 next;         // number of bytes not yet loaded (index one past the next byte to load)
+    u64 cont;
+    int avail;        // valid bits in cont (left-aligned)
+    i64 total;        // payload bits in the stream (excludes padding + end mark)
+    i64 used;         // bits consumed so far
+
+    HD bool init(const u8 *src, size_t n)
+    {
+        p = src; next = (i64)n; cont = 0; avail = 0; used = 0; total = 0;
+        if (n == 0) return false;
+        u8 last = src[n - 1];
+        if (last == 0) return false;
+        int pad = 8 - hibit(last);            // zero padding bits + the end-mark bit
+        total = (i64)n * 8 - pad;
+        refill();
+        cont <<= pad; avail -= pad;
+        refill();
+        return true;
+    }
+    HD void refill()
+    {
+        while (avail <= 32) {
+            u32 w;
+            if (next >= 4) {
+                w = (u32)p[next - 4] | ((u32)p[next - 3] << 8) | ((u32)p[next - 2] << 16) | ((u32)p[next - 1] << 24);
+                next -= 4;
+            } else if (next > 0) {
+                w = 0;
+                for (int k = 0; k < 4; k++) { i64 idx = next - 4 + k; if (idx >= 0) w |= (u32)p[idx] << (8 * k); }
+                next = 0;
+            } else {
+                w = 0;                        // below the start: zero bits
+            }
+            cont |= (u64)w << (32 - avail);
+            avail += 32;
+        }
+    }
+    HD u32 peek(int n) const { return n ? (u32)(cont >> (64 - n)) : 0u; }
+    HD void skip(int n) { cont <<= n; avail -= n; used += n; }
+    HD u32 read(int n) { if (avail < n) refill(); u32 v = peek(n); skip(n); return v; }   // n <= 32
+    HD bool overrun() const { return used > total; }
+    HD bool exact() const { return used == total; }
+};
+
+// ------------------------------------------------------------------ FSE
+// Table entry: symbol | nbBits << 8 | baseline << 16.  Replaces decompress/zstd_decompress_block.c:508
+// ZSTD_buildFSETable and common/fse_decompress.c FSE_buildDTable_internal.
+HD u32 fse_sym(u32 e) { return e & 0xFF; }
+HD u32 fse_nb(u32 e) { return (e >> 8) & 0xFF; }
+HD u32 fse_base(u32 e) { return e >> 16; }
+
+// norm[s] in {-1, 0, 1..}; returns false on an inconsistent distribution.  `tmp` = nsym u16 scratch.
+HD bool fse_build_table(u32 *table, const short *norm, int nsym, int log, u16 *next)
+{
+    const int size = 1 << log;
+    int high = size - 1;
+    for (int s = 0; s < nsym; s++) {
+        if (norm[s] == -1) { table[high--] = (u32)s; next[s] = 1; }
+        else next[s] = (u16)norm[s];
+    }
+    const int step = (size >> 1) + (size >> 3) + 3, mask = size - 1;
+    int pos = 0;
+    for (int s = 0; s < nsym; s++) {
+        for (int i = 0; i < norm[s]; i++) {
+            table[pos] = (u32)s;
+            do { pos = (pos + step) & mask; } while (pos > high);
+        }
+    }
+    if (pos != 0) return false;
+    for (int i = 0; i < size; i++) {
+        u32 s = table[i];
+        u32 n = next[s]++;
+        int nb = log - hibit(n);
+        table[i] = s | ((u32)nb << 8) | ((((n << nb) - (u32)size) & 0xFFFF) << 16);
+    }
+    return true;
+}
+
+// Forward LSB-first bit peek used by the FSE table description (spec "FSE Table Description").
+HD u32 fwd_peek(const u8 *p, size_t n, size_t bitpos, int nb)
+{
+    u64 v = 0; size_t byte = bitpos >> 3;
+    for (int i = 0; i < 5; i++) if (byte + i < n) v |= (u64)p[byte + i] << (8 * i);
+    v >>= (bitpos & 7);
+    return (u32)(v & ((1ull << nb) - 1));
+}
+
+// Replaces common/entropy_common.c:64 FSE_readNCount_body.  Returns bytes used, 0 on error.
+HD size_t fse_read_ncount(const u8 *p, size_t n, short *norm, int *nsym, int max_sym, int max_log, int *log_out)
+{
+    if (n < 1) return 0;
+    size_t bit = 0;
+    int log = (int)fwd_peek(p, n, bit, 4) + 5; bit += 4;
+    if (log > max_log) return 0;
+    int remaining = 1 << log, sym = 0;
+    while (remaining > 0 && sym <= max_sym) {
+        int bits = hibit((u32)remaining + 1) + 1;
+        u32 val = fwd_peek(p, n, bit, bits);
+        u32 lower = (1u << (bits - 1)) - 1;
+        u32 thresh = (1u << bits) - 1 - (u32)(remaining + 1);
+        if ((val & lower) < thresh) { bit += bits - 1; val &= lower; }
+        else { bit += bits; if (val > lower) val -= thresh; }
+        int proba = (int)val - 1;
+        remaining -= proba < 0 ? 1 : proba;
+        norm[sym++] = (short)proba;
+        if (proba == 0) {
+            u32 rep;
+            do {
+                rep = fwd_peek(p, n, bit, 2); bit += 2;
+                for (u32 i = 0; i < rep && sym <= max_sym; i++) norm[sym++] = 0;
+            } while (rep == 3);
+        }
+        if ((bit >> 3) > n + 4) return 0;
+    }
+    if (remaining != 0 || sym > max_sym + 1) return 0;
+    size_t used = (bit + 7) >> 3;
+    if (used > n) return 0;
+    *nsym = sym; *log_out = log;
+    return used;
+}
+
+// ------------------------------------------------------------------ predefined distributions / code tables
+// spec "Default Distributions", "Literals length codes", "Match length codes"
+// (common/zstd_internal.h:185-242).
+#ifdef __CUDA_ARCH__
+#define ZCONST __constant__
+#else
+#define ZCONST static const
+#endif
+
+struct SeqConsts {
+    short ll_norm[36]; short ml_norm[53]; short of_norm[29];
+    u32 ll_base[36]; u8 ll_bits[36]; u32 ml_base[53]; u8 ml_bits[53];
+};
+
+HD void seq_consts_init(SeqConsts &c)
+{
+    const short ll[36] = { 4,3,2,2,2,2,2,2,2,2,2,2,2,1,1,1,2,2,2,2,2,2,2,2,2,3,2,1,1,1,1,1,-1,-1,-1,-1 };
+    const short ml[53] = { 1,4,3,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,
+                           1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1,-1,-1 };
+    const short of[29] = { 1,1,1,1,1,1,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,-1,-1,-1,-1,-1 };
+    for (int i = 0; i < 36; i++) c.ll_norm[i] = ll[i];
+    for (int i = 0; i < 53; i++) c.ml_norm[i] = ml[i];
+    for (int i = 0; i < 29; i++) c.of_norm[i] = of[i];
+}
+
+HD u32 ll_base_of(u32 c) { return c < 16 ? c : (c < 20 ? 16 + ((c - 16) << 1) : (c < 22 ? 24 + ((c - 20) << 2) : (c < 24 ? 32 + ((c - 22) << 3) : (c == 24 ? 48u : (1u << (c - 19)))))); }
+HD u32 ll_bits_of(u32 c) { return c < 16 ? 0 : (c < 20 ? 1 : (c < 22 ? 2 : (c < 24 ? 3 : (c == 24 ? 4 : c - 19)))); }
+HD u32 ml_base_of(u32 c)
+{
+    if (c < 32) return c + 3;
+    if (c < 36) return 35 + ((c - 32) << 1);
+    if (c < 38) return 43 + ((c - 36) << 2);
+    if (c < 40) return 51 + ((c - 38) << 3);
+    if (c < 42) return 67 + ((c - 40) << 4);
+    if (c == 42) return 99;
+    return (1u << (c - 36)) + 3;      // 43 -> 131, 44 -> 259, ... 52 -> 65539
+}
+HD u32 ml_bits_of(u32 c)
+{
+    if (c < 32) return 0;
+    if (c < 36) return 1;
+    if (c < 38) return 2;
+    if (c < 40) return 3;
+    if (c < 42) return 4;
+    if (c == 42) return 5;
+    return c - 36;                    // 43 -> 7 ... 52 -> 16
+}
+
+// ------------------------------------------------------------------ Huffman
+// Decode table entry (u16): symbol | nbBits << 8; 1 << max_bits entries.
+// Replaces decompress/huf_decompress.c:142 HUF_readDTableX1_wksp + common/entropy_common.c:265 HUF_readStats_body.
+
+// Reads the tree description into weights[0..*nw) (implied last weight appended).  Returns bytes used, 0 on error.
+HD size_t huf_read_weights(const u8 *p, size_t n, u8 *weights, int *nw_out, int *max_bits_out)
+{
+    if (n < 1) return 0;
+    int hb = p[0], nw = 0; size_t used;
+    if (hb >= 128) {
+        nw = hb - 127;
+        size_t bytes = (size_t)(nw + 1) / 2;
+        if (1 + bytes > n) return 0;
+        for (int i = 0; i < nw; i++) weights[i] = (i & 1) ? (p[1 + i / 2] & 15) : (p[1 + i / 2] >> 4);
+        used = 1 + bytes;
+    } else {
+        if (hb == 0 || (size_t)1 + hb > n) return 0;
+        short norm[16]; int nsym, log; u16 next[16]; u32 table[64];
+        size_t hdr = fse_read_ncount(p + 1, hb, norm, &nsym, 12, 6, &log);
+        if (hdr == 0 || hdr >= (size_t)hb) return 0;
+        if (!fse_build_table(table, norm, nsym, log, next)) return 0;
+        BackBits b;
+        if (!b.init(p + 1 + hdr, (size_t)hb - hdr)) return 0;
+        u32 s1 = b.read(log), s2 = b.read(log);
+        if (b.overrun()) return 0;
+        for (;;) {
+            if (nw >= 254) return 0;
+            u32 e = table[s1]; weights[nw++] = (u8)fse_sym(e);
+            s1 = fse_base(e) + b.read((int)fse_nb(e));
+            if (b.overrun()) { weights[nw++] = (u8)fse_sym(table[s2]); break; }
+            if (nw >= 254) return 0;
+            e = table[s2]; weights[nw++] = (u8)fse_sym(e);
+            s2 = fse_base(e) + b.read((int)fse_nb(e));
+            if (b.overrun()) { weights[nw++] = (u8)fse_sym(table[s1]); break; }
+        }
+        used = 1 + (size_t)hb;
+    }
+    if (nw > 255) return 0;
+    u32 total = 0;
+    for (int i = 0; i < nw; i++) { if (weights[i] > 11) return 0; if (weights[i]) total += 1u << (weights[i] - 1); }
+    if (total == 0) return 0;
+    int max_bits = hibit(total) + 1;
+    if (max_bits > 11) return 0;
+    u32 left = (1u << max_bits) - total;
+    if (left & (left - 1)) return 0;
+    weights[nw++] = (u8)(hibit(left) + 1);
+    *nw_out = nw; *max_bits_out = max_bits;
+    return used;
+}
+
+// Fills table[0 .. 1<<max_bits).  Longer codes take the numerically lower slots, equal lengths in
+// symbol order (spec "Huffman Tree Description": conversion of weights into prefix codes).
+HD bool huf_build_table(u16 *table, const u8 *weights, int nw, int max_bits)
+{
+    u32 rank_count[13], rank_idx[13];
+    for (int i = 0; i < 13; i++) rank_count[i] = 0;
+    for (int i = 0; i < nw; i++) if (weights[i]) rank_count[max_bits + 1 - weights[i]]++;
+    rank_idx[max_bits] = 0;
+    for (int b = max_bits; b >= 1; b--) rank_idx[b - 1] = rank_idx[b] + rank_count[b] * (1u << (max_bits - b));
+    if (rank_idx[0] != (1u << max_bits)) return false;
+    for (int i = 0; i < nw; i++) {
+        if (!weights[i]) continue;
+        int bits = max_bits + 1 - weights[i];
+        u32 len = 1u << (max_bits - bits), at = rank_idx[bits];
+        u16 e = (u16)((u32)i | ((u32)bits << 8));
+        for (u32 k = 0; k < len; k++) table[at + k] = e;
+        rank_idx[bits] = at + len;
+    }
+    return true;
+}
+
+// One Huffman-coded stream -> nout symbols.  Replaces decompress/huf_decompress.c:350
+// HUF_decompress4X1_usingDTable_internal_body's per-stream loop (and the 1X1 variant :285).
+HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t n, u8 *dst, size_t nout)
+{
+    BackBits b;
+    if (!b.init(src, n)) return false;
+    for (size_t i = 0; i < nout; i++) {
+        if (b.avail < max_bits) b.refill();
+        u32 e = table[b.peek(max_bits)];
+        dst[i] = (u8)e;
+        b.skip((int)(e >> 8));
+    }
+    return b.exact();
+}
+
+// ------------------------------------------------------------------ literals section header
+// spec "Literals_Section_Header"; replaces decompress/zstd_decompress_block.c:79 ZSTD_decodeLiteralsBlock's parsing.
+struct LitHeader {
+    u32 type;        // 0 raw, 1 RLE, 2 compressed, 3 treeless
+    u32 streams;     // 1 or 4
+    u32 regen;       // regenerated size
+    u32 csize;       // compressed payload size (tree + jump table + streams); raw: regen; RLE: 1
+    u32 hdr;         // header bytes
+};
+
+HD int lit_header_parse(const u8 *p, size_t n, LitHeader &h)
+{
+    if (n < 1) return Z_ERR_TRUNCATED;
+    u32 type = p[0] & 3, sf = (p[0] >> 2) & 3;
+    h.type = type; h.streams = 1;
+    if (type < 2) {
+        if ((sf & 1) == 0) { h.regen = p[0] >> 3; h.hdr = 1; }
+        else if (sf == 1) { if (n < 2) return Z_ERR_TRUNCATED; h.regen = (p[0] >> 4) | ((u32)p[1] << 4); h.hdr = 2; }
+        else { if (n < 3) return Z_ERR_TRUNCATED; h.regen = (p[0] >> 4) | ((u32)p[1] << 4) | ((u32)p[2] << 12); h.hdr = 3; }
+        h.csize = type == 0 ? h.regen : 1;
+    } else {
+        if (sf < 2) {
+            if (n < 3) return Z_ERR_TRUNCATED;
+            u32 v = p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16);
+            h.regen = (v >> 4) & 0x3FF; h.csize = (v >> 14) & 0x3FF; h.hdr = 3; h.streams = sf == 0 ? 1 : 4;
+        } else if (sf == 2) {
+            if (n < 4) return Z_ERR_TRUNCATED;
+            u32 v = p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24);
+            h.regen = (v >> 4) & 0x3FFF; h.csize = (v >> 18) & 0x3FFF; h.hdr = 4; h.streams = 4;
+        } else {
+            if (n < 5) return Z_ERR_TRUNCATED;
+            u64 v = p[0] | ((u64)p[1] << 8) | ((u64)p[2] << 16) | ((u64)p[3] << 24) | ((u64)p[4] << 32);
+            h.regen = (u32)((v >> 4) & 0x3FFFF); h.csize = (u32)((v >> 22) & 0x3FFFF); h.hdr = 5; h.streams = 4;
+        }
+    }
+    if (h.regen > 128 * 1024) return Z_ERR_LIT_HEADER;
+    if ((size_t)h.hdr + h.csize > n) return Z_ERR_TRUNCATED;
+    return Z_OK;
+}
+
+// ------------------------------------------------------------------ sequences section header
+// spec "Sequences_Section_Header"; replaces decompress/zstd_decompress_block.c:577 ZSTD_decodeSeqHeaders' first part.
+// Returns bytes used (nbSeq field + modes byte if nbSeq > 0), 0 on error.
+HD size_t seq_header_parse(const u8 *p, size_t n, u32 *nseq, u32 *modes)
+{
+    if (n < 1) return 0;
+    size_t pos;
+    if (p[0] < 128) { *nseq = p[0]; pos = 1; }
+    else if (p[0] < 255) { if (n < 2) return 0; *nseq = ((u32)(p[0] - 128) << 8) + p[1]; pos = 2; }
+    else { if (n < 3) return 0; *nseq = (u32)p[1] + ((u32)p[2] << 8) + 0x7F00; pos = 3; }
+    *modes = 0;
+    if (*nseq == 0) return pos;
+    if (pos >= n) return 0;
+    *modes = p[pos++];
+    return pos;
+}
+
+// ------------------------------------------------------------------ repeat offsets as transfer functions
+// spec "Repeat Offsets".  To decode blocks in parallel, each block first computes how it maps the
+// repeat-offset history it receives to the history it leaves (RepFn); a scan composes them.
+// A slot value is either a concrete offset (src < 0) or "incoming slot src, plus delta" (delta <= 0).
+struct RepSlot { i32 src; i32 delta; u32 value; };
+struct RepFn { RepSlot s[3]; };
+
+HD RepFn repfn_identity()
+{
+    RepFn f;
+    for (int i = 0; i < 3; i++) { f.s[i].src = i; f.s[i].delta = 0; f.s[i].value = 0; }
+    return f;
+}
+HD RepSlot repslot_concrete(u32 v) { RepSlot r; r.src = -1; r.delta = 0; r.value = v; return r; }
+
+// Apply one sequence's offset_value / literal length to a symbolic history.  Returns the slot
+// describing the actual offset used by this sequence.
+HD RepSlot repfn_step(RepFn &f, u32 ofv, u32 ll)
+{
+    RepSlot used;
+    if (ofv > 3) {
+        used = repslot_concrete(ofv - 3);
+        f.s[2] = f.s[1]; f.s[1] = f.s[0]; f.s[0] = used;
+        return used;
+    }
+    u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
+    if (idx == 0) return f.s[0];
+    if (idx == 3) { used = f.s[0]; if (used.src < 0) used.value -= 1; else used.delta -= 1; }
+    else used = f.s[idx];
+    if (idx != 1) f.s[2] = f.s[1];
+    f.s[1] = f.s[0]; f.s[0] = used;
+    return used;
+}
+
+HD u32 repslot_eval(const RepSlot &s, const u32 in[3]) { return s.src < 0 ? s.value : in[s.src] + (u32)s.delta; }
+
+// history after applying f to `in`
+HD void repfn_apply(const RepFn &f, const u32 in[3], u32 out[3])
+{
+    u32 t0 = repslot_eval(f.s[0], in), t1 = repslot_eval(f.s[1], in), t2 = repslot_eval(f.s[2], in);
+    out[0] = t0; out[1] = t1; out[2] = t2;
+}
+
+}  // namespace nafz
