@@ -1,0 +1,271 @@
+// api.cu — the extern "C" boundary declared in include/nafgpu.h.
+#include "common.cuh"
+#include "container.hpp"
+#include "zstd_dec.cuh"
+
+namespace nafg {
+DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o);
+EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
+SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
+EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log);
+}
+
+using namespace nafg;
+
+static thread_local std::string g_create_error;
+
+template <class F> static int guarded(nafgpu_ctx *ctx, F f)
+{
+    if (!ctx) return NAFGPU_E_ARG;
+    try {
+        ctx->err.clear();
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        ctx->arena.reset();
+        f();
+        return NAFGPU_OK;
+    } catch (const NafError &e) {
+        ctx->err = e.msg; cudaStreamSynchronize(ctx->stream); return e.code;
+    } catch (const CudaError &e) {
+        char buf[512];
+        snprintf(buf, sizeof buf, "CUDA error: %s (%s) at %s:%d\n", cudaGetErrorString(e.e), e.what, e.file, e.line);
+        ctx->err = buf; cudaGetLastError(); return NAFGPU_E_CUDA;
+    } catch (const std::exception &e) {
+        ctx->err = std::string("internal error: ") + e.what() + "\n"; return NAFGPU_E_CUDA;
+    }
+}
+
+extern "C" {
+
+const char *nafgpu_version(void) { return NAFGPU_VERSION; }
+
+int nafgpu_create(int device, nafgpu_ctx **out)
+{
+    if (!out) return NAFGPU_E_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (libnafgpu has no CPU path)\n";
+        cudaGetLastError();
+        return NAFGPU_E_CUDA;
+    }
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        g_create_error = "device is not sm_100 (Blackwell): libnafgpu is built for sm_100a only\n";
+        return NAFGPU_E_CUDA;
+    }
+    nafgpu_ctx *c = new nafgpu_ctx();
+    c->device = device;
+    try {
+        CUDA_TRY(cudaSetDevice(device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+        u32 predef[nafz::FSE_SLOT_ENTRIES];
+        nafz::zstd_build_predef(predef);
+        CUDA_TRY(cudaMalloc(&c->d_predef, sizeof predef));
+        CUDA_TRY(cudaMemcpy(c->d_predef, predef, sizeof predef, cudaMemcpyHostToDevice));
+    } catch (const CudaError &er) {
+        g_create_error = std::string("CUDA error during context creation: ") + cudaGetErrorString(er.e) + "\n";
+        delete c; return NAFGPU_E_CUDA;
+    }
+    *out = c;
+    return NAFGPU_OK;
+}
+
+void nafgpu_destroy(nafgpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->arena.release(); c->pinned_out.release(); c->pinned_aux.release();
+    if (c->d_predef) cudaFree(c->d_predef);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char *nafgpu_last_error(const nafgpu_ctx *c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+int nafgpu_get_timing(const nafgpu_ctx *c, nafgpu_timing *t) { if (!c || !t) return NAFGPU_E_ARG; *t = c->timing; return 0; }
+void *nafgpu_stream(nafgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int nafgpu_host_alloc(size_t n, void **p) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : NAFGPU_E_CUDA; }
+void nafgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"
+
+// host buffer -> device copy with 64 bytes of zero padding after it
+static u8 *to_device(Ctx &c, CudaExec &ex, const u8 *h, size_t n)
+{
+    u8 *d = ex.alloc<u8>(n + 64);
+    if (n) CUDA_TRY(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c.stream));
+    CUDA_TRY(cudaMemsetAsync(d + n, 0, 64, c.stream));
+    return d;
+}
+static const u8 *to_pinned(Ctx &c, const u8 *d, size_t n)
+{
+    u8 *h = c.pinned_out.ensure(n + 1);
+    if (n) CUDA_TRY(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c.stream));
+    return h;
+}
+static void finish_timing(Ctx &c, CudaExec &ex)
+{
+    CUDA_TRY(cudaEventRecord(c.ev[3], c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    CUDA_TRY(cudaGetLastError());
+    cudaEventElapsedTime(&c.timing.h2d_ms, c.ev[0], c.ev[1]);
+    cudaEventElapsedTime(&c.timing.kernels_ms, c.ev[1], c.ev[2]);
+    cudaEventElapsedTime(&c.timing.d2h_ms, c.ev[2], c.ev[3]);
+    cudaEventElapsedTime(&c.timing.total_ms, c.ev[0], c.ev[3]);
+    c.timing.kernel_launches = ex.launches;
+}
+
+extern "C" {
+
+int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts, const uint8_t **text, size_t *text_size)
+{
+    if (!naf || !opts || !text || !text_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *text = nullptr; *text_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        nafc::Header h; std::string err;
+        if (!nafc::read_header(naf, n, h, false, err)) fail(NAFGPU_E_FORMAT, err);      // fail before any transfer
+        u8 *d_naf = to_device(*c, ex, naf, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        DecodeOut r = decode_on_device(*c, ex, d_naf, naf, n, *opts);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *text = to_pinned(*c, r.d_text, r.size); *text_size = r.size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_decode_device(nafgpu_ctx *c, const uint8_t *d_naf, size_t n, const uint8_t *host_copy, const nafgpu_dec_opts *opts,
+                         const uint8_t **d_text, size_t *text_size)
+{
+    if (!d_naf || !opts || !d_text || !text_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *d_text = nullptr; *text_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        const u8 *h = host_copy;
+        if (!h) {                                     // no host mirror: fetch the compressed bytes once for the header walk
+            u8 *tmp = c->pinned_aux.ensure(n + 1);
+            CUDA_TRY(cudaMemcpyAsync(tmp, d_naf, n, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            h = tmp;
+        }
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        DecodeOut r = decode_on_device(*c, ex, d_naf, h, n, *opts);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *d_text = r.d_text; *text_size = r.size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_zstd_decompress(nafgpu_ctx *c, const uint8_t *src, size_t n, size_t expected_size, int one_frame,
+                           const uint8_t **out, size_t *out_size)
+{
+    if (!src || !out || !out_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *out = nullptr; *out_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        u8 *d_in = to_device(*c, ex, src, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        // unknown size: bound it by walking the headers is not possible for compressed blocks, so take
+        // the format's worst case of 128 KB per block (cheap: the arena is virtual until touched).
+        nafz::ZDecPlan plan;
+        u64 cap = expected_size;
+        if (!cap) {
+            std::vector<nafz::ZBlock> blocks; std::string werr; u64 used = 0;
+            nafz::ZStreamDesc probe{0, n, 0, ~0ull, one_frame, 0};
+            if (nafz::zstd_walk_stream(src, probe, 0, blocks, &used, werr)) fail(NAFGPU_E_FORMAT, werr + "\n");
+            for (auto &b : blocks) cap += b.type == 2 ? 128 * 1024 : b.rsize;
+        }
+        u8 *d_out = ex.alloc<u8>(cap + 256);
+        plan.streams.push_back(nafz::ZStreamDesc{0, n, 0, cap, one_frame, 0});
+        std::string zerr;
+        int rc = nafz::zstd_decode_batch(ex, d_in, src, d_out, plan, c->d_predef, zerr);
+        if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, zerr + "\n");
+        if (expected_size && plan.results[0].out_size != expected_size) fail(NAFGPU_E_FORMAT, "zstd stream size mismatch\n");
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *out = to_pinned(*c, d_out, plan.results[0].out_size); *out_size = plan.results[0].out_size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_encode(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_opts *opts, const uint8_t **naf, size_t *naf_size,
+                  nafgpu_enc_info *info)
+{
+    if ((!text && n) || !opts || !naf || !naf_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *naf = nullptr; *naf_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        u8 *d_text = to_device(*c, ex, text, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *naf = to_pinned(*c, r.d_naf, r.size); *naf_size = r.size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_encode_device(nafgpu_ctx *c, const uint8_t *d_text, size_t n, const nafgpu_enc_opts *opts, const uint8_t **d_naf,
+                         size_t *naf_size, nafgpu_enc_info *info)
+{
+    if ((!d_text && n) || !opts || !d_naf || !naf_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *d_naf = nullptr; *naf_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *d_naf = r.d_naf; *naf_size = r.size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_zstd_compress(nafgpu_ctx *c, const uint8_t *src, size_t n, int window_log, const uint8_t **out, size_t *out_size)
+{
+    if ((!src && n) || !out || !out_size) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        *out = nullptr; *out_size = 0;
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        u8 *d_in = to_device(*c, ex, src, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        EncodeOut r = zstd_compress_on_device(*c, ex, d_in, n, window_log);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *out = to_pinned(*c, r.d_naf, r.size); *out_size = r.size;
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_opts *opts, const uint8_t *streams[6], size_t sizes[6],
+                 nafgpu_enc_info *info)
+{
+    if ((!text && n) || !opts || !streams || !sizes) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        CudaExec ex{c->stream, &c->arena};
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        u8 *d_text = to_device(*c, ex, text, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        SplitOut r = split_on_device(*c, ex, d_text, n, *opts, info);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        u64 total = 0;
+        for (int k = 0; k < 6; k++) total += (r.size[k] + 63) & ~63ull;
+        u8 *h = c->pinned_out.ensure(total + 64);
+        u64 off = 0;
+        for (int k = 0; k < 6; k++) {
+            streams[k] = h + off; sizes[k] = r.size[k];
+            if (r.size[k]) CUDA_TRY(cudaMemcpyAsync(h + off, r.d[k], r.size[k], cudaMemcpyDeviceToHost, c->stream));
+            off += (r.size[k] + 63) & ~63ull;
+        }
+        finish_timing(*c, ex);
+    });
+}
+
+}  // extern "C"

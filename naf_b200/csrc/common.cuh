@@ -1,0 +1,201 @@
+// common.cuh — context, device arena, CUDA executor and scan primitives shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/nafgpu.h"
+#include "zstd_hd.cuh"
+
+namespace nafg {
+
+using nafz::u8; using nafz::u16; using nafz::u32; using nafz::u64; using nafz::i32; using nafz::i64;
+
+struct CudaError { cudaError_t e; const char *what; const char *file; int line; };
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) throw nafg::CudaError{e_, #expr, __FILE__, __LINE__};        \
+    } while (0)
+
+struct NafError { int code; std::string msg; };
+[[noreturn]] inline void fail(int code, const std::string &msg) { throw NafError{code, msg}; }
+
+// ------------------------------------------------------------------ device arena
+// Bump allocator over cudaMalloc'd slabs.  reset() at the start of every call; if a call needed more
+// than one slab they are merged into a single bigger one afterwards, so steady state is one slab and
+// zero cudaMalloc calls per encode/decode.
+struct Arena {
+    struct Slab { u8 *p; size_t cap; size_t used; };
+    std::vector<Slab> slabs;
+    size_t high_water = 0, cur_total = 0;
+
+    void *alloc_bytes(size_t n)
+    {
+        n = (n + 255) & ~(size_t)255;
+        if (n == 0) n = 256;
+        cur_total += n;
+        if (cur_total > high_water) high_water = cur_total;
+        for (auto &s : slabs)
+            if (s.cap - s.used >= n) { void *r = s.p + s.used; s.used += n; return r; }
+        size_t cap = n > (size_t)(256u << 20) ? n : (size_t)(256u << 20);
+        Slab s; s.cap = cap; s.used = n;
+        CUDA_TRY(cudaMalloc(&s.p, cap));
+        slabs.push_back(s);
+        return s.p;
+    }
+    void reset()
+    {
+        if (slabs.size() > 1 || (slabs.size() == 1 && slabs[0].cap < high_water)) {
+            for (auto &s : slabs) cudaFree(s.p);
+            slabs.clear();
+            Slab s; s.cap = high_water + (high_water >> 3) + (1u << 20); s.used = 0;
+            CUDA_TRY(cudaMalloc(&s.p, s.cap));
+            slabs.push_back(s);
+        }
+        for (auto &s : slabs) s.used = 0;
+        cur_total = 0;
+    }
+    void release() { for (auto &s : slabs) cudaFree(s.p); slabs.clear(); }
+};
+
+struct PinnedBuf {
+    u8 *p = nullptr; size_t cap = 0;
+    u8 *ensure(size_t n)
+    {
+        if (n <= cap) return p;
+        if (p) cudaFreeHost(p);
+        cap = n + (n >> 3) + 4096; p = nullptr;
+        CUDA_TRY(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
+        return p;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+// ------------------------------------------------------------------ generic kernels for HD bodies
+template <class F> __global__ void k_for_each(size_t n, F f)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+template <class F> __global__ void k_for_each_group(F f) { f((size_t)blockIdx.x, threadIdx.x, blockDim.x); }
+
+struct CudaExec {
+    cudaStream_t stream;
+    Arena *arena;
+    u32 launches = 0;
+
+    template <class T> T *alloc(size_t count) { return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1)); }
+    void upload(void *dst, const void *src, size_t n) { if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream)); }
+    void download(void *dst, const void *src, size_t n)
+    {
+        if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+    }
+    void zero(void *p, size_t n) { if (n) CUDA_TRY(cudaMemsetAsync(p, 0, n, stream)); }
+    void fill(void *p, int v, size_t n) { if (n) CUDA_TRY(cudaMemsetAsync(p, v, n, stream)); }
+    template <class F> void for_each(size_t n, F f)
+    {
+        if (!n) return;
+        k_for_each<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, f);
+        launches++;
+    }
+    template <class F> void for_each_group(size_t ngroups, int threads, F f)
+    {
+        if (!ngroups) return;
+        k_for_each_group<<<(unsigned)ngroups, threads, 0, stream>>>(f);
+        launches++;
+    }
+    void check() { CUDA_TRY(cudaGetLastError()); }
+};
+
+// ------------------------------------------------------------------ device-wide exclusive scan (u64 sums)
+// Reduce-then-scan over tiles of SCAN_TILE items: (1) per-tile sums, (2) one CTA scans the tile sums,
+// (3) per-tile local scan + tile prefix.  Input is a functor so predicates (byte == 0, unit != 255 ...)
+// are scanned without being materialised.  out has n + 1 entries; out[n] = total.
+static const int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u64 warp_incl_scan(u64 v)
+{
+    const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { u64 t = __shfl_up_sync(0xFFFFFFFFu, v, d); if (lane >= (unsigned)d) v += t; }
+    return v;
+}
+// exclusive scan across the CTA of one value per thread; returns exclusive prefix, *total = CTA sum
+__device__ __forceinline__ u64 block_excl_scan(u64 v, u64 *total, u64 *smem /* >= 33 */)
+{
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    u64 incl = warp_incl_scan(v);
+    if (lane == 31) smem[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = lane < nwarps ? smem[lane] : 0;
+        u64 wi = warp_incl_scan(w);
+        smem[lane] = wi - w;
+        if (lane == 31) smem[32] = wi;
+    }
+    __syncthreads();
+    u64 r = smem[warp] + incl - v;
+    *total = smem[32];
+    __syncthreads();
+    return r;
+}
+
+template <class In> __global__ void k_scan_reduce(In in, size_t n, u64 *tile_sums)
+{
+    __shared__ u64 sm[33];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    u64 s = 0;
+#pragma unroll 4
+    for (int k = 0; k < SCAN_ITEMS; k++) if (base + k < n) s += in(base + k);
+    u64 total; block_excl_scan(s, &total, sm);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void k_scan_tiles(u64 *tile_sums, size_t ntiles, u64 *grand_total);
+template <class In> __global__ void k_scan_apply(In in, size_t n, const u64 *tile_prefix, u64 *out)
+{
+    __shared__ u64 sm[33];
+    size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    u64 v[SCAN_ITEMS]; u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { v[k] = base + k < n ? in(base + k) : 0; s += v[k]; }
+    u64 total; u64 p = block_excl_scan(s, &total, sm) + tile_prefix[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) { if (base + k < n) out[base + k] = p; p += v[k]; }
+    if (base <= n && n < base + SCAN_ITEMS) out[n] = p - 0;      // thread owning position n writes the total
+}
+
+template <class In> void exclusive_scan(CudaExec &ex, In in, size_t n, u64 *out)
+{
+    size_t ntiles = (n + SCAN_TILE) / SCAN_TILE;          // >= 1, and covers index n
+    u64 *tiles = ex.alloc<u64>(ntiles + 1);
+    k_scan_reduce<<<(unsigned)ntiles, SCAN_THREADS, 0, ex.stream>>>(in, n, tiles);
+    k_scan_tiles<<<1, 1024, 0, ex.stream>>>(tiles, ntiles, tiles + ntiles);
+    k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, ex.stream>>>(in, n, tiles, out);
+    ex.launches += 3;
+}
+
+// ------------------------------------------------------------------ context
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Arena arena;
+    PinnedBuf pinned_out, pinned_aux;
+    u32 *d_predef = nullptr;                 // predefined FSE tables
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::string err;
+    nafgpu_timing timing{};
+    std::vector<u8> host_scratch;
+};
+
+struct DecodeOut { const u8 *d_text; u64 size; };
+struct EncodeOut { const u8 *d_naf; u64 size; };
+struct SplitOut { const u8 *d[6]; u64 size[6]; };
+
+}  // namespace nafg
+
+struct nafgpu_ctx : nafg::Ctx {};

@@ -1,0 +1,540 @@
+// naf_dec.cu — .naf -> text on the GPU.
+//
+// Replaces unnaf's decode path after the header is parsed:
+//   load_ids / load_names / load_lengths / load_mask      unnaf/src/input.c:145-246
+//   the ZSTD_decompressStream loops                       unnaf/src/output.c:640-650, input.c:352-440
+//   init_tables + write_4bit_as_fasta (4-bit -> ASCII)    unnaf/src/utils.c:74, output.c:445
+//   mask_dna_buffer (+32 over masked runs)                unnaf/src/output.c:295
+//   print_dna_buffer_as_fasta / print_dna_split_into_lines / print_name   output.c:369,339,105
+//   print_fastq                                           unnaf/src/output-fastq.c:100
+//   print_dna (--seq), print_sequences, print_4bit, print_ids, print_names, print_charcount
+//
+// The reference streams 128 KB at a time through one core.  Here the whole file is resident in HBM:
+// all streams are entropy-decoded together (zstd_dec.cuh), prefix sums give every record its place in
+// the output text, and ONE kernel (k_write_text) then materialises the text: each thread produces 16
+// consecutive output bytes, wherever they fall — header, wrapped sequence line, '+' line or quality.
+#include "common.cuh"
+#include "container.hpp"
+#include "zstd_dec.cuh"
+
+namespace nafg {
+
+// ------------------------------------------------------------------ small kernels
+
+__global__ void k_scan_tiles(u64 *tile_sums, size_t ntiles, u64 *grand_total)
+{
+    __shared__ u64 sm[33];
+    u64 carry = 0;
+    for (size_t base = 0; base < ntiles; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        u64 v = i < ntiles ? tile_sums[i] : 0, total;
+        u64 p = block_excl_scan(v, &total, sm);
+        if (i < ntiles) tile_sums[i] = carry + p;
+        carry += total;
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+// positions of the '\0' terminators of a string stream (ids / comments): end[r] = index of r-th zero
+static const int ZT = 4096;
+__global__ void k_zero_count(const u8 *s, u64 n, u64 *tile_counts)
+{
+    __shared__ u64 sm[33];
+    u64 base = (u64)blockIdx.x * ZT + (u64)threadIdx.x * 16;
+    u64 c = 0;
+    for (int k = 0; k < 16; k++) if (base + k < n && s[base + k] == 0) c++;
+    u64 total; block_excl_scan(c, &total, sm);
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = total;
+}
+__global__ void k_zero_scatter(const u8 *s, u64 n, const u64 *tile_prefix, u32 *end, u64 max_records)
+{
+    __shared__ u64 sm[33];
+    u64 base = (u64)blockIdx.x * ZT + (u64)threadIdx.x * 16;
+    u64 c = 0;
+    for (int k = 0; k < 16; k++) if (base + k < n && s[base + k] == 0) c++;
+    u64 total; u64 r = block_excl_scan(c, &total, sm) + tile_prefix[blockIdx.x];
+    for (int k = 0; k < 16; k++) if (base + k < n && s[base + k] == 0) { if (r < max_records) end[r] = (u32)(base + k); r++; }
+}
+
+// ------------------------------------------------------------------ text layout
+
+struct TextArgs {
+    // record structure
+    u8  prefix;           // '>' / '@' / 0
+    u8  with_name;        // name bytes present
+    u8  name_nl;          // '\n' after the name part
+    u8  has_ids, has_names, sep;
+    u8  seq_present;      // sequence area present
+    u8  seq_nl;           // 0: no newline after the sequence, 1: only when L > 0 (FASTA), 2: always
+    u8  with_qual;        // "+\n" qual "\n"
+    u8  packed;           // 4-bit sequence stream
+    u8  upper;            // toupper() on raw sequence bytes (protein/text with --no-mask)
+    u64 W;                // line width inside the sequence area, 0 = unlimited
+    // streams
+    const u8 *ids, *comm, *seq, *qual;
+    const u32 *id_end, *cm_end;      // per record: index of its '\0'
+    const u64 *L, *seq_start;        // per record: bases, first base index
+    const u32 *maskbits;             // 1 bit per base or nullptr
+    const u64 *out_start;            // per record: first output byte; [N] = total
+    u64 N, total, total_bases;
+    u32 lut[4];                      // code_to_nuc as 16 bytes
+    u8 *out;
+};
+
+struct RecInfo { u64 a, b, c, d, e; u64 L, sbase; u32 id_s, id_len, cm_s, cm_len; };
+
+__device__ __forceinline__ u64 seq_area_len(const TextArgs &A, u64 L)
+{
+    if (!A.seq_present) return 0;
+    u64 nl = A.seq_nl == 0 ? 0 : (A.seq_nl == 2 ? 1 : (L > 0));
+    if (A.W > 0 && A.seq_nl == 1) nl = (L + A.W - 1) / A.W;
+    return L + nl;
+}
+__device__ __forceinline__ u32 name_len_of(const TextArgs &A, u32 id_len, u32 cm_len)
+{
+    if (!A.with_name) return 0;
+    if (A.has_ids && A.has_names) return id_len + (cm_len ? 1 + cm_len : 0);
+    return A.has_ids ? id_len : cm_len;
+}
+__device__ __forceinline__ void load_rec(const TextArgs &A, u64 i, RecInfo &R)
+{
+    R.id_s = R.id_len = R.cm_s = R.cm_len = 0;
+    if (A.with_name) {
+        if (A.has_ids) { R.id_s = i ? A.id_end[i - 1] + 1 : 0; R.id_len = A.id_end[i] - R.id_s; }
+        if (A.has_names) { R.cm_s = i ? A.cm_end[i - 1] + 1 : 0; R.cm_len = A.cm_end[i] - R.cm_s; }
+    }
+    R.L = A.seq_present ? A.L[i] : 0; R.sbase = A.seq_present ? A.seq_start[i] : 0;
+    R.a = A.prefix ? 1 : 0;
+    R.b = R.a + name_len_of(A, R.id_len, R.cm_len);
+    R.c = R.b + A.name_nl;
+    R.d = R.c + seq_area_len(A, R.L);
+    R.e = R.d + (A.with_qual ? R.L + 3 : 0);
+}
+__host__ __device__ __forceinline__ u64 rec_text_size(u8 prefix, u32 name_len, u8 name_nl, u8 seq_present, u8 seq_nl, u8 with_qual, u64 W, u64 L)
+{
+    u64 s = (prefix ? 1 : 0) + name_len + name_nl;
+    if (seq_present) {
+        u64 nl = seq_nl == 0 ? 0 : (seq_nl == 2 ? 1 : (L > 0));
+        if (W > 0 && seq_nl == 1) nl = (L + W - 1) / W;
+        s += L + nl;
+    }
+    if (with_qual) s += L + 3;
+    return s;
+}
+
+// 16 consecutive nibbles starting at base index `bi` of the packed stream -> u64 (low nibble first)
+__device__ __forceinline__ u64 load_nibbles16(const u8 *seq, u64 bi)
+{
+    u64 off = bi >> 1;
+    const u64 *al = (const u64 *)((uintptr_t)(seq + off) & ~(uintptr_t)7);
+    u32 sh = (u32)((uintptr_t)(seq + off) & 7) * 8 + (u32)(bi & 1) * 4;
+    u64 w0 = __ldg(al), w1 = __ldg(al + 1);
+    return sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0;
+}
+// 4 nibbles (16 bits) -> 4 ASCII bytes through the 16-entry table held in 4 registers
+__device__ __forceinline__ u32 nib4_to_ascii(u32 x, const u32 lut[4])
+{
+    u32 sel = x & 0x7777;
+    u32 lo = __byte_perm(lut[0], lut[1], sel), hi = __byte_perm(lut[2], lut[3], sel);
+    u32 m = ((x >> 3) & 1) | (((x >> 7) & 1) << 8) | (((x >> 11) & 1) << 16) | (((x >> 15) & 1) << 24);
+    m *= 0xFF;
+    return (lo & ~m) | (hi & m);
+}
+__device__ __forceinline__ u32 bits4_to_case(u32 b) { return ((b & 1) | ((b & 2) << 7) | ((b & 4) << 14) | ((b & 8) << 21)) * 0x20; }
+// 16 mask bits starting at base index bi
+__device__ __forceinline__ u32 load_maskbits16(const u32 *mb, u64 bi)
+{
+    u64 w = bi >> 5; u32 sh = (u32)(bi & 31);
+    u64 v = (u64)__ldg(mb + w) | ((u64)__ldg(mb + w + 1) << 32);
+    return (u32)(v >> sh) & 0xFFFF;
+}
+// 16 raw bytes starting at p (any alignment); buffers are padded so the over-read is safe
+__device__ __forceinline__ uint4 load_bytes16(const u8 *p)
+{
+    const u64 *al = (const u64 *)((uintptr_t)p & ~(uintptr_t)7);
+    u32 sh = (u32)((uintptr_t)p & 7) * 8;
+    u64 w0 = __ldg(al), w1 = __ldg(al + 1), w2 = __ldg(al + 2);
+    u64 lo = sh ? (w0 >> sh) | (w1 << (64 - sh)) : w0, hi = sh ? (w1 >> sh) | (w2 << (64 - sh)) : w1;
+    return make_uint4((u32)lo, (u32)(lo >> 32), (u32)hi, (u32)(hi >> 32));
+}
+__device__ __forceinline__ u32 upper4(u32 w)
+{
+    // per byte: if 'a' <= c <= 'z' then c - 32
+    u32 r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { u32 c = (w >> (8 * k)) & 0xFF; if (c >= 'a' && c <= 'z') c -= 32; r |= c << (8 * k); }
+    return r;
+}
+__device__ __forceinline__ u8 base_at(const TextArgs &A, u64 bi)
+{
+    u8 c;
+    if (A.packed) {
+        u8 byte = __ldg(A.seq + (bi >> 1));
+        u32 code = (bi & 1) ? byte >> 4 : byte & 15;
+        c = (u8)(A.lut[code >> 2] >> (8 * (code & 3)));
+        if (A.maskbits && ((__ldg(A.maskbits + (bi >> 5)) >> (bi & 31)) & 1)) c += 32;
+    } else {
+        c = __ldg(A.seq + bi);
+        if (A.upper && c >= 'a' && c <= 'z') c -= 32;
+    }
+    return c;
+}
+
+static const int WT_THREADS = 256, WT_ITERS = 4, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 16 KB of text per CTA
+static const int WT_MAXREC = 8192;    // records whose start lies inside one tile (min record = 2 bytes; 1-byte records fall back)
+
+// Each CTA: find the record containing its first byte (32-ary search by warp 0), stage the starts of
+// the records that begin inside the tile in shared memory, then every thread emits 16-byte chunks.
+__global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
+{
+    __shared__ u32 rec_rel[WT_MAXREC + 1];      // out_start[first + 1 + k] - tile_start, ascending
+    __shared__ u64 s_first; __shared__ u32 s_nrec;
+    const u64 tile0 = (u64)blockIdx.x * WT_TILE;
+    const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
+
+    if (threadIdx.x < 32) {
+        // largest i in [0, N) with out_start[i] <= tile0
+        u64 lo = 0, hi = A.N;                    // invariant: out_start[lo] <= tile0 < out_start[hi]
+        while (hi - lo > 1) {
+            u64 span = hi - lo, step = (span + 31) / 32;
+            u64 probe = lo + step * (threadIdx.x + 1);
+            bool le = probe < hi && A.out_start[probe] <= tile0;
+            unsigned m = __ballot_sync(0xFFFFFFFFu, le);
+            int cnt = __popc(m);                 // probes are ascending, so `le` is a prefix
+            u64 nlo = lo + step * cnt, nhi = lo + step * (cnt + 1);
+            lo = nlo; if (nhi < hi) hi = nhi;
+        }
+        if (threadIdx.x == 0) s_first = lo;
+    }
+    __syncthreads();
+    const u64 first = s_first;
+    // records first+1, first+2, ... that start before tile1
+    {
+        u32 cnt = 0;
+        for (u64 base = first + 1;; base += WT_THREADS) {
+            u64 i = base + threadIdx.x;
+            bool in = i < A.N && A.out_start[i] < tile1;
+            if (in) { u32 k = (u32)(i - first - 1); if (k < WT_MAXREC) rec_rel[k] = (u32)(A.out_start[i] - tile0); }
+            int any = __syncthreads_count(in);
+            cnt += any;
+            if (any < WT_THREADS) break;
+        }
+        if (threadIdx.x == 0) s_nrec = cnt;
+    }
+    __syncthreads();
+    const u32 nrec = s_nrec;
+    const bool overflow = nrec > WT_MAXREC;
+
+    for (int it = 0; it < WT_ITERS; it++) {
+        const u64 q0 = tile0 + (u64)it * (WT_THREADS * 16) + (u64)threadIdx.x * 16;
+        if (q0 >= tile1) break;
+        // record containing q0
+        u64 rec;
+        if (!overflow) {
+            u32 rel = (u32)(q0 - tile0);
+            u32 lo = 0, hi = nrec;               // number of staged records with start <= rel
+            while (lo < hi) { u32 mid = (lo + hi) >> 1; if (rec_rel[mid] <= rel) lo = mid + 1; else hi = mid; }
+            rec = first + lo;
+        } else {
+            u64 lo = first, hi = A.N;
+            while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (A.out_start[mid] <= q0) lo = mid; else hi = mid; }
+            rec = lo;
+        }
+        RecInfo R; load_rec(A, rec, R);
+        u64 r = q0 - A.out_start[rec];
+        const int nvalid = tile1 - q0 >= 16 ? 16 : (int)(tile1 - q0);
+        u32 w[4] = {0, 0, 0, 0};
+        bool done = false;
+
+        if (nvalid == 16) {
+            // fast path 1: 16 bytes inside one sequence line
+            if (r >= R.c && r + 16 <= R.d) {
+                u64 s = r - R.c, bi; bool ok;
+                if (A.W > 0 && A.seq_nl == 1) { u64 line = s / (A.W + 1), col = s - line * (A.W + 1); bi = line * A.W + col; ok = col + 16 <= A.W && bi + 16 <= R.L; }
+                else { bi = s; ok = s + 16 <= R.L; }
+                if (ok) {
+                    bi += R.sbase;
+                    if (A.packed) {
+                        u64 nib = load_nibbles16(A.seq, bi);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) w[k] = nib4_to_ascii((u32)(nib >> (16 * k)) & 0xFFFF, A.lut);
+                        if (A.maskbits) {
+                            u32 mb = load_maskbits16(A.maskbits, bi);
+#pragma unroll
+                            for (int k = 0; k < 4; k++) w[k] += bits4_to_case((mb >> (4 * k)) & 15);
+                        }
+                    } else {
+                        uint4 v = load_bytes16(A.seq + bi);
+                        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                        if (A.upper) { for (int k = 0; k < 4; k++) w[k] = upper4(w[k]); }
+                    }
+                    done = true;
+                }
+            }
+            // fast path 2: 16 bytes inside the quality string
+            else if (A.with_qual && r >= R.d + 2 && r + 16 <= R.d + 2 + R.L) {
+                uint4 v = load_bytes16(A.qual + R.sbase + (r - R.d - 2));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+                done = true;
+            }
+        }
+        if (!done) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                if (j < nvalid) {
+                    while (r >= R.e && rec + 1 < A.N) { rec++; load_rec(A, rec, R); r = 0; }
+                    u32 c;
+                    if (r < R.a) c = A.prefix;
+                    else if (r < R.b) {
+                        u32 k = (u32)(r - R.a);
+                        if (A.has_ids && k < R.id_len) c = __ldg(A.ids + R.id_s + k);
+                        else if (A.has_ids && A.has_names) c = k == R.id_len ? A.sep : __ldg(A.comm + R.cm_s + (k - R.id_len - 1));
+                        else c = __ldg(A.comm + R.cm_s + k);
+                    }
+                    else if (r < R.c) c = '\n';
+                    else if (r < R.d) {
+                        u64 s = r - R.c;
+                        if (s >= R.L && A.W == 0) c = '\n';
+                        else if (A.W > 0 && A.seq_nl == 1) {
+                            u64 line = s / (A.W + 1), col = s - line * (A.W + 1);
+                            c = (col == A.W || r + 1 == R.d) ? '\n' : base_at(A, R.sbase + line * A.W + col);
+                        }
+                        else c = s < R.L ? base_at(A, R.sbase + s) : '\n';
+                    }
+                    else {
+                        u64 t = r - R.d;
+                        c = t == 0 ? '+' : (t == 1 ? '\n' : (t < 2 + R.L ? __ldg(A.qual + R.sbase + (t - 2)) : '\n'));
+                    }
+                    w[j >> 2] |= c << (8 * (j & 3));
+                    r++;
+                }
+            }
+        }
+        if (nvalid == 16) *(uint4 *)(A.out + q0) = make_uint4(w[0], w[1], w[2], w[3]);
+        else for (int j = 0; j < nvalid; j++) A.out[q0 + j] = (u8)(w[j >> 2] >> (8 * (j & 3)));
+    }
+}
+
+// histogram of the produced text (unnaf --charcount, output.c:544)
+__global__ void k_charcount(const u8 *text, u64 n, unsigned long long *counts)
+{
+    __shared__ u32 h[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) atomicAdd(&h[text[i]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+}
+
+// ------------------------------------------------------------------ decode orchestration
+
+static inline u64 align256(u64 v) { return (v + 255) & ~255ull; }
+
+// d_naf: the whole file on the device; h_naf: the same bytes on the host (header + block walk)
+DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o)
+{
+    using namespace nafc;
+    Header h; std::string err;
+    if (!read_header(h_naf, n, h, true, err)) fail(NAFGPU_E_FORMAT, err);
+    int view = o.out_type;
+    if (view == NAFGPU_OUT_DEFAULT) view = h.has_quality ? NAFGPU_OUT_FASTQ : NAFGPU_OUT_FASTA;
+    if (view == NAFGPU_OUT_4BIT && h.seq_type >= NAFGPU_PROTEIN)
+        fail(NAFGPU_E_INPUT, std::string("input has no 4-bit encoded data, but ") + (h.seq_type == 2 ? "protein" : "text") + " sequences\n");
+    if (view == NAFGPU_OUT_FASTQ && !h.has_quality && h.n_sequences > 0) fail(NAFGPU_E_INPUT, "FASTQ output requested, but input has no qualities\n");
+    const u64 N = h.n_sequences;
+    DecodeOut none{nullptr, 0};
+    if (N == 0) return none;                                              // unnaf.c:409
+    const bool packed = h.seq_type < NAFGPU_PROTEIN;
+    const u64 W = o.have_line_length ? o.line_length : h.line_length;
+
+    // which sections does this view need?
+    bool need[6] = {false, false, false, false, false, false};
+    switch (view) {
+    case NAFGPU_OUT_FASTA:     need[SEC_IDS] = need[SEC_NAMES] = need[SEC_LEN] = need[SEC_DATA] = true; need[SEC_MASK] = !o.no_mask; break;
+    case NAFGPU_OUT_FASTQ:     need[SEC_IDS] = need[SEC_NAMES] = need[SEC_LEN] = need[SEC_DATA] = need[SEC_QUAL] = true; break;
+    case NAFGPU_OUT_SEQ: case NAFGPU_OUT_CHARCOUNT: need[SEC_DATA] = true; need[SEC_MASK] = !o.no_mask; break;
+    case NAFGPU_OUT_SEQUENCES: need[SEC_LEN] = need[SEC_DATA] = true; need[SEC_MASK] = !o.no_mask; break;
+    case NAFGPU_OUT_4BIT:      need[SEC_DATA] = true; break;
+    case NAFGPU_OUT_IDS:       need[SEC_IDS] = true; break;
+    case NAFGPU_OUT_NAMES:     need[SEC_IDS] = need[SEC_NAMES] = true; break;
+    case NAFGPU_OUT_LENGTHS:   need[SEC_LEN] = true; break;
+    case NAFGPU_OUT_MASK:      need[SEC_MASK] = true; break;
+    default: fail(NAFGPU_E_ARG, "unknown output requested\n");
+    }
+    if (!packed) need[SEC_MASK] = need[SEC_MASK] && false;                // protein/text never carry a mask
+    for (int k = 0; k < 6; k++) need[k] = need[k] && h.sec[k].present;
+    if ((view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQ || view == NAFGPU_OUT_SEQUENCES ||
+         view == NAFGPU_OUT_CHARCOUNT || view == NAFGPU_OUT_4BIT) && !h.has_data) return none;
+    if (view == NAFGPU_OUT_LENGTHS && !h.has_lengths) return none;
+    if (view == NAFGPU_OUT_MASK && !h.has_mask) return none;
+
+    // ---- entropy stage: all needed streams in one batch
+    nafz::ZDecPlan plan;
+    int sidx[6]; u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
+    for (int k = 0; k < 6; k++) {
+        sidx[k] = -1; sbytes[k] = 0; soff[k] = 0;
+        if (!need[k]) continue;
+        u64 expect = h.sec[k].orig;
+        if (k == SEC_DATA && packed) expect = (h.sec[k].orig + 1) / 2;
+        sbytes[k] = expect; soff[k] = arena_sz;
+        nafz::ZStreamDesc sd; sd.src_off = h.sec[k].off; sd.src_len = h.sec[k].comp; sd.out_off = arena_sz; sd.out_size = expect;
+        sd.one_frame = (k == SEC_DATA || k == SEC_QUAL) ? 1 : 0; sd.no_magic = 1;
+        sidx[k] = (int)plan.streams.size(); plan.streams.push_back(sd);
+        arena_sz += align256(expect + 64);
+    }
+    u8 *d_streams = ex.alloc<u8>(arena_sz + 256);
+    // padding bytes between streams are read by the 16-byte loaders: keep them defined
+    ex.zero(d_streams, arena_sz + 256);
+    static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
+    {
+        std::string zerr;
+        int rc = nafz::zstd_decode_batch(ex, d_naf, h_naf, d_streams, plan, ctx.d_predef, zerr);
+        if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, std::string("can't decompress: ") + zerr + "\n");
+        for (int k = 0; k < 6; k++) {
+            if (sidx[k] < 0) continue;
+            u64 got = plan.results[sidx[k]].out_size;
+            bool exact = !(k == SEC_DATA || k == SEC_QUAL);
+            if (exact ? got != sbytes[k] : got < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+        }
+    }
+    const u8 *d_ids = d_streams + soff[SEC_IDS], *d_comm = d_streams + soff[SEC_NAMES], *d_mask = d_streams + soff[SEC_MASK];
+    const u8 *d_seq = d_streams + soff[SEC_DATA], *d_qual = d_streams + soff[SEC_QUAL];
+    const u32 *d_len = (const u32 *)(d_streams + soff[SEC_LEN]);
+    const u64 nL = sbytes[SEC_LEN] / 4, nM = sbytes[SEC_MASK], total_bases = h.sec[SEC_DATA].orig;
+
+    // raw views
+    if (view == NAFGPU_OUT_4BIT) return DecodeOut{d_seq, plan.results[sidx[SEC_DATA]].out_size};
+    if (view == NAFGPU_OUT_LENGTHS) return DecodeOut{(const u8 *)d_len, sbytes[SEC_LEN]};
+    if (view == NAFGPU_OUT_MASK) return DecodeOut{d_mask, nM};
+
+    TextArgs A; memset(&A, 0, sizeof A);
+    A.ids = d_ids; A.comm = d_comm; A.seq = d_seq; A.qual = d_qual;
+    A.has_ids = need[SEC_IDS]; A.has_names = need[SEC_NAMES]; A.sep = h.sep; A.packed = packed; A.W = W;
+    A.total_bases = total_bases;
+    {
+        char lut[17] = "-TGKCYSBAWRDMHVN";
+        if (h.seq_type == NAFGPU_RNA) lut[1] = 'U';
+        memcpy(A.lut, lut, 16);
+    }
+    A.upper = (!packed && o.no_mask && view != NAFGPU_OUT_FASTQ) ? 1 : 0;   // output.c:500,663; FASTQ path never uppercases
+
+    // ---- ids / comments: terminator positions; the reference insists on a final '\0' (input.c:157,185)
+    u32 *d_id_end = nullptr, *d_cm_end = nullptr;
+    auto find_ends = [&](const u8 *s, u64 bytes, const char *name) -> u32 * {
+        if (bytes == 0) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - not 0-terminated\n");
+        u64 ntiles = (bytes + ZT - 1) / ZT;
+        u64 *counts = ex.alloc<u64>(ntiles + 1), *prefix = ex.alloc<u64>(ntiles + 2);
+        u32 *end = ex.alloc<u32>(N + 1);
+        k_zero_count<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, counts); ex.launches++;
+        const u64 *c = counts;
+        exclusive_scan(ex, [c] __device__ (size_t i) { return c[i]; }, ntiles, prefix);
+        k_zero_scatter<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, prefix, end, N); ex.launches++;
+        u64 nzero; u8 last;
+        ex.download(&nzero, prefix + ntiles, 8);
+        ex.download(&last, s + bytes - 1, 1);
+        if (last != 0) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - not 0-terminated\n");
+        if (nzero < N) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - can't read all records\n");
+        return end;
+    };
+    if (A.has_ids) d_id_end = find_ends(d_ids, sbytes[SEC_IDS], "ids");
+    if (A.has_names) d_cm_end = find_ends(d_comm, sbytes[SEC_NAMES], "names");
+    A.id_end = d_id_end; A.cm_end = d_cm_end;
+
+    // ---- lengths: merge 0xFFFFFFFF continuation units (output.c:390-393), prefix-sum into base offsets
+    u64 *d_L = nullptr, *d_seq_start = nullptr;
+    u64 NR = N;      // records in the text
+    const bool rec_views = view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQUENCES;
+    if (rec_views) {
+        if (nL == 0) fail(NAFGPU_E_FORMAT, "can't decompress lengths\n");
+        u64 *rank = ex.alloc<u64>(nL + 1);
+        const u32 *len = d_len;
+        exclusive_scan(ex, [len] __device__ (size_t k) { return (u64)(len[k] != 0xFFFFFFFFu); }, nL, rank);
+        u64 nrec_len; ex.download(&nrec_len, rank + nL, 8);
+        if (view == NAFGPU_OUT_SEQUENCES) NR = nrec_len;                   // print_sequences walks length units, not N
+        else if (nrec_len < N) NR = nrec_len;                              // output.c:413 stops at n_lengths
+        d_L = ex.alloc<u64>(NR + 1); d_seq_start = ex.alloc<u64>(NR + 2);
+        ex.zero(d_L, (NR + 1) * 8);
+        u64 *L = d_L; const u64 nr = NR;
+        ex.for_each(nL, [=] __device__ (size_t k) { u64 r = rank[k]; if (r < nr) atomicAdd((unsigned long long *)(L + r), (unsigned long long)len[k]); });
+        exclusive_scan(ex, [L] __device__ (size_t i) { return L[i]; }, NR, d_seq_start);
+        // clamp to the bases actually present (print_dna_buffer_as_fasta never prints past total_seq_length)
+        u64 sum; ex.download(&sum, d_seq_start + NR, 8);
+        if (sum > total_bases) fail(NAFGPU_E_FORMAT, "corrupted lengths - sum exceeds the sequence size\n");
+    }
+    A.L = d_L; A.seq_start = d_seq_start;
+
+    // ---- mask: run-length units -> one bit per base (output.c:295 semantics, two-scan formulation)
+    if (need[SEC_MASK] && packed && nM > 0 && view != NAFGPU_OUT_FASTQ) {
+        u64 words = (total_bases + 31) / 32 + 2;
+        u32 *bits = ex.alloc<u32>(words);
+        ex.zero(bits, words * 4);
+        u64 *ustart = ex.alloc<u64>(nM + 1), *utog = ex.alloc<u64>(nM + 1);
+        const u8 *m = d_mask;
+        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)m[k]; }, nM, ustart);
+        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)(m[k] != 255); }, nM, utog);
+        const u64 tb = total_bases;
+        ex.for_each(nM, [=] __device__ (size_t k) {
+            if (!(utog[k] & 1)) return;
+            u64 lo = ustart[k], hi = lo + m[k];
+            if (hi > tb) hi = tb;
+            if (lo < hi) nafz::set_bits(bits, lo, hi);
+        });
+        A.maskbits = bits;
+    }
+
+    // ---- record layout per view
+    switch (view) {
+    case NAFGPU_OUT_FASTA:     A.prefix = '>'; A.with_name = 1; A.name_nl = 1; A.seq_present = 1; A.seq_nl = 1; break;
+    case NAFGPU_OUT_FASTQ:     A.prefix = '@'; A.with_name = 1; A.name_nl = 1; A.seq_present = 1; A.seq_nl = 2; A.with_qual = 1; A.W = 0; A.maskbits = nullptr; break;
+    case NAFGPU_OUT_SEQUENCES: A.seq_present = 1; A.seq_nl = 2; A.W = 0; break;
+    case NAFGPU_OUT_IDS:       A.with_name = 1; A.name_nl = 1; A.has_names = 0; break;
+    case NAFGPU_OUT_NAMES:     A.with_name = 1; A.name_nl = 1; break;
+    default: break;            // SEQ / CHARCOUNT: handled below as one pseudo-record
+    }
+    if (view == NAFGPU_OUT_IDS && !A.has_ids) return none;
+    if (view == NAFGPU_OUT_NAMES && !A.has_ids && !A.has_names) return none;
+    if (view == NAFGPU_OUT_SEQUENCES && total_bases == 0) return none;    // output-sequences.c: nothing is flushed without bases
+
+    u64 *d_out_start;
+    if (view == NAFGPU_OUT_SEQ || view == NAFGPU_OUT_CHARCOUNT) {
+        // one pseudo-record holding every base, no newline
+        A.seq_present = 1; A.seq_nl = 0; A.W = 0; NR = 1;
+        u64 hl[2] = { total_bases, 0 }, hs[3] = { 0, total_bases, 0 };
+        d_L = ex.alloc<u64>(2); d_seq_start = ex.alloc<u64>(3); d_out_start = ex.alloc<u64>(3);
+        ex.upload(d_L, hl, 16); ex.upload(d_seq_start, hs, 24); ex.upload(d_out_start, hs, 24);
+        A.L = d_L; A.seq_start = d_seq_start;
+    } else {
+        d_out_start = ex.alloc<u64>(NR + 2);
+        const TextArgs B = A;
+        exclusive_scan(ex, [B] __device__ (size_t i) {
+            u32 idl = 0, cml = 0;
+            if (B.with_name) {
+                if (B.has_ids) { u32 s = i ? B.id_end[i - 1] + 1 : 0; idl = B.id_end[i] - s; }
+                if (B.has_names) { u32 s = i ? B.cm_end[i - 1] + 1 : 0; cml = B.cm_end[i] - s; }
+            }
+            u32 nl = !B.with_name ? 0 : ((B.has_ids && B.has_names) ? idl + (cml ? 1 + cml : 0) : (B.has_ids ? idl : cml));
+            return rec_text_size(B.prefix, nl, B.name_nl, B.seq_present, B.seq_nl, B.with_qual, B.W, B.seq_present ? B.L[i] : 0);
+        }, NR, d_out_start);
+    }
+    A.N = NR; A.out_start = d_out_start;
+    u64 total; ex.download(&total, d_out_start + NR, 8);
+    A.total = total;
+    if (total == 0) return none;
+    u8 *d_text = ex.alloc<u8>(total + 64);
+    A.out = d_text;
+    {
+        u64 ntiles = (total + WT_TILE - 1) / WT_TILE;
+        k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A); ex.launches++;
+    }
+    if (view == NAFGPU_OUT_CHARCOUNT) {
+        unsigned long long *counts = ex.alloc<unsigned long long>(256);
+        ex.zero(counts, 256 * 8);
+        k_charcount<<<148 * 8, 256, 0, ex.stream>>>(d_text, total, counts); ex.launches++;
+        return DecodeOut{(const u8 *)counts, 256 * 8};
+    }
+    ex.check();
+    return DecodeOut{d_text, total};
+}
+
+}  // namespace nafg

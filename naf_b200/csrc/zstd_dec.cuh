@@ -73,6 +73,7 @@ struct ZStreamDesc {
     u64 src_off, src_len;       // compressed bytes (starting with the zstd magic) in the input buffer
     u64 out_off, out_size;      // region of the output arena; out_size = expected regenerated size
     int one_frame;              // 1: stop after the first frame like the reference's streaming loops
+    int no_magic;               // 1: the first frame's 4-byte magic was stripped (.naf sections, compressor.c:158)
 };
 
 struct ZStreamResult { u64 out_size; u64 nseq; u64 consumed; };
@@ -88,17 +89,21 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
 {
     const u8 *p = h + sd.src_off; const u64 n = sd.src_len;
     u64 pos = 0; int frames = 0; bool first_in_stream = true;
+    bool skip_magic = sd.no_magic != 0;
     while (pos < n) {
-        if (n - pos < 4) { err = "trailing bytes after zstd frame"; return -1; }
-        u32 magic = p[pos] | (p[pos + 1] << 8) | (p[pos + 2] << 16) | ((u32)p[pos + 3] << 24);
-        if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
-            if (n - pos < 8) { err = "skippable frame truncated"; return -1; }
-            u64 sz = p[pos + 4] | (p[pos + 5] << 8) | (p[pos + 6] << 16) | ((u64)p[pos + 7] << 24);
-            if (n - pos - 8 < sz) { err = "skippable frame truncated"; return -1; }
-            pos += 8 + sz; continue;
+        if (!skip_magic) {
+            if (n - pos < 4) { err = "trailing bytes after zstd frame"; return -1; }
+            u32 magic = p[pos] | (p[pos + 1] << 8) | (p[pos + 2] << 16) | ((u32)p[pos + 3] << 24);
+            if ((magic & 0xFFFFFFF0u) == 0x184D2A50u) {
+                if (n - pos < 8) { err = "skippable frame truncated"; return -1; }
+                u64 sz = p[pos + 4] | (p[pos + 5] << 8) | (p[pos + 6] << 16) | ((u64)p[pos + 7] << 24);
+                if (n - pos - 8 < sz) { err = "skippable frame truncated"; return -1; }
+                pos += 8 + sz; continue;
+            }
+            if (magic != 0xFD2FB528u) { err = "bad zstd magic"; return -1; }
+            pos += 4;
         }
-        if (magic != 0xFD2FB528u) { err = "bad zstd magic"; return -1; }
-        pos += 4;
+        skip_magic = false;
         if (n - pos < 2) { err = "zstd frame header truncated"; return -1; }
         u32 fhd = p[pos++];
         u32 fcs_flag = fhd >> 6, single = (fhd >> 5) & 1, checksum = (fhd >> 2) & 1, did = fhd & 3;

@@ -18,7 +18,7 @@ int main(int argc, char **argv)
     std::vector<u8> out(cap);
     HostExec ex;
     ZDecPlan plan;
-    plan.streams.push_back(ZStreamDesc{0, in.size(), 64, cap - 64, one});
+    plan.streams.push_back(ZStreamDesc{0, in.size(), 64, cap - 64, one, 0});
     u32 predef[FSE_SLOT_ENTRIES]; zstd_build_predef(predef);
     std::string err;
     int rc = zstd_decode_batch(ex, in.data(), in.data(), out.data(), plan, predef, err);

@@ -1,0 +1,31 @@
+"""not-gpu: the decoder's HD kernel bodies (naf_b200/csrc/zstd_dec.cuh), run through the test-only host
+executor in tests/emu, against the golden frames.  This checks the device logic of the thread-serial
+kernels (headers, Huffman/FSE tables, sequence decode, repeat-offset scan, pointer jumping) on the CPU;
+the shipped library never contains this executor."""
+import os
+import subprocess
+
+import pytest
+
+import helpers
+
+ROOT = helpers.ROOT
+EXE = os.path.join(ROOT, "tests", "_build", "emu_zstd")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "emu", "emu_zstd.cpp")
+    deps = [src, os.path.join(ROOT, "naf_b200/csrc/zstd_dec.cuh"), os.path.join(ROOT, "naf_b200/csrc/zstd_hd.cuh")]
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unused-function", "-o", EXE, src], check=True)
+    return EXE
+
+
+def test_emu_decoder_on_golden_frames(emu, tmp_path):
+    out = str(tmp_path / "o.bin")
+    for e in helpers.manifest("zstd"):
+        p = subprocess.run([emu, os.path.join(helpers.GOLDEN, "zstd", e["frame"]), out], capture_output=True)
+        assert p.returncode == 0, (e["frame"], p.stderr)
+        assert helpers.sha(open(out, "rb").read()) == e["sha256"], e["frame"]

@@ -1,0 +1,81 @@
+"""GPU parity: decode of REFERENCE-produced .naf files must be byte-identical to the reference unnaf
+(north_star: "our unnaf on a reference-produced .naf yields byte-identical FASTA/FASTQ").
+Everything goes through the C ABI (naf_b200 -> libnafgpu.so); expected bytes come from the committed
+goldens (made by the unmodified reference, tools/make_golden.py) and from the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from naf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_zstd_frames_golden(gpu, oracle):
+    """every committed frame (libzstd levels -5..19, decodecorpus: all block/literal/sequence modes)"""
+    n = 0
+    for e in helpers.manifest("zstd"):
+        z = helpers.golden("zstd", e["frame"])
+        out = gpu.zstd_decompress(z)
+        assert len(out) == e["size"], e["frame"]
+        assert helpers.sha(out) == e["sha256"], e["frame"]
+        assert out == oracle.zstd_decompress(z), e["frame"]
+        n += 1
+    assert n >= 100
+
+
+def test_ref_suite_decode(gpu):
+    """the reference's own perl-suite cases: decode the reference-made .naf with the same unnaf flags"""
+    for case in helpers.manifest("ref_suite"):
+        naf = helpers.golden("ref_suite", case["naf"])
+        kw = helpers.parse_unnaf_args(case["unnaf_args"])
+        expect = helpers.golden("ref_suite", case["set"], case["name"] + ".out")
+        got = gpu.unnaf(naf, **kw)
+        assert got == expect, (case["name"], got[:200], expect[:200])
+
+
+def test_cases_all_views(gpu, oracle):
+    """FASTQ / RNA / protein / text / mask edge cases / multi-block streams at levels 1,3,19 / --long 31"""
+    for case in helpers.manifest("cases"):
+        naf = helpers.golden("cases", case["name"] + ".naf")
+        for key, exp in case["views"].items():
+            parts = key.split()
+            kw = helpers.parse_unnaf_args(["--" + parts[0]] + parts[1:])
+            if exp["rc"] != 0:
+                with pytest.raises(Exception):
+                    gpu.unnaf(naf, **kw)
+                continue
+            got = gpu.unnaf(naf, **kw)
+            assert len(got) == exp["size"], (case["name"], key)
+            assert helpers.sha(got) == exp["sha256"], (case["name"], key)
+
+
+@pytest.mark.skipif(not helpers.have_ref(), reason="oracle/_ref binaries not built")
+def test_medium_fastq_vs_reference(gpu, tmp_path):
+    """200k x 150 bp FASTQ (config-2 shape, multi-block every stream): reference ennaf -> our decode"""
+    text = synth.fastq(200_000, 150, seed=21)
+    rc, naf, err = helpers.ref_run("ennaf", ["-c"], text, tmp=str(tmp_path))
+    assert rc == 0, err
+    assert gpu.decode(naf) == text
+
+
+@pytest.mark.skipif(not helpers.have_ref(), reason="oracle/_ref binaries not built")
+@pytest.mark.parametrize("level", ["-1", "-9"])
+def test_medium_fasta_vs_reference(gpu, tmp_path, level):
+    """30 Mbp soft-masked FASTA with repeats: LZ sequences, treeless literals, Repeat_Mode"""
+    text = synth.fasta_softmasked(30_000_000, width=60, seed=22, n_records=3, repeats=True, n_gaps=2)
+    rc, naf, err = helpers.ref_run("ennaf", [level, "-c"], text, tmp=str(tmp_path))
+    assert rc == 0, err
+    assert gpu.decode(naf) == text
+    rc, seq, _ = helpers.ref_run("unnaf", ["--seq", "--no-mask"], naf)
+    assert gpu.decode(naf, "seq", no_mask=True) == seq
+
+
+def test_oracle_roundtrip_property(gpu, oracle):
+    """size-independent property: oracle encode (raw-block frames) -> GPU decode == input, ONT-like config-3 shape"""
+    text = synth.ont_fasta(40, 10000, 50000, seed=23)
+    naf, _ = oracle.encode(text)
+    assert gpu.decode(naf) == text
+    assert gpu.decode(naf, "fasta", line_length=0) == oracle.decode(naf, "fasta", line_length=0)
