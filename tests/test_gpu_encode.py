@@ -1,0 +1,198 @@
+"""GPU parity, encode side.  Stream level: the six streams the GPU parser/packer produce are byte-identical
+to the oracle's restatement of process.c/encoders.c.  File level: the .naf we emit is decoded by the
+oracle and by the UNMODIFIED reference unnaf back to the reference's pinned output (north_star: "the
+encode path emits a format-valid .naf that the reference unnaf decodes back to the byte-identical input")."""
+import random
+
+import numpy as np
+import pytest
+
+import helpers
+import naf_b200
+from naf_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+STREAMS = ["ids", "comments", "lengths", "mask", "sequence", "quality"]
+
+
+def check_split(gpu, oracle, text, **kw):
+    try:
+        want, winfo = oracle.split(text, **kw)
+    except ValueError as e:
+        with pytest.raises(naf_b200.NafGpuError) as ge:
+            gpu.split(text, **kw)
+        assert ge.value.message == str(e), (ge.value.message, str(e))
+        return
+    got, info = gpu.split(text, **kw)
+    if not winfo["store_mask"]:
+        want[3] = b""
+    if not winfo["store_qual"]:
+        want[5] = b""
+    for k in range(6):
+        assert got[k] == want[k], (STREAMS[k], kw, len(got[k]), len(want[k]), got[k][:80], want[k][:80])
+    assert info.n_sequences == winfo["n_sequences"]
+    assert info.longest_line == winfo["longest_line"], (info.longest_line, winfo["longest_line"])
+    assert info.n_bases == winfo["seq_size"]
+    for k in range(4):
+        assert list(info.unexpected[k]) == winfo["unexpected"][k], ("unexpected", k)
+
+
+def test_split_reference_suite_inputs(gpu, oracle):
+    seen = set()
+    for case in helpers.manifest("ref_suite"):
+        key = (case["input"], tuple(case["ennaf_args"]))
+        if key in seen:
+            continue
+        seen.add(key)
+        kw = helpers.parse_ennaf_args(case["ennaf_args"])
+        kw.pop("level", None)
+        check_split(gpu, oracle, helpers.golden("ref_suite", case["input"]), **kw)
+
+
+def test_split_cases(gpu, oracle):
+    for case in helpers.manifest("cases"):
+        kw = helpers.parse_ennaf_args(case["ennaf_args"])
+        kw.pop("level", None); kw.pop("title", None)
+        check_split(gpu, oracle, helpers.golden("cases", case["name"] + ".txt.gz"), **kw)
+
+
+def _fuzz_fasta(rng):
+    out = bytearray()
+    if rng.random() < 0.3:
+        out += rng.choice([b"\n", b" \n", b"\r\n\n", b"\t\n"])
+    for _ in range(rng.randint(0, 6)):
+        out += b">" + bytes(rng.choice(b"abcXYZ019|._\xc3\xfe") for _ in range(rng.randint(0, 8)))
+        if rng.random() < 0.6:
+            out += rng.choice([b" ", b"\t", b"  "]) + bytes(rng.choice(b"abc def\t\x02>@\xfe") for _ in range(rng.randint(0, 10)))
+        out += rng.choice([b"\n", b"\r\n", b"\n\n", b"\x0b", b""])
+        for _ in range(rng.randint(0, 4)):
+            out += bytes(rng.choice(b"ACGTacgtNnRYKMSWBDHV-UuXxZ*> \t.12\xe0") for _ in range(rng.randint(0, 90)))
+            out += rng.choice([b"\n", b"\r\n", b"\n\n", b"\n \n", b"\x0c", b""])
+    return bytes(out)
+
+
+def _fuzz_fastq(rng):
+    out = bytearray()
+    for _ in range(rng.randint(1, 6)):
+        out += b"@" + bytes(rng.choice(b"abcXYZ019") for _ in range(rng.randint(0, 8)))
+        if rng.random() < 0.6:
+            out += b" " + bytes(rng.choice(b"abc def/12") for _ in range(rng.randint(0, 10)))
+        out += b"\n"
+        L = rng.randint(1, 100)
+        s = bytes(rng.choice(b"ACGTacgtNnRY.x") for _ in range(L))
+        if rng.random() < 0.2:
+            s = s[:L // 2] + b" " + s[L // 2:]
+        out += s + rng.choice([b"\n", b"\n\n"]) + b"+" + rng.choice([b"", b"xyz"]) + rng.choice([b"\n", b"\n\n"])
+        q = bytes(rng.choice(b"!#$%IJK@+~") for _ in range(L))
+        if rng.random() < 0.1:
+            q = q[:L // 2] + b"\x01" + q[L // 2 + 1:]
+        if rng.random() < 0.05:
+            q = q[:-1]
+        if rng.random() < 0.03:
+            out += q + b"\nGARBAGE\n"
+            continue
+        out += q + rng.choice([b"\n", b"\n\n", b""])
+    return bytes(out)
+
+
+def test_split_fuzz_non_well_formed(gpu, oracle):
+    """blank lines, CR/LF, tabs, unexpected bytes, '>' mid-line, truncated / malformed FASTQ (error strings too)"""
+    rng = random.Random(1234)
+    for it in range(300):
+        text = _fuzz_fastq(rng) if rng.random() < 0.35 else _fuzz_fasta(rng)
+        kw = {"seq_type": rng.choice(["dna", "rna", "protein", "text"])}
+        if rng.random() < 0.25:
+            kw["no_mask"] = True
+        if rng.random() < 0.1:
+            kw["strict"] = True
+        check_split(gpu, oracle, text, **kw)
+
+
+def test_split_tile_boundaries(gpu, oracle):
+    """records and lines straddling the 64-byte thread chunks and the 16 KB tiles, headers longer than a tile"""
+    rng = np.random.default_rng(5)
+    parts = []
+    for i in range(40):
+        name = b"r%d " % i + bytes(rng.integers(97, 123, int(rng.integers(0, 40000)) if i % 7 == 0 else 5).astype(np.uint8))
+        L = int(rng.integers(0, 70000))
+        seq = bytes(np.frombuffer(b"ACGTacgtN", dtype=np.uint8)[rng.integers(0, 9, L)])
+        w = int(rng.choice([0, 1, 60, 61, 63, 64, 65, 16384]))
+        body = seq if w == 0 else b"\n".join(seq[k:k + w] for k in range(0, L, w))
+        parts.append(b">" + name + b"\n" + body + (b"\n" if L else b""))
+    check_split(gpu, oracle, b"".join(parts))
+    check_split(gpu, oracle, b"".join(parts)[:-1])          # no final newline
+    check_split(gpu, oracle, synth.fastq(5000, 151, seed=9))
+
+
+def test_zstd_compress_roundtrip(gpu, oracle):
+    """our frames are valid zstd: the oracle decoder (pinned to libzstd) regenerates the input"""
+    rng = np.random.default_rng(3)
+    datasets = [b"", b"A", b"AB", b"A" * 70000, bytes(range(256)) * 300]
+    for n in [2, 3, 15, 16, 17, 255, 256, 1023, 1024, 1025, 5000, 65535, 65536, 65537, 200000]:
+        datasets.append(bytes(rng.choice(np.frombuffer(b"\x11\x12\x14\x18\x21\x22\x24\x28\x41\x42\x44\x48\x81\x82\x84\x88", dtype=np.uint8), n)))
+        datasets.append((np.clip(np.round(rng.normal(34, 6, n)), 2, 40).astype(np.uint8) + 33).tobytes())
+    datasets.append(b"".join(b"SRR1.%d\0" % i for i in range(30000)))
+    datasets.append(np.tile(np.array([150, 0, 0, 0], dtype=np.uint8), 50000).tobytes())
+    datasets.append(rng.integers(0, 256, 300000, dtype=np.uint8).tobytes())
+    datasets.append(bytes(rng.choice(np.arange(200, dtype=np.uint8), 100000, p=np.r_[[0.5], np.full(199, 0.5 / 199)])))
+    for d in datasets:
+        z = gpu.zstd_compress(d)
+        assert z[:4] == b"\x28\xb5\x2f\xfd"
+        assert oracle.zstd_decompress(z) == d, len(d)
+        assert gpu.zstd_decompress(z) == d, len(d)
+
+
+def test_encode_reference_suite(gpu, oracle):
+    """the reference's 60 suite cases with OUR ennaf in the pipeline: oracle unnaf (and the reference unnaf when
+    built) must print the pinned stdout; our stderr report must equal the pinned ennaf stderr."""
+    from naf_b200 import cli_text
+    for case in helpers.manifest("ref_suite"):
+        text = helpers.golden("ref_suite", case["input"])
+        ekw, ukw = helpers.parse_ennaf_args(case["ennaf_args"]), helpers.parse_unnaf_args(case["unnaf_args"])
+        expect = helpers.golden("ref_suite", case["set"], case["name"] + ".out")
+        naf, info = gpu.encode_with_info(text, **ekw)
+        assert cli_text.unexpected_report(info, ekw.get("seq_type", "dna")) == helpers.golden("ref_suite", case["set"], case["name"] + ".e.err"), case["name"]
+        assert oracle.decode(naf, **ukw) == expect, case["name"]
+        assert gpu.unnaf(naf, **ukw) == expect, case["name"]
+        if helpers.have_ref():
+            rc, out, err = helpers.ref_run("unnaf", case["unnaf_args"], naf)
+            assert rc == 0 and out == expect, (case["name"], err)
+
+
+def test_encode_cases_decoded_by_reference(gpu, oracle):
+    for case in helpers.manifest("cases"):
+        text = helpers.golden("cases", case["name"] + ".txt.gz")
+        ekw = helpers.parse_ennaf_args(case["ennaf_args"])
+        naf = gpu.encode(text, **ekw)
+        for key in ("fasta", "fastq", "seq", "sequences", "4bit", "ids", "names", "lengths", "mask", "charcount", "title", "number"):
+            exp = case["views"][key]
+            if exp["rc"] != 0:
+                continue
+            got = oracle.decode(naf, key)
+            assert (len(got), helpers.sha(got)) == (exp["size"], exp["sha256"]), (case["name"], key)
+            if helpers.have_ref():
+                rc, out, err = helpers.ref_run("unnaf", ["--" + key], naf)
+                assert rc == 0 and helpers.sha(out) == exp["sha256"], (case["name"], key, err)
+
+
+@pytest.mark.skipif(not helpers.have_ref(), reason="oracle/_ref binaries not built")
+def test_encode_medium_configs_decoded_by_reference(gpu):
+    """config-2 / 3 / 4 / 5 shapes at sizes the reference decodes in seconds"""
+    for text, kw, args in [
+        (synth.fastq(200_000, 150, seed=31), {}, []),
+        (synth.ont_fasta(300, 10000, 50000, seed=32), {}, []),
+        (synth.protein_fasta(100_000, 300, seed=33), {"seq_type": "protein"}, []),
+        (synth.fasta_softmasked(40_000_000, 60, seed=34, n_records=2, repeats=True, n_gaps=3), {}, []),
+    ]:
+        naf = gpu.encode(text, **kw)
+        rc, out, err = helpers.ref_run("unnaf", args, naf)
+        assert rc == 0, err
+        assert out == text
+        assert gpu.decode(naf) == text
+
+
+def test_error_messages_match_reference_strings(gpu, oracle):
+    for text, kw in [(b"ACGT\n", {}), (b"x>a\nAC\n", {}), (b"@r\nACGT\n+\nII\n", {}), (b"@r\nACGT\n", {}), (b"@r", {}),
+                     (b"@r\nAC\nXX\nII\n", {}), (b"@r\nAC\n+\nII\nzz\n", {}), (b">a\nACZT\n", {"strict": True})]:
+        check_split(gpu, oracle, text, **kw)
