@@ -116,6 +116,11 @@ const char *nafgpu_version(void);
 int  nafgpu_get_timing(const nafgpu_ctx *ctx, nafgpu_timing *t);
 void *nafgpu_stream(nafgpu_ctx *ctx);                 /* the cudaStream_t all work is launched on */
 
+/* Per-kernel timing with CUDA events on ctx's stream (for roofline reports; adds an event pair per
+ * launch, so leave it off in timed runs).  The report of the last call is "name\tlaunches\tms\n" lines. */
+int  nafgpu_profile(nafgpu_ctx *ctx, int enable);
+const char *nafgpu_profile_report(const nafgpu_ctx *ctx);
+
 /* Pinned host memory for zero-staging transfers (optional; pageable pointers are accepted too). */
 int  nafgpu_host_alloc(size_t n, void **p);
 void nafgpu_host_free(void *p);

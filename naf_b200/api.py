@@ -50,7 +50,8 @@ class Timing(C.Structure):
 EXPORTS = [
     "nafgpu_create", "nafgpu_destroy", "nafgpu_last_error", "nafgpu_version", "nafgpu_get_timing", "nafgpu_stream",
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
-    "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_split",
+    "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_split", "nafgpu_profile",
+    "nafgpu_profile_report",
 ]
 
 _lib = None
@@ -80,6 +81,9 @@ def load_library():
     lib.nafgpu_get_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.nafgpu_stream.argtypes = [vp]
     lib.nafgpu_stream.restype = vp
+    lib.nafgpu_profile.argtypes = [vp, C.c_int]
+    lib.nafgpu_profile_report.argtypes = [vp]
+    lib.nafgpu_profile_report.restype = C.c_char_p
     lib.nafgpu_host_alloc.argtypes = [sz, C.POINTER(vp)]
     lib.nafgpu_host_free.argtypes = [vp]
     lib.nafgpu_host_free.restype = None
@@ -166,6 +170,17 @@ class NafGpu:
         t = Timing()
         self.lib.nafgpu_get_timing(self.h, C.byref(t))
         return t
+
+    def profile(self, enable: bool):
+        self.lib.nafgpu_profile(self.h, int(enable))
+
+    def profile_report(self):
+        """[(kernel name, launches, total ms)] of the last call (CUDA events on the context's stream)."""
+        out = []
+        for line in (self.lib.nafgpu_profile_report(self.h) or b"").decode().splitlines():
+            name, cnt, ms = line.split("\t")
+            out.append((name, int(cnt), float(ms)))
+        return out
 
     # ---- hot path, host buffers
     def encode_raw(self, text, opts: EncOpts):

@@ -89,6 +89,9 @@ const char *nafgpu_last_error(const nafgpu_ctx *c) { return c ? c->err.c_str() :
 int nafgpu_get_timing(const nafgpu_ctx *c, nafgpu_timing *t) { if (!c || !t) return NAFGPU_E_ARG; *t = c->timing; return 0; }
 void *nafgpu_stream(nafgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
 
+int nafgpu_profile(nafgpu_ctx *c, int enable) { if (!c) return NAFGPU_E_ARG; c->prof.on = enable != 0; return 0; }
+const char *nafgpu_profile_report(const nafgpu_ctx *c) { return c ? c->prof_report.c_str() : ""; }
+
 int nafgpu_host_alloc(size_t n, void **p) { return cudaHostAlloc(p, n ? n : 1, cudaHostAllocDefault) == cudaSuccess ? 0 : NAFGPU_E_CUDA; }
 void nafgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
@@ -118,6 +121,21 @@ static void finish_timing(Ctx &c, CudaExec &ex)
     cudaEventElapsedTime(&c.timing.d2h_ms, c.ev[2], c.ev[3]);
     cudaEventElapsedTime(&c.timing.total_ms, c.ev[0], c.ev[3]);
     c.timing.kernel_launches = ex.launches;
+    if (c.prof.on) {
+        // aggregate per kernel name, in first-launch order
+        std::vector<std::string> names; std::vector<double> ms; std::vector<int> cnt;
+        for (auto &r : c.prof.recs) {
+            float t = 0; cudaEventElapsedTime(&t, r.a, r.b);
+            size_t k = 0; while (k < names.size() && names[k] != r.name) k++;
+            if (k == names.size()) { names.push_back(r.name); ms.push_back(0); cnt.push_back(0); }
+            ms[k] += t; cnt[k]++;
+            c.prof.pool.push_back(r.a); c.prof.pool.push_back(r.b);
+        }
+        c.prof.recs.clear();
+        c.prof_report.clear();
+        char line[256];
+        for (size_t k = 0; k < names.size(); k++) { snprintf(line, sizeof line, "%s\t%d\t%.6f\n", names[k].c_str(), cnt[k], ms[k]); c.prof_report += line; }
+    }
 }
 
 extern "C" {
@@ -127,7 +145,7 @@ int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_
     if (!naf || !opts || !text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         nafc::Header h; std::string err;
         if (!nafc::read_header(naf, n, h, false, err)) fail(NAFGPU_E_FORMAT, err);      // fail before any transfer
@@ -146,7 +164,7 @@ int nafgpu_decode_device(nafgpu_ctx *c, const uint8_t *d_naf, size_t n, const ui
     if (!d_naf || !opts || !d_text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         const u8 *h = host_copy;
         if (!h) {                                     // no host mirror: fetch the compressed bytes once for the header walk
@@ -169,7 +187,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx *c, const uint8_t *src, size_t n, size_t e
     if (!src || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -201,7 +219,7 @@ int nafgpu_encode(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc
     if ((!text && n) || !opts || !naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -218,7 +236,7 @@ int nafgpu_encode_device(nafgpu_ctx *c, const uint8_t *d_text, size_t n, const n
     if ((!d_text && n) || !opts || !d_naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
@@ -233,7 +251,7 @@ int nafgpu_zstd_compress(nafgpu_ctx *c, const uint8_t *src, size_t n, int window
     if ((!src && n) || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -249,7 +267,7 @@ int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_
 {
     if ((!text && n) || !opts || !streams || !sizes) return NAFGPU_E_ARG;
     return guarded(c, [&] {
-        CudaExec ex{c->stream, &c->arena};
+        CudaExec ex{c->stream, &c->arena, &c->prof};
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));

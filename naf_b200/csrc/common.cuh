@@ -83,10 +83,23 @@ template <class F> __global__ void k_for_each(size_t n, F f)
 }
 template <class F> __global__ void k_for_each_group(F f) { f((size_t)blockIdx.x, threadIdx.x, blockDim.x); }
 
+// Optional per-launch timing with CUDA events (bench.py's live roofline; off during timed steps).
+struct Prof {
+    bool on = false;
+    struct Rec { const char *name; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+};
+
 struct CudaExec {
     cudaStream_t stream;
     Arena *arena;
+    Prof *prof = nullptr;
     u32 launches = 0;
+
+    void prof_begin(const char *name) { if (prof && prof->on) { Prof::Rec r{name, prof->get(), prof->get()}; cudaEventRecord(r.a, stream); prof->recs.push_back(r); } }
+    void prof_end() { if (prof && prof->on) cudaEventRecord(prof->recs.back().b, stream); launches++; }
 
     template <class T> T *alloc(size_t count) { return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1)); }
     void upload(void *dst, const void *src, size_t n) { if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream)); }
@@ -97,17 +110,21 @@ struct CudaExec {
     }
     void zero(void *p, size_t n) { if (n) CUDA_TRY(cudaMemsetAsync(p, 0, n, stream)); }
     void fill(void *p, int v, size_t n) { if (n) CUDA_TRY(cudaMemsetAsync(p, v, n, stream)); }
-    template <class F> void for_each(size_t n, F f)
+    // threads: CTA size.  Thread-serial bodies with long per-item loops use small CTAs so that few
+    // thousand items still spread over all 148 SMs.
+    template <class F> void for_each(size_t n, F f, const char *name = "for_each", int threads = 256)
     {
         if (!n) return;
-        k_for_each<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, f);
-        launches++;
+        prof_begin(name);
+        k_for_each<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(n, f);
+        prof_end();
     }
-    template <class F> void for_each_group(size_t ngroups, int threads, F f)
+    template <class F> void for_each_group(size_t ngroups, int threads, F f, const char *name = "for_each_group")
     {
         if (!ngroups) return;
+        prof_begin(name);
         k_for_each_group<<<(unsigned)ngroups, threads, 0, stream>>>(f);
-        launches++;
+        prof_end();
     }
     void check() { CUDA_TRY(cudaGetLastError()); }
 };
@@ -173,10 +190,11 @@ template <class In> void exclusive_scan(CudaExec &ex, In in, size_t n, u64 *out)
 {
     size_t ntiles = (n + SCAN_TILE) / SCAN_TILE;          // >= 1, and covers index n
     u64 *tiles = ex.alloc<u64>(ntiles + 1);
+    ex.prof_begin("scan");
     k_scan_reduce<<<(unsigned)ntiles, SCAN_THREADS, 0, ex.stream>>>(in, n, tiles);
     k_scan_tiles<<<1, 1024, 0, ex.stream>>>(tiles, ntiles, tiles + ntiles);
     k_scan_apply<<<(unsigned)ntiles, SCAN_THREADS, 0, ex.stream>>>(in, n, tiles, out);
-    ex.launches += 3;
+    ex.prof_end(); ex.launches += 2;
 }
 
 // ------------------------------------------------------------------ context
@@ -190,7 +208,11 @@ struct Ctx {
     std::string err;
     nafgpu_timing timing{};
     std::vector<u8> host_scratch;
+    Prof prof;
+    std::string prof_report;
 };
+
+#define KLAUNCH(ex, name, ...) do { (ex).prof_begin(name); __VA_ARGS__; (ex).prof_end(); } while (0)
 
 struct DecodeOut { const u8 *d_text; u64 size; };
 struct EncodeOut { const u8 *d_naf; u64 size; };

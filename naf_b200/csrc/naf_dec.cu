@@ -181,13 +181,35 @@ __device__ __forceinline__ u8 base_at(const TextArgs &A, u64 bi)
 }
 
 static const int WT_THREADS = 256, WT_ITERS = 4, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 16 KB of text per CTA
-static const int WT_MAXREC = 8192;    // records whose start lies inside one tile (min record = 2 bytes; 1-byte records fall back)
+static const int WT_MAXREC = 1024;    // records staged in shared memory per tile (more than that: read them from HBM)
 
-// Each CTA: find the record containing its first byte (32-ary search by warp 0), stage the starts of
-// the records that begin inside the tile in shared memory, then every thread emits 16-byte chunks.
+struct RecS { u64 out0, L, sbase; u32 id_s, id_len, cm_s, cm_len; };
+
+__device__ __forceinline__ void rec_bounds(const TextArgs &A, const RecS &s, RecInfo &R)
+{
+    R.id_s = s.id_s; R.id_len = s.id_len; R.cm_s = s.cm_s; R.cm_len = s.cm_len; R.L = s.L; R.sbase = s.sbase;
+    R.a = A.prefix ? 1 : 0;
+    R.b = R.a + name_len_of(A, s.id_len, s.cm_len);
+    R.c = R.b + A.name_nl;
+    R.d = R.c + seq_area_len(A, s.L);
+    R.e = R.d + (A.with_qual ? s.L + 3 : 0);
+}
+__device__ __forceinline__ void rec_fetch(const TextArgs &A, u64 i, RecS &s)
+{
+    s.id_s = s.id_len = s.cm_s = s.cm_len = 0;
+    if (A.with_name) {
+        if (A.has_ids) { s.id_s = i ? A.id_end[i - 1] + 1 : 0; s.id_len = A.id_end[i] - s.id_s; }
+        if (A.has_names) { s.cm_s = i ? A.cm_end[i - 1] + 1 : 0; s.cm_len = A.cm_end[i] - s.cm_s; }
+    }
+    s.L = A.seq_present ? A.L[i] : 0; s.sbase = A.seq_present ? A.seq_start[i] : 0;
+    s.out0 = A.out_start[i];
+}
+
+// Each CTA: find the record containing its first byte (32-ary search by warp 0), stage the descriptors of
+// the records that intersect the tile in shared memory, then every thread emits 16-byte chunks.
 __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
 {
-    __shared__ u32 rec_rel[WT_MAXREC + 1];      // out_start[first + 1 + k] - tile_start, ascending
+    __shared__ RecS recs[WT_MAXREC];
     __shared__ u64 s_first; __shared__ u32 s_nrec;
     const u64 tile0 = (u64)blockIdx.x * WT_TILE;
     const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
@@ -208,40 +230,38 @@ __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
     }
     __syncthreads();
     const u64 first = s_first;
-    // records first+1, first+2, ... that start before tile1
+    // records first, first+1, ... that start before tile1
     {
         u32 cnt = 0;
-        for (u64 base = first + 1;; base += WT_THREADS) {
+        for (u64 base = first;; base += WT_THREADS) {
             u64 i = base + threadIdx.x;
-            bool in = i < A.N && A.out_start[i] < tile1;
-            if (in) { u32 k = (u32)(i - first - 1); if (k < WT_MAXREC) rec_rel[k] = (u32)(A.out_start[i] - tile0); }
+            bool in = i < A.N && (i == first || A.out_start[i] < tile1);
+            if (in) { u32 k = (u32)(i - first); if (k < WT_MAXREC) rec_fetch(A, i, recs[k]); }
             int any = __syncthreads_count(in);
             cnt += any;
-            if (any < WT_THREADS) break;
+            if (any < WT_THREADS || cnt >= WT_MAXREC) break;
         }
         if (threadIdx.x == 0) s_nrec = cnt;
     }
     __syncthreads();
-    const u32 nrec = s_nrec;
-    const bool overflow = nrec > WT_MAXREC;
+    const u32 nrec = s_nrec < (u32)WT_MAXREC ? s_nrec : (u32)WT_MAXREC;     // staged records: first .. first+nrec-1
 
     for (int it = 0; it < WT_ITERS; it++) {
         const u64 q0 = tile0 + (u64)it * (WT_THREADS * 16) + (u64)threadIdx.x * 16;
         if (q0 >= tile1) break;
-        // record containing q0
-        u64 rec;
-        if (!overflow) {
-            u32 rel = (u32)(q0 - tile0);
-            u32 lo = 0, hi = nrec;               // number of staged records with start <= rel
-            while (lo < hi) { u32 mid = (lo + hi) >> 1; if (rec_rel[mid] <= rel) lo = mid + 1; else hi = mid; }
-            rec = first + lo;
-        } else {
-            u64 lo = first, hi = A.N;
-            while (hi - lo > 1) { u64 mid = (lo + hi) >> 1; if (A.out_start[mid] <= q0) lo = mid; else hi = mid; }
-            rec = lo;
+        // record containing q0: last staged record with out0 <= q0; if that is the final staged one, more may follow in HBM
+        u32 lo = 0, hi = nrec;                   // invariant: recs[lo].out0 <= q0
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (recs[mid].out0 <= q0) lo = mid; else hi = mid; }
+        u64 rec = first + lo;
+        RecS cur = recs[lo];
+        if (lo + 1 == nrec && rec + 1 < A.N && s_nrec >= (u32)WT_MAXREC) {
+            // tile holds more records than staged: finish the search in global memory
+            u64 glo = rec, ghi = A.N;
+            while (ghi - glo > 1) { u64 mid = (glo + ghi) >> 1; if (A.out_start[mid] <= q0) glo = mid; else ghi = mid; }
+            if (glo != rec) { rec = glo; rec_fetch(A, rec, cur); }
         }
-        RecInfo R; load_rec(A, rec, R);
-        u64 r = q0 - A.out_start[rec];
+        RecInfo R; rec_bounds(A, cur, R);
+        u64 r = q0 - cur.out0;
         const int nvalid = tile1 - q0 >= 16 ? 16 : (int)(tile1 - q0);
         u32 w[4] = {0, 0, 0, 0};
         bool done = false;
@@ -279,10 +299,15 @@ __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
             }
         }
         if (!done) {
+            u32 li = lo;                          // index of `rec` among the staged records (valid while rec == first + li)
 #pragma unroll
             for (int j = 0; j < 16; j++) {
                 if (j < nvalid) {
-                    while (r >= R.e && rec + 1 < A.N) { rec++; load_rec(A, rec, R); r = 0; }
+                    while (r >= R.e && rec + 1 < A.N) {
+                        rec++; li++;
+                        if (rec == first + li && li < nrec) cur = recs[li]; else rec_fetch(A, rec, cur);
+                        rec_bounds(A, cur, R); r = 0;
+                    }
                     u32 c;
                     if (r < R.a) c = A.prefix;
                     else if (r < R.b) {
@@ -426,10 +451,10 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         u64 ntiles = (bytes + ZT - 1) / ZT;
         u64 *counts = ex.alloc<u64>(ntiles + 1), *prefix = ex.alloc<u64>(ntiles + 2);
         u32 *end = ex.alloc<u32>(N + 1);
-        k_zero_count<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, counts); ex.launches++;
+        KLAUNCH(ex, "k_zero_count", k_zero_count<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, counts));
         const u64 *c = counts;
         exclusive_scan(ex, [c] __device__ (size_t i) { return c[i]; }, ntiles, prefix);
-        k_zero_scatter<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, prefix, end, N); ex.launches++;
+        KLAUNCH(ex, "k_zero_scatter", k_zero_scatter<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, prefix, end, N));
         u64 nzero; u8 last;
         ex.download(&nzero, prefix + ntiles, 8);
         ex.download(&last, s + bytes - 1, 1);
@@ -525,12 +550,12 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     A.out = d_text;
     {
         u64 ntiles = (total + WT_TILE - 1) / WT_TILE;
-        k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A); ex.launches++;
+        KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A));
     }
     if (view == NAFGPU_OUT_CHARCOUNT) {
         unsigned long long *counts = ex.alloc<unsigned long long>(256);
         ex.zero(counts, 256 * 8);
-        k_charcount<<<148 * 8, 256, 0, ex.stream>>>(d_text, total, counts); ex.launches++;
+        KLAUNCH(ex, "k_charcount", k_charcount<<<148 * 8, 256, 0, ex.stream>>>(d_text, total, counts));
         return DecodeOut{(const u8 *)counts, 256 * 8};
     }
     ex.check();

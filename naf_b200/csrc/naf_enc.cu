@@ -8,8 +8,8 @@
 //   tail flush + container header/sections                 ennaf/src/ennaf.c:511-589
 //
 // The reference walks the text one byte at a time through a 16 KB fread buffer.  Here the parser is
-// restated as a byte-level finite-state machine (4 states for FASTA, 10 for FASTQ; the same machine as
-// oracle/naf_oracle.c) and run data-parallel:
+// restated as a byte-level finite-state machine (4 states for FASTA, 11 for FASTQ; tests check it against a
+// sequential CPU restatement of process.c) and run data-parallel:
 //   pass 1  every thread folds its 64 bytes into a state->state map; maps compose associatively, so a
 //           scan over tiles yields the parser state entering every tile              (k_fsm_reduce, k_fsm_scan)
 //   pass 2  with the entry state known, count what each tile emits per stream        (k_fsm_emit<COUNT>)
@@ -528,13 +528,13 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     const u64 body = n - p0, ntiles = (body + PTILE - 1) / PTILE;
     ParseArgs P; P.text = d_text; P.n = n; P.p0 = p0; P.cfg = C; P.tab = d_tab; P.ntiles = ntiles;
     P.tile_map = ex.alloc<u64>(ntiles + 1); P.tile_state = ex.alloc<u8>(ntiles + 2);
-    if (ntiles) { k_fsm_reduce<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P); ex.launches++; }
-    k_fsm_scan<<<1, 1024, 0, ex.stream>>>(P); ex.launches++;
+    if (ntiles) { KLAUNCH(ex, "k_fsm_reduce", k_fsm_reduce<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
+    KLAUNCH(ex, "k_fsm_scan", k_fsm_scan<<<1, 1024, 0, ex.stream>>>(P));
 
     EmitArgs E; memset(&E, 0, sizeof E);
     E.P = P;
     E.tile = ex.alloc<TileCounts>(ntiles + 1);
-    if (ntiles) { k_fsm_emit<false><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E); ex.launches++; }
+    if (ntiles) { KLAUNCH(ex, "k_fsm_emit", k_fsm_emit<false><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E)); }
     // exclusive sums of the six counters + exclusive max of the line-end marker
     u64 *pre[7];
     for (int k = 0; k < 7; k++) pre[k] = ex.alloc<u64>(ntiles + 2);
@@ -562,14 +562,14 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         else if (end_state == FA_COMMENT) add_comm = 1;
         add_rec = 1;
     } else {
-        static const char *no_qual = "truncated FASTQ input: last sequence has no quality\n";
+    
         switch (end_state) {
         case FQ_NAME: case FQ_COMMENT: /* decided below, after earlier errors */ break;
         case FQ_QUAL: add_rec = 1; break;
         case FQ_BEFORE_QUAL: if (C.wf) add_rec = 1; break;       // well-formed: empty last quality line without '\n'
         default: break;
         }
-        (void)no_qual;
+
     }
     const u64 n_ids = tot[0] + add_ids, n_comm = tot[1] + add_comm, n_seq = tot[2], n_cnt = tot[3], n_qual = tot[4], n_rec = tot[5] + add_rec;
 
@@ -584,7 +584,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     E.ids = S.ids; E.comm = S.comm; E.bases = bases; E.qual = S.qual;
     E.rec_seq_end = rec_seq_end; E.rec_qual_end = rec_qual_end; E.rec_pos = rec_pos;
     E.unexpected = d_unexp; E.longest = d_longest; E.first_bad = d_first_bad;
-    if (ntiles) { k_fsm_emit<true><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E); ex.launches++; }
+    if (ntiles) { KLAUNCH(ex, "k_fsm_emit", k_fsm_emit<true><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E)); }
     // end-of-input additions
     {
         u8 *ids = S.ids, *comm = S.comm; const u64 a = tot[0], b = tot[1], r = tot[5], cnt = n_cnt, ql = n_qual, nn = n;
@@ -696,17 +696,17 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         S.seq = ex.alloc<u8>(S.n_seq + 64);
         u64 nwords = (n_seq + 31) / 32;
         u32 *casebits = ex.alloc<u32>(nwords + 2);
-        if (nwords) { k_pack4<<<(unsigned)((nwords + 255) / 256), 256, 0, ex.stream>>>(bases, n_seq, S.seq, casebits, S.store_mask, d_lut); ex.launches++; }
+        if (nwords) { KLAUNCH(ex, "k_pack4", k_pack4<<<(unsigned)((nwords + 255) / 256), 256, 0, ex.stream>>>(bases, n_seq, S.seq, casebits, S.store_mask, d_lut)); }
         if (S.store_mask && n_seq) {
             // case flips -> runs -> units (encoders.c:98-151; final run flushed by ennaf.c:511)
             u64 ft = (nwords + 255) / 256;
             u64 *fcount = ex.alloc<u64>(ft + 1), *fpre = ex.alloc<u64>(ft + 2);
-            k_flip_count<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fcount); ex.launches++;
+            KLAUNCH(ex, "k_flip_count", k_flip_count<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fcount));
             const u64 *fc = fcount;
             exclusive_scan(ex, [fc] __device__ (size_t i) { return fc[i]; }, ft, fpre);
             u64 R; ex.download(&R, fpre + ft, 8);                          // number of flips; runs = R + 1
             u64 *flip_pos = ex.alloc<u64>(R + 2);
-            k_flip_scatter<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fpre, flip_pos); ex.launches++;
+            KLAUNCH(ex, "k_flip_scatter", k_flip_scatter<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fpre, flip_pos));
             // casebits beyond n_seq are zero, so a masked tail produces one spurious flip at n_seq: drop it
             RunCalc rc{flip_pos, R, n_seq};
             u64 *upre = ex.alloc<u64>(R + 3);

@@ -449,16 +449,36 @@ HD void k_literals(const ZDecArgs &a, u32 t)
 }
 
 // K6 — raw / RLE blocks and raw / RLE literal sections (one thread group per block)
+// word-wise copy / fill shared by a thread group (source may be unaligned: two aligned loads + funnel shift;
+// input buffers carry >= 8 bytes of padding so the last aligned load stays in bounds)
+HD void copy_span(u8 *d, const u8 *s, u32 n, u32 tid, u32 nt)
+{
+    u32 head = (u32)((4 - ((uintptr_t)d & 3)) & 3); if (head > n) head = n;
+    for (u32 k = tid; k < head; k += nt) d[k] = s[k];
+    const u32 nw = (n - head) / 4;
+    const u8 *s2 = s + head; u32 *dw = (u32 *)(d + head);
+    const u32 sh = (u32)((uintptr_t)s2 & 3) * 8; const u32 *sa = (const u32 *)((uintptr_t)s2 & ~(uintptr_t)3);
+    for (u32 k = tid; k < nw; k += nt) { u32 lo = sa[k]; dw[k] = sh ? (lo >> sh) | (sa[k + 1] << (32 - sh)) : lo; }
+    for (u32 k = head + nw * 4 + tid; k < n; k += nt) d[k] = s[k];
+}
+HD void fill_span(u8 *d, u8 v, u32 n, u32 tid, u32 nt)
+{
+    u32 head = (u32)((4 - ((uintptr_t)d & 3)) & 3); if (head > n) head = n;
+    for (u32 k = tid; k < head; k += nt) d[k] = v;
+    const u32 nw = (n - head) / 4; u32 *dw = (u32 *)(d + head); const u32 vv = v * 0x01010101u;
+    for (u32 k = tid; k < nw; k += nt) dw[k] = vv;
+    for (u32 k = head + nw * 4 + tid; k < n; k += nt) d[k] = v;
+}
 HD void k_copy_block(const ZDecArgs &a, u32 i, u32 tid, u32 nthreads)
 {
     const ZBlock &b = a.blk[i];
-    if (b.type == 0) { const u8 *s = a.in + b.src; u8 *d = a.out + b.out_off; for (u32 k = tid; k < b.rsize; k += nthreads) d[k] = s[k]; return; }
-    if (b.type == 1) { u8 v = a.in[b.src]; u8 *d = a.out + b.out_off; for (u32 k = tid; k < b.rsize; k += nthreads) d[k] = v; return; }
+    if (b.type == 0) { copy_span(a.out + b.out_off, a.in + b.src, b.rsize, tid, nthreads); return; }
+    if (b.type == 1) { fill_span(a.out + b.out_off, a.in[b.src], b.rsize, tid, nthreads); return; }
     if (b.lit_type >= 2) return;
     u8 *d = b.nseq == 0 ? a.out + b.out_off : a.lit_scratch + b.lit_off;
     const u8 *s = a.in + b.src + b.lit_hdr;
-    if (b.lit_type == 0) for (u32 k = tid; k < b.lit_regen; k += nthreads) d[k] = s[k];
-    else { u8 v = s[0]; for (u32 k = tid; k < b.lit_regen; k += nthreads) d[k] = v; }
+    if (b.lit_type == 0) copy_span(d, s, b.lit_regen, tid, nthreads);
+    else fill_span(d, s[0], b.lit_regen, tid, nthreads);
 }
 
 // K7 — resolve repeat offsets of one block and validate them (spec "Repeat Offsets")
@@ -469,21 +489,28 @@ HD void k_seq_resolve(const ZDecArgs &a, u32 i)
     if (b.type != 2 || b.nseq == 0) return;
     u32 r0 = b.rep_in[0], r1 = b.rep_in[1], r2 = b.rep_in[2];
     ZSeq *seq = a.seq + b.seq_base;
-    for (u32 k = 0; k < b.nseq; k++) {
-        u32 ofv = seq[k].of, ll = seq[k].ll, off;
-        if (ofv > 3) { off = ofv - 3; r2 = r1; r1 = r0; r0 = off; }
-        else {
-            u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
-            if (idx == 0) off = r0;
+    // batches of 8: all loads of a batch are issued before the (serial) history update needs them
+    for (u32 k0 = 0; k0 < b.nseq; k0 += 8) {
+        const u32 m = b.nseq - k0 < 8 ? b.nseq - k0 : 8;
+        u32 ofv[8], ll[8], dr[8];
+        for (u32 j = 0; j < 8; j++) if (j < m) { ofv[j] = seq[k0 + j].of; ll[j] = seq[k0 + j].ll; dr[j] = seq[k0 + j].dst_rel; }
+        for (u32 j = 0; j < 8; j++) if (j < m) {
+            u32 off;
+            if (ofv[j] > 3) { off = ofv[j] - 3; r2 = r1; r1 = r0; r0 = off; }
             else {
-                off = idx == 1 ? r1 : (idx == 2 ? r2 : r0 - 1);
-                if (idx != 1) r2 = r1;
-                r1 = r0; r0 = off;
+                u32 idx = ofv[j] - 1 + (ll[j] == 0 ? 1u : 0u);
+                if (idx == 0) off = r0;
+                else {
+                    off = idx == 1 ? r1 : (idx == 2 ? r2 : r0 - 1);
+                    if (idx != 1) r2 = r1;
+                    r1 = r0; r0 = off;
+                }
             }
+            u64 match_pos = b.out_off + dr[j] + ll[j];
+            if (off == 0 || off > match_pos - b.frame_out) { zerr(a, Z_ERR_OFFSET, i); off = 0; seq[k0 + j].ml = 0; }
+            ofv[j] = off;
         }
-        u64 match_pos = b.out_off + seq[k].dst_rel + ll;
-        if (off == 0 || off > match_pos - b.frame_out) { zerr(a, Z_ERR_OFFSET, i); off = 0; seq[k].ml = 0; }
-        seq[k].of = off;
+        for (u32 j = 0; j < 8; j++) if (j < m) seq[k0 + j].of = ofv[j];
     }
 }
 
@@ -630,10 +657,10 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
     ex.zero(d_res, sizeof(ZStreamResult) * plan.streams.size());
 
     if (n_comp) {
-        ex.for_each(nblk, [=] HDN (size_t i) { k_block_headers(a, (u32)i); });
-        ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan1_phase1(a, (u32)c); });
-        ex.for_each(1, [=] HDN (size_t) { k_scan1_phase2(a); });
-        ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan1_phase3(a, (u32)c); });
+        ex.for_each(nblk, [=] HDN (size_t i) { k_block_headers(a, (u32)i); }, "zd_block_headers");
+        ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan1_phase1(a, (u32)c); }, "zd_scan1");
+        ex.for_each(1, [=] HDN (size_t) { k_scan1_phase2(a); }, "zd_scan1");
+        ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan1_phase3(a, (u32)c); }, "zd_scan1");
     }
     // Sizes of the pools / scratch are bounded without a device round trip:
     //   Huffman tables <= compressed blocks, FSE slots <= compressed blocks, literal scratch and number of
@@ -650,16 +677,16 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
     a.lit_scratch = ex.template alloc<u8>(tot_lit + 16);
     a.seq = ex.template alloc<ZSeq>(tot_seq + 1);
 
-    if (tot_huf) ex.for_each(nblk, [=] HDN (size_t i) { k_huf_table(a, (u32)i); });
+    if (tot_huf) ex.for_each(nblk, [=] HDN (size_t i) { k_huf_table(a, (u32)i); }, "zd_huf_table", 64);
     if (tot_seq) {
-        ex.for_each(nblk, [=] HDN (size_t i) { k_fse_tables(a, (u32)i); });
-        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_decode(a, (u32)i); });
+        ex.for_each(nblk, [=] HDN (size_t i) { k_fse_tables(a, (u32)i); }, "zd_fse_tables", 32);
+        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_decode(a, (u32)i); }, "zd_seq_decode", 32);
     }
-    ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan2_phase1(a, (u32)c); });
-    ex.for_each(1, [=] HDN (size_t) { k_scan2_phase2(a); });
-    ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan2_phase3(a, (u32)c); });
-    ex.for_each(nblk, [=] HDN (size_t i) { k_frame_out(a, (u32)i); });
-    ex.for_each(nblk, [=] HDN (size_t i) { k_stream_totals(a, (u32)i, d_res); });
+    ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan2_phase1(a, (u32)c); }, "zd_scan2");
+    ex.for_each(1, [=] HDN (size_t) { k_scan2_phase2(a); }, "zd_scan2");
+    ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan2_phase3(a, (u32)c); }, "zd_scan2");
+    ex.for_each(nblk, [=] HDN (size_t i) { k_frame_out(a, (u32)i); }, "zd_scan2");
+    ex.for_each(nblk, [=] HDN (size_t i) { k_stream_totals(a, (u32)i, d_res); }, "zd_scan2");
 
     // The regenerated sizes must match what the container promised before anything is written.
     {
@@ -674,8 +701,8 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         }
     }
 
-    if (n_comp) ex.for_each((size_t)nblk * 4, [=] HDN (size_t t) { k_literals(a, (u32)t); });
-    ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_copy_block(a, (u32)i, tid, nt); });
+    if (n_comp) ex.for_each((size_t)nblk * 4, [=] HDN (size_t t) { k_literals(a, (u32)t); }, "zd_literals", 64);
+    ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_copy_block(a, (u32)i, tid, nt); }, "zd_copy_block");
 
     if (tot_seq) {
         // span of the arena that pointer jumping may touch: streams that contain sequences
@@ -692,12 +719,12 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         a.link = ex.template alloc<u32>(span + 1);
         a.bitmap = ex.template alloc<u32>(words + 1);
         ex.zero(a.bitmap, (words + 1) * 4);
-        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_resolve(a, (u32)i); });
-        ex.for_each(tot_seq, [=] HDN (size_t j) { k_seq_exec_small(a, j); });
-        ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_seq_exec_big(a, (u32)i, tid, nt); });
+        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_resolve(a, (u32)i); }, "zd_seq_resolve", 32);
+        ex.for_each(tot_seq, [=] HDN (size_t j) { k_seq_exec_small(a, j); }, "zd_seq_exec_small");
+        ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_seq_exec_big(a, (u32)i, tid, nt); }, "zd_seq_exec_big");
         for (int round = 0; round < 40; round++) {
             ex.zero(a.status + 2, 4);
-            for (int k = 0; k < 4; k++) ex.for_each(words, [=] HDN (size_t w) { k_jump(a, w); });
+            for (int k = 0; k < 4; k++) ex.for_each(words, [=] HDN (size_t w) { k_jump(a, w); }, "zd_jump");
             u32 st[4]; ex.download(st, a.status, 16);
             if (st[0]) { err = "corrupt zstd sequences (code " + std::to_string(st[0]) + ", block " + std::to_string(st[1]) + ")"; return -1; }
             if (!st[2]) break;

@@ -357,7 +357,7 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     ex.upload(b.d_blocks, blocks.data(), sizeof(ZEncBlock) * b.nblocks);
     CUDA_TRY(cudaStreamSynchronize(ex.stream));                 // `blocks` is a local vector
     ZEncArgs A{b.d_blocks, b.d_slots};
-    k_zenc_block<<<b.nblocks, 256, 0, ex.stream>>>(A); ex.launches++;
+    KLAUNCH(ex, "k_zenc_block", k_zenc_block<<<b.nblocks, 256, 0, ex.stream>>>(A));
     b.d_off = ex.alloc<u64>(b.nblocks + 2);
     const ZEncBlock *db = b.d_blocks;
     exclusive_scan(ex, [db] __device__ (size_t i) { return (u64)db[i].csize + 3; }, b.nblocks, b.d_off);
@@ -377,7 +377,7 @@ static void zstd_gather_frames(Ctx &ctx, CudaExec &ex, ZEncBatch &b, bool skip_m
     u8 **d_dest = ex.alloc<u8 *>(ns); u32 *d_first = ex.alloc<u32>(ns + 1); int *d_wlog = ex.alloc<int>(ns);
     ex.upload(d_dest, b.dest.data(), ns * sizeof(u8 *)); ex.upload(d_first, b.first_block.data(), (ns + 1) * 4); ex.upload(d_wlog, b.wlog.data(), ns * 4);
     ZGatherArgs G{b.d_blocks, b.d_slots, b.d_off, d_dest, d_first, d_wlog, skip_magic ? 1 : 0};
-    k_zenc_gather<<<b.nblocks, 256, 0, ex.stream>>>(G); ex.launches++;
+    KLAUNCH(ex, "k_zenc_gather", k_zenc_gather<<<b.nblocks, 256, 0, ex.stream>>>(G));
     CUDA_TRY(cudaStreamSynchronize(ex.stream));                 // host vectors above
     (void)ctx;
 }

@@ -13,10 +13,10 @@ struct HostExec {
     void upload(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
     void download(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
     void zero(void *p, size_t n) { memset(p, 0, n); }
-    template <class F> void for_each(size_t n, F f) { launches++; for (size_t i = 0; i < n; i++) f(i); }
+    template <class F> void for_each(size_t n, F f, const char * = nullptr, int = 0) { launches++; for (size_t i = 0; i < n; i++) f(i); }
     // group kernels are written as strided loops: emulate once with 1 thread and once more with an
     // awkward thread count to catch stride bugs (results must be idempotent).
-    template <class F> void for_each_group(size_t ngroups, int, F f)
+    template <class F> void for_each_group(size_t ngroups, int, F f, const char * = nullptr)
     {
         launches++;
         for (size_t g = 0; g < ngroups; g++) for (unsigned t = 0; t < 3; t++) f(g, t, 3u);
