@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py — NAF encode+decode throughput on B200 (BASELINE.json metric), one process per GPU.
+
+A *step* is one pass of the hot path over one batch of synthetic reads: encode (text -> .naf) followed by
+decode (.naf -> text).  Workload at N=1: BASELINE.json configs[1], 10 M x 150 bp synthetic Illumina FASTQ
+(`--records` scales it).  With N>1 every rank gets its own shard of as many records (records shard
+naturally; no data-path collective) and `value` is all ranks' bases / max-over-ranks time ("weak").
+
+  value   device-resident: text and .naf already in HBM, CUDA events on the library's stream around
+          nafgpu_encode_device + nafgpu_decode_device (host walk of the zstd block headers included)
+  e2e     the same step through the host-buffer C ABI (nafgpu_encode / nafgpu_decode): pinned host text in,
+          pinned host text out, every H2D / D2H copy inside the timed region
+  roofline  the dominant kernel of the step, timed live with CUDA events (library profiler, separate
+          un-timed step), algorithmic bytes per base from DESIGN.md
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref ennaf + unnaf, 1 thread: that is all it has) on a
+          bounded sample of the same workload, timed on this box's host cores
+
+`--impl reference` times the reference's own CPU implementation on all host cores (record-aligned pieces,
+one ennaf/unnaf process per core) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Gbases/s encode+decode (round trip: text -> .naf -> text), bit-exact"
+UNIT = "Gbases/s"
+READ_LEN = 150
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--records", type=int, default=10_000_000, help="150 bp reads per GPU (config 2 = 10 M)")
+    ap.add_argument("--cpu-sample-records", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.thread.start()
+
+    def stop(self):
+        self.stop_flag = True
+        self.thread.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+def ref_bin(tool):
+    p = os.path.join(ROOT, "oracle", "_ref", tool)
+    return p if os.access(p, os.X_OK) else None
+
+
+def split_fastq_pieces(text: bytes, pieces: int):
+    """record-aligned pieces: every record of this workload is `rec` lines of 4, found by scanning to '\\n@SRR'"""
+    n, cuts = len(text), [0]
+    for k in range(1, pieces):
+        at = text.find(b"\n@SRR1.", k * n // pieces)
+        if at < 0 or at + 1 <= cuts[-1]:
+            continue
+        cuts.append(at + 1)
+    cuts.append(n)
+    return [text[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
+
+
+def time_reference(text: bytes, n_bases: int, procs: int, tmp="/dev/shm"):
+    """one round trip with `procs` independent ennaf / unnaf processes; returns (t_enc, t_dec) wall seconds"""
+    work = os.path.join(tmp, f"nafbench_{os.getpid()}")
+    os.makedirs(work, exist_ok=True)
+    pieces = split_fastq_pieces(text, procs) if procs > 1 else [text]
+    for i, p in enumerate(pieces):
+        with open(os.path.join(work, f"in{i}.fq"), "wb") as f:
+            f.write(p)
+    env = dict(os.environ, TMPDIR=work)
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([ref_bin("ennaf"), os.path.join(work, f"in{i}.fq"), "-o", os.path.join(work, f"x{i}.naf")], env=env)
+          for i in range(len(pieces))]
+    assert all(p.wait() == 0 for p in ps), "reference ennaf failed"
+    t1 = time.perf_counter()
+    ps = [subprocess.Popen([ref_bin("unnaf"), os.path.join(work, f"x{i}.naf"), "-o", os.path.join(work, f"out{i}.fq")], env=env)
+          for i in range(len(pieces))]
+    assert all(p.wait() == 0 for p in ps), "reference unnaf failed"
+    t2 = time.perf_counter()
+    ok = all(open(os.path.join(work, f"out{i}.fq"), "rb").read() == pieces[i] for i in range(len(pieces)))
+    naf_bytes = sum(os.path.getsize(os.path.join(work, f"x{i}.naf")) for i in range(len(pieces)))
+    for f in os.listdir(work):
+        os.remove(os.path.join(work, f))
+    os.rmdir(work)
+    assert ok, "reference round trip is not bit-exact"
+    return t1 - t0, t2 - t1, naf_bytes
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from naf_b200 import synth
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    # bounded sample of the workload: ~4 M reads keeps K+W round trips within a few minutes on one socket
+    records = min(args.records, max(procs * 50_000, 4_000_000))
+    text = synth.fastq(records, READ_LEN, seed=42)
+    bases = records * READ_LEN
+    kind = "reference" if ref_bin("ennaf") and ref_bin("unnaf") else None
+    if kind is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ennaf and unnaf are not built"}))
+        return
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        time_reference(text, bases, procs)
+    ts = []
+    for _ in range(args.steps):
+        te, td, _ = time_reference(text, bases, procs)
+        ts.append((te, td))
+    te = sum(t[0] for t in ts) / len(ts)
+    td = sum(t[1] for t in ts) / len(ts)
+    value = bases / (te + td) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": (te + td) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{records} x {READ_LEN} bp synthetic Illumina FASTQ (bounded sample of BASELINE configs[1])",
+                   "records": records, "read_len": READ_LEN, "level": 1},
+        "encode_gbases_s": bases / te / 1e9, "decode_gbases_s": bases / td / 1e9,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference",
+                         "sample": f"{records} reads split into {procs} record-aligned pieces, one ennaf -1 / unnaf process per core, files on /dev/shm"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm (GPU)
+ALGO_BYTES_PER_BASE = {
+    # algorithmic HBM bytes per base of each kernel on the config-2 workload (DESIGN.md "Kernels and rooflines")
+    # text = 2.18 B/base (2 x 151 + 25 header bytes per 150-base record), ids+comments 0.14, lengths 0.027
+    "k_fsm_reduce": 2.18, "k_fsm_emit": 2.18 + (1.0 + 1.0 + 0.14) / 2,        # two launches: count reads text, scatter reads text and writes streams
+    "k_pack4": 1.0 + 0.5,
+    "k_zenc_block": 2 * (0.5 + 1.0 + 0.17) + 0.92, "k_zenc_gather": 2 * 0.92,
+    "zd_literals": 0.92 + 0.5 + 1.0 + 0.17, "k_write_text": 0.5 + 1.0 + 0.17 + 2.18,
+}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import naf_b200
+    from naf_b200 import api, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (libnafgpu has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    ctx = naf_b200.NafGpu(local)
+    records = args.records
+    bases = records * READ_LEN
+    text_np = synth.fastq_array(records, READ_LEN, seed=42 + rank, first_index=1 + rank * records)
+    n_text = int(text_np.size)
+    # pinned host input (what the CLI gets from a file read) and a device-resident copy
+    h_text = torch.empty(n_text + 64, dtype=torch.uint8).pin_memory()
+    h_text[:n_text] = torch.from_numpy(text_np)
+    del text_np
+    d_text = torch.empty(n_text + 64, dtype=torch.uint8, device="cuda")
+    d_text[:n_text].copy_(h_text[:n_text])
+    d_text[n_text:].zero_()
+    torch.cuda.synchronize()
+
+    eopts, dopts = api.make_enc_opts(), api.make_dec_opts()
+    stream = torch.cuda.ExternalStream(ctx.lib.nafgpu_stream(ctx.h))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import ctypes as C
+    naf_keep = {}
+
+    # ---- device-resident step: encode_device, (un-timed: mirror .naf to host), decode_device
+    def device_round(timed):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        addr, size, info = ctx.encode_device(d_text.data_ptr(), n_text, eopts)
+        ev[1].record(stream)
+        l1 = ctx.timing().kernel_launches
+        h = naf_keep.get("h")
+        if h is None or h.numel() < size + 64:
+            h = torch.empty(size + (size >> 3) + 64, dtype=torch.uint8).pin_memory()
+            naf_keep["h"] = h
+            naf_keep["d"] = torch.empty(size + (size >> 3) + 64, dtype=torch.uint8, device="cuda")
+        d_naf = naf_keep["d"]
+        # keep the .naf in our own device buffer (the arena is recycled by the next call) + host mirror
+        torch.cuda.synchronize()
+        ctx_copy_d2d(d_naf, addr, size)
+        h[:size].copy_(d_naf[:size])
+        torch.cuda.synchronize()
+        ev[2].record(stream)
+        taddr, tsize = ctx.decode_device(d_naf.data_ptr(), size, (h.data_ptr(), size), dopts)
+        ev[3].record(stream)
+        l2 = ctx.timing().kernel_launches
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3]), size, taddr, tsize, l1 + l2
+
+    cudart = C.CDLL("libcudart.so")
+    cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+
+    def ctx_copy_d2d(dst_tensor, src_addr, nbytes):
+        # plain device-to-device copy of the arena result into a tensor we own (outside the timed regions)
+        rc = cudart.cudaMemcpy(dst_tensor.data_ptr(), src_addr, nbytes, 3)
+        assert rc == 0, f"cudaMemcpy failed: {rc}"
+
+    # ---- warm-up (also grows the arena / pinned buffers to their steady size)
+    for _ in range(max(args.warmup, 3)):
+        te, td, naf_size, taddr, tsize, launches = device_round(False)
+    if not args.no_verify:
+        out = torch.empty(tsize, dtype=torch.uint8, device="cuda")
+        ctx_copy_d2d(out, taddr, tsize)
+        assert tsize == n_text and torch.equal(out, d_text[:n_text]), "device round trip is not bit-exact"
+        del out
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    enc_ms, dec_ms, launches_total = 0.0, 0.0, 0
+    for _ in range(args.steps):
+        te, td, naf_size, taddr, tsize, launches = device_round(True)
+        enc_ms += te; dec_ms += td; launches_total += launches
+    barrier()
+    dev_ms = (enc_ms + dec_ms) / args.steps
+
+    # ---- e2e: host buffers through the public C ABI, copies inside the timed region
+    def e2e_round():
+        t0 = time.perf_counter()
+        addr, size, info = ctx.encode_raw((h_text.data_ptr(), n_text), eopts)
+        t1 = time.perf_counter()
+        # the .naf is in ctx-owned pinned memory that the next call reuses: hand decode a stable copy (a file, in real use)
+        hn = naf_keep["h"]
+        C.memmove(hn.data_ptr(), addr, size)
+        t2 = time.perf_counter()
+        taddr, tsize = ctx.decode_raw((hn.data_ptr(), size), dopts)
+        t3 = time.perf_counter()
+        return (t1 - t0) * 1e3, (t3 - t2) * 1e3, size, taddr, tsize
+
+    for _ in range(2):
+        e2e_round()
+    if not args.no_verify:
+        _, _, _, taddr2, tsize2 = e2e_round()
+        got = torch.frombuffer((C.c_uint8 * tsize2).from_address(taddr2), dtype=torch.uint8)
+        assert tsize2 == n_text and torch.equal(got, h_text[:n_text]), "e2e round trip is not bit-exact"
+    barrier()
+    e_enc, e_dec = 0.0, 0.0
+    for _ in range(args.steps):
+        a, b, naf_size2, _, _ = e2e_round()
+        e_enc += a; e_dec += b
+    barrier()
+    clocks = sampler.stop()
+    e2e_ms = (e_enc + e_dec) / args.steps
+
+    # ---- live per-kernel times (CUDA events around every launch; separate, un-timed step)
+    ctx.profile(True)
+    ctx.encode_device(d_text.data_ptr(), n_text, eopts)
+    prof = {n: (c, ms) for n, c, ms in ctx.profile_report()}
+    ctx.decode_device(naf_keep["d"].data_ptr(), naf_size, (naf_keep["h"].data_ptr(), naf_size), dopts)
+    for n, c, ms in ctx.profile_report():
+        c0, m0 = prof.get(n, (0, 0.0))
+        prof[n] = (c0 + c, m0 + ms)
+    ctx.profile(False)
+
+    # ---- reduce over ranks: max time
+    t = torch.tensor([dev_ms, e2e_ms, enc_ms / args.steps, dec_ms / args.steps, e_enc / args.steps, e_dec / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, enc_ms1, dec_ms1, e_enc1, e_dec1 = [float(x) for x in t.tolist()]
+    total_bases = bases * world
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else (None, (0, 0.0))
+        name, (cnt, ms) = dom
+        bpb = ALGO_BYTES_PER_BASE.get(name)
+        roofline = {"bound": "hbm", "kernel": name, "launches_per_step": cnt, "ms_per_step": ms, "achieved": None, "peak": peak,
+                    "unit": "GB/s", "frac": None, "traffic": None, "peak_source": peak_src,
+                    "all_kernels_ms": {k: round(v[1], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}}
+        if bpb and ms > 0:
+            ach = bpb * bases / (ms * 1e-3) / 1e9
+            roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_base": bpb})
+        line = {
+            "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{records} x {READ_LEN} bp synthetic Illumina FASTQ per GPU (BASELINE configs[1])", "records_per_gpu": records,
+                       "read_len": READ_LEN, "text_bytes_per_gpu": n_text, "naf_bytes_per_gpu": int(naf_size),
+                       "l2": "inputs (3.3 GB text, 1.3 GB .naf at 10 M reads) are larger than the 126 MB L2; no explicit flush",
+                       "parallelism": f"{world} x independent record shards, no data-path collective"},
+            "encode_gbases_s": total_bases / (enc_ms1 * 1e-3) / 1e9, "decode_gbases_s": total_bases / (dec_ms1 * 1e-3) / 1e9,
+            "e2e": {"value": total_bases / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": n_text + int(naf_size),
+                    "d2h_bytes_per_step": int(naf_size) + n_text, "encode_gbases_s": total_bases / (e_enc1 * 1e-3) / 1e9,
+                    "decode_gbases_s": total_bases / (e_dec1 * 1e-3) / 1e9, "ms_per_step": e2e_ms},
+            "gpu_launches": launches_total,
+            "clocks": clocks,
+            "roofline": roofline,
+        }
+        if not args.no_cpu_baseline and ref_bin("ennaf") and ref_bin("unnaf"):
+            srec = min(records, args.cpu_sample_records)
+            sample = synth.fastq(srec, READ_LEN, seed=42)
+            te, td, _ = time_reference(sample, srec * READ_LEN, 1)
+            line["cpu_baseline"] = {"value": srec * READ_LEN / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
+                                    "encode_gbases_s": srec * READ_LEN / te / 1e9, "decode_gbases_s": srec * READ_LEN / td / 1e9,
+                                    "sample": f"first {srec} reads of the same workload, oracle/_ref ennaf -1 + unnaf (single-threaded tools), /dev/shm"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "container.hpp"
 #include "zstd_dec.cuh"
+#include "zstd_dec_cuda.cuh"
 
 namespace nafg {
 DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o);

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "container.hpp"
 #include "zstd_dec.cuh"
+#include "zstd_dec_cuda.cuh"
 
 namespace nafg {
 
@@ -263,80 +264,86 @@ __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
         RecInfo R; rec_bounds(A, cur, R);
         u64 r = q0 - cur.out0;
         const int nvalid = tile1 - q0 >= 16 ? 16 : (int)(tile1 - q0);
-        u32 w[4] = {0, 0, 0, 0};
-        bool done = false;
-
-        if (nvalid == 16) {
-            // fast path 1: 16 bytes inside one sequence line
-            if (r >= R.c && r + 16 <= R.d) {
-                u64 s = r - R.c, bi; bool ok;
-                if (A.W > 0 && A.seq_nl == 1) { u64 line = s / (A.W + 1), col = s - line * (A.W + 1); bi = line * A.W + col; ok = col + 16 <= A.W && bi + 16 <= R.L; }
-                else { bi = s; ok = s + 16 <= R.L; }
-                if (ok) {
+        // The 16 output bytes are composed from at most a handful of segments (prefix char, id, separator,
+        // comment, newline, a run of bases, '+', a run of qualities ...).  Each segment contributes one
+        // unaligned 16-byte read (or one constant byte) shifted into place: no per-byte loop.
+        u64 olo = 0, ohi = 0;
+        int j = 0;
+        u32 li = lo;
+        while (j < nvalid) {
+            while (r >= R.e && rec + 1 < A.N) {
+                rec++; li++;
+                if (rec == first + li && li < nrec) cur = recs[li]; else rec_fetch(A, rec, cur);
+                rec_bounds(A, cur, R); r = 0;
+            }
+            u64 slo = 0, shi = 0; u32 take = 1;             // segment bytes (first byte in the low end) and how many
+            if (r < R.a) slo = A.prefix;
+            else if (r < R.b) {
+                const u32 k = (u32)(r - R.a);
+                const u8 *src; u32 len;
+                if (A.has_ids && k < R.id_len) { src = A.ids + R.id_s + k; len = R.id_len - k; }
+                else if (A.has_ids && A.has_names) {
+                    if (k == R.id_len) { src = nullptr; len = 1; slo = A.sep; }
+                    else { const u32 kk = k - R.id_len - 1; src = A.comm + R.cm_s + kk; len = R.cm_len - kk; }
+                } else { src = A.comm + R.cm_s + k; len = R.cm_len - k; }
+                if (src) { const uint4 v = load_bytes16(src); slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32); }
+                take = len;
+            }
+            else if (r < R.c) slo = '\n';
+            else if (r < R.d) {
+                const u64 s = r - R.c;
+                u64 bi; u64 run;
+                if (A.W > 0 && A.seq_nl == 1) {
+                    const u64 line = s / (A.W + 1), col = s - line * (A.W + 1);
+                    bi = line * A.W + col;
+                    run = (col == A.W || r + 1 == R.d) ? 0 : min(A.W - col, R.L - bi);
+                } else { bi = s; run = s < R.L ? R.L - s : 0; }
+                if (run == 0) slo = '\n';
+                else {
                     bi += R.sbase;
                     if (A.packed) {
-                        u64 nib = load_nibbles16(A.seq, bi);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) w[k] = nib4_to_ascii((u32)(nib >> (16 * k)) & 0xFFFF, A.lut);
+                        const u64 nib = load_nibbles16(A.seq, bi);
+                        u32 w0 = nib4_to_ascii((u32)nib & 0xFFFF, A.lut), w1 = nib4_to_ascii((u32)(nib >> 16) & 0xFFFF, A.lut);
+                        u32 w2 = nib4_to_ascii((u32)(nib >> 32) & 0xFFFF, A.lut), w3 = nib4_to_ascii((u32)(nib >> 48) & 0xFFFF, A.lut);
                         if (A.maskbits) {
-                            u32 mb = load_maskbits16(A.maskbits, bi);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) w[k] += bits4_to_case((mb >> (4 * k)) & 15);
+                            const u32 mb = load_maskbits16(A.maskbits, bi);
+                            w0 += bits4_to_case(mb & 15); w1 += bits4_to_case((mb >> 4) & 15); w2 += bits4_to_case((mb >> 8) & 15); w3 += bits4_to_case((mb >> 12) & 15);
                         }
+                        slo = (u64)w0 | ((u64)w1 << 32); shi = (u64)w2 | ((u64)w3 << 32);
                     } else {
                         uint4 v = load_bytes16(A.seq + bi);
-                        w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                        if (A.upper) { for (int k = 0; k < 4; k++) w[k] = upper4(w[k]); }
+                        if (A.upper) { v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w); }
+                        slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
                     }
-                    done = true;
+                    take = run > 16 ? 16u : (u32)run;
                 }
             }
-            // fast path 2: 16 bytes inside the quality string
-            else if (A.with_qual && r >= R.d + 2 && r + 16 <= R.d + 2 + R.L) {
-                uint4 v = load_bytes16(A.qual + R.sbase + (r - R.d - 2));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
-                done = true;
-            }
-        }
-        if (!done) {
-            u32 li = lo;                          // index of `rec` among the staged records (valid while rec == first + li)
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                if (j < nvalid) {
-                    while (r >= R.e && rec + 1 < A.N) {
-                        rec++; li++;
-                        if (rec == first + li && li < nrec) cur = recs[li]; else rec_fetch(A, rec, cur);
-                        rec_bounds(A, cur, R); r = 0;
-                    }
-                    u32 c;
-                    if (r < R.a) c = A.prefix;
-                    else if (r < R.b) {
-                        u32 k = (u32)(r - R.a);
-                        if (A.has_ids && k < R.id_len) c = __ldg(A.ids + R.id_s + k);
-                        else if (A.has_ids && A.has_names) c = k == R.id_len ? A.sep : __ldg(A.comm + R.cm_s + (k - R.id_len - 1));
-                        else c = __ldg(A.comm + R.cm_s + k);
-                    }
-                    else if (r < R.c) c = '\n';
-                    else if (r < R.d) {
-                        u64 s = r - R.c;
-                        if (s >= R.L && A.W == 0) c = '\n';
-                        else if (A.W > 0 && A.seq_nl == 1) {
-                            u64 line = s / (A.W + 1), col = s - line * (A.W + 1);
-                            c = (col == A.W || r + 1 == R.d) ? '\n' : base_at(A, R.sbase + line * A.W + col);
-                        }
-                        else c = s < R.L ? base_at(A, R.sbase + s) : '\n';
-                    }
-                    else {
-                        u64 t = r - R.d;
-                        c = t == 0 ? '+' : (t == 1 ? '\n' : (t < 2 + R.L ? __ldg(A.qual + R.sbase + (t - 2)) : '\n'));
-                    }
-                    w[j >> 2] |= c << (8 * (j & 3));
-                    r++;
+            else {
+                const u64 t = r - R.d;
+                if (t == 0) slo = '+';
+                else if (t == 1 || t >= 2 + R.L) slo = '\n';
+                else {
+                    const uint4 v = load_bytes16(A.qual + R.sbase + (t - 2));
+                    slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
+                    const u64 run = R.L - (t - 2);
+                    take = run > 16 ? 16u : (u32)run;
                 }
             }
+            if (take > (u32)(16 - j)) take = 16 - j;
+            // keep `take` bytes, shift them to byte position j, merge
+            if (take < 16) {
+                if (take >= 8) shi &= take == 8 ? 0ull : ((1ull << (8 * (take - 8))) - 1);
+                else { shi = 0; slo &= (1ull << (8 * take)) - 1; }
+            }
+            if (j) {
+                if (j < 8) { shi = (shi << (8 * j)) | (slo >> (64 - 8 * j)); slo <<= 8 * j; }
+                else { shi = slo << (8 * (j - 8)); slo = 0; }
+            }
+            olo |= slo; ohi |= shi;
+            j += (int)take; r += take;
         }
-        if (nvalid == 16) *(uint4 *)(A.out + q0) = make_uint4(w[0], w[1], w[2], w[3]);
-        else for (int j = 0; j < nvalid; j++) A.out[q0 + j] = (u8)(w[j >> 2] >> (8 * (j & 3)));
+        if (nvalid == 16) *(uint4 *)(A.out + q0) = make_uint4((u32)olo, (u32)(olo >> 32), (u32)ohi, (u32)(ohi >> 32));
+        else for (int k = 0; k < nvalid; k++) A.out[q0 + k] = (u8)((k < 8 ? olo >> (8 * k) : ohi >> (8 * (k - 8))));
     }
 }
 

@@ -19,381 +19,9 @@
 #include "common.cuh"
 #include "container.hpp"
 
+#include "naf_parse.cuh"
+
 namespace nafg {
-
-// ------------------------------------------------------------------ byte classes and the two machines
-enum : u32 { F_EOL = 1, F_SPACE = 2, F_ID_OK = 4, F_COMM_OK = 8, F_SEQ_OK = 16, F_QUAL_OK = 32, F_START = 64, F_PLUS = 128 };
-
-enum { FA_NAME = 0, FA_COMMENT = 1, FA_SEQ_LS = 2, FA_SEQ_MID = 3, FA_NSTATES = 4 };
-enum { FQ_NAME = 0, FQ_COMMENT = 1, FQ_SEQ = 2, FQ_AFTER_SEQ = 3, FQ_PLUS = 4, FQ_BEFORE_QUAL = 5, FQ_QUAL = 6, FQ_AFTER_QUAL = 7,
-       FQ_ERR_NOPLUS = 8, FQ_ERR_NOAT = 9, FQ_ERR_NOTWF = 10, FQ_NSTATES = 11 };
-
-struct FsmTables {
-    u8  cls[256];          // byte -> F_* flags
-    u64 trans[256];        // flags -> packed transition map (4 bits per source state)
-    u8  idem[256];         // map is idempotent (applying it twice == once)
-};
-
-__host__ __device__ inline u32 fa_next(u32 s, u32 f)
-{
-    switch (s) {
-    case FA_NAME:    return (f & F_ID_OK) ? FA_NAME : ((f & F_SPACE) ? ((f & F_EOL) ? FA_SEQ_LS : FA_COMMENT) : FA_NAME);
-    case FA_COMMENT: return (f & F_EOL) ? FA_SEQ_LS : FA_COMMENT;        // COMM_OK bytes are never EOL
-    case FA_SEQ_LS:  return (f & F_START) ? FA_NAME : ((f & F_EOL) ? FA_SEQ_LS : FA_SEQ_MID);
-    default:         return (f & F_EOL) ? FA_SEQ_LS : FA_SEQ_MID;
-    }
-}
-__host__ __device__ inline u32 fq_next(u32 s, u32 f, bool wf)
-{
-    switch (s) {
-    case FQ_NAME:        return (f & F_ID_OK) ? FQ_NAME : ((f & F_SPACE) ? ((f & F_EOL) ? FQ_SEQ : FQ_COMMENT) : FQ_NAME);
-    case FQ_COMMENT:     return (f & F_EOL) ? FQ_SEQ : FQ_COMMENT;
-    case FQ_SEQ:         return (f & F_EOL) ? FQ_AFTER_SEQ : FQ_SEQ;
-    case FQ_AFTER_SEQ:   if (wf) return (f & F_PLUS) ? FQ_PLUS : FQ_ERR_NOTWF;
-                         return (f & F_EOL) ? FQ_AFTER_SEQ : ((f & F_PLUS) ? FQ_PLUS : FQ_ERR_NOPLUS);
-    case FQ_PLUS:        if (wf) return (f & F_EOL) ? FQ_BEFORE_QUAL : FQ_ERR_NOTWF;
-                         return (f & F_EOL) ? FQ_BEFORE_QUAL : FQ_PLUS;
-    case FQ_BEFORE_QUAL: if (wf) return (f & F_EOL) ? FQ_AFTER_QUAL : FQ_QUAL;
-                         return (f & F_EOL) ? FQ_BEFORE_QUAL : FQ_QUAL;
-    case FQ_QUAL:        return (f & F_EOL) ? FQ_AFTER_QUAL : FQ_QUAL;
-    case FQ_AFTER_QUAL:  if (wf) return (f & F_START) ? FQ_NAME : FQ_ERR_NOTWF;
-                         return (f & F_EOL) ? FQ_AFTER_QUAL : ((f & F_START) ? FQ_NAME : FQ_ERR_NOAT);
-    default:             return s;
-    }
-}
-
-struct ParseCfg {
-    int fastq, wf, seq_type, text_fasta, no_mask, strict, nstates;
-    u8 repl;
-};
-
-static void build_tables(const ParseCfg &c, FsmTables &t)
-{
-    auto is_eol = [](int ch) { return ch >= 0x0A && ch <= 0x0D; };
-    auto is_space = [&](int ch) { return (ch >= 0x09 && ch <= 0x0D) || ch == 0x20; };
-    auto in_set = [](int ch, const char *set) { if (ch >= 'a' && ch <= 'z') ch -= 32; return ch > 0 && strchr(set, ch) != nullptr; };
-    for (int ch = 0; ch < 256; ch++) {
-        u32 f = 0;
-        if (c.wf) {                                                      // tables.c:61 is_well_formed_space
-            if (ch == '\n') f |= F_EOL | F_SPACE;
-            if (ch == ' ') f |= F_SPACE;
-            if (!(f & F_SPACE)) f |= F_ID_OK;
-            if (!(f & F_EOL)) f |= F_COMM_OK | F_SEQ_OK | F_QUAL_OK;
-        } else {
-            if (is_eol(ch)) f |= F_EOL;
-            if (is_space(ch)) f |= F_SPACE;
-            if (!(ch <= 32 || ch == 127 || ch == 255)) f |= F_ID_OK;     // tables.c:115
-            if (!(ch < 32 || ch == 127 || ch == 255)) f |= F_COMM_OK;    // tables.c:126
-            if (ch >= 33 && ch <= 126) f |= F_QUAL_OK;                   // tables.c:137
-            bool ok;
-            switch (c.seq_type) {
-            case NAFGPU_DNA:     ok = in_set(ch, "-ABCDGHKMNRSTVWY"); break;           // tables.c:72
-            case NAFGPU_RNA:     ok = in_set(ch, "-ABCDGHKMNRSUVWY"); break;           // tables.c:82
-            case NAFGPU_PROTEIN: ok = in_set(ch, "*-ABCDEFGHIJKLMNOPQRSTUVWXYZ"); break; // tables.c:104
-            default:             ok = !(ch <= 32 || ch == 127 || ch == 255); break;
-            }
-            if (ok) f |= F_SEQ_OK;
-            if (c.text_fasta && ch == '>') f &= ~(F_SEQ_OK | F_ID_OK);   // ennaf.c:466 flips the shared table entry
-        }
-        if (ch == (c.fastq ? '@' : '>')) f |= F_START;
-        if (ch == '+') f |= F_PLUS;
-        t.cls[ch] = (u8)f;
-    }
-    for (int f = 0; f < 256; f++) {
-        u64 m = 0;
-        for (int s = 0; s < c.nstates; s++) m |= (u64)(c.fastq ? fq_next(s, f, c.wf) : fa_next(s, f)) << (4 * s);
-        t.trans[f] = m;
-        u64 mm = 0;
-        for (int s = 0; s < c.nstates; s++) mm |= ((m >> (4 * ((m >> (4 * s)) & 15))) & 15) << (4 * s);
-        t.idem[f] = mm == m;
-    }
-}
-
-__device__ __forceinline__ u64 map_compose(u64 f, u64 g, int ns)     // first f, then g
-{
-    u64 h = 0;
-    for (int s = 0; s < ns; s++) h |= ((g >> (4 * ((f >> (4 * s)) & 15))) & 15) << (4 * s);
-    return h;
-}
-__device__ __forceinline__ u64 map_identity(int ns) { u64 m = 0; for (int s = 0; s < ns; s++) m |= (u64)s << (4 * s); return m; }
-
-// ------------------------------------------------------------------ pass 1: per-tile state maps
-static const int PT = 256, PB = 64, PTILE = PT * PB;       // threads, bytes per thread, bytes per tile (16 KB)
-
-struct ParseArgs {
-    const u8 *text; u64 n, p0;                // p0: first byte after the leading '>' / '@'
-    ParseCfg cfg;
-    const FsmTables *tab;
-    u64 *tile_map; u8 *tile_state;            // per tile: map, entry state
-    u64 ntiles;
-};
-
-__device__ __forceinline__ u64 fold_bytes(const ParseArgs &A, const FsmTables *T, u64 lo, u64 hi, int ns)
-{
-    u64 f = map_identity(ns);
-    u32 prev = 0xFFFFFFFFu;
-    for (u64 p = lo; p < hi; p++) {
-        u32 fl = T->cls[A.text[p]];
-        if (fl == prev && T->idem[fl]) continue;     // same class as the previous byte and idempotent: nothing new
-        f = map_compose(f, T->trans[fl], ns);
-        prev = fl;
-    }
-    return f;
-}
-
-__global__ void __launch_bounds__(PT) k_fsm_reduce(const ParseArgs A)
-{
-    __shared__ FsmTables T;
-    __shared__ u64 wmap[PT / 32];
-    for (int i = threadIdx.x; i < (int)sizeof(FsmTables) / 4; i += PT) ((u32 *)&T)[i] = ((const u32 *)A.tab)[i];
-    __syncthreads();
-    const int ns = A.cfg.nstates;
-    u64 lo = A.p0 + (u64)blockIdx.x * PTILE + (u64)threadIdx.x * PB, hi = lo + PB;
-    if (lo > A.n) lo = A.n; if (hi > A.n) hi = A.n;
-    u64 f = fold_bytes(A, &T, lo, hi, ns);
-    // ordered reduction: lane i absorbs lane i+d
-    for (int d = 1; d < 32; d <<= 1) {
-        u64 g = __shfl_down_sync(0xFFFFFFFFu, f, d);
-        if ((threadIdx.x & 31) + d < 32 && ((threadIdx.x & 31) % (2 * d)) == 0) f = map_compose(f, g, ns);
-    }
-    if ((threadIdx.x & 31) == 0) wmap[threadIdx.x >> 5] = f;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u64 m = wmap[0];
-        for (int w = 1; w < PT / 32; w++) m = map_compose(m, wmap[w], ns);
-        A.tile_map[blockIdx.x] = m;
-    }
-}
-
-// one CTA: chunked scan of the tile maps -> entry state of every tile (initial state = NAME)
-__global__ void __launch_bounds__(1024) k_fsm_scan(const ParseArgs A)
-{
-    __shared__ u64 cmap[1024];
-    const int ns = A.cfg.nstates;
-    u64 per = (A.ntiles + 1023) / 1024;
-    u64 lo = (u64)threadIdx.x * per, hi = lo + per;
-    if (lo > A.ntiles) lo = A.ntiles; if (hi > A.ntiles) hi = A.ntiles;
-    u64 f = map_identity(ns);
-    for (u64 t = lo; t < hi; t++) f = map_compose(f, A.tile_map[t], ns);
-    cmap[threadIdx.x] = f;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 s = 0;                                      // NAME for both machines
-        for (int c = 0; c < 1024; c++) { u64 m = cmap[c]; cmap[c] = s; s = (u32)((m >> (4 * s)) & 15); }
-    }
-    __syncthreads();
-    u32 s = (u32)cmap[threadIdx.x];
-    for (u64 t = lo; t < hi; t++) { A.tile_state[t] = (u8)s; s = (u32)((A.tile_map[t] >> (4 * s)) & 15); }
-    if (hi == A.ntiles && lo < hi) A.tile_state[A.ntiles] = (u8)s;      // state at end of input
-    if (A.ntiles == 0 && threadIdx.x == 0) A.tile_state[0] = 0;
-}
-
-// ------------------------------------------------------------------ pass 2 / 3: emit
-struct TileCounts { u64 ids, comm, seq, seq_counted, qual, rec, line_last; u32 has_line; u32 pad; };
-
-struct EmitArgs {
-    ParseArgs P;
-    TileCounts *tile;                        // COUNT: per-tile totals
-    // SCATTER inputs: exclusive prefixes per tile
-    const u64 *pre_ids, *pre_comm, *pre_seq, *pre_cnt, *pre_qual, *pre_rec, *pre_line;   // pre_line: global counted-seq value at the last line end before the tile
-    u8 *ids, *comm, *bases, *qual;           // outputs
-    u64 *rec_seq_end, *rec_qual_end, *rec_pos;   // per record: counted-seq / qual totals at its end, text offset of its end
-    unsigned long long *unexpected;          // [4][257]
-    unsigned long long *longest;             // atomicMax target (FASTA)
-    unsigned long long *first_bad;           // strict / FSM error: min over (pos << 8 | kind)
-};
-
-enum { BAD_ID = 1, BAD_COMMENT = 2, BAD_SEQ = 3, BAD_QUAL = 4, BAD_NOPLUS = 5, BAD_NOAT = 6, BAD_NOTWF = 7 };
-
-struct Emit { u32 ids, comm, seq, cnt, qual, rec; };
-
-// Walk bytes [lo, hi) from state s.  COUNT mode tallies; SCATTER mode writes at the running offsets in `o`.
-template <bool SCATTER>
-__device__ __forceinline__ u32 walk(const EmitArgs &E, const FsmTables *T, u64 lo, u64 hi, u32 s, Emit &n, u64 o_ids, u64 o_comm,
-                                    u64 o_seq, u64 o_cnt, u64 o_qual, u64 o_rec, u64 &line_base, bool &line_base_valid,
-                                    u64 &line_max, u64 &line_last, bool &has_line)
-{
-    const ParseCfg &C = E.P.cfg;
-    const u8 *text = E.P.text;
-    for (u64 p = lo; p < hi; p++) {
-        const u32 c = text[p], f = T->cls[c];
-        u32 ns;
-        int to_ids = -1, to_comm = -1, to_seq = -1, to_qual = -1; bool counted = true, rec_end = false, line_end = false; int bad = 0, badk = -1;
-        if (!C.fastq) {
-            ns = fa_next(s, f);
-            switch (s) {
-            case FA_NAME:
-                if (f & F_ID_OK) to_ids = c;
-                else if (f & F_SPACE) { to_ids = 0; if (f & F_EOL) to_comm = 0; }
-                else { bad = BAD_ID; badk = 0; to_seq = '?'; counted = false; }          // process.c:366 (reference quirk, restated)
-                break;
-            case FA_COMMENT:
-                if (f & F_COMM_OK) to_comm = c;
-                else if (f & F_EOL) to_comm = 0;
-                else { bad = BAD_COMMENT; badk = 1; to_comm = '?'; }
-                break;
-            default:
-                if (s == FA_SEQ_LS && (f & F_START)) { rec_end = true; break; }
-                if (f & F_SEQ_OK) to_seq = c;
-                else if (f & F_EOL) line_end = true;
-                else if (f & F_SPACE) {}
-                else if (C.text_fasta && c == '>') to_seq = c;                           // process.c:413
-                else { bad = BAD_SEQ; badk = 2; to_seq = C.repl; }
-                break;
-            }
-        } else {
-            ns = fq_next(s, f, C.wf);
-            switch (s) {
-            case FQ_NAME:
-                if (f & F_ID_OK) to_ids = c;
-                else if (f & F_SPACE) { to_ids = 0; if (f & F_EOL) to_comm = 0; }
-                else { bad = BAD_ID; badk = 0; to_seq = '?'; counted = false; }          // process.c:485
-                break;
-            case FQ_COMMENT:
-                if (f & F_COMM_OK) to_comm = c;
-                else if (f & F_EOL) to_comm = 0;
-                else { bad = BAD_COMMENT; badk = 1; to_comm = '?'; }
-                break;
-            case FQ_SEQ:
-                if (f & F_SEQ_OK) to_seq = c;
-                else if (f & F_EOL) {}
-                else if (f & F_SPACE) {}
-                else { bad = BAD_SEQ; badk = 2; to_seq = C.repl; }
-                break;
-            case FQ_BEFORE_QUAL:
-                if (!(f & F_EOL)) to_qual = c;                                            // process.c:523: unvalidated
-                else if (C.wf) rec_end = true;                                            // empty quality line
-                break;
-            case FQ_QUAL:
-                if (f & F_QUAL_OK) to_qual = c;
-                else if (f & F_EOL) rec_end = true;
-                else if (f & F_SPACE) {}
-                else { bad = BAD_QUAL; badk = 3; to_qual = '!'; }
-                break;
-            default: break;
-            }
-            if (ns >= FQ_ERR_NOPLUS && s < FQ_ERR_NOPLUS) { bad = ns == FQ_ERR_NOPLUS ? BAD_NOPLUS : (ns == FQ_ERR_NOAT ? BAD_NOAT : BAD_NOTWF); badk = -2; }
-        }
-        if (SCATTER) {
-            if (to_ids >= 0) E.ids[o_ids + n.ids] = (u8)to_ids;
-            if (to_comm >= 0) E.comm[o_comm + n.comm] = (u8)to_comm;
-            if (to_seq >= 0) {
-                u8 b = (u8)to_seq;
-                if (C.seq_type >= NAFGPU_PROTEIN && C.no_mask && b >= 'a' && b <= 'z') b -= 32;   // process.c:49
-                E.bases[o_seq + n.seq] = b;
-            }
-            if (to_qual >= 0) E.qual[o_qual + n.qual] = (u8)to_qual;
-            if (bad) {
-                if (badk >= 0) atomicAdd(&E.unexpected[badk * 257 + c], 1ull);
-                if (badk == -2 || C.strict) atomicMin(E.first_bad, (unsigned long long)((p << 8) | (u32)bad));
-            }
-        }
-        n.ids += to_ids >= 0; n.comm += to_comm >= 0; n.qual += to_qual >= 0;
-        if (to_seq >= 0) { n.seq++; if (counted) n.cnt++; }
-        if (line_end) {
-            // sequence bytes since the previous line end (FASTA only; FASTQ takes max read length)
-            u64 v = o_cnt + n.cnt;
-            if (line_base_valid) { u64 d = v - line_base; if (d > line_max) line_max = d; }
-            line_base = v; line_base_valid = true; line_last = v; has_line = true;
-        }
-        if (rec_end) {
-            if (SCATTER) {
-                u64 r = o_rec + n.rec;
-                E.rec_seq_end[r] = o_cnt + n.cnt;
-                if (C.fastq) E.rec_qual_end[r] = o_qual + n.qual;
-                E.rec_pos[r] = p;
-            }
-            n.rec++;
-        }
-        s = ns;
-    }
-    return s;
-}
-
-template <bool SCATTER>
-__global__ void __launch_bounds__(PT) k_fsm_emit(const EmitArgs E)
-{
-    __shared__ FsmTables T;
-    __shared__ u64 sm[33];
-    __shared__ u64 wmap[PT / 32];
-    __shared__ u32 wstate[PT / 32];
-    const ParseArgs &A = E.P;
-    for (int i = threadIdx.x; i < (int)sizeof(FsmTables) / 4; i += PT) ((u32 *)&T)[i] = ((const u32 *)A.tab)[i];
-    __syncthreads();
-    const int ns = A.cfg.nstates;
-    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    u64 lo = A.p0 + (u64)blockIdx.x * PTILE + (u64)threadIdx.x * PB, hi = lo + PB;
-    if (lo > A.n) lo = A.n; if (hi > A.n) hi = A.n;
-    // entry state of this thread: tile entry state pushed through the maps of the threads before me
-    u64 f = fold_bytes(A, &T, lo, hi, ns);
-    u64 incl = f;
-    for (int d = 1; d < 32; d <<= 1) { u64 g = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= (unsigned)d) incl = map_compose(g, incl, ns); }
-    if (lane == 31) wmap[warp] = incl;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 s = A.tile_state[blockIdx.x];
-        for (int w = 0; w < PT / 32; w++) { wstate[w] = s; s = (u32)((wmap[w] >> (4 * s)) & 15); }
-    }
-    __syncthreads();
-    u64 excl = __shfl_up_sync(0xFFFFFFFFu, incl, 1);
-    u32 s0 = wstate[warp];
-    if (lane > 0) s0 = (u32)((excl >> (4 * s0)) & 15);
-
-    Emit n = {0, 0, 0, 0, 0, 0};
-    u64 line_base = 0, line_max = 0, line_last = 0; bool lbv = false, has_line = false;
-    if (!SCATTER) {
-        walk<false>(E, &T, lo, hi, s0, n, 0, 0, 0, 0, 0, 0, line_base, lbv, line_max, line_last, has_line);
-        // tile totals; line_last of the tile = counted-seq offset (tile-relative) at the last line end in the tile
-        u64 tot, pre;
-        TileCounts tc;
-        pre = block_excl_scan(n.ids, &tot, sm); tc.ids = tot;
-        pre = block_excl_scan(n.comm, &tot, sm); tc.comm = tot;
-        pre = block_excl_scan(n.seq, &tot, sm); tc.seq = tot;
-        u64 pre_cnt = block_excl_scan(n.cnt, &tot, sm); tc.seq_counted = tot;
-        pre = block_excl_scan(n.qual, &tot, sm); tc.qual = tot;
-        pre = block_excl_scan(n.rec, &tot, sm); tc.rec = tot;
-        (void)pre;
-        // last line end in the tile: max over threads of (pre_cnt + local line_last) among threads that saw one
-        u64 v = has_line ? pre_cnt + line_last + 1 : 0;       // +1 so that 0 means "none"
-        for (int d = 16; d; d >>= 1) { u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, d); if (o > v) v = o; }
-        if (lane == 0) sm[warp] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            u64 m = 0; for (int w = 0; w < PT / 32; w++) if (sm[w] > m) m = sm[w];
-            tc.has_line = m != 0; tc.line_last = m ? m - 1 : 0; tc.pad = 0;
-            E.tile[blockIdx.x] = tc;
-        }
-        return;
-    }
-    // SCATTER: first count (cheap re-walk) to get this thread's offsets, then write
-    walk<false>(E, &T, lo, hi, s0, n, 0, 0, 0, 0, 0, 0, line_base, lbv, line_max, line_last, has_line);
-    u64 tot;
-    u64 o_ids = block_excl_scan(n.ids, &tot, sm) + E.pre_ids[blockIdx.x];
-    u64 o_comm = block_excl_scan(n.comm, &tot, sm) + E.pre_comm[blockIdx.x];
-    u64 o_seq = block_excl_scan(n.seq, &tot, sm) + E.pre_seq[blockIdx.x];
-    u64 o_cnt = block_excl_scan(n.cnt, &tot, sm) + E.pre_cnt[blockIdx.x];
-    u64 o_qual = block_excl_scan(n.qual, &tot, sm) + E.pre_qual[blockIdx.x];
-    u64 o_rec = block_excl_scan(n.rec, &tot, sm) + E.pre_rec[blockIdx.x];
-    // counted-seq value at the last line end before this thread (exclusive max-scan; values are monotone)
-    u64 mine = has_line ? o_cnt + line_last + 1 : 0;
-    u64 run = mine;
-    for (int d = 1; d < 32; d <<= 1) { u64 g = __shfl_up_sync(0xFFFFFFFFu, run, d); if (lane >= (unsigned)d && g > run) run = g; }
-    if (lane == 31) sm[warp] = run;
-    __syncthreads();
-    u64 before = E.pre_line[blockIdx.x] + 1;                  // tile carry (+1 encoding; >= 1 because line base 0 = start of data)
-    for (unsigned w = 0; w < warp; w++) if (sm[w] > before) before = sm[w];
-    u64 prev_lane = __shfl_up_sync(0xFFFFFFFFu, run, 1);
-    if (lane > 0 && prev_lane > before) before = prev_lane;
-    __syncthreads();
-    Emit m = {0, 0, 0, 0, 0, 0};
-    line_base = before - 1; lbv = true; line_max = 0; line_last = 0; has_line = false;
-    walk<true>(E, &T, lo, hi, s0, m, o_ids, o_comm, o_seq, o_cnt, o_qual, o_rec, line_base, lbv, line_max, line_last, has_line);
-    if (!A.cfg.fastq) {
-        // pending (unterminated) last line of the input: counted bytes after the last line end
-        if (hi == A.n && lo < hi) { u64 d = o_cnt + m.cnt - line_base; if (d > line_max) line_max = d; }
-        if (line_max) atomicMax(E.longest, (unsigned long long)line_max);
-    }
-}
 
 // ------------------------------------------------------------------ 4-bit pack + case bits
 // encoders.c:30 encode_dna (first base in the low nibble; odd tail has a zero high nibble, ennaf.c:525)
@@ -525,30 +153,38 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     FsmTables *d_tab = ex.alloc<FsmTables>(1);
     ex.upload(d_tab, &ht, sizeof ht);
 
-    const u64 body = n - p0, ntiles = (body + PTILE - 1) / PTILE;
-    ParseArgs P; P.text = d_text; P.n = n; P.p0 = p0; P.cfg = C; P.tab = d_tab; P.ntiles = ntiles;
-    P.tile_map = ex.alloc<u64>(ntiles + 1); P.tile_state = ex.alloc<u8>(ntiles + 2);
+    const u64 ntiles = (n + PTILE - 1) / PTILE;               // tiles cover the text from offset 0; bytes before p0 are skipped
+    ParseArgs P; memset(&P, 0, sizeof P);
+    P.text = d_text; P.n = n; P.p0 = p0; P.cfg = C; P.tab = d_tab; P.ntiles = ntiles;
+    P.thread_map = ex.alloc<u64>(ntiles * PT + 1); P.tile_map = ex.alloc<u64>(ntiles + 1); P.tile_state = ex.alloc<u8>(ntiles + 2);
+    P.tinfo = ex.alloc<ThreadInfo>(ntiles * PT + 1); P.tile = ex.alloc<TileCounts>(ntiles + 1);
     if (ntiles) { KLAUNCH(ex, "k_fsm_reduce", k_fsm_reduce<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
     KLAUNCH(ex, "k_fsm_scan", k_fsm_scan<<<1, 1024, 0, ex.stream>>>(P));
-
-    EmitArgs E; memset(&E, 0, sizeof E);
-    E.P = P;
-    E.tile = ex.alloc<TileCounts>(ntiles + 1);
-    if (ntiles) { KLAUNCH(ex, "k_fsm_emit", k_fsm_emit<false><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E)); }
+    if (ntiles) { KLAUNCH(ex, "k_fsm_count", k_fsm_count<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
     // exclusive sums of the six counters + exclusive max of the line-end marker
     u64 *pre[7];
     for (int k = 0; k < 7; k++) pre[k] = ex.alloc<u64>(ntiles + 2);
-    const TileCounts *tc = E.tile;
+    const TileCounts *tc = P.tile;
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].ids; }, ntiles, pre[0]);
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].comm; }, ntiles, pre[1]);
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].seq; }, ntiles, pre[2]);
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].seq_counted; }, ntiles, pre[3]);
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].qual; }, ntiles, pre[4]);
     exclusive_scan(ex, [tc] __device__ (size_t i) { return tc[i].rec; }, ntiles, pre[5]);
-    // pre_line[t] = counted-seq value at the last line end in tiles < t (0 if none): sequential max over few 100k tiles
+    // pre_line[t] = counted-seq value at the last line end in tiles < t (0 if none): chunked exclusive max-scan
     {
         u64 *pl = pre[6]; const u64 *pc = pre[3]; const u64 nt = ntiles;
-        ex.for_each(1, [=] __device__ (size_t) { u64 m = 0; for (u64 t = 0; t < nt; t++) { pl[t] = m; if (tc[t].has_line) { u64 v = pc[t] + tc[t].line_last; if (v > m) m = v; } } pl[nt] = m; });
+        const u64 nchunks = 1024, per = (nt + nchunks - 1) / nchunks;
+        u64 *cmax = ex.alloc<u64>(nchunks + 1);
+        ex.for_each(nchunks, [=] __device__ (size_t c) {
+            u64 lo = c * per, hi = lo + per; if (lo > nt) lo = nt; if (hi > nt) hi = nt;
+            u64 m = 0; for (u64 t = lo; t < hi; t++) if (tc[t].has_line) { u64 v = pc[t] + tc[t].line_last; if (v > m) m = v; }
+            cmax[c] = m; }, "line_scan");
+        ex.for_each(1, [=] __device__ (size_t) { u64 m = 0; for (u64 c = 0; c < nchunks; c++) { u64 v = cmax[c]; cmax[c] = m; if (v > m) m = v; } }, "line_scan");
+        ex.for_each(nchunks, [=] __device__ (size_t c) {
+            u64 lo = c * per, hi = lo + per; if (lo > nt) lo = nt; if (hi > nt) hi = nt;
+            u64 m = cmax[c];
+            for (u64 t = lo; t < hi; t++) { pl[t] = m; if (tc[t].has_line) { u64 v = pc[t] + tc[t].line_last; if (v > m) m = v; } } }, "line_scan");
     }
     u64 tot[6]; u8 end_state;
     for (int k = 0; k < 6; k++) ex.download(&tot[k], pre[k] + ntiles, 8);
@@ -580,11 +216,12 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     ex.zero(d_unexp, (4 * 257 + 4) * 8);
     unsigned long long *d_longest = d_unexp + 4 * 257, *d_first_bad = d_unexp + 4 * 257 + 1;
     ex.fill(d_first_bad, 0xFF, 8);
-    E.pre_ids = pre[0]; E.pre_comm = pre[1]; E.pre_seq = pre[2]; E.pre_cnt = pre[3]; E.pre_qual = pre[4]; E.pre_rec = pre[5]; E.pre_line = pre[6];
-    E.ids = S.ids; E.comm = S.comm; E.bases = bases; E.qual = S.qual;
-    E.rec_seq_end = rec_seq_end; E.rec_qual_end = rec_qual_end; E.rec_pos = rec_pos;
-    E.unexpected = d_unexp; E.longest = d_longest; E.first_bad = d_first_bad;
-    if (ntiles) { KLAUNCH(ex, "k_fsm_emit", k_fsm_emit<true><<<(unsigned)ntiles, PT, 0, ex.stream>>>(E)); }
+    P.pre_ids = pre[0]; P.pre_comm = pre[1]; P.pre_seq = pre[2]; P.pre_cnt = pre[3]; P.pre_qual = pre[4]; P.pre_rec = pre[5]; P.pre_line = pre[6];
+    P.ids = S.ids; P.comm = S.comm; P.bases = bases; P.qual = S.qual;
+    P.rec_seq_end = rec_seq_end; P.rec_qual_end = rec_qual_end; P.rec_pos = rec_pos;
+    P.unexpected = d_unexp; P.longest = d_longest; P.first_bad = d_first_bad;
+    CUDA_TRY(cudaFuncSetAttribute(k_fsm_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
+    if (ntiles) { KLAUNCH(ex, "k_fsm_scatter", k_fsm_scatter<<<(unsigned)ntiles, PT, SCATTER_SMEM, ex.stream>>>(P)); }
     // end-of-input additions
     {
         u8 *ids = S.ids, *comm = S.comm; const u64 a = tot[0], b = tot[1], r = tot[5], cnt = n_cnt, ql = n_qual, nn = n;
@@ -610,7 +247,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         ex.for_each(n_rec, [=] __device__ (size_t i) {
             u64 sl = rec_seq_end[i] - (i ? rec_seq_end[i - 1] : 0), ql = rec_qual_end[i] - (i ? rec_qual_end[i - 1] : 0);
             if (sl != ql) atomicMin(d_m, (unsigned long long)i);
-        });
+        }, "qual_len_check");
         unsigned long long m; ex.download(&m, d_m, 8);
         if (m != ~0ull) {
             mism_rec = m;
@@ -670,11 +307,15 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
             u64 L = rse[i] - (i ? rse[i - 1] : 0); u64 at = units_pre[i];
             while (L >= 0xFFFFFFFFull) { len[at++] = 0xFFFFFFFFu; L -= 0xFFFFFFFFull; }
             len[at] = (u32)L;
-        });
+        }, "length_units");
         // longest line: FASTA tracked line ends; FASTQ = longest read (process.c:495)
         if (C.fastq) {
             unsigned long long *dl = d_longest;
-            ex.for_each(n_rec, [=] __device__ (size_t i) { u64 L = rse[i] - (i ? rse[i - 1] : 0); if (L) atomicMax(dl, (unsigned long long)L); });
+            ex.for_each(n_rec, [=] __device__ (size_t i) {
+                u64 L = rse[i] - (i ? rse[i - 1] : 0);
+                // reads are identical for most inputs: skip the atomic unless this record beats the current maximum
+                if (L > *(volatile unsigned long long *)dl) atomicMax(dl, (unsigned long long)L);
+            }, "longest_read");
         }
         unsigned long long lg; ex.download(&lg, d_longest, 8);
         S.longest = lg;

@@ -417,7 +417,8 @@ HD void k_stream_totals(const ZDecArgs &a, u32 i, ZStreamResult *res)
 }
 
 // K5 — one Huffman stream (thread t = 4*block + k)
-HD void k_literals(const ZDecArgs &a, u32 t)
+// `staged`: the block's decode table already copied next to the thread (shared memory on the GPU), or nullptr
+HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr)
 {
     u32 i = t >> 2, k = t & 3;
     const ZBlock &b = a.blk[i];
@@ -426,7 +427,7 @@ HD void k_literals(const ZDecArgs &a, u32 t)
     if (b.huf_src < 0) return;
     const ZBlock &hb = a.blk[b.huf_src];
     if (hb.huf_bits == 0) return;
-    const u16 *table = a.huf_pool + (size_t)hb.huf_slot * HUF_SLOT_ENTRIES;
+    const u16 *table = staged ? staged : a.huf_pool + (size_t)hb.huf_slot * HUF_SLOT_ENTRIES;
     u32 tree = b.lit_type == 2 ? b.tree_len : 0;
     const u8 *p = a.in + b.src + b.lit_hdr + tree;
     if (tree > b.lit_csize) { zerr(a, Z_ERR_HUF_STREAM, i); return; }
@@ -615,6 +616,13 @@ HD void k_jump(const ZDecArgs &a, u64 w)
     if (clear != bits) a.status[2] = 1;
 }
 
+// K5 launch: generic executors run one thread per Huffman stream straight from the table pool; the CUDA
+// executor overloads this (zstd_dec_cuda.cuh) with a kernel that first stages the tables in shared memory.
+template <class Exec> void launch_literals(Exec &ex, const ZDecArgs &a)
+{
+    ex.for_each((size_t)a.nblk * 4, [=] HDN (size_t t) { k_literals(a, (u32)t); }, "zd_literals", 64);
+}
+
 // ------------------------------------------------------------------ orchestration (templated on the executor)
 //
 // Exec provides:
@@ -701,7 +709,7 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         }
     }
 
-    if (n_comp) ex.for_each((size_t)nblk * 4, [=] HDN (size_t t) { k_literals(a, (u32)t); }, "zd_literals", 64);
+    if (n_comp) launch_literals(ex, a);
     ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_copy_block(a, (u32)i, tid, nt); }, "zd_copy_block");
 
     if (tot_seq) {

@@ -126,6 +126,12 @@ __device__ u32 fse_compress_weights(const u8 *w, int n, u8 *dst, u32 cap)
 
 struct ZEncArgs { ZEncBlock *blk; u8 *slots; };
 
+// The block's bytes are staged in shared memory once (coalesced 128-bit loads during the histogram pass) and
+// read from there by the two later passes.  4 bytes of padding per 256 keep the per-thread 256-byte ranges of
+// those passes on different banks.
+__device__ __forceinline__ u32 zpad(u32 i) { return i + ((i >> 8) << 2); }
+static const u32 ZSTAGE_BYTES = ZBS + (ZBS >> 8) * 4 + 16;
+
 // One CTA (256 threads) per block.
 __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
 {
@@ -138,6 +144,7 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
     __shared__ u32 s_nsym, s_maxbits, s_mode, s_tree_len, s_lit_hdr, s_nstreams, s_payload0;
     __shared__ u32 s_stream_bytes[4];
 
+    extern __shared__ __align__(16) u8 sb[];      // staged block bytes, zpad() layout
     ZEncBlock &B = A.blk[blockIdx.x];
     const u8 *src = B.src; const u32 n = B.n;
     u8 *slot = A.slots + (size_t)blockIdx.x * ZSLOT;
@@ -155,13 +162,15 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
         for (u32 i = tid; i < nvec; i += 256) {
             uint4 x = v[i];
             u32 w[4] = {x.x, x.y, x.z, x.w};
+            u32 *st = (u32 *)(sb + zpad(i * 16));
+            st[0] = w[0]; st[1] = w[1]; st[2] = w[2]; st[3] = w[3];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 atomicAdd(&hist_w[warp][w[k] & 0xFF], 1u); atomicAdd(&hist_w[warp][(w[k] >> 8) & 0xFF], 1u);
                 atomicAdd(&hist_w[warp][(w[k] >> 16) & 0xFF], 1u); atomicAdd(&hist_w[warp][w[k] >> 24], 1u);
             }
         }
-        for (u32 i = nvec * 16 + tid; i < n; i += 256) atomicAdd(&hist_w[warp][src[i]], 1u);
+        for (u32 i = nvec * 16 + tid; i < n; i += 256) { u8 c = src[i]; sb[zpad(i)] = c; atomicAdd(&hist_w[warp][c], 1u); }
     }
     __syncthreads();
     { u32 h = 0; for (int w = 0; w < 8; w++) h += hist_w[w][tid]; hist[tid] = h; len_of[tid] = 0; weight[tid] = 0; ctab[tid] = 0; }
@@ -247,7 +256,13 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
     const u32 per = (slen + tps - 1) / tps;
     u32 t0 = sbeg + q * per, t1 = t0 + per; if (t0 > send) t0 = send; if (t1 > send) t1 = send;
     u32 bits = 0;
-    for (u32 i = t0; i < t1; i++) bits += ctab[src[i]] >> 16;
+    for (u32 i = t0; i < t1;) {
+        if (!(i & 3) && i + 4 <= t1) {                        // aligned word of four symbols
+            const u32 x = *(const u32 *)(sb + zpad(i));
+            bits += (ctab[x & 0xFF] >> 16) + (ctab[(x >> 8) & 0xFF] >> 16) + (ctab[(x >> 16) & 0xFF] >> 16) + (ctab[x >> 24] >> 16);
+            i += 4;
+        } else { bits += ctab[sb[zpad(i)]] >> 16; i++; }
+    }
     u64 total_bits;
     u64 pre = block_excl_scan(bits, &total_bits, smscan);
     pre_bits[tid] = (u32)pre; if (tid == 255) pre_bits[256] = (u32)total_bits;
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
         const u64 abs0 = (u64)byte_base * 8;
         u64 acc = 0; u32 fill = 0;
         for (u32 i = t1; i > t0; i--) {
-            u32 e = ctab[src[i - 1]];
+            u32 e = ctab[sb[zpad(i - 1)]];
             acc |= (u64)(e & 0xFFFF) << fill; fill += e >> 16;
             if (fill >= 32) {
                 u64 ab = abs0 + bitpos; u32 wi = (u32)(ab >> 5), sh = (u32)(ab & 31); u32 v = (u32)acc;
@@ -357,7 +372,8 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     ex.upload(b.d_blocks, blocks.data(), sizeof(ZEncBlock) * b.nblocks);
     CUDA_TRY(cudaStreamSynchronize(ex.stream));                 // `blocks` is a local vector
     ZEncArgs A{b.d_blocks, b.d_slots};
-    KLAUNCH(ex, "k_zenc_block", k_zenc_block<<<b.nblocks, 256, 0, ex.stream>>>(A));
+    CUDA_TRY(cudaFuncSetAttribute(k_zenc_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSTAGE_BYTES));
+    KLAUNCH(ex, "k_zenc_block", k_zenc_block<<<b.nblocks, 256, ZSTAGE_BYTES, ex.stream>>>(A));
     b.d_off = ex.alloc<u64>(b.nblocks + 2);
     const ZEncBlock *db = b.d_blocks;
     exclusive_scan(ex, [db] __device__ (size_t i) { return (u64)db[i].csize + 3; }, b.nblocks, b.d_off);

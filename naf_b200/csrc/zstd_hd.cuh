@@ -49,59 +49,45 @@ HD int hibit(u32 v)
 // `consumed() > total`.  Replaces common/bitstream.h BIT_initDStream/BIT_reloadDStream.
 struct BackBits {
     const u8 *p;      // stream start
-    i64 next;         // number of bytes not yet loaded (index one past the next byte to load)
-    u64 cont;
-    int avail;        // valid bits in cont (left-aligned)
-    i64 total;        // payload bits in the stream (excludes padding + end mark)
-    i64 used;         // bits consumed so far
-    i64 size;         // stream bytes
+    i64 pos;          // byte offset (may be negative near the start) of the 8 bytes held in `cont`
+    u64 cont;         // bytes p[pos .. pos+8), little endian: the stream's next bit is bit (63 - consumed)
+    u32 consumed;     // bits of `cont` already used, counted from its top
+    i64 left;         // payload bits not yet consumed (excludes padding + end mark); < 0 = read past the start
 
+    // 8 bytes at any alignment: two aligned loads + funnel shift.  May touch up to 7 bytes on either side of
+    // [q, q+8): callers keep >= 8 readable bytes before the first stream and after the last one.
+    static HD u64 load64(const u8 *q)
+    {
+        const u64 *al = (const u64 *)((uintptr_t)q & ~(uintptr_t)7);
+        const u32 sh = (u32)((uintptr_t)q & 7) * 8;
+        const u64 lo = al[0];
+        return sh ? (lo >> sh) | (al[1] << (64 - sh)) : lo;
+    }
     HD bool init(const u8 *src, size_t n)
     {
-        p = src; next = (i64)n; size = (i64)n; cont = 0; avail = 0; used = 0; total = 0;
+        p = src; pos = (i64)n - 8; cont = 0; consumed = 0; left = 0;
         if (n == 0) return false;
-        u8 last = src[n - 1];
+        const u8 last = src[n - 1];
         if (last == 0) return false;
-        int pad = 8 - hibit(last);            // zero padding bits + the end-mark bit
-        total = (i64)n * 8 - pad;
-        refill();
-        cont <<= pad; avail -= pad;
-        refill();
+        const int pad = 8 - hibit(last);          // zero padding bits + the end-mark bit
+        cont = load64(src + pos);
+        consumed = (u32)pad; left = (i64)n * 8 - pad;
         return true;
     }
-    HD void refill()
+    // drop whole consumed bytes and fetch 8 fresh ones: afterwards at least 57 bits are available.
+    // Bits below the start of the stream are whatever precedes it in memory (the format only ever needs
+    // them as "don't care": Huffman prefixes are already decided, FSE overruns are detected by `left`).
+    HD void reload()
     {
-        while (avail <= 32) {
-            u32 w;
-            if (next >= 4 && next + 4 <= size) {
-                // bytes [next-4, next) as one little-endian word: two aligned 32-bit loads + funnel shift
-                // (a block's content never starts in the first 4 bytes of its buffer, so the aligned word
-                // below p[next-4] is always readable)
-                const u8 *q = p + next - 4;
-                const u32 *al = (const u32 *)((uintptr_t)q & ~(uintptr_t)3);
-                const u32 sh = (u32)((uintptr_t)q & 3) * 8;
-                const u32 lo = al[0];
-                w = sh ? (lo >> sh) | (al[1] << (32 - sh)) : lo;
-                next -= 4;
-            } else if (next >= 4) {                       // last word of the stream: stay inside it
-                w = (u32)p[next - 4] | ((u32)p[next - 3] << 8) | ((u32)p[next - 2] << 16) | ((u32)p[next - 1] << 24);
-                next -= 4;
-            } else if (next > 0) {
-                w = 0;
-                for (int k = 0; k < 4; k++) { i64 idx = next - 4 + k; if (idx >= 0) w |= (u32)p[idx] << (8 * k); }
-                next = 0;
-            } else {
-                w = 0;                        // below the start: zero bits
-            }
-            cont |= (u64)w << (32 - avail);
-            avail += 32;
-        }
+        pos -= (i64)(consumed >> 3); consumed &= 7;
+        if (pos < -8) pos = -8;
+        cont = load64(p + pos);
     }
-    HD u32 peek(int n) const { return n ? (u32)(cont >> (64 - n)) : 0u; }
-    HD void skip(int n) { cont <<= n; avail -= n; used += n; }
-    HD u32 read(int n) { if (avail < n) refill(); u32 v = peek(n); skip(n); return v; }   // n <= 32
-    HD bool overrun() const { return used > total; }
-    HD bool exact() const { return used == total; }
+    HD u32 peek(int n) const { return n ? (u32)((cont << consumed) >> (64 - n)) : 0u; }
+    HD void skip(int n) { consumed += (u32)n; left -= n; }
+    HD u32 read(int n) { if (consumed + (u32)n > 64) reload(); u32 v = peek(n); skip(n); return v; }   // n <= 32
+    HD bool overrun() const { return left < 0; }
+    HD bool exact() const { return left == 0; }
 };
 
 // ------------------------------------------------------------------ FSE
@@ -309,23 +295,23 @@ HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t 
     size_t i = 0;
     // head: byte stores until dst is 16-byte aligned
     while (i < nout && (((uintptr_t)(dst + i)) & 15)) {
-        if (b.avail < max_bits) b.refill();
+        b.reload();
         u32 e = table[b.peek(max_bits)];
         dst[i++] = (u8)e; b.skip((int)(e >> 8));
     }
-    // body: 16 symbols per 128-bit store (one transaction per lane instead of sixteen)
+    // body: 16 symbols per 128-bit store; one reload per 4 symbols (4 x 11 bits <= 57 available)
     for (; i + 16 <= nout; i += 16) {
         u32 w[4];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int k = 0; k < 4; k++) {
+            b.reload();
             u32 v = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int j = 0; j < 4; j++) {
-                if (b.avail < max_bits) b.refill();
                 u32 e = table[b.peek(max_bits)];
                 v |= (e & 0xFF) << (8 * j); b.skip((int)(e >> 8));
             }
@@ -338,7 +324,7 @@ HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t 
 #endif
     }
     for (; i < nout; i++) {
-        if (b.avail < max_bits) b.refill();
+        b.reload();
         u32 e = table[b.peek(max_bits)];
         dst[i] = (u8)e; b.skip((int)(e >> 8));
     }
