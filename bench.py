@@ -170,7 +170,7 @@ def run_reference(args):
 ALGO_BYTES_PER_BASE = {
     # algorithmic HBM bytes per base of each kernel on the config-2 workload (DESIGN.md "Kernels and rooflines")
     # text = 2.18 B/base (2 x 151 + 25 header bytes per 150-base record), ids+comments 0.14, lengths 0.027
-    "k_fsm_reduce": 2.18, "k_fsm_emit": 2.18 + (1.0 + 1.0 + 0.14) / 2,        # two launches: count reads text, scatter reads text and writes streams
+    "k_fsm_reduce": 2.18, "k_fsm_count": 2.18, "k_fsm_scatter": 2.18 + 1.0 + 1.0 + 0.14 + 0.027,   # scatter: reads text, writes bases + qualities + ids/comments + record ends
     "k_pack4": 1.0 + 0.5,
     "k_zenc_block": 2 * (0.5 + 1.0 + 0.17) + 0.92, "k_zenc_gather": 2 * 0.92,
     "zd_literals": 0.92 + 0.5 + 1.0 + 0.17, "k_write_text": 0.5 + 1.0 + 0.17 + 2.18,
