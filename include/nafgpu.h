@@ -80,6 +80,9 @@ typedef struct {
     int32_t  level;             /* ennaf -#: accepted for CLI compatibility; the GPU encoder has one parse */
     int32_t  window_log;        /* ennaf --long N: declared window of the SEQ frame (0 = default) */
     const char *title;          /* ennaf --title, NULL = none */
+    int32_t  general_parser;    /* 1: skip the canonical-input fast parser and use the general (process.c-exact FSM) one;
+                                   results are identical either way -- for tests and profiling */
+    int32_t  reserved;
 } nafgpu_enc_opts;
 
 typedef struct {
@@ -105,7 +108,8 @@ typedef struct {
 typedef struct {
     float h2d_ms, kernels_ms, d2h_ms, total_ms;
     uint32_t kernel_launches;         /* launches of this library's own kernels in the last call */
-    uint32_t reserved;
+    uint32_t parser_fallback;         /* encode / split: 1 if the canonical-input parser declined the input and the general
+                                         (process.c-exact) parser redid the split; 0 otherwise */
 } nafgpu_timing;
 
 /* ---- context ---- */

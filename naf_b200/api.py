@@ -27,7 +27,8 @@ class NafGpuError(RuntimeError):
 class EncOpts(C.Structure):
     _fields_ = [("seq_type", C.c_int32), ("input_format", C.c_int32), ("no_mask", C.c_int32), ("strict", C.c_int32),
                 ("well_formed", C.c_int32), ("have_line_length", C.c_int32), ("line_length", C.c_uint64),
-                ("level", C.c_int32), ("window_log", C.c_int32), ("title", C.c_char_p)]
+                ("level", C.c_int32), ("window_log", C.c_int32), ("title", C.c_char_p), ("general_parser", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class DecOpts(C.Structure):
@@ -43,7 +44,7 @@ class EncInfo(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("kernels_ms", C.c_float), ("d2h_ms", C.c_float), ("total_ms", C.c_float),
-                ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("parser_fallback", C.c_uint32)]
 
 
 # every symbol include/nafgpu.h declares (tests check the .so exports exactly these)
@@ -117,7 +118,7 @@ def _as_ptr(buf):
 
 
 def make_enc_opts(seq_type="dna", fmt=0, no_mask=False, strict=False, well_formed=False, line_length=None, level=1,
-                  window_log=0, title: Optional[str] = None) -> EncOpts:
+                  window_log=0, title: Optional[str] = None, general_parser=False) -> EncOpts:
     o = EncOpts()
     o.seq_type = _SEQ_TYPES.get(seq_type, seq_type) if isinstance(seq_type, str) else int(seq_type)
     o.input_format = {"fasta": 1, "fastq": 2}.get(fmt, fmt) if isinstance(fmt, str) else int(fmt)
@@ -126,6 +127,7 @@ def make_enc_opts(seq_type="dna", fmt=0, no_mask=False, strict=False, well_forme
     o.line_length = int(line_length or 0)
     o.level, o.window_log = int(level), int(window_log)
     o.title = title.encode() if title is not None else None
+    o.general_parser = int(general_parser)
     return o
 
 

@@ -19,13 +19,13 @@ template <class F> static int guarded(nafgpu_ctx *ctx, F f)
 {
     if (!ctx) return NAFGPU_E_ARG;
     try {
-        ctx->err.clear();
+        ctx->err.clear(); ctx->fast_fallbacks = 0;
         CUDA_TRY(cudaSetDevice(ctx->device));
         ctx->arena.reset();
         f();
         return NAFGPU_OK;
     } catch (const NafError &e) {
-        ctx->err = e.msg; cudaStreamSynchronize(ctx->stream); return e.code;
+        ctx->err = e.msg; cudaStreamSynchronize(ctx->stream); ctx->timing.parser_fallback = ctx->fast_fallbacks != 0; return e.code;
     } catch (const CudaError &e) {
         char buf[512];
         snprintf(buf, sizeof buf, "CUDA error: %s (%s) at %s:%d\n", cudaGetErrorString(e.e), e.what, e.file, e.line);
@@ -122,6 +122,7 @@ static void finish_timing(Ctx &c, CudaExec &ex)
     cudaEventElapsedTime(&c.timing.d2h_ms, c.ev[2], c.ev[3]);
     cudaEventElapsedTime(&c.timing.total_ms, c.ev[0], c.ev[3]);
     c.timing.kernel_launches = ex.launches;
+    c.timing.parser_fallback = c.fast_fallbacks != 0;
     if (c.prof.on) {
         // aggregate per kernel name, in first-launch order
         std::vector<std::string> names; std::vector<double> ms; std::vector<int> cnt;

@@ -60,6 +60,14 @@ struct Arena {
         cur_total = 0;
     }
     void release() { for (auto &s : slabs) cudaFree(s.p); slabs.clear(); }
+    // roll back to an earlier allocation state (an abandoned attempt's scratch is reused by the retry)
+    struct Mark { std::vector<size_t> used; size_t total; };
+    Mark mark() const { Mark m; m.total = cur_total; for (auto &s : slabs) m.used.push_back(s.used); return m; }
+    void rewind(const Mark &m)
+    {
+        for (size_t i = 0; i < slabs.size(); i++) slabs[i].used = i < m.used.size() ? m.used[i] : 0;
+        cur_total = m.total;
+    }
 };
 
 struct PinnedBuf {
@@ -210,6 +218,7 @@ struct Ctx {
     std::vector<u8> host_scratch;
     Prof prof;
     std::string prof_report;
+    u64 fast_fallbacks = 0;                  // encode calls that had to be redone by the general parser
 };
 
 #define KLAUNCH(ex, name, ...) do { (ex).prof_begin(name); __VA_ARGS__; (ex).prof_end(); } while (0)

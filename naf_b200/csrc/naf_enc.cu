@@ -20,13 +20,16 @@
 #include "container.hpp"
 
 #include "naf_parse.cuh"
+#include "naf_parse_fast.cuh"
 
 namespace nafg {
 
 // ------------------------------------------------------------------ 4-bit pack + case bits
 // encoders.c:30 encode_dna (first base in the low nibble; odd tail has a zero high nibble, ennaf.c:525)
 // and the predicate of encoders.c:134 (masked <=> byte >= 96).  One thread: 32 bases -> 16 bytes + 1 word.
-__global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int want_mask, const u8 *nuc_code)
+// nuc_code[] here carries bit 7 = "not an expected code for this alphabet" (tables.c:72,82); the general parser has
+// already replaced such bytes, the canonical-input parser has not and learns about them through *flag (condition C4).
+__global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int want_mask, const u8 *nuc_code, u32 *flag)
 {
     __shared__ u8 c_nuc_code[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) c_nuc_code[i] = nuc_code[i];
@@ -34,7 +37,7 @@ __global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int w
     u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 b0 = g * 32;
     if (b0 >= n) return;
-    u32 out[4] = {0, 0, 0, 0}, mbits = 0;
+    u32 out[4] = {0, 0, 0, 0}, mbits = 0, inv = 0;
     if (b0 + 32 <= n) {
         const uint4 *src = (const uint4 *)(bases + b0);
         uint4 v0 = src[0], v1 = src[1];
@@ -43,7 +46,8 @@ __global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int w
         for (int k = 0; k < 8; k++) {
             u32 x = w[k];
             u32 c0 = c_nuc_code[x & 0xFF], c1 = c_nuc_code[(x >> 8) & 0xFF], c2 = c_nuc_code[(x >> 16) & 0xFF], c3 = c_nuc_code[x >> 24];
-            u32 two = c0 | (c1 << 4) | (c2 << 8) | (c3 << 12);
+            inv |= c0 | c1 | c2 | c3;
+            u32 two = (c0 & 15) | ((c1 & 15) << 4) | ((c2 & 15) << 8) | ((c3 & 15) << 12);
             out[k >> 1] |= two << (16 * (k & 1));
             // case bit: byte >= 96
             u32 ge = ((x & 0xFF) >= 96) | ((((x >> 8) & 0xFF) >= 96) << 1) | ((((x >> 16) & 0xFF) >= 96) << 2) | (((x >> 24) >= 96) << 3);
@@ -53,11 +57,13 @@ __global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int w
     } else {
         for (u64 i = b0; i < n; i += 2) {
             u32 c0 = c_nuc_code[bases[i]], c1 = i + 1 < n ? c_nuc_code[bases[i + 1]] : 0;
-            packed[i >> 1] = (u8)(c0 | (c1 << 4));
+            inv |= c0 | c1;
+            packed[i >> 1] = (u8)((c0 & 15) | ((c1 & 15) << 4));
         }
         for (u64 i = b0; i < n; i++) if (bases[i] >= 96) mbits |= 1u << (i - b0);
     }
     if (want_mask) casebits[g] = mbits;
+    if (inv & 0x80) atomicOr(flag, (u32)FF_SEQ);
 }
 
 // flips[w] = positions where the case differs from the previous base (case before base 0 = unmasked)
@@ -110,7 +116,9 @@ struct SplitDev {
 
 static void die_input(const std::string &m) { fail(NAFGPU_E_INPUT, m); }
 
-static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)
+struct FastFallback {};      // thrown inside split_streams_impl when the canonical-input parser meets input it does not cover
+
+static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info, bool use_fast)
 {
     SplitDev S; memset(&S, 0, sizeof S);
     if (info) memset(info, 0, sizeof *info);
@@ -156,11 +164,33 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     const u64 ntiles = (n + PTILE - 1) / PTILE;               // tiles cover the text from offset 0; bytes before p0 are skipped
     ParseArgs P; memset(&P, 0, sizeof P);
     P.text = d_text; P.n = n; P.p0 = p0; P.cfg = C; P.tab = d_tab; P.ntiles = ntiles;
-    P.thread_map = ex.alloc<u64>(ntiles * PT + 1); P.tile_map = ex.alloc<u64>(ntiles + 1); P.tile_state = ex.alloc<u8>(ntiles + 2);
+    if (!use_fast) { P.thread_map = ex.alloc<u64>(ntiles * PT + 1); P.tile_map = ex.alloc<u64>(ntiles + 1); }
+    P.tile_state = ex.alloc<u8>(ntiles + 2);
     P.tinfo = ex.alloc<ThreadInfo>(ntiles * PT + 1); P.tile = ex.alloc<TileCounts>(ntiles + 1);
-    if (ntiles) { KLAUNCH(ex, "k_fsm_reduce", k_fsm_reduce<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
-    KLAUNCH(ex, "k_fsm_scan", k_fsm_scan<<<1, 1024, 0, ex.stream>>>(P));
-    if (ntiles) { KLAUNCH(ex, "k_fsm_count", k_fsm_count<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
+    // canonical-input parser (naf_parse_fast.cuh): same passes, same records; raises *flag when the input needs the general one
+    FastArgs F; memset(&F, 0, sizeof F);
+    u32 *d_flag = ex.alloc<u32>(1);
+    ex.zero(d_flag, 4);
+    auto check_fast_flag = [&]() { u32 f; ex.download(&f, d_flag, 4); if (f) throw FastFallback{}; };
+    if (use_fast) {
+        F.tile_elem = ex.alloc<u32>(ntiles + 1); F.tile_entry = ex.alloc<u32>(ntiles + 2); F.flag = d_flag;
+        F.upper = o.seq_type >= NAFGPU_PROTEIN && o.no_mask;
+        F.seq_check = o.seq_type == NAFGPU_PROTEIN ? 1 : (o.seq_type == NAFGPU_TEXT ? (C.text_fasta ? 3 : 2) : 0);
+        F.P = P;
+        if (C.fastq) {
+            if (ntiles) { KLAUNCH(ex, "k_fast_tiles", k_fast_tiles<true><<<(unsigned)ntiles, PT, 0, ex.stream>>>(F)); }
+            KLAUNCH(ex, "k_fast_scan", k_fast_scan<true><<<1, 1024, 0, ex.stream>>>(F));
+            if (ntiles) { KLAUNCH(ex, "k_fast_count", k_fast_count<true><<<(unsigned)ntiles, PT, 0, ex.stream>>>(F)); }
+        } else {
+            if (ntiles) { KLAUNCH(ex, "k_fast_tiles", k_fast_tiles<false><<<(unsigned)ntiles, PT, 0, ex.stream>>>(F)); }
+            KLAUNCH(ex, "k_fast_scan", k_fast_scan<false><<<1, 1024, 0, ex.stream>>>(F));
+            if (ntiles) { KLAUNCH(ex, "k_fast_count", k_fast_count<false><<<(unsigned)ntiles, PT, 0, ex.stream>>>(F)); }
+        }
+    } else {
+        if (ntiles) { KLAUNCH(ex, "k_fsm_reduce", k_fsm_reduce<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
+        KLAUNCH(ex, "k_fsm_scan", k_fsm_scan<<<1, 1024, 0, ex.stream>>>(P));
+        if (ntiles) { KLAUNCH(ex, "k_fsm_count", k_fsm_count<<<(unsigned)ntiles, PT, 0, ex.stream>>>(P)); }
+    }
     // exclusive sums of the six counters + exclusive max of the line-end marker
     u64 *pre[7];
     for (int k = 0; k < 7; k++) pre[k] = ex.alloc<u64>(ntiles + 2);
@@ -190,6 +220,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     for (int k = 0; k < 6; k++) ex.download(&tot[k], pre[k] + ntiles, 8);
     ex.download(&end_state, P.tile_state + ntiles, 1);
     if (ntiles == 0) end_state = 0;
+    if (use_fast) check_fast_flag();
 
     // ---- what the end of input adds (process.c:417-425, :535-543): pending terminators and the last record
     u64 add_ids = 0, add_comm = 0, add_rec = 0;
@@ -220,8 +251,19 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     P.ids = S.ids; P.comm = S.comm; P.bases = bases; P.qual = S.qual;
     P.rec_seq_end = rec_seq_end; P.rec_qual_end = rec_qual_end; P.rec_pos = rec_pos;
     P.unexpected = d_unexp; P.longest = d_longest; P.first_bad = d_first_bad;
-    CUDA_TRY(cudaFuncSetAttribute(k_fsm_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
-    if (ntiles) { KLAUNCH(ex, "k_fsm_scatter", k_fsm_scatter<<<(unsigned)ntiles, PT, SCATTER_SMEM, ex.stream>>>(P)); }
+    if (use_fast) {
+        F.P = P;
+        if (C.fastq) {
+            CUDA_TRY(cudaFuncSetAttribute(k_fast_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SCATTER_SMEM));
+            if (ntiles) { KLAUNCH(ex, "k_fast_scatter", k_fast_scatter<true><<<(unsigned)ntiles, PT, FAST_SCATTER_SMEM, ex.stream>>>(F)); }
+        } else {
+            CUDA_TRY(cudaFuncSetAttribute(k_fast_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SCATTER_SMEM));
+            if (ntiles) { KLAUNCH(ex, "k_fast_scatter", k_fast_scatter<false><<<(unsigned)ntiles, PT, FAST_SCATTER_SMEM, ex.stream>>>(F)); }
+        }
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(k_fsm_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCATTER_SMEM));
+        if (ntiles) { KLAUNCH(ex, "k_fsm_scatter", k_fsm_scatter<<<(unsigned)ntiles, PT, SCATTER_SMEM, ex.stream>>>(P)); }
+    }
     // end-of-input additions
     {
         u8 *ids = S.ids, *comm = S.comm; const u64 a = tot[0], b = tot[1], r = tot[5], cnt = n_cnt, ql = n_qual, nn = n;
@@ -236,6 +278,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     unsigned long long h_tail[2 + 0]; (void)h_tail;
     std::vector<unsigned long long> h_unexp(4 * 257 + 4);
     ex.download(h_unexp.data(), d_unexp, h_unexp.size() * 8);
+    if (use_fast) check_fast_flag();
     const unsigned long long first_bad = h_unexp[4 * 257 + 1];
     u64 bad_pos = ~0ull; int bad_kind = 0;
     if (first_bad != ~0ull) { bad_pos = first_bad >> 8; bad_kind = (int)(first_bad & 0xFF); }
@@ -329,6 +372,9 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
             int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
             const char *order = "-TGKCYSBAWRDMHV"; const char *q = u ? strchr(order, u) : nullptr;
             lut[c] = u == 'U' ? 1 : (q ? (u8)(q - order) : 15);
+            // bit 7: not an expected code (tables.c:72 DNA, :82 RNA) -- only the canonical-input parser can still meet one here
+            const char *ok = o.seq_type == NAFGPU_RNA ? "-ABCDGHKMNRSUVWY" : "-ABCDGHKMNRSTVWY";
+            if (!(u && strchr(ok, u))) lut[c] |= 0x80;
         }
         u8 *d_lut = ex.alloc<u8>(256);
         ex.upload(d_lut, lut, 256);
@@ -337,7 +383,8 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         S.seq = ex.alloc<u8>(S.n_seq + 64);
         u64 nwords = (n_seq + 31) / 32;
         u32 *casebits = ex.alloc<u32>(nwords + 2);
-        if (nwords) { KLAUNCH(ex, "k_pack4", k_pack4<<<(unsigned)((nwords + 255) / 256), 256, 0, ex.stream>>>(bases, n_seq, S.seq, casebits, S.store_mask, d_lut)); }
+        if (nwords) { KLAUNCH(ex, "k_pack4", k_pack4<<<(unsigned)((nwords + 255) / 256), 256, 0, ex.stream>>>(bases, n_seq, S.seq, casebits, S.store_mask, d_lut, d_flag)); }
+        if (use_fast) check_fast_flag();
         if (S.store_mask && n_seq) {
             // case flips -> runs -> units (encoders.c:98-151; final run flushed by ennaf.c:511)
             u64 ft = (nwords + 255) / 256;
@@ -366,6 +413,23 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     if (!S.mask) S.mask = ex.alloc<u8>(64);
     if (info) { info->n_sequences = n_rec; info->longest_line = S.longest; info->n_bases = n_seq; }
     return S;
+}
+
+// Canonical input goes through the fast parser; anything it does not cover (or any input error, so that the message
+// comes from the exact restatement) is redone by the general one.  --well-formed has its own tables: general only.
+static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)
+{
+    static const bool env_general = getenv("NAFGPU_GENERAL_PARSER") != nullptr;
+    if (!o.well_formed && !env_general && !o.general_parser) {
+        const Arena::Mark mk = ex.arena->mark();
+        try { return split_streams_impl(ctx, ex, d_text, n, o, info, true); }
+        catch (const FastFallback &) {}
+        catch (const NafError &) {}
+        CUDA_TRY(cudaStreamSynchronize(ex.stream));
+        ex.arena->rewind(mk);
+        ctx.fast_fallbacks++;
+    }
+    return split_streams_impl(ctx, ex, d_text, n, o, info, false);
 }
 
 SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)

@@ -16,15 +16,24 @@ pytestmark = pytest.mark.gpu
 STREAMS = ["ids", "comments", "lengths", "mask", "sequence", "quality"]
 
 
-def check_split(gpu, oracle, text, **kw):
+def check_split(gpu, oracle, text, expect_fast=None, **kw):
+    """both parsers: the canonical-input one (with its fallback) and the general FSM one must give the oracle's streams"""
+    _check_split(gpu, oracle, text, **kw)
+    if expect_fast is not None:
+        assert (gpu.timing().parser_fallback == 0) == expect_fast, "fast parser %s this input" % ("declined" if expect_fast else "accepted")
+    _check_split(gpu, oracle, text, general_parser=True, **kw)
+
+
+def _check_split(gpu, oracle, text, general_parser=False, **kw):
+    gkw = dict(kw, general_parser=general_parser)
     try:
         want, winfo = oracle.split(text, **kw)
     except ValueError as e:
         with pytest.raises(naf_b200.NafGpuError) as ge:
-            gpu.split(text, **kw)
+            gpu.split(text, **gkw)
         assert ge.value.message == str(e), (ge.value.message, str(e))
         return
-    got, info = gpu.split(text, **kw)
+    got, info = gpu.split(text, **gkw)
     if not winfo["store_mask"]:
         want[3] = b""
     if not winfo["store_qual"]:
@@ -122,7 +131,29 @@ def test_split_tile_boundaries(gpu, oracle):
         parts.append(b">" + name + b"\n" + body + (b"\n" if L else b""))
     check_split(gpu, oracle, b"".join(parts))
     check_split(gpu, oracle, b"".join(parts)[:-1])          # no final newline
-    check_split(gpu, oracle, synth.fastq(5000, 151, seed=9))
+    check_split(gpu, oracle, synth.fastq(5000, 151, seed=9), expect_fast=True)
+
+
+def test_split_canonical_uses_fast_parser(gpu, oracle):
+    """BASELINE-shaped inputs must be accepted by the canonical-input parser (and equal the oracle); one stray
+    byte anywhere must send the whole input through the general parser with identical results"""
+    rng = np.random.default_rng(17)
+    fq = synth.fastq(30000, 150, seed=41)
+    fa = synth.fasta_softmasked(3_000_000, width=60, seed=42, n_records=5, repeats=True, n_gaps=2)
+    cases = [(fq, {}), (fq[:-1], {}), (fa, {}), (fa[:-1], {}), (synth.ont_fasta(40, 1000, 50000, seed=43), {}),
+             (synth.protein_fasta(20000, 300, seed=44), {"seq_type": "protein"}), (synth.protein_fasta(2000, 300, seed=44), {"seq_type": "protein", "no_mask": True}),
+             (synth.protein_fasta(2000, 300, seed=45), {"seq_type": "text"}), (synth.fastq(3000, 150, seed=46, lowercase=True, iupac=True), {}),
+             (synth.fastq(3000, 150, seed=46, lowercase=True), {"no_mask": True}), (synth.fasta_reads(3000, 150, seed=47).replace(b"T", b"U"), {"seq_type": "rna"})]
+    for L in (1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000):
+        cases.append((b"".join(b"@q%d %d/1\n" % (i, i) + bytes(np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, L)]) + b"\n+\n" +
+                               bytes(rng.integers(33, 127, L).astype(np.uint8)) + b"\n" for i in range(700)), {}))
+    for w in (1, 2, 59, 63, 64, 65, 16383, 16384, 16385):
+        s = bytes(np.frombuffer(b"ACGTacgtN-", dtype=np.uint8)[rng.integers(0, 10, 20 * w + 7)])
+        cases.append((b"".join(b">r%d some comment here\n" % i + b"\n".join(s[k:k + w] for k in range(0, len(s), w)) + b"\n" for i in range(4)), {}))
+    for text, kw in cases:
+        check_split(gpu, oracle, text, expect_fast=True, **kw)
+    for text, at, byte in [(fq, 1_000_003, b"\r"), (fq, len(fq) - 5, b" "), (fa, 2_000_000, b"Z"), (fa, 17, b"\t"), (fa, 1_500_000, b"\x7f")]:
+        check_split(gpu, oracle, text[:at] + byte + text[at + 1:], expect_fast=False)
 
 
 def test_zstd_compress_roundtrip(gpu, oracle):
