@@ -79,7 +79,7 @@ void nafgpu_destroy(nafgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->arena.release(); c->pinned_out.release(); c->pinned_aux.release();
+    c->arena.release(); c->pinned_out.release(); c->pinned_aux.release(); c->pinned_stage.release();
     if (c->d_predef) cudaFree(c->d_predef);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -147,7 +147,7 @@ int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_
     if (!naf || !opts || !text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         nafc::Header h; std::string err;
         if (!nafc::read_header(naf, n, h, false, err)) fail(NAFGPU_E_FORMAT, err);      // fail before any transfer
@@ -166,7 +166,7 @@ int nafgpu_decode_device(nafgpu_ctx *c, const uint8_t *d_naf, size_t n, const ui
     if (!d_naf || !opts || !d_text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         const u8 *h = host_copy;
         if (!h) {                                     // no host mirror: fetch the compressed bytes once for the header walk
@@ -189,7 +189,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx *c, const uint8_t *src, size_t n, size_t e
     if (!src || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -198,7 +198,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx *c, const uint8_t *src, size_t n, size_t e
         nafz::ZDecPlan plan;
         u64 cap = expected_size;
         if (!cap) {
-            std::vector<nafz::ZBlock> blocks; std::string werr; u64 used = 0;
+            std::vector<nafz::ZBlockHead> blocks; std::string werr; u64 used = 0;
             nafz::ZStreamDesc probe{0, n, 0, ~0ull, one_frame, 0};
             if (nafz::zstd_walk_stream(src, probe, 0, blocks, &used, werr)) fail(NAFGPU_E_FORMAT, werr + "\n");
             for (auto &b : blocks) cap += b.type == 2 ? 128 * 1024 : b.rsize;
@@ -221,7 +221,7 @@ int nafgpu_encode(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc
     if ((!text && n) || !opts || !naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -238,7 +238,7 @@ int nafgpu_encode_device(nafgpu_ctx *c, const uint8_t *d_text, size_t n, const n
     if ((!d_text && n) || !opts || !d_naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
@@ -253,7 +253,7 @@ int nafgpu_zstd_compress(nafgpu_ctx *c, const uint8_t *src, size_t n, int window
     if ((!src && n) || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -269,7 +269,7 @@ int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_
 {
     if ((!text && n) || !opts || !streams || !sizes) return NAFGPU_E_ARG;
     return guarded(c, [&] {
-        CudaExec ex{c->stream, &c->arena, &c->prof};
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));

@@ -111,6 +111,18 @@ struct CudaExec {
 
     template <class T> T *alloc(size_t count) { return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1)); }
     void upload(void *dst, const void *src, size_t n) { if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream)); }
+    // upload of a bigger host array that lives in pageable memory: through the context's pinned staging so the DMA is
+    // asynchronous and the source may be reused as soon as this returns
+    PinnedBuf *staging = nullptr;
+    void upload_staged(void *dst, const void *src, size_t n)
+    {
+        if (!n) return;
+        if (!staging) { upload(dst, src, n); CUDA_TRY(cudaStreamSynchronize(stream)); return; }
+        CUDA_TRY(cudaStreamSynchronize(stream));                 // the staging buffer may still feed an earlier copy
+        u8 *p = staging->ensure(n);
+        memcpy(p, src, n);
+        CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyHostToDevice, stream));
+    }
     void download(void *dst, const void *src, size_t n)
     {
         if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
@@ -210,7 +222,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     Arena arena;
-    PinnedBuf pinned_out, pinned_aux;
+    PinnedBuf pinned_out, pinned_aux, pinned_stage;
+    std::vector<nafz::ZBlockHead> zblock_cache;   // keeps the capacity of the decoder's host block list between calls
     u32 *d_predef = nullptr;                 // predefined FSE tables
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;

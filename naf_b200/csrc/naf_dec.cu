@@ -206,12 +206,115 @@ __device__ __forceinline__ void rec_fetch(const TextArgs &A, u64 i, RecS &s)
     s.out0 = A.out_start[i];
 }
 
-// Each CTA: find the record containing its first byte (32-ary search by warp 0), stage the descriptors of
-// the records that intersect the tile in shared memory, then every thread emits 16-byte chunks.
+// The generic composer of one 16-byte chunk of text starting at q0: the chunk is assembled from at most a handful of
+// segments (prefix char, id, separator, comment, newline, a run of bases, '+', a run of qualities ...).  Each segment
+// contributes one unaligned 16-byte read (or one constant byte) shifted into place: no per-byte loop.
+__device__ __noinline__ void wt_chunk_generic(const TextArgs &A, const RecS *recs, u64 first, u32 nrec, u32 nrec_total, u64 q0, u64 tile1)
+{
+    // record containing q0: last staged record with out0 <= q0; if that is the final staged one, more may follow in HBM
+    u32 lo = 0, hi = nrec;                   // invariant: recs[lo].out0 <= q0
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (recs[mid].out0 <= q0) lo = mid; else hi = mid; }
+    u64 rec = first + lo;
+    RecS cur = recs[lo];
+    if (lo + 1 == nrec && rec + 1 < A.N && nrec_total >= (u32)WT_MAXREC) {
+        // tile holds more records than staged: finish the search in global memory
+        u64 glo = rec, ghi = A.N;
+        while (ghi - glo > 1) { u64 mid = (glo + ghi) >> 1; if (A.out_start[mid] <= q0) glo = mid; else ghi = mid; }
+        if (glo != rec) { rec = glo; rec_fetch(A, rec, cur); }
+    }
+    RecInfo R; rec_bounds(A, cur, R);
+    u64 r = q0 - cur.out0;
+    const int nvalid = tile1 - q0 >= 16 ? 16 : (int)(tile1 - q0);
+    u64 olo = 0, ohi = 0;
+    int j = 0;
+    u32 li = lo;
+    while (j < nvalid) {
+        while (r >= R.e && rec + 1 < A.N) {
+            rec++; li++;
+            if (rec == first + li && li < nrec) cur = recs[li]; else rec_fetch(A, rec, cur);
+            rec_bounds(A, cur, R); r = 0;
+        }
+        u64 slo = 0, shi = 0; u32 take = 1;             // segment bytes (first byte in the low end) and how many
+        if (r < R.a) slo = A.prefix;
+        else if (r < R.b) {
+            const u32 k = (u32)(r - R.a);
+            const u8 *src; u32 len;
+            if (A.has_ids && k < R.id_len) { src = A.ids + R.id_s + k; len = R.id_len - k; }
+            else if (A.has_ids && A.has_names) {
+                if (k == R.id_len) { src = nullptr; len = 1; slo = A.sep; }
+                else { const u32 kk = k - R.id_len - 1; src = A.comm + R.cm_s + kk; len = R.cm_len - kk; }
+            } else { src = A.comm + R.cm_s + k; len = R.cm_len - k; }
+            if (src) { const uint4 v = load_bytes16(src); slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32); }
+            take = len;
+        }
+        else if (r < R.c) slo = '\n';
+        else if (r < R.d) {
+            const u64 s = r - R.c;
+            u64 bi; u64 run;
+            if (A.W > 0 && A.seq_nl == 1) {
+                const u64 line = s / (A.W + 1), col = s - line * (A.W + 1);
+                bi = line * A.W + col;
+                run = (col == A.W || r + 1 == R.d) ? 0 : min(A.W - col, R.L - bi);
+            } else { bi = s; run = s < R.L ? R.L - s : 0; }
+            if (run == 0) slo = '\n';
+            else {
+                bi += R.sbase;
+                if (A.packed) {
+                    const u64 nib = load_nibbles16(A.seq, bi);
+                    u32 w0 = nib4_to_ascii((u32)nib & 0xFFFF, A.lut), w1 = nib4_to_ascii((u32)(nib >> 16) & 0xFFFF, A.lut);
+                    u32 w2 = nib4_to_ascii((u32)(nib >> 32) & 0xFFFF, A.lut), w3 = nib4_to_ascii((u32)(nib >> 48) & 0xFFFF, A.lut);
+                    if (A.maskbits) {
+                        const u32 mb = load_maskbits16(A.maskbits, bi);
+                        w0 += bits4_to_case(mb & 15); w1 += bits4_to_case((mb >> 4) & 15); w2 += bits4_to_case((mb >> 8) & 15); w3 += bits4_to_case((mb >> 12) & 15);
+                    }
+                    slo = (u64)w0 | ((u64)w1 << 32); shi = (u64)w2 | ((u64)w3 << 32);
+                } else {
+                    uint4 v = load_bytes16(A.seq + bi);
+                    if (A.upper) { v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w); }
+                    slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
+                }
+                take = run > 16 ? 16u : (u32)run;
+            }
+        }
+        else {
+            const u64 t = r - R.d;
+            if (t == 0) slo = '+';
+            else if (t == 1 || t >= 2 + R.L) slo = '\n';
+            else {
+                const uint4 v = load_bytes16(A.qual + R.sbase + (t - 2));
+                slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
+                const u64 run = R.L - (t - 2);
+                take = run > 16 ? 16u : (u32)run;
+            }
+        }
+        if (take > (u32)(16 - j)) take = 16 - j;
+        // keep `take` bytes, shift them to byte position j, merge
+        if (take < 16) {
+            if (take >= 8) shi &= take == 8 ? 0ull : ((1ull << (8 * (take - 8))) - 1);
+            else { shi = 0; slo &= (1ull << (8 * take)) - 1; }
+        }
+        if (j) {
+            if (j < 8) { shi = (shi << (8 * j)) | (slo >> (64 - 8 * j)); slo <<= 8 * j; }
+            else { shi = slo << (8 * (j - 8)); slo = 0; }
+        }
+        olo |= slo; ohi |= shi;
+        j += (int)take; r += take;
+    }
+    if (nvalid == 16) *(uint4 *)(A.out + q0) = make_uint4((u32)olo, (u32)(olo >> 32), (u32)ohi, (u32)(ohi >> 32));
+    else for (int k = 0; k < nvalid; k++) A.out[q0 + k] = (u8)((k < 8 ? olo >> (8 * k) : ohi >> (8 * (k - 8))));
+}
+
+// Each CTA: find the record containing its first byte (32-ary search by warp 0), stage the descriptors of the records
+// that intersect the tile in shared memory, then
+//   pass 1  every thread looks at its 16-byte chunks: a chunk that lies inside one run of bases or one run of
+//           qualities (about three quarters of them) is produced on the spot; the others are only listed
+//   pass 2  the listed chunks are shared out again over all threads, so that the long generic composer runs in
+//           full warps instead of a few lanes per warp
 __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
 {
     __shared__ RecS recs[WT_MAXREC];
-    __shared__ u64 s_first; __shared__ u32 s_nrec;
+    __shared__ u64 s_first; __shared__ u32 s_nrec, s_nslow;
+    __shared__ u16 slow[WT_THREADS * WT_ITERS];
     const u64 tile0 = (u64)blockIdx.x * WT_TILE;
     const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
 
@@ -227,7 +330,7 @@ __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
             u64 nlo = lo + step * cnt, nhi = lo + step * (cnt + 1);
             lo = nlo; if (nhi < hi) hi = nhi;
         }
-        if (threadIdx.x == 0) s_first = lo;
+        if (threadIdx.x == 0) { s_first = lo; s_nslow = 0; }
     }
     __syncthreads();
     const u64 first = s_first;
@@ -245,106 +348,73 @@ __global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
         if (threadIdx.x == 0) s_nrec = cnt;
     }
     __syncthreads();
-    const u32 nrec = s_nrec < (u32)WT_MAXREC ? s_nrec : (u32)WT_MAXREC;     // staged records: first .. first+nrec-1
+    const u32 nrec_total = s_nrec;
+    const u32 nrec = nrec_total < (u32)WT_MAXREC ? nrec_total : (u32)WT_MAXREC;     // staged records: first .. first+nrec-1
+    const bool wrapped = A.W > 0 && A.seq_nl == 1;
+    const u32 W32 = (u32)A.W;
 
     for (int it = 0; it < WT_ITERS; it++) {
         const u64 q0 = tile0 + (u64)it * (WT_THREADS * 16) + (u64)threadIdx.x * 16;
-        if (q0 >= tile1) break;
-        // record containing q0: last staged record with out0 <= q0; if that is the final staged one, more may follow in HBM
-        u32 lo = 0, hi = nrec;                   // invariant: recs[lo].out0 <= q0
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (recs[mid].out0 <= q0) lo = mid; else hi = mid; }
-        u64 rec = first + lo;
-        RecS cur = recs[lo];
-        if (lo + 1 == nrec && rec + 1 < A.N && s_nrec >= (u32)WT_MAXREC) {
-            // tile holds more records than staged: finish the search in global memory
-            u64 glo = rec, ghi = A.N;
-            while (ghi - glo > 1) { u64 mid = (glo + ghi) >> 1; if (A.out_start[mid] <= q0) glo = mid; else ghi = mid; }
-            if (glo != rec) { rec = glo; rec_fetch(A, rec, cur); }
-        }
-        RecInfo R; rec_bounds(A, cur, R);
-        u64 r = q0 - cur.out0;
-        const int nvalid = tile1 - q0 >= 16 ? 16 : (int)(tile1 - q0);
-        // The 16 output bytes are composed from at most a handful of segments (prefix char, id, separator,
-        // comment, newline, a run of bases, '+', a run of qualities ...).  Each segment contributes one
-        // unaligned 16-byte read (or one constant byte) shifted into place: no per-byte loop.
-        u64 olo = 0, ohi = 0;
-        int j = 0;
-        u32 li = lo;
-        while (j < nvalid) {
-            while (r >= R.e && rec + 1 < A.N) {
-                rec++; li++;
-                if (rec == first + li && li < nrec) cur = recs[li]; else rec_fetch(A, rec, cur);
-                rec_bounds(A, cur, R); r = 0;
-            }
-            u64 slo = 0, shi = 0; u32 take = 1;             // segment bytes (first byte in the low end) and how many
-            if (r < R.a) slo = A.prefix;
-            else if (r < R.b) {
-                const u32 k = (u32)(r - R.a);
-                const u8 *src; u32 len;
-                if (A.has_ids && k < R.id_len) { src = A.ids + R.id_s + k; len = R.id_len - k; }
-                else if (A.has_ids && A.has_names) {
-                    if (k == R.id_len) { src = nullptr; len = 1; slo = A.sep; }
-                    else { const u32 kk = k - R.id_len - 1; src = A.comm + R.cm_s + kk; len = R.cm_len - kk; }
-                } else { src = A.comm + R.cm_s + k; len = R.cm_len - k; }
-                if (src) { const uint4 v = load_bytes16(src); slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32); }
-                take = len;
-            }
-            else if (r < R.c) slo = '\n';
-            else if (r < R.d) {
-                const u64 s = r - R.c;
-                u64 bi; u64 run;
-                if (A.W > 0 && A.seq_nl == 1) {
-                    const u64 line = s / (A.W + 1), col = s - line * (A.W + 1);
-                    bi = line * A.W + col;
-                    run = (col == A.W || r + 1 == R.d) ? 0 : min(A.W - col, R.L - bi);
-                } else { bi = s; run = s < R.L ? R.L - s : 0; }
-                if (run == 0) slo = '\n';
-                else {
-                    bi += R.sbase;
-                    if (A.packed) {
-                        const u64 nib = load_nibbles16(A.seq, bi);
-                        u32 w0 = nib4_to_ascii((u32)nib & 0xFFFF, A.lut), w1 = nib4_to_ascii((u32)(nib >> 16) & 0xFFFF, A.lut);
-                        u32 w2 = nib4_to_ascii((u32)(nib >> 32) & 0xFFFF, A.lut), w3 = nib4_to_ascii((u32)(nib >> 48) & 0xFFFF, A.lut);
-                        if (A.maskbits) {
-                            const u32 mb = load_maskbits16(A.maskbits, bi);
-                            w0 += bits4_to_case(mb & 15); w1 += bits4_to_case((mb >> 4) & 15); w2 += bits4_to_case((mb >> 8) & 15); w3 += bits4_to_case((mb >> 12) & 15);
-                        }
-                        slo = (u64)w0 | ((u64)w1 << 32); shi = (u64)w2 | ((u64)w3 << 32);
-                    } else {
-                        uint4 v = load_bytes16(A.seq + bi);
-                        if (A.upper) { v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w); }
-                        slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
+        bool is_slow = false;
+        if (q0 < tile1) {
+            is_slow = true;
+            u32 lo = 0, hi = nrec;
+            while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (recs[mid].out0 <= q0) lo = mid; else hi = mid; }
+            // (when the tile holds more records than were staged, chunks that map to the last staged record go the generic way)
+            if (q0 + 16 <= tile1 && !(lo + 1 == nrec && nrec_total >= (u32)WT_MAXREC)) {
+                const RecS *c = &recs[lo];
+                const u64 L = c->L, r = q0 - c->out0;
+                const u64 cpos = (A.prefix ? 1 : 0) + name_len_of(A, c->id_len, c->cm_len) + A.name_nl;     // start of the sequence area
+                if (A.seq_present && r >= cpos) {
+                    const u64 s = r - cpos;
+                    u64 bi = ~0ull;                                // first base of the chunk if it is one run of 16 bases
+                    if (!wrapped) { if (s + 16 <= L) bi = s; }
+                    else if (s < 0xFFFFFFFFull && A.W < 0xFFFFFFFFull) {
+                        const u32 line = (u32)s / (W32 + 1), col = (u32)s - line * (W32 + 1);
+                        const u64 b = (u64)line * W32 + col;
+                        if (col + 16 <= W32 && b + 16 <= L) bi = b;
                     }
-                    take = run > 16 ? 16u : (u32)run;
+                    if (bi != ~0ull) {
+                        bi += c->sbase;
+                        uint4 v;
+                        if (A.packed) {
+                            const u64 nib = load_nibbles16(A.seq, bi);
+                            v.x = nib4_to_ascii((u32)nib & 0xFFFF, A.lut); v.y = nib4_to_ascii((u32)(nib >> 16) & 0xFFFF, A.lut);
+                            v.z = nib4_to_ascii((u32)(nib >> 32) & 0xFFFF, A.lut); v.w = nib4_to_ascii((u32)(nib >> 48) & 0xFFFF, A.lut);
+                            if (A.maskbits) {
+                                const u32 mb = load_maskbits16(A.maskbits, bi);
+                                v.x += bits4_to_case(mb & 15); v.y += bits4_to_case((mb >> 4) & 15); v.z += bits4_to_case((mb >> 8) & 15); v.w += bits4_to_case((mb >> 12) & 15);
+                            }
+                        } else {
+                            v = load_bytes16(A.seq + bi);
+                            if (A.upper) { v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w); }
+                        }
+                        *(uint4 *)(A.out + q0) = v;
+                        is_slow = false;
+                    } else if (A.with_qual) {
+                        const u64 d = cpos + seq_area_len(A, L);       // start of the "+\n" qual "\n" area
+                        if (r >= d + 2 && r - d - 2 + 16 <= L) {
+                            *(uint4 *)(A.out + q0) = load_bytes16(A.qual + c->sbase + (r - d - 2));
+                            is_slow = false;
+                        }
+                    }
                 }
             }
-            else {
-                const u64 t = r - R.d;
-                if (t == 0) slo = '+';
-                else if (t == 1 || t >= 2 + R.L) slo = '\n';
-                else {
-                    const uint4 v = load_bytes16(A.qual + R.sbase + (t - 2));
-                    slo = (u64)v.x | ((u64)v.y << 32); shi = (u64)v.z | ((u64)v.w << 32);
-                    const u64 run = R.L - (t - 2);
-                    take = run > 16 ? 16u : (u32)run;
-                }
-            }
-            if (take > (u32)(16 - j)) take = 16 - j;
-            // keep `take` bytes, shift them to byte position j, merge
-            if (take < 16) {
-                if (take >= 8) shi &= take == 8 ? 0ull : ((1ull << (8 * (take - 8))) - 1);
-                else { shi = 0; slo &= (1ull << (8 * take)) - 1; }
-            }
-            if (j) {
-                if (j < 8) { shi = (shi << (8 * j)) | (slo >> (64 - 8 * j)); slo <<= 8 * j; }
-                else { shi = slo << (8 * (j - 8)); slo = 0; }
-            }
-            olo |= slo; ohi |= shi;
-            j += (int)take; r += take;
         }
-        if (nvalid == 16) *(uint4 *)(A.out + q0) = make_uint4((u32)olo, (u32)(olo >> 32), (u32)ohi, (u32)(ohi >> 32));
-        else for (int k = 0; k < nvalid; k++) A.out[q0 + k] = (u8)((k < 8 ? olo >> (8 * k) : ohi >> (8 * (k - 8))));
+        // list the chunks left for pass 2 (one shared-memory atomic per warp)
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, is_slow);
+        if (m) {
+            const unsigned lane = threadIdx.x & 31;
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&s_nslow, (u32)__popc(m));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (is_slow) slow[base + __popc(m & ((1u << lane) - 1))] = (u16)(it * WT_THREADS + threadIdx.x);
+        }
     }
+    __syncthreads();
+    const u32 nslow = s_nslow;
+    for (u32 k = threadIdx.x; k < nslow; k += WT_THREADS)
+        wt_chunk_generic(A, recs, first, nrec, nrec_total, tile0 + (u64)slow[k] * 16, tile1);
 }
 
 // histogram of the produced text (unnaf --charcount, output.c:544)
@@ -403,6 +473,8 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
 
     // ---- entropy stage: all needed streams in one batch
     nafz::ZDecPlan plan;
+    plan.blocks.swap(ctx.zblock_cache);                                   // reuse last call's capacity
+    struct GiveBack { nafz::ZDecPlan &p; Ctx &c; ~GiveBack() { p.blocks.swap(c.zblock_cache); } } give_back{plan, ctx};
     int sidx[6]; u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
     for (int k = 0; k < 6; k++) {
         sidx[k] = -1; sbytes[k] = 0; soff[k] = 0;

@@ -154,7 +154,7 @@ static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, siz
     if (info) info->format = fmt;
     if (fmt == 0) return S;                                   // empty input: zero sequences, empty streams (process.c:589)
     C.fastq = fmt == NAFGPU_FMT_FASTQ;
-    C.nstates = C.fastq ? FQ_NSTATES : FA_NSTATES;
+    C.nstates = C.fastq ? (int)FQ_NSTATES : (int)FA_NSTATES;
     C.text_fasta = o.seq_type == NAFGPU_TEXT && !C.fastq;
 
     FsmTables ht; build_tables(C, ht);

@@ -31,7 +31,7 @@
 
 namespace nafz {
 
-// ------------------------------------------------------------------ per-block record (host walk fills the head)
+// ------------------------------------------------------------------ per-block record
 struct ZBlock {
     // --- host walk ---
     u64 src;            // offset of the block content in the input buffer
@@ -84,7 +84,7 @@ static const int FSE_OF_AT = 512, FSE_ML_AT = 768;
 
 // ------------------------------------------------------------------ host: frame / block walk
 // spec "Frame_Header" / "Block_Header"; replaces zstd_decompress.c:819 ZSTD_decompressFrame's header handling.
-inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, std::vector<ZBlock> &blocks,
+inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, std::vector<ZBlockHead> &blocks,
                             u64 *consumed, std::string &err)
 {
     const u8 *p = h + sd.src_off; const u64 n = sd.src_len;
@@ -120,11 +120,10 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
             pos += 3;
             u32 last = bh & 1, type = (bh >> 1) & 3, bsize = bh >> 3;
             if (type == 3) { err = "reserved zstd block type"; return -1; }
-            ZBlock b; memset(&b, 0, sizeof b);
+            ZBlockHead b;
             b.src = sd.src_off + pos; b.type = (u8)type; b.stream = (u8)stream_idx;
             b.first_in_frame = first_in_frame; b.first_in_stream = first_in_stream; b.frame_first_blk = frame_first;
             b.out_base = sd.out_off;
-            b.huf_src = b.ll_src = b.of_src = b.ml_src = -1;
             if (type == 1) { b.csize = 1; b.rsize = bsize; }
             else { b.csize = bsize; b.rsize = type == 0 ? bsize : 0; }
             if (bsize > 128 * 1024 && type != 1) { err = "zstd block larger than 128 KB"; return -1; }
@@ -631,7 +630,7 @@ template <class Exec> void launch_literals(Exec &ex, const ZDecArgs &a)
 //   void for_each(n, F(index))                 grid of n threads
 //   void for_each_group(ngroups, threads, F(group, tid, nthreads))
 struct ZDecPlan {
-    std::vector<ZBlock> blocks;
+    std::vector<ZBlockHead> blocks;
     std::vector<ZStreamDesc> streams;
     std::vector<ZStreamResult> results;
 };
@@ -656,7 +655,19 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
     a.in = d_in; a.out = d_out; a.nblk = nblk; a.predef = d_predef;
     a.blk = ex.template alloc<ZBlock>(nblk);
     a.status = ex.template alloc<u32>(4);
-    ex.upload(a.blk, plan.blocks.data(), sizeof(ZBlock) * nblk);
+    {
+        ZBlockHead *heads = ex.template alloc<ZBlockHead>(nblk);
+        ex.upload_staged(heads, plan.blocks.data(), sizeof(ZBlockHead) * nblk);
+        ZBlock *blk = a.blk;
+        ex.for_each(nblk, [=] HDN (size_t i) {
+            const ZBlockHead h = heads[i];
+            ZBlock b; memset(&b, 0, sizeof b);
+            b.src = h.src; b.out_base = h.out_base; b.csize = h.csize; b.rsize = h.rsize; b.frame_first_blk = h.frame_first_blk;
+            b.type = h.type; b.first_in_frame = h.first_in_frame; b.first_in_stream = h.first_in_stream; b.stream = h.stream;
+            b.huf_src = b.ll_src = b.of_src = b.ml_src = -1;
+            blk[i] = b;
+        }, "zd_block_headers");
+    }
     ex.zero(a.status, 16);
     a.nchunks = nblk < 4096 ? (nblk + 7) / 8 : 1024; if (a.nchunks == 0) a.nchunks = 1;
     a.scan_a = ex.template alloc<ScanA>(a.nchunks + 1);

@@ -6,13 +6,14 @@
 // (SURVEY §8a row 19), so the parse is chosen for the GPU:
 //   * one frame per stream (unnaf's SEQ/QUAL loops stop after the first frame: SURVEY A.2), FHD 0x00,
 //     declared window 128 KB, no content size / checksum / dictionary — what ennaf's frames look like
-//   * 64 KB blocks, each independent of every other: own Huffman table, no sequences, so both our
+//   * 32 KB blocks, each independent of every other: own Huffman table, no sequences, so both our
 //     decoder and libzstd can start anywhere; RLE block when a block is one repeated byte, raw block
 //     when Huffman would not shrink it
 //   * literals: canonical length-limited (<= 11 bit) Huffman, 4 streams (1 stream below 1 KB), tree
 //     description as FSE-compressed weights when smaller / required (> 128 listed weights)
-// One CTA per block does histogram -> code lengths -> tree description -> bit-exact sizes -> encode into
-// a fixed slot; a scan over block sizes then lets k_zenc_gather lay the blocks out as frames.
+// Per block: histogram -> code lengths -> tree description -> bit-exact sizes -> encode into a fixed slot
+// (k_zenc_hist / k_zenc_tables / k_zenc_encode); a scan over block sizes then lets k_zenc_gather lay the blocks
+// out as frames.
 //
 // Format: zstd/doc/zstd_compression_format.md ("Huffman Tree Description", "Huffman-coded streams",
 // "FSE Table Description"); reference counterparts: compress/huf_compress.c:513 HUF_buildCTable_wksp,
@@ -21,7 +22,7 @@
 
 namespace nafg {
 
-static const u32 ZBS = 64 * 1024;            // uncompressed bytes per block
+static const u32 ZBS = 32 * 1024;            // uncompressed bytes per block
 static const u32 ZSLOT = ZBS + 512;          // bytes reserved per block for its compressed content
 static const int ZWINDOW_LOG = 17;
 
@@ -125,89 +126,127 @@ __device__ u32 fse_compress_weights(const u8 *w, int n, u8 *dst, u32 cap)
 }
 
 struct ZEncArgs { ZEncBlock *blk; u8 *slots; };
+struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u32 first[9]; u32 ns; };
+struct ZEncFirstBlocks { u32 v[9]; };
 
-// The block's bytes are staged in shared memory once (coalesced 128-bit loads during the histogram pass) and
-// read from there by the two later passes.  4 bytes of padding per 256 keep the per-thread 256-byte ranges of
-// those passes on different banks.
-__device__ __forceinline__ u32 zpad(u32 i) { return i + ((i >> 8) << 2); }
-static const u32 ZSTAGE_BYTES = ZBS + (ZBS >> 8) * 4 + 16;
+// Three kernels per batch of 32 KB blocks.  Shared-memory atomics cost 32-64 cycles per warp instruction on this
+// part and a single thread building a Huffman code stalls its whole CTA, so neither appears here:
+//   k_zenc_hist    one CTA per block: every thread counts its own 128 bytes into a PRIVATE column of byte
+//                  counters (256 bins x 256 threads = 64 KB, bank = lane: conflict-free LDS/ADD/STS), then thread b
+//                  sums row b with dp4a -> 256 x u16 counts per block in HBM
+//   k_zenc_tables  one THREAD per block (a hundred thousand of them at once hide each other's latency): rank the
+//                  symbols, two-queue Huffman, limit to 11 bits, canonical codes, tree description
+//   k_zenc_encode  one CTA per block: exact stream sizes, then the bits are assembled in shared memory — words a
+//                  thread covers completely are plain stores, only its first / last partial word is an atomicOr —
+//                  and the finished block goes to its slot with 128-bit stores
+static const u32 ZET = 256, ZEPER = ZBS / ZET;                    // threads per CTA, bytes per thread in a full block
+static const u32 ZHIST_SMEM = 65536;
+static const u32 ZENC_SMEM = ZBS + 1024;
 
-// One CTA (256 threads) per block.
-__global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
+struct ZEncMeta {            // k_zenc_tables -> k_zenc_encode
+    u16 ctab[256];           // code | len << 12 (len 0 = symbol absent)
+    u8  tree[132];           // Huffman tree description
+    u8  mode;                // 0 raw (tree not describable), 1 RLE, 2 Huffman
+    u8  rle_sym;
+    u16 tree_len;
+};
+
+// A full block's thread range is 128 aligned bytes: read with 128-bit loads; ragged tail blocks go byte by byte.
+template <class F> __device__ __forceinline__ void zenc_each(bool full, const u8 *src, u32 t0, u32 t1, F f)
 {
-    __shared__ u32 hist_w[8][256];
-    __shared__ u32 hist[256];
-    __shared__ u32 ctab[256];                  // code | len << 16
-    __shared__ u8  sorted[256], len_of[256], weight[257];
-    __shared__ u32 pre_bits[257];
-    __shared__ u64 smscan[33];
-    __shared__ u32 s_nsym, s_maxbits, s_mode, s_tree_len, s_lit_hdr, s_nstreams, s_payload0;
-    __shared__ u32 s_stream_bytes[4];
+    if (full) {
+        const uint4 *v = (const uint4 *)(src + t0);
+#pragma unroll 2
+        for (int i = 0; i < (int)(ZEPER / 16); i++) {
+            const uint4 x = __ldg(v + i);
+            const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) { f(w[k] & 0xFF); f((w[k] >> 8) & 0xFF); f((w[k] >> 16) & 0xFF); f(w[k] >> 24); }
+        }
+    } else for (u32 i = t0; i < t1; i++) f((u32)src[i]);
+}
+template <class F> __device__ __forceinline__ void zenc_each_rev(bool full, const u8 *src, u32 t0, u32 t1, F f)
+{
+    if (full) {
+        const uint4 *v = (const uint4 *)(src + t0);
+#pragma unroll 2
+        for (int i = (int)(ZEPER / 16) - 1; i >= 0; i--) {
+            const uint4 x = __ldg(v + i);
+            const u32 w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int k = 3; k >= 0; k--) { f(w[k] >> 24); f((w[k] >> 16) & 0xFF); f((w[k] >> 8) & 0xFF); f(w[k] & 0xFF); }
+        }
+    } else for (u32 i = t1; i > t0; i--) f((u32)src[i - 1]);
+}
 
-    extern __shared__ __align__(16) u8 sb[];      // staged block bytes, zpad() layout
-    ZEncBlock &B = A.blk[blockIdx.x];
+__global__ void __launch_bounds__(256, 3) k_zenc_hist(const ZEncArgs A, u16 *hists)
+{
+    extern __shared__ __align__(16) u8 R[];
+    const ZEncBlock &B = A.blk[blockIdx.x];
     const u8 *src = B.src; const u32 n = B.n;
-    u8 *slot = A.slots + (size_t)blockIdx.x * ZSLOT;
-    const u32 tid = threadIdx.x, warp = tid >> 5;
-
-    if (n == 0) { if (tid == 0) { B.type = 0; B.csize = 0; } return; }
-
-    // ---- 1. histogram
-    for (int i = tid; i < 8 * 256; i += 256) (&hist_w[0][0])[i] = 0;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        uint4 *z = (uint4 *)R;
+#pragma unroll
+        for (int i = 0; i < 16; i++) z[tid + 256 * i] = make_uint4(0, 0, 0, 0);
+    }
     __syncthreads();
     {
-        const bool aligned = (((uintptr_t)src) & 15) == 0;
-        u32 nvec = aligned ? n / 16 : 0;
-        const uint4 *v = (const uint4 *)src;
-        for (u32 i = tid; i < nvec; i += 256) {
-            uint4 x = v[i];
-            u32 w[4] = {x.x, x.y, x.z, x.w};
-            u32 *st = (u32 *)(sb + zpad(i * 16));
-            st[0] = w[0]; st[1] = w[1]; st[2] = w[2]; st[3] = w[3];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                atomicAdd(&hist_w[warp][w[k] & 0xFF], 1u); atomicAdd(&hist_w[warp][(w[k] >> 8) & 0xFF], 1u);
-                atomicAdd(&hist_w[warp][(w[k] >> 16) & 0xFF], 1u); atomicAdd(&hist_w[warp][w[k] >> 24], 1u);
-            }
-        }
-        for (u32 i = nvec * 16 + tid; i < n; i += 256) { u8 c = src[i]; sb[zpad(i)] = c; atomicAdd(&hist_w[warp][c], 1u); }
+        const bool full = n == ZBS && (((uintptr_t)src) & 15) == 0;
+        const u32 per = (n + ZET - 1) / ZET;                      // <= 128: a byte counter cannot overflow
+        u32 t0 = tid * per, t1 = t0 + per; if (t0 > n) t0 = n; if (t1 > n) t1 = n;
+        u8 *col = R + lane * 4 + (warp >> 2) * 128 + (warp & 3);  // word = lane (+32), byte = warp & 3: bank == lane
+        zenc_each(full, src, t0, t1, [&](u32 c) { col[c << 8]++; });
     }
     __syncthreads();
-    { u32 h = 0; for (int w = 0; w < 8; w++) h += hist_w[w][tid]; hist[tid] = h; len_of[tid] = 0; weight[tid] = 0; ctab[tid] = 0; }
-    if (tid == 0) { s_nsym = 0; s_mode = 2; weight[256] = 0; }
-    __syncthreads();
-    // ---- 2. rank symbols by (count, symbol): sorted[0] = rarest present symbol
-    if (hist[tid]) {
-        u32 mine = hist[tid], r = 0;
-        for (int j = 0; j < 256; j++) { u32 h = hist[j]; if (h && (h < mine || (h == mine && j < (int)tid))) r++; }
-        sorted[r] = (u8)tid;
-        atomicAdd(&s_nsym, 1u);
+    u32 h = 0;
+    const u32 *row = (const u32 *)(R + tid * 256);
+#pragma unroll 8
+    for (u32 j = 0; j < 64; j++) h = __dp4a(row[(j + tid) & 63], 0x01010101u, h);
+    hists[(size_t)blockIdx.x * 256 + tid] = (u16)h;               // <= 32768
+}
+
+// one thread per block
+__global__ void __launch_bounds__(64) k_zenc_tables(const ZEncArgs A, u32 nblocks, const u16 *hists, ZEncMeta *metas)
+{
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    ZEncMeta &M = metas[b];
+    const u16 *hist = hists + (size_t)b * 256;
+    M.mode = 2; M.tree_len = 0; M.rle_sym = 0;
+    if (A.blk[b].n == 0) { M.mode = 0; return; }
+    // symbols that occur, sorted by (count, symbol): insertion sort (alphabets here are tens of symbols)
+    u8 sorted[256]; u16 cnt[256]; u32 nsym = 0;
+    for (u32 s = 0; s < 256; s++) {
+        const u16 h = hist[s];
+        if (!h) continue;
+        u32 j = nsym++;
+        while (j > 0 && cnt[j - 1] > h) { cnt[j] = cnt[j - 1]; sorted[j] = sorted[j - 1]; j--; }      // equal counts keep symbol order
+        cnt[j] = h; sorted[j] = (u8)s;
     }
-    __syncthreads();
-    const u32 nsym = s_nsym;
-    if (nsym == 1) {                                          // RLE block
-        if (tid == 0) { slot[0] = sorted[0]; B.type = 1; B.csize = 1; }
-        return;
-    }
-    // ---- 3. code lengths (thread 0): two-queue Huffman over the sorted counts, then limit to 11 bits
-    if (tid == 0) {
-        // reuse hist_w as scratch: [0]=leaf weight, [1]=internal weight, [2]=leaf parent, [3]=internal parent, [4]=internal depth
-        u32 *lw = hist_w[0], *iw = hist_w[1], *lp = hist_w[2], *ip = hist_w[3], *idp = hist_w[4];
-        for (u32 i = 0; i < nsym; i++) lw[i] = hist[sorted[i]];
+    for (u32 s = 0; s < 256; s++) M.ctab[s] = 0;
+    if (nsym == 1) { M.mode = 1; M.rle_sym = sorted[0]; return; }
+    // code lengths: two-queue Huffman over the sorted counts, then limit to 11 bits
+    u8 len_of[256], weight[257];
+    for (u32 s = 0; s < 256; s++) { len_of[s] = 0; weight[s] = 0; }
+    weight[256] = 0;
+    u32 maxbits = 0;
+    {
+        u32 iw[256]; u16 lp[256], ip[256]; u8 idp[256];
         u32 li = 0, ii = 0;
-        for (u32 k = 0; k + 1 < nsym; k++) {
+        for (u32 m = 0; m + 1 < nsym; m++) {
             u32 wsum = 0;
             for (int t = 0; t < 2; t++) {
-                bool take_leaf = li < nsym && (ii >= k || lw[li] <= iw[ii]);
-                if (take_leaf) { wsum += lw[li]; lp[li++] = k; } else { wsum += iw[ii]; ip[ii++] = k; }
+                const bool take_leaf = li < nsym && (ii >= m || cnt[li] <= iw[ii]);
+                if (take_leaf) { wsum += cnt[li]; lp[li++] = (u16)m; } else { wsum += iw[ii]; ip[ii++] = (u16)m; }
             }
-            iw[k] = wsum;
+            iw[m] = wsum;
         }
         const u32 root = nsym - 2;
         idp[root] = 0;
-        for (int k = (int)root - 1; k >= 0; k--) idp[k] = idp[ip[k]] + 1;
+        for (int m = (int)root - 1; m >= 0; m--) { const u32 d = idp[ip[m]] + 1u; idp[m] = (u8)(d > 60 ? 60 : d); }
         u32 num[40]; for (int i = 0; i < 40; i++) num[i] = 0;
-        for (u32 i = 0; i < nsym; i++) { u32 d = idp[lp[i]] + 1; if (d > 39) d = 39; num[d]++; }
+        for (u32 i = 0; i < nsym; i++) { u32 d = idp[lp[i]] + 1u; if (d > 39) d = 39; num[d]++; }
         const u32 MAXB = 11;
         for (u32 i = MAXB + 1; i < 40; i++) { num[MAXB] += num[i]; num[i] = 0; }
         u32 total = 0;
@@ -217,62 +256,84 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
             for (u32 i = MAXB - 1; i > 0; i--) if (num[i]) { num[i]--; num[i + 1] += 2; break; }
             total--;
         }
-        u32 idx = 0, maxbits = 0;
+        u32 idx = 0;
         for (u32 l = MAXB; l >= 1; l--) { if (num[l] && !maxbits) maxbits = l; for (u32 c = 0; c < num[l]; c++) len_of[sorted[idx++]] = (u8)l; }
-        s_maxbits = maxbits;
     }
-    __syncthreads();
-    const u32 maxbits = s_maxbits;
-    // ---- 4. canonical codes exactly as the decoder rebuilds them (longer codes first, symbols ascending)
-    if (len_of[tid]) {
-        u32 l = len_of[tid], start = 0;
-        for (int j = 0; j < 256; j++) { u32 lj = len_of[j]; if (lj > l || (lj == l && j < (int)tid)) start += 1u << (maxbits - lj); }
-        ctab[tid] = (start >> (maxbits - l)) | (l << 16);
-        weight[tid] = (u8)(maxbits + 1 - l);
+    // canonical codes exactly as the decoder rebuilds them: longer codes take the numerically lower values, equal
+    // lengths in symbol order
+    {
+        u32 next[13];                                         // next code value (at full maxbits resolution) per length
+        u32 acc = 0;
+        u32 count_len[13]; for (int i = 0; i < 13; i++) count_len[i] = 0;
+        for (u32 s = 0; s < 256; s++) count_len[len_of[s]]++;
+        for (u32 l = maxbits; l >= 1; l--) { next[l] = acc; acc += count_len[l] << (maxbits - l); }
+        for (u32 s = 0; s < 256; s++) {
+            const u32 l = len_of[s];
+            if (!l) continue;
+            M.ctab[s] = (u16)((next[l] >> (maxbits - l)) | (l << 12));
+            next[l] += 1u << (maxbits - l);
+            weight[s] = (u8)(maxbits + 1 - l);
+        }
     }
-    __syncthreads();
-    // ---- 5. tree description into a scratch area at the end of the slot (thread 0)
-    u8 *tree_tmp = slot + ZBS + 256;                          // <= 130 bytes
-    if (tid == 0) {
-        int last_sym = 255; while (last_sym > 0 && !weight[last_sym]) last_sym--;
-        int nlisted = last_sym;                               // weights of symbols 0 .. last_sym-1; the last one is implied
-        u32 fse = fse_compress_weights(weight, nlisted, tree_tmp + 1, 127);
-        u32 direct = nlisted <= 128 ? 1 + (nlisted + 1) / 2 : 0xFFFFFFFFu;
-        if (fse && fse < 128 && 1 + fse < direct) { tree_tmp[0] = (u8)fse; s_tree_len = 1 + fse; }
-        else if (direct != 0xFFFFFFFFu) {
-            tree_tmp[0] = (u8)(127 + nlisted);
-            for (int i = 0; i < nlisted; i += 2) tree_tmp[1 + i / 2] = (u8)((weight[i] << 4) | (i + 1 < nlisted ? weight[i + 1] : 0));
-            s_tree_len = direct;
-        } else s_mode = 0;                                    // cannot describe the tree: raw block
-        s_nstreams = n <= 1023 ? 1 : 4;
-    }
-    __syncthreads();
-    // ---- 6. exact size of every stream
-    const u32 nstreams = s_nstreams, tps = 256 / nstreams;    // threads per stream
+    // tree description
+    int last_sym = 255; while (last_sym > 0 && !weight[last_sym]) last_sym--;
+    const int nlisted = last_sym;                             // weights of symbols 0 .. last_sym-1; the last one is implied
+    u8 tmp[132];
+    const u32 fse = fse_compress_weights(weight, nlisted, tmp + 1, 127);
+    const u32 direct = nlisted <= 128 ? 1 + (nlisted + 1) / 2 : 0xFFFFFFFFu;
+    if (fse && fse < 128 && 1 + fse < direct) { tmp[0] = (u8)fse; M.tree_len = (u16)(1 + fse); }
+    else if (direct != 0xFFFFFFFFu) {
+        tmp[0] = (u8)(127 + nlisted);
+        for (int i = 0; i < nlisted; i += 2) tmp[1 + i / 2] = (u8)((weight[i] << 4) | (i + 1 < nlisted ? weight[i + 1] : 0));
+        M.tree_len = (u16)direct;
+    } else { M.mode = 0; return; }                            // cannot describe the tree: raw block
+    for (u32 i = 0; i < M.tree_len; i++) M.tree[i] = tmp[i];
+}
+
+__global__ void __launch_bounds__(256) k_zenc_encode(const ZEncArgs A, const ZEncMeta *metas)
+{
+    extern __shared__ __align__(16) u8 R[];   // the block being assembled
+    __shared__ u32 ctab[256];                  // code | len << 16
+    __shared__ u32 pre_bits[257];
+    __shared__ u64 smscan[33];
+    __shared__ u32 s_mode, s_lit_hdr, s_payload0;
+    __shared__ u32 s_stream_bytes[4];
+
+    ZEncBlock &B = A.blk[blockIdx.x];
+    const ZEncMeta &M = metas[blockIdx.x];
+    const u8 *src = B.src; const u32 n = B.n;
+    u8 *slot = A.slots + (size_t)blockIdx.x * ZSLOT;
+    const u32 tid = threadIdx.x;
+
+    if (n == 0 || M.mode == 0) { if (tid == 0) { B.type = 0; B.csize = n; } return; }
+    if (M.mode == 1) { if (tid == 0) { slot[0] = M.rle_sym; B.type = 1; B.csize = 1; } return; }
+    { const u32 e = M.ctab[tid]; ctab[tid] = (e & 0xFFF) | ((e >> 12) << 16); }
+    if (tid == 0) s_mode = 2;
+    const u32 tree_len = M.tree_len;
+
+    // my symbols: stream k = [k*seg, ...), split evenly over the stream's threads (same split in both passes)
+    const u32 nstreams = n <= 1023 ? 1 : 4, tps = ZET / nstreams;
     const u32 seg = nstreams == 4 ? (n + 3) / 4 : n;
     const u32 k = tid / tps, q = tid % tps;
     const u32 sbeg = k * seg, send = (k == nstreams - 1) ? n : (sbeg + seg < n ? sbeg + seg : n);
     const u32 slen = send > sbeg ? send - sbeg : 0;
     const u32 per = (slen + tps - 1) / tps;
     u32 t0 = sbeg + q * per, t1 = t0 + per; if (t0 > send) t0 = send; if (t1 > send) t1 = send;
+    const bool full = n == ZBS && (((uintptr_t)src) & 15) == 0;    // then t0 = 128 * tid, t1 = t0 + 128
+    __syncthreads();
+    // ---- exact size of every stream
     u32 bits = 0;
-    for (u32 i = t0; i < t1;) {
-        if (!(i & 3) && i + 4 <= t1) {                        // aligned word of four symbols
-            const u32 x = *(const u32 *)(sb + zpad(i));
-            bits += (ctab[x & 0xFF] >> 16) + (ctab[(x >> 8) & 0xFF] >> 16) + (ctab[(x >> 16) & 0xFF] >> 16) + (ctab[x >> 24] >> 16);
-            i += 4;
-        } else { bits += ctab[sb[zpad(i)]] >> 16; i++; }
-    }
+    zenc_each(full, src, t0, t1, [&](u32 c) { bits += ctab[c] >> 16; });
     u64 total_bits;
-    u64 pre = block_excl_scan(bits, &total_bits, smscan);
+    const u64 pre = block_excl_scan(bits, &total_bits, smscan);
     pre_bits[tid] = (u32)pre; if (tid == 255) pre_bits[256] = (u32)total_bits;
     __syncthreads();
-    if (tid < nstreams) { u32 b = pre_bits[(tid + 1) * tps] - pre_bits[tid * tps]; s_stream_bytes[tid] = b / 8 + 1; }
+    if (tid < nstreams) { const u32 b = pre_bits[(tid + 1) * tps] - pre_bits[tid * tps]; s_stream_bytes[tid] = b / 8 + 1; }
     __syncthreads();
-    if (tid == 0 && s_mode == 2) {
-        u32 payload = s_tree_len + (nstreams == 4 ? 6 : 0);
+    if (tid == 0) {
+        u32 payload = tree_len + (nstreams == 4 ? 6 : 0);
         for (u32 j = 0; j < nstreams; j++) payload += s_stream_bytes[j];
-        u32 lh = nstreams == 1 ? 3 : ((n <= 16383 && payload <= 16383) ? 4 : 5);
+        const u32 lh = nstreams == 1 ? 3 : ((n <= 16383 && payload <= 16383) ? 4 : 5);
         if (nstreams == 1 && payload > 1023) s_mode = 0;
         if (lh + payload + 1 >= n) s_mode = 0;                // no gain: raw block
         if (n < 4 * 4 && nstreams == 4) s_mode = 0;
@@ -280,51 +341,59 @@ __global__ void __launch_bounds__(256) k_zenc_block(const ZEncArgs A)
     }
     __syncthreads();
     if (s_mode == 0) { if (tid == 0) { B.type = 0; B.csize = n; } return; }
-    const u32 lit_hdr = s_lit_hdr, tree_len = s_tree_len, payload = s_payload0;
+    const u32 lit_hdr = s_lit_hdr, payload = s_payload0;
     const u32 content = lit_hdr + payload + 1;
-    // ---- 7. zero the words we will OR into, write the headers, then every thread ORs its codes in
-    u32 *slotw = (u32 *)slot;
-    for (u32 i = tid; i < (content + 3) / 4 + 1; i += 256) slotw[i] = 0;
+    // ---- assemble the block in shared memory
+    u32 *outw = (u32 *)R;
+    for (u32 i = tid; i < content / 4 + 2; i += ZET) outw[i] = 0;
     __syncthreads();
     if (tid == 0) {
         // Literals_Section_Header: type 2 (compressed), size format by stream count / sizes
-        if (nstreams == 1) { u32 v = 2 | (0 << 2) | (n << 4) | (payload << 14); slot[0] = (u8)v; slot[1] = (u8)(v >> 8); slot[2] = (u8)(v >> 16); }
-        else if (lit_hdr == 4) { u32 v = 2 | (2 << 2) | (n << 4) | (payload << 18); slot[0] = (u8)v; slot[1] = (u8)(v >> 8); slot[2] = (u8)(v >> 16); slot[3] = (u8)(v >> 24); }
-        else { u64 v = 2 | (3 << 2) | ((u64)n << 4) | ((u64)payload << 22); for (int i = 0; i < 5; i++) slot[i] = (u8)(v >> (8 * i)); }
-        for (u32 i = 0; i < tree_len; i++) slot[lit_hdr + i] = tree_tmp[i];
+        if (nstreams == 1) { u32 v = 2 | (0 << 2) | (n << 4) | (payload << 14); R[0] = (u8)v; R[1] = (u8)(v >> 8); R[2] = (u8)(v >> 16); }
+        else if (lit_hdr == 4) { u32 v = 2 | (2 << 2) | (n << 4) | (payload << 18); R[0] = (u8)v; R[1] = (u8)(v >> 8); R[2] = (u8)(v >> 16); R[3] = (u8)(v >> 24); }
+        else { u64 v = 2 | (3 << 2) | ((u64)n << 4) | ((u64)payload << 22); for (int i = 0; i < 5; i++) R[i] = (u8)(v >> (8 * i)); }
         if (nstreams == 4) {
-            u8 *jt = slot + lit_hdr + tree_len;
+            u8 *jt = R + lit_hdr + tree_len;
             for (int j = 0; j < 3; j++) { jt[2 * j] = (u8)s_stream_bytes[j]; jt[2 * j + 1] = (u8)(s_stream_bytes[j] >> 8); }
         }
-        slot[content - 1] = 0;                                // Sequences_Section_Header: 0 sequences
-        B.type = 2; B.csize = content;
+        R[content - 1] = 0;                                   // Sequences_Section_Header: 0 sequences
     }
+    if (tid < tree_len) R[lit_hdr + tid] = M.tree[tid];
     __syncthreads();
     {
         u32 byte_base = lit_hdr + tree_len + (nstreams == 4 ? 6 : 0);
         for (u32 j = 0; j < k; j++) byte_base += s_stream_bytes[j];
         // symbols later in the stream sit at lower bit positions: my first bit = bits of all threads after me in my stream
-        const u32 stream_bits = pre_bits[(k + 1) * tps] - pre_bits[k * tps];
-        u32 bitpos = pre_bits[(k + 1) * tps] - (pre_bits[tid] + bits);
-        const u64 abs0 = (u64)byte_base * 8;
+        u64 ab = (u64)byte_base * 8 + (pre_bits[(k + 1) * tps] - (pre_bits[tid] + bits));     // absolute bit position of my next bit
         u64 acc = 0; u32 fill = 0;
-        for (u32 i = t1; i > t0; i--) {
-            u32 e = ctab[sb[zpad(i - 1)]];
-            acc |= (u64)(e & 0xFFFF) << fill; fill += e >> 16;
-            if (fill >= 32) {
-                u64 ab = abs0 + bitpos; u32 wi = (u32)(ab >> 5), sh = (u32)(ab & 31); u32 v = (u32)acc;
-                atomicOr(&slotw[wi], v << sh); if (sh) atomicOr(&slotw[wi + 1], v >> (32 - sh));
-                acc >>= 32; fill -= 32; bitpos += 32;
+        bool aligned = (ab & 31) == 0;
+        auto flush32 = [&]() {                                // acc holds >= 32 bits
+            if (aligned) { outw[ab >> 5] = (u32)acc; acc >>= 32; fill -= 32; ab += 32; }
+            else {                                            // first partial word: top it up, then run aligned
+                const u32 sh = (u32)(ab & 31), take = 32 - sh;
+                atomicOr(&outw[ab >> 5], (u32)acc << sh);
+                acc >>= take; fill -= take; ab += take; aligned = true;
             }
-        }
+        };
+        zenc_each_rev(full, src, t0, t1, [&](u32 c) {
+            const u32 e = ctab[c];
+            acc |= (u64)(e & 0xFFFF) << fill; fill += e >> 16;
+            if (fill >= 32) flush32();
+        });
         if (q == 0) { acc |= 1ull << fill; fill++; }          // end mark right above the first symbol's code
-        (void)stream_bits;
-        while (fill) {
-            u32 take = fill > 32 ? 32 : fill;
-            u64 ab = abs0 + bitpos; u32 wi = (u32)(ab >> 5), sh = (u32)(ab & 31); u32 v = (u32)(acc & (take == 32 ? 0xFFFFFFFFull : ((1ull << take) - 1)));
-            if (v) { atomicOr(&slotw[wi], v << sh); if (sh && (v >> (32 - sh))) atomicOr(&slotw[wi + 1], v >> (32 - sh)); }
-            acc >>= take; fill -= take; bitpos += take;
+        while (fill >= 32) flush32();
+        if (fill) {                                           // remainder (< 32 bits): may still straddle a word when not aligned yet
+            const u32 sh = (u32)(ab & 31);
+            const u32 v = (u32)acc & ((1u << fill) - 1);
+            atomicOr(&outw[ab >> 5], v << sh);
+            if (sh && sh + fill > 32) atomicOr(&outw[(ab >> 5) + 1], v >> (32 - sh));
         }
+    }
+    __syncthreads();
+    {
+        uint4 *d = (uint4 *)slot; const uint4 *sv = (const uint4 *)R;
+        for (u32 i = tid; i < (content + 15) / 16; i += ZET) d[i] = sv[i];
+        if (tid == 0) { B.type = 2; B.csize = content; }
     }
 }
 
@@ -347,43 +416,64 @@ __global__ void __launch_bounds__(256) k_zenc_gather(const ZGatherArgs A)
         u32 bh = (B.last & 1) | (B.type << 1) | (size_field << 3);
         dst[0] = (u8)bh; dst[1] = (u8)(bh >> 8); dst[2] = (u8)(bh >> 16);
     }
+    // content: 128-bit stores aligned to the destination, each fed by one unaligned 16-byte read (load_bytes16, naf_dec.cu)
     const u8 *from = B.type == 0 ? B.src : A.slots + (size_t)blockIdx.x * ZSLOT;
-    for (u32 i = threadIdx.x; i < B.csize; i += 256) dst[3 + i] = from[i];
+    u8 *d0 = dst + 3; const u32 nbytes = B.csize;
+    const u32 head = min(nbytes, (u32)((16 - ((uintptr_t)d0 & 15)) & 15));
+    if (threadIdx.x < head) d0[threadIdx.x] = from[threadIdx.x];
+    const u32 nv = (nbytes - head) / 16, done = head + nv * 16;
+    for (u32 i = threadIdx.x; i < nv; i += 256) *(uint4 *)(d0 + head + 16 * i) = load_bytes16(from + head + 16 * i);
+    if (threadIdx.x < nbytes - done) d0[done + threadIdx.x] = from[done + threadIdx.x];
 }
 
 static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
 {
     const size_t ns = b.src.size();
-    std::vector<ZEncBlock> blocks;
+    // block list: stream s contributes ceil(n / ZBS) blocks (an empty stream: one empty raw last block); built on the device
     b.first_block.assign(ns + 1, 0);
-    for (size_t s = 0; s < ns; s++) {
-        b.first_block[s] = (u32)blocks.size();
-        u64 nb = b.n[s] ? (b.n[s] + ZBS - 1) / ZBS : 1;         // an empty stream is one empty raw last block
-        for (u64 k = 0; k < nb; k++) {
-            ZEncBlock e; memset(&e, 0, sizeof e);
-            e.src = b.src[s] + k * ZBS; e.n = (u32)(b.n[s] - k * ZBS < ZBS ? b.n[s] - k * ZBS : ZBS); e.stream = (u32)s; e.last = k + 1 == nb;
-            blocks.push_back(e);
-        }
-    }
-    b.first_block[ns] = (u32)blocks.size();
-    b.nblocks = (u32)blocks.size();
+    for (size_t s = 0; s < ns; s++) b.first_block[s + 1] = b.first_block[s] + (u32)(b.n[s] ? (b.n[s] + ZBS - 1) / ZBS : 1);
+    b.nblocks = b.first_block[ns];
     b.d_blocks = ex.alloc<ZEncBlock>(b.nblocks);
     b.d_slots = ex.alloc<u8>((size_t)b.nblocks * ZSLOT);
-    ex.upload(b.d_blocks, blocks.data(), sizeof(ZEncBlock) * b.nblocks);
-    CUDA_TRY(cudaStreamSynchronize(ex.stream));                 // `blocks` is a local vector
+    {
+        ZEncStreamTab tab;
+        if (ns > 8) fail(NAFGPU_E_ARG, "too many streams in one compression batch\n");
+        memset(&tab, 0, sizeof tab);
+        for (size_t s = 0; s < ns; s++) { tab.src[s] = b.src[s]; tab.n[s] = b.n[s]; tab.first[s] = b.first_block[s]; }
+        tab.first[ns] = b.nblocks; tab.ns = (u32)ns;
+        ZEncBlock *blk = b.d_blocks;
+        ex.for_each(b.nblocks, [=] __device__ (size_t i) {
+            u32 s = 0;
+            while (s + 1 < tab.ns && (u32)i >= tab.first[s + 1]) s++;
+            const u64 k = i - tab.first[s], off = k * ZBS, left = tab.n[s] - (tab.n[s] < off ? tab.n[s] : off);
+            ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < ZBS ? left : ZBS); e.stream = s; e.last = (u32)i + 1 == tab.first[s + 1];
+            e.type = 0; e.csize = 0;
+            blk[i] = e;
+        }, "zenc_init_blocks");
+    }
     ZEncArgs A{b.d_blocks, b.d_slots};
-    CUDA_TRY(cudaFuncSetAttribute(k_zenc_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZSTAGE_BYTES));
-    KLAUNCH(ex, "k_zenc_block", k_zenc_block<<<b.nblocks, 256, ZSTAGE_BYTES, ex.stream>>>(A));
+    u16 *d_hists = ex.alloc<u16>((size_t)b.nblocks * 256);
+    ZEncMeta *d_metas = ex.alloc<ZEncMeta>(b.nblocks);
+    CUDA_TRY(cudaFuncSetAttribute(k_zenc_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZHIST_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(k_zenc_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZENC_SMEM));
+    KLAUNCH(ex, "k_zenc_hist", k_zenc_hist<<<b.nblocks, 256, ZHIST_SMEM, ex.stream>>>(A, d_hists));
+    KLAUNCH(ex, "k_zenc_tables", k_zenc_tables<<<(b.nblocks + 63) / 64, 64, 0, ex.stream>>>(A, b.nblocks, d_hists, d_metas));
+    KLAUNCH(ex, "k_zenc_encode", k_zenc_encode<<<b.nblocks, 256, ZENC_SMEM, ex.stream>>>(A, d_metas));
     b.d_off = ex.alloc<u64>(b.nblocks + 2);
     const ZEncBlock *db = b.d_blocks;
     exclusive_scan(ex, [db] __device__ (size_t i) { return (u64)db[i].csize + 3; }, b.nblocks, b.d_off);
-    // frame sizes: one small download of the offsets at the stream boundaries
-    std::vector<u64> h_off(b.nblocks + 1);
-    if (ns <= 8) {
-        for (size_t s = 0; s <= ns; s++) ex.download(&h_off[b.first_block[s]], b.d_off + b.first_block[s], 8);
-    } else ex.download(h_off.data(), b.d_off, (b.nblocks + 1) * 8);
+    // frame sizes: the offsets at the stream boundaries, one small download
+    u64 *d_fs = ex.alloc<u64>(16);
+    {
+        u32 fb[9]; for (size_t s = 0; s <= ns; s++) fb[s] = b.first_block[s];
+        ZEncFirstBlocks fbs; memcpy(fbs.v, fb, sizeof fb);
+        const u64 *off = b.d_off; const u32 nss = (u32)ns;
+        ex.for_each(ns, [=] __device__ (size_t s) { if (s < nss) d_fs[s] = 6 + off[fbs.v[s + 1]] - off[fbs.v[s]]; }, "zenc_frame_sizes");
+    }
+    u64 h_fs[8];
+    ex.download(h_fs, d_fs, ns * 8);
     b.frame_size.assign(ns, 0); b.dest.assign(ns, nullptr);
-    for (size_t s = 0; s < ns; s++) b.frame_size[s] = 6 + h_off[b.first_block[s + 1]] - h_off[b.first_block[s]];
+    for (size_t s = 0; s < ns; s++) b.frame_size[s] = h_fs[s];
     (void)ctx;
 }
 

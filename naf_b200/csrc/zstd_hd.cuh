@@ -26,6 +26,19 @@ namespace nafz {
 typedef uint8_t u8; typedef uint16_t u16; typedef uint32_t u32; typedef uint64_t u64;
 typedef int32_t i32; typedef int64_t i64;
 
+// What the host walk knows about a block (32 bytes: a file of 100 k blocks uploads 3 MB, not the full records)
+struct ZBlockHead {
+    u64 src;            // offset of the block content in the input buffer
+    u64 out_base;       // first_in_stream: arena offset where this stream's output starts
+    u32 csize;          // content bytes (raw: size, RLE: 1, compressed: Block_Size)
+    u32 rsize;          // raw / RLE: regenerated size
+    u32 frame_first_blk;// index of the first block of my frame
+    u8  type;           // 0 raw, 1 RLE, 2 compressed
+    u8  first_in_frame;
+    u8  first_in_stream;
+    u8  stream;
+};
+
 enum : int {
     Z_OK = 0,
     Z_ERR_TRUNCATED = 1, Z_ERR_LIT_HEADER = 2, Z_ERR_HUF_TREE = 3, Z_ERR_HUF_STREAM = 4, Z_ERR_FSE_HEADER = 5,
@@ -286,33 +299,94 @@ HD bool huf_build_table(u16 *table, const u8 *weights, int nw, int max_bits)
     return true;
 }
 
+// Backward bit reader for the Huffman streams, built so that every byte of the stream crosses the memory system
+// once: the compressed bytes are fetched as ALIGNED 16-byte chunks into a four-register queue and enter a 64-bit
+// bit buffer 32 bits at a time.  (BackBits above re-reads two aligned 8-byte words around its cursor on every
+// reload: with thousands of streams in flight per SM those lines do not survive in L1 and each reload becomes two
+// 32-byte sector requests to L2 for two or three useful bytes.)
+struct BackBitsQ {
+    u64 bb; int nb;              // next bit = MSB of bb; nb valid bits (32 < nb <= 64 after refill())
+    i64 left;                    // payload bits not yet consumed; < 0 = read past the start
+    const u8 *src;               // stream start: chunks entirely below it are not fetched (read as zero)
+    const u32 *cp;               // lowest 16-byte chunk fetched so far
+    u32 w0, w1, w2, w3; int qn;  // queued aligned words, the next one is w3
+    u32 hi, sh;                  // aligned word holding the cursor, cursor misalignment in bits
+
+    HD void fetch()
+    {
+        cp -= 4;
+        if ((uintptr_t)(cp + 4) > (uintptr_t)src) {
+#ifdef __CUDA_ARCH__
+            const uint4 v = *(const uint4 *)cp; w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+#else
+            w0 = cp[0]; w1 = cp[1]; w2 = cp[2]; w3 = cp[3];
+#endif
+        } else w0 = w1 = w2 = w3 = 0;
+        qn = 4;
+    }
+    HD u32 pop() { if (qn == 0) fetch(); const u32 x = w3; w3 = w2; w2 = w1; w1 = w0; qn--; return x; }
+    HD bool init(const u8 *s, size_t n)
+    {
+        src = s; bb = 0; nb = 0; left = 0; qn = 0; hi = 0; sh = 0; w0 = w1 = w2 = w3 = 0; cp = nullptr;
+        if (n == 0) return false;
+        const u8 last = s[n - 1];
+        if (last == 0) return false;
+        const int pad = 8 - hibit(last);          // zero padding bits + the end-mark bit
+        const u8 *p = s + n - 8;                  // the top 8 bytes (may start below s for tiny streams: don't-care bits)
+        bb = BackBits::load64(p) << pad; nb = 64 - pad; left = (i64)n * 8 - pad;
+        const u32 a = (u32)((uintptr_t)p & 3);
+        sh = a * 8;
+        const u8 *wa = p - a;                     // aligned word holding the cursor
+        if (a) hi = *(const u32 *)wa;
+        const u8 *na = wa - 4;                    // next aligned word below the cursor
+        const u32 j = (u32)(((uintptr_t)na >> 2) & 3);
+        cp = (const u32 *)((uintptr_t)na & ~(uintptr_t)15) + 4;
+        fetch();                                  // chunk holding `na`; its words above index j are not part of the queue
+        for (u32 k = j; k < 3; k++) { w3 = w2; w2 = w1; w1 = w0; }
+        qn = (int)j + 1;
+        return true;
+    }
+    HD void refill()
+    {
+        if (nb <= 32) {
+            const u32 lo = pop();
+            const u32 v = sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+            hi = lo;
+            bb |= (u64)v << (32 - nb); nb += 32;
+        }
+    }
+    HD u32 peek(int n) const { return (u32)(bb >> (64 - n)); }      // 1 <= n <= 32
+    HD void skip(int n) { bb <<= n; nb -= n; left -= n; }
+    HD bool exact() const { return left == 0; }
+};
+
 // One Huffman-coded stream -> nout symbols.  Replaces decompress/huf_decompress.c:350
 // HUF_decompress4X1_usingDTable_internal_body's per-stream loop (and the 1X1 variant :285).
 HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t n, u8 *dst, size_t nout)
 {
-    BackBits b;
+    BackBitsQ b;
     if (!b.init(src, n)) return false;
     size_t i = 0;
     // head: byte stores until dst is 16-byte aligned
     while (i < nout && (((uintptr_t)(dst + i)) & 15)) {
-        b.reload();
-        u32 e = table[b.peek(max_bits)];
+        b.refill();
+        const u32 e = table[b.peek(max_bits)];
         dst[i++] = (u8)e; b.skip((int)(e >> 8));
     }
-    // body: 16 symbols per 128-bit store; one reload per 4 symbols (4 x 11 bits <= 57 available)
+    // body: 16 symbols per 128-bit store; one refill per 2 symbols (2 x 11 bits <= the 33 bits refill() guarantees)
     for (; i + 16 <= nout; i += 16) {
         u32 w[4];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int k = 0; k < 4; k++) {
-            b.reload();
             u32 v = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
             for (int j = 0; j < 4; j++) {
-                u32 e = table[b.peek(max_bits)];
+                if (!(j & 1)) b.refill();
+                const u32 e = table[b.peek(max_bits)];
                 v |= (e & 0xFF) << (8 * j); b.skip((int)(e >> 8));
             }
             w[k] = v;
@@ -324,8 +398,8 @@ HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t 
 #endif
     }
     for (; i < nout; i++) {
-        b.reload();
-        u32 e = table[b.peek(max_bits)];
+        b.refill();
+        const u32 e = table[b.peek(max_bits)];
         dst[i] = (u8)e; b.skip((int)(e >> 8));
     }
     return b.exact();

@@ -11,6 +11,7 @@ struct HostExec {
     ~HostExec() { for (void *p : owned) free(p); }
     template <class T> T *alloc(size_t count) { void *p = calloc(count ? count : 1, sizeof(T)); owned.push_back(p); return (T *)p; }
     void upload(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
+    void upload_staged(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
     void download(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
     void zero(void *p, size_t n) { memset(p, 0, n); }
     template <class F> void for_each(size_t n, F f, const char * = nullptr, int = 0) { launches++; for (size_t i = 0; i < n; i++) f(i); }
