@@ -181,8 +181,8 @@ __device__ __forceinline__ u8 base_at(const TextArgs &A, u64 bi)
     return c;
 }
 
-static const int WT_THREADS = 256, WT_ITERS = 4, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 16 KB of text per CTA
-static const int WT_MAXREC = 1024;    // records staged in shared memory per tile (more than that: read them from HBM)
+static const int WT_THREADS = 256, WT_ITERS = 1, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 4 KB of text per CTA: one 16-byte chunk per thread
+static const int WT_MAXREC = 128;     // records staged in shared memory per tile (more than that: read them from HBM)
 
 struct RecS { u64 out0, L, sbase; u32 id_s, id_len, cm_s, cm_len; };
 
@@ -310,43 +310,29 @@ __device__ __noinline__ void wt_chunk_generic(const TextArgs &A, const RecS *rec
 //           qualities (about three quarters of them) is produced on the spot; the others are only listed
 //   pass 2  the listed chunks are shared out again over all threads, so that the long generic composer runs in
 //           full warps instead of a few lanes per warp
-__global__ void __launch_bounds__(WT_THREADS) k_write_text(const TextArgs A)
+// record holding the first byte of every tile (+ one past the end): one binary search per tile, all tiles at once
+__global__ void k_tile_first(const u64 *out_start, u64 N, u64 ntiles, u32 *tile_first)
+{
+    const u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) return;
+    const u64 q = t * WT_TILE;
+    u64 lo = 0, hi = N;                          // invariant: out_start[lo] <= q < out_start[hi]   (out_start[N] = total > q unless t == ntiles)
+    while (hi - lo > 1) { const u64 mid = (lo + hi) >> 1; if (out_start[mid] <= q) lo = mid; else hi = mid; }
+    tile_first[t] = (u32)lo;
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 5) k_write_text(const __grid_constant__ TextArgs A, const u32 *tile_first)
 {
     __shared__ RecS recs[WT_MAXREC];
-    __shared__ u64 s_first; __shared__ u32 s_nrec, s_nslow;
+    __shared__ u32 s_nslow;
     __shared__ u16 slow[WT_THREADS * WT_ITERS];
     const u64 tile0 = (u64)blockIdx.x * WT_TILE;
     const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
-
-    if (threadIdx.x < 32) {
-        // largest i in [0, N) with out_start[i] <= tile0
-        u64 lo = 0, hi = A.N;                    // invariant: out_start[lo] <= tile0 < out_start[hi]
-        while (hi - lo > 1) {
-            u64 span = hi - lo, step = (span + 31) / 32;
-            u64 probe = lo + step * (threadIdx.x + 1);
-            bool le = probe < hi && A.out_start[probe] <= tile0;
-            unsigned m = __ballot_sync(0xFFFFFFFFu, le);
-            int cnt = __popc(m);                 // probes are ascending, so `le` is a prefix
-            u64 nlo = lo + step * cnt, nhi = lo + step * (cnt + 1);
-            lo = nlo; if (nhi < hi) hi = nhi;
-        }
-        if (threadIdx.x == 0) { s_first = lo; s_nslow = 0; }
-    }
-    __syncthreads();
-    const u64 first = s_first;
-    // records first, first+1, ... that start before tile1
-    {
-        u32 cnt = 0;
-        for (u64 base = first;; base += WT_THREADS) {
-            u64 i = base + threadIdx.x;
-            bool in = i < A.N && (i == first || A.out_start[i] < tile1);
-            if (in) { u32 k = (u32)(i - first); if (k < WT_MAXREC) rec_fetch(A, i, recs[k]); }
-            int any = __syncthreads_count(in);
-            cnt += any;
-            if (any < WT_THREADS || cnt >= WT_MAXREC) break;
-        }
-        if (threadIdx.x == 0) s_nrec = cnt;
-    }
+    // records first .. last intersect this tile (last = the record holding the first byte of the next tile)
+    const u64 first = tile_first[blockIdx.x];
+    const u32 s_nrec = tile_first[blockIdx.x + 1] - (u32)first + 1;
+    if (threadIdx.x == 0) s_nslow = 0;
+    if (threadIdx.x < s_nrec && threadIdx.x < WT_MAXREC) rec_fetch(A, first + threadIdx.x, recs[threadIdx.x]);
     __syncthreads();
     const u32 nrec_total = s_nrec;
     const u32 nrec = nrec_total < (u32)WT_MAXREC ? nrec_total : (u32)WT_MAXREC;     // staged records: first .. first+nrec-1
@@ -628,8 +614,11 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     u8 *d_text = ex.alloc<u8>(total + 64);
     A.out = d_text;
     {
+        if (NR >= 0xFFFFFFFFull) fail(NAFGPU_E_UNSUPPORTED, "more than 2^32 - 1 records in one file are not supported by this build\n");
         u64 ntiles = (total + WT_TILE - 1) / WT_TILE;
-        KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A));
+        u32 *tile_first = ex.alloc<u32>(ntiles + 2);
+        KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(d_out_start, NR, ntiles, tile_first));
+        KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A, tile_first));
     }
     if (view == NAFGPU_OUT_CHARCOUNT) {
         unsigned long long *counts = ex.alloc<unsigned long long>(256);

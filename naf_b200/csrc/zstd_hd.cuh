@@ -308,26 +308,28 @@ struct BackBitsQ {
     u64 bb; int nb;              // next bit = MSB of bb; nb valid bits (32 < nb <= 64 after refill())
     i64 left;                    // payload bits not yet consumed; < 0 = read past the start
     const u8 *src;               // stream start: chunks entirely below it are not fetched (read as zero)
-    const u32 *cp;               // lowest 16-byte chunk fetched so far
+    const u32 *cp;               // lowest 16-byte chunk requested so far
     u32 w0, w1, w2, w3; int qn;  // queued aligned words, the next one is w3
+    u32 n0, n1, n2, n3;          // the chunk below the queue, requested one queue ahead: its load latency is covered by
+                                 // the decoding of the four queued words instead of stalling the warp
     u32 hi, sh;                  // aligned word holding the cursor, cursor misalignment in bits
 
-    HD void fetch()
+    HD void request()
     {
         cp -= 4;
         if ((uintptr_t)(cp + 4) > (uintptr_t)src) {
 #ifdef __CUDA_ARCH__
-            const uint4 v = *(const uint4 *)cp; w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w;
+            const uint4 v = *(const uint4 *)cp; n0 = v.x; n1 = v.y; n2 = v.z; n3 = v.w;
 #else
-            w0 = cp[0]; w1 = cp[1]; w2 = cp[2]; w3 = cp[3];
+            n0 = cp[0]; n1 = cp[1]; n2 = cp[2]; n3 = cp[3];
 #endif
-        } else w0 = w1 = w2 = w3 = 0;
-        qn = 4;
+        } else n0 = n1 = n2 = n3 = 0;
     }
+    HD void fetch() { w0 = n0; w1 = n1; w2 = n2; w3 = n3; qn = 4; request(); }
     HD u32 pop() { if (qn == 0) fetch(); const u32 x = w3; w3 = w2; w2 = w1; w1 = w0; qn--; return x; }
     HD bool init(const u8 *s, size_t n)
     {
-        src = s; bb = 0; nb = 0; left = 0; qn = 0; hi = 0; sh = 0; w0 = w1 = w2 = w3 = 0; cp = nullptr;
+        src = s; bb = 0; nb = 0; left = 0; qn = 0; hi = 0; sh = 0; w0 = w1 = w2 = w3 = 0; n0 = n1 = n2 = n3 = 0; cp = nullptr;
         if (n == 0) return false;
         const u8 last = s[n - 1];
         if (last == 0) return false;
@@ -341,7 +343,7 @@ struct BackBitsQ {
         const u8 *na = wa - 4;                    // next aligned word below the cursor
         const u32 j = (u32)(((uintptr_t)na >> 2) & 3);
         cp = (const u32 *)((uintptr_t)na & ~(uintptr_t)15) + 4;
-        fetch();                                  // chunk holding `na`; its words above index j are not part of the queue
+        request(); fetch();                       // chunk holding `na` (its words above index j are not part of the queue) + the one below
         for (u32 k = j; k < 3; k++) { w3 = w2; w2 = w1; w1 = w0; }
         qn = (int)j + 1;
         return true;
