@@ -168,6 +168,41 @@ int nafgpu_zstd_compress(nafgpu_ctx *ctx, const uint8_t *src, size_t n, int wind
 int nafgpu_split(nafgpu_ctx *ctx, const uint8_t *text, size_t n, const nafgpu_enc_opts *opts,
                  const uint8_t *streams[6], size_t sizes[6], nafgpu_enc_info *info);
 
+/* ---- one .naf from several shards: the multi-GPU form of nafgpu_encode ----
+ * Every rank encodes a record-aligned piece of the text; one small all-gather of nafgpu_shard_counts in between
+ * lets each rank finish on its own (4-bit nibble parity, mask runs that cross shard boundaries, Last_Block), and
+ * rank 0 concatenates the zstd *blocks* of all ranks into ONE frame per stream -- the reference unnaf stops after
+ * the first frame of the sequence / quality streams (zstd_decompress.c:2129-2140, output.c:640).
+ *   nafgpu_shard_begin    parse + split + pack this shard (text: host pointer, or device pointer if text_on_device)
+ *   (caller)              all-gather the counts, derive this shard's nafgpu_shard_link (naf_b200/sharded.py: link_for)
+ *   nafgpu_shard_finish   nibble shift, boundary mask runs, zstd blocks; raw[k] / body[k] = uncompressed / compressed
+ *                         bytes of stream k as this shard contributes them (body = blocks only: no frame header)
+ *   nafgpu_shard_fetch    copy the blocks of stream k to dst (host or device memory, cudaMemcpyDefault)
+ *   (caller)              rank 0 writes header + per stream VLE sizes, frame header, all ranks' blocks in rank order */
+typedef struct {
+    uint64_t n_records, n_bases, longest_line;
+    uint64_t n_flips;           /* case changes strictly inside the shard's concatenated sequence */
+    uint64_t last_flip;         /* position (in the shard's bases) of the last of them, if n_flips > 0 */
+    uint8_t  first_code;        /* 4-bit code of the shard's first base */
+    uint8_t  first_case, last_case;   /* 1 = masked (byte >= 96, encoders.c:134) */
+    uint8_t  format;            /* NAFGPU_FMT_FASTA / FASTQ, 0 for an empty shard */
+    uint8_t  pad[4];
+} nafgpu_shard_counts;
+
+typedef struct {
+    uint64_t bases_before;      /* bases in the shards before this one */
+    uint64_t run_carry;         /* bases since the last case change before this shard (= bases_before if there is none) */
+    uint8_t  prev_last_case;    /* case of the last base before this shard (0 if there is none) */
+    uint8_t  next_first_code;   /* 4-bit code of the first base after this shard (0 if there is none) */
+    uint8_t  is_last;           /* last shard: sets Last_Block and writes the trailing mask run */
+    uint8_t  pad[5];
+} nafgpu_shard_link;
+
+int nafgpu_shard_begin(nafgpu_ctx *ctx, const uint8_t *text, size_t n, int text_on_device, const nafgpu_enc_opts *opts,
+                       nafgpu_shard_counts *counts, nafgpu_enc_info *info);
+int nafgpu_shard_finish(nafgpu_ctx *ctx, const nafgpu_shard_link *link, uint64_t raw[6], uint64_t body[6]);
+int nafgpu_shard_fetch(nafgpu_ctx *ctx, int stream, void *dst);
+
 #ifdef __cplusplus
 }
 #endif

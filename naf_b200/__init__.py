@@ -14,6 +14,8 @@ from .api import (  # noqa: F401
     DecOpts,
     EncInfo,
     Timing,
+    ShardCounts,
+    ShardLink,
     ennaf,
     unnaf,
     load_library,

@@ -47,12 +47,23 @@ class Timing(C.Structure):
                 ("kernel_launches", C.c_uint32), ("parser_fallback", C.c_uint32)]
 
 
+class ShardCounts(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_bases", C.c_uint64), ("longest_line", C.c_uint64), ("n_flips", C.c_uint64),
+                ("last_flip", C.c_uint64), ("first_code", C.c_uint8), ("first_case", C.c_uint8), ("last_case", C.c_uint8),
+                ("format", C.c_uint8), ("pad", C.c_uint8 * 4)]
+
+
+class ShardLink(C.Structure):
+    _fields_ = [("bases_before", C.c_uint64), ("run_carry", C.c_uint64), ("prev_last_case", C.c_uint8),
+                ("next_first_code", C.c_uint8), ("is_last", C.c_uint8), ("pad", C.c_uint8 * 5)]
+
+
 # every symbol include/nafgpu.h declares (tests check the .so exports exactly these)
 EXPORTS = [
     "nafgpu_create", "nafgpu_destroy", "nafgpu_last_error", "nafgpu_version", "nafgpu_get_timing", "nafgpu_stream",
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
     "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_split", "nafgpu_profile",
-    "nafgpu_profile_report",
+    "nafgpu_profile_report", "nafgpu_shard_begin", "nafgpu_shard_finish", "nafgpu_shard_fetch",
 ]
 
 _lib = None
@@ -95,6 +106,9 @@ def load_library():
     lib.nafgpu_zstd_decompress.argtypes = [vp, vp, sz, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_zstd_compress.argtypes = [vp, vp, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_split.argtypes = [vp, vp, sz, C.POINTER(EncOpts), C.POINTER(vp * 6), C.POINTER(sz * 6), C.POINTER(EncInfo)]
+    lib.nafgpu_shard_begin.argtypes = [vp, vp, sz, C.c_int, C.POINTER(EncOpts), C.POINTER(ShardCounts), C.POINTER(EncInfo)]
+    lib.nafgpu_shard_finish.argtypes = [vp, C.POINTER(ShardLink), C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64 * 6)]
+    lib.nafgpu_shard_fetch.argtypes = [vp, C.c_int, vp]
     _lib = lib
     return lib
 
@@ -242,6 +256,23 @@ class NafGpu:
         out, size = C.c_void_p(), C.c_size_t()
         self._check(self.lib.nafgpu_decode_device(self.h, d_ptr, n, hp, C.byref(opts), C.byref(out), C.byref(size)))
         return out.value or 0, size.value
+
+    # ---- one file from several shards (driven by naf_b200.sharded)
+    def shard_begin(self, text, opts: EncOpts, on_device: bool = False):
+        """-> (ShardCounts, EncInfo); text: host buffer, or (device address, nbytes) with on_device=True"""
+        p, n, keep = _as_ptr(text)
+        counts, info = ShardCounts(), EncInfo()
+        self._check(self.lib.nafgpu_shard_begin(self.h, p, n, int(on_device), C.byref(opts), C.byref(counts), C.byref(info)))
+        return counts, info
+
+    def shard_finish(self, link: ShardLink):
+        """-> (raw sizes[6], body sizes[6]) of this shard's streams"""
+        raw, body = (C.c_uint64 * 6)(), (C.c_uint64 * 6)()
+        self._check(self.lib.nafgpu_shard_finish(self.h, C.byref(link), C.byref(raw), C.byref(body)))
+        return list(raw), list(body)
+
+    def shard_fetch(self, stream: int, dst_address: int):
+        self._check(self.lib.nafgpu_shard_fetch(self.h, stream, dst_address))
 
     # ---- stages
     def zstd_decompress(self, frame, expected_size: int = 0, one_frame: bool = False) -> bytes:

@@ -9,6 +9,8 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
 EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
 SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
 EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log);
+void shard_begin_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_shard_counts *counts, nafgpu_enc_info *info);
+void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &link, uint64_t raw[6], uint64_t body[6]);
 }
 
 using namespace nafg;
@@ -21,7 +23,8 @@ template <class F> static int guarded(nafgpu_ctx *ctx, F f)
     try {
         ctx->err.clear(); ctx->fast_fallbacks = 0;
         CUDA_TRY(cudaSetDevice(ctx->device));
-        ctx->arena.reset();
+        if (!ctx->keep_arena) { ctx->arena.reset(); ctx->shard.active = false; }
+        ctx->keep_arena = false;
         f();
         return NAFGPU_OK;
     } catch (const NafError &e) {
@@ -285,6 +288,50 @@ int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_
             off += (r.size[k] + 63) & ~63ull;
         }
         finish_timing(*c, ex);
+    });
+}
+
+
+/* ---- one file from several shards (multi-GPU encode; naf_b200/sharded.py drives the exchange) ---- */
+
+int nafgpu_shard_begin(nafgpu_ctx *c, const uint8_t *text, size_t n, int text_on_device, const nafgpu_enc_opts *opts,
+                       nafgpu_shard_counts *counts, nafgpu_enc_info *info)
+{
+    if ((!text && n) || !opts || !counts) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        const u8 *d_text = text_on_device ? text : to_device(*c, ex, text, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        shard_begin_on_device(*c, ex, d_text, n, *opts, counts, info);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_shard_finish(nafgpu_ctx *c, const nafgpu_shard_link *link, uint64_t raw[6], uint64_t body[6])
+{
+    if (!c || !link || !raw || !body) return NAFGPU_E_ARG;
+    if (!c->shard.active) { c->err = "nafgpu_shard_finish without nafgpu_shard_begin\n"; return NAFGPU_E_ARG; }
+    c->keep_arena = true;
+    return guarded(c, [&] {
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        shard_finish_on_device(*c, ex, *link, raw, body);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_shard_fetch(nafgpu_ctx *c, int stream, void *dst)
+{
+    if (!c || stream < 0 || stream > 5 || !dst) return NAFGPU_E_ARG;
+    if (!c->shard.active || !c->shard.finished) { c->err = "nafgpu_shard_fetch without nafgpu_shard_finish\n"; return NAFGPU_E_ARG; }
+    c->keep_arena = true;
+    return guarded(c, [&] {
+        if (c->shard.body_size[stream]) CUDA_TRY(cudaMemcpyAsync(dst, c->shard.body[stream], c->shard.body_size[stream], cudaMemcpyDefault, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
     });
 }
 

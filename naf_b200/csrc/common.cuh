@@ -232,6 +232,17 @@ struct Ctx {
     Prof prof;
     std::string prof_report;
     u64 fast_fallbacks = 0;                  // encode calls that had to be redone by the general parser
+    // a shard between nafgpu_shard_begin and nafgpu_shard_finish / _fetch (device pointers into the arena, which is kept)
+    struct Shard {
+        bool active = false, finished = false;
+        nafgpu_enc_opts opts{};
+        u8 *stream[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; u64 raw[6] = {0, 0, 0, 0, 0, 0};
+        u64 n_bases = 0, n_records = 0, longest = 0, n_flips = 0;
+        const u64 *flip_pos = nullptr;
+        int store_mask = 0, store_qual = 0, format = 0; u32 first_case = 0;
+        const u8 *body[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; u64 body_size[6] = {0, 0, 0, 0, 0, 0};
+    } shard;
+    bool keep_arena = false;                 // next guarded call must not reset the arena (shard in progress)
 };
 
 #define KLAUNCH(ex, name, ...) do { (ex).prof_begin(name); __VA_ARGS__; (ex).prof_end(); } while (0)

@@ -66,44 +66,65 @@ __global__ void k_pack4(const u8 *bases, u64 n, u8 *packed, u32 *casebits, int w
     if (inv & 0x80) atomicOr(flag, (u32)FF_SEQ);
 }
 
-// flips[w] = positions where the case differs from the previous base (case before base 0 = unmasked)
-__global__ void k_flip_count(const u32 *casebits, u64 nwords, u64 *tile_counts)
+// flips[w] = positions where the case differs from the previous base (case before base 0 = prev0: unmasked for a whole
+// file, encoders.c:126; for a shard of a file, whatever keeps position 0 from counting as a flip)
+__global__ void k_flip_count(const u32 *casebits, u64 nwords, u64 *tile_counts, u32 prev0)
 {
     __shared__ u64 sm[33];
     u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 c = 0;
-    if (w < nwords) { u32 cur = casebits[w], prev = w ? casebits[w - 1] >> 31 : 0; c = __popc(cur ^ ((cur << 1) | prev)); }
+    if (w < nwords) { u32 cur = casebits[w], prev = w ? casebits[w - 1] >> 31 : prev0; c = __popc(cur ^ ((cur << 1) | prev)); }
     u64 tot; block_excl_scan(c, &tot, sm);
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
 }
-__global__ void k_flip_scatter(const u32 *casebits, u64 nwords, const u64 *tile_prefix, u64 *flip_pos)
+__global__ void k_flip_scatter(const u32 *casebits, u64 nwords, const u64 *tile_prefix, u64 *flip_pos, u32 prev0)
 {
     __shared__ u64 sm[33];
     u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u32 fl = 0;
-    if (w < nwords) { u32 cur = casebits[w], prev = w ? casebits[w - 1] >> 31 : 0; fl = cur ^ ((cur << 1) | prev); }
+    if (w < nwords) { u32 cur = casebits[w], prev = w ? casebits[w - 1] >> 31 : prev0; fl = cur ^ ((cur << 1) | prev); }
     u64 tot; u64 r = block_excl_scan(__popc(fl), &tot, sm) + tile_prefix[blockIdx.x];
     while (fl) { int k = __ffs(fl) - 1; fl &= fl - 1; flip_pos[r++] = (w << 5) + k; }
 }
 
 // runs of equal case: run k = [flip[k-1], flip[k]) (run 0 starts at 0, run R ends at n).  casebits beyond n are
 // zero, so a masked tail produces one spurious flip at n; clamping to n makes that final run empty.
+// For one shard of a file: `bnd` = a flip sits exactly at my position 0 (my first base differs in case from the last
+// base before me), `carry` = bases since the last flip in the shards before me (they lengthen my first run),
+// `emit_final` = the run after my last flip is written by me (last shard) and not carried into the next shard.
 struct RunCalc {
-    const u64 *fp; u64 R, nb;
+    const u64 *fp; u64 R, nb; u64 carry; u32 bnd, emit_final;      // R counts the boundary flip
+    __device__ u64 flip(size_t k) const { if (bnd) return k ? fp[k - 1] : 0; return fp[k]; }
     __device__ u64 len(size_t k) const
     {
-        u64 s = k ? fp[k - 1] : 0, e = k < R ? fp[k] : nb;
+        u64 s = k ? flip(k - 1) : 0, e = k < R ? flip(k) : nb;
         if (s > nb) s = nb;
         if (e > nb) e = nb;
-        return e - s;
+        return e - s + (k == 0 ? carry : 0);
     }
     __device__ u64 units(size_t k) const                      // encoders.c:98 add_mask: L/255 bytes of 255, then L%255
     {
         u64 L = len(k);
-        if (k == R && L == 0) return 0;                         // final run only if > 0 (ennaf.c:511)
+        if (k == R && (L == 0 || !emit_final)) return 0;        // final run only if > 0 (ennaf.c:511)
         return L / 255 + 1;
     }
 };
+
+struct SplitDev;
+// case flips -> runs -> mask units (encoders.c:98-151; final run flushed by ennaf.c:511)
+static void build_mask_units(CudaExec &ex, const u64 *flip_pos, u64 R_interior, u64 n_seq, u32 bnd, u64 carry, u32 emit_final, u8 **mask, u64 *n_mask)
+{
+    RunCalc rc{flip_pos, R_interior + bnd, n_seq, carry, bnd, emit_final};
+    const u64 R = rc.R;
+    u64 *upre = ex.alloc<u64>(R + 3);
+    exclusive_scan(ex, [rc] __device__ (size_t k) { return rc.units(k); }, R + 1, upre);
+    u64 n_units; ex.download(&n_units, upre + R + 1, 8);
+    *n_mask = n_units;
+    *mask = ex.alloc<u8>(n_units + 64);
+    ex.fill(*mask, 0xFF, n_units);
+    u8 *mk = *mask;
+    ex.for_each(R + 1, [=] __device__ (size_t k) { u64 u = rc.units(k); if (u) mk[upre[k] + u - 1] = (u8)(rc.len(k) % 255); }, "mask_units");
+}
 
 // ------------------------------------------------------------------ split orchestration
 
@@ -112,13 +133,16 @@ struct SplitDev {
     u64 n_ids, n_comm, n_len, n_mask, n_seq, n_qual;     // bytes
     u64 n_bases, n_records, longest;
     int format, store_mask, store_qual;
+    // shard mode (nafgpu_shard_begin): the mask is not built yet; what the link step needs instead
+    const u64 *flip_pos; u64 n_flips; u32 first_case, last_case, first_code;
 };
 
 static void die_input(const std::string &m) { fail(NAFGPU_E_INPUT, m); }
 
 struct FastFallback {};      // thrown inside split_streams_impl when the canonical-input parser meets input it does not cover
 
-static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info, bool use_fast)
+static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info, bool use_fast,
+                                   bool shard = false)
 {
     SplitDev S; memset(&S, 0, sizeof S);
     if (info) memset(info, 0, sizeof *info);
@@ -385,26 +409,30 @@ static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, siz
         u32 *casebits = ex.alloc<u32>(nwords + 2);
         if (nwords) { KLAUNCH(ex, "k_pack4", k_pack4<<<(unsigned)((nwords + 255) / 256), 256, 0, ex.stream>>>(bases, n_seq, S.seq, casebits, S.store_mask, d_lut, d_flag)); }
         if (use_fast) check_fast_flag();
+        if (shard && n_seq) {
+            u8 fb; ex.download(&fb, S.seq, 1);
+            S.first_code = fb & 15;
+        }
         if (S.store_mask && n_seq) {
-            // case flips -> runs -> units (encoders.c:98-151; final run flushed by ennaf.c:511)
+            u32 prev0 = 0;
+            if (shard) {                                                   // no flip at my position 0: the link step decides about that one
+                u32 cw[2]; ex.download(&cw[0], casebits, 4); ex.download(&cw[1], casebits + (n_seq - 1) / 32, 4);
+                S.first_case = cw[0] & 1; S.last_case = (cw[1] >> ((n_seq - 1) & 31)) & 1;
+                prev0 = S.first_case;
+            }
             u64 ft = (nwords + 255) / 256;
             u64 *fcount = ex.alloc<u64>(ft + 1), *fpre = ex.alloc<u64>(ft + 2);
-            KLAUNCH(ex, "k_flip_count", k_flip_count<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fcount));
+            KLAUNCH(ex, "k_flip_count", k_flip_count<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fcount, prev0));
             const u64 *fc = fcount;
             exclusive_scan(ex, [fc] __device__ (size_t i) { return fc[i]; }, ft, fpre);
             u64 R; ex.download(&R, fpre + ft, 8);                          // number of flips; runs = R + 1
             u64 *flip_pos = ex.alloc<u64>(R + 2);
-            KLAUNCH(ex, "k_flip_scatter", k_flip_scatter<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fpre, flip_pos));
-            // casebits beyond n_seq are zero, so a masked tail produces one spurious flip at n_seq: drop it
-            RunCalc rc{flip_pos, R, n_seq};
-            u64 *upre = ex.alloc<u64>(R + 3);
-            exclusive_scan(ex, [rc] __device__ (size_t k) { return rc.units(k); }, R + 1, upre);
-            u64 n_units; ex.download(&n_units, upre + R + 1, 8);
-            S.n_mask = n_units;
-            S.mask = ex.alloc<u8>(n_units + 64);
-            ex.fill(S.mask, 0xFF, n_units);
-            u8 *mk = S.mask;
-            ex.for_each(R + 1, [=] __device__ (size_t k) { u64 u = rc.units(k); if (u) mk[upre[k] + u - 1] = (u8)(rc.len(k) % 255); });
+            KLAUNCH(ex, "k_flip_scatter", k_flip_scatter<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fpre, flip_pos, prev0));
+            if (shard) {
+                // the spurious flip at n_seq after a masked tail is not a flip of mine
+                if (R) { u64 lastf; ex.download(&lastf, flip_pos + R - 1, 8); if (lastf >= n_seq) R--; }
+                S.flip_pos = flip_pos; S.n_flips = R;
+            } else build_mask_units(ex, flip_pos, R, n_seq, 0, 0, 1, &S.mask, &S.n_mask);
         }
     } else {
         S.seq = bases; S.n_seq = n_seq;
@@ -506,6 +534,102 @@ EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_
     zstd_gather_frames(ctx, ex, batch, false);
     ex.check();
     return EncodeOut{out, batch.frame_size[0]};
+}
+
+
+// ------------------------------------------------------------------ shards of one file (multi-GPU encode)
+
+// packed stream of bases[1:] from the packed stream of bases[0:]: out[j] = in[j] >> 4 | in[j+1] << 4
+__global__ void k_nibble_shift(const u8 *in, u64 n_out, u8 *out)
+{
+    const u64 g = (u64)blockIdx.x * blockDim.x + threadIdx.x, j0 = g * 8;
+    if (j0 >= n_out) return;
+    // 9 input bytes -> 8 output bytes; `in` is padded, bytes past its end are zero
+    u64 lo = 0; u8 hi = in[j0 + 8];
+    for (int k = 0; k < 8; k++) lo |= (u64)in[j0 + k] << (8 * k);
+    const u64 v = (lo >> 4) | ((u64)hi << 60);
+    for (int k = 0; k < 8 && j0 + k < n_out; k++) out[j0 + k] = (u8)(v >> (8 * k));
+}
+
+void shard_begin_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_shard_counts *counts, nafgpu_enc_info *info)
+{
+    nafgpu_enc_info local; if (!info) info = &local;
+    SplitDev S;
+    bool done = false;
+    static const bool env_general = getenv("NAFGPU_GENERAL_PARSER") != nullptr;
+    if (!o.well_formed && !env_general && !o.general_parser) {
+        const Arena::Mark mk = ex.arena->mark();
+        try { S = split_streams_impl(ctx, ex, d_text, n, o, info, true, true); done = true; }
+        catch (const FastFallback &) {}
+        catch (const NafError &) {}
+        if (!done) { CUDA_TRY(cudaStreamSynchronize(ex.stream)); ex.arena->rewind(mk); ctx.fast_fallbacks++; }
+    }
+    if (!done) S = split_streams_impl(ctx, ex, d_text, n, o, info, false, true);
+    Ctx::Shard &H = ctx.shard;
+    H = Ctx::Shard();
+    H.opts = o; H.opts.title = nullptr;
+    u8 *sp[6] = { S.ids, S.comm, S.len, S.mask, S.seq, S.qual };
+    const u64 ss[6] = { S.n_ids, S.n_comm, S.n_len, 0, S.n_seq, S.n_qual };
+    for (int k = 0; k < 6; k++) { H.stream[k] = sp[k]; H.raw[k] = ss[k]; }
+    H.n_bases = S.n_bases; H.n_records = S.n_records; H.longest = S.longest; H.n_flips = S.n_flips; H.flip_pos = S.flip_pos;
+    H.store_mask = S.store_mask; H.store_qual = S.store_qual; H.format = S.format; H.first_case = S.first_case;
+    memset(counts, 0, sizeof *counts);
+    counts->n_records = S.n_records; counts->n_bases = S.n_bases; counts->longest_line = S.longest;
+    counts->n_flips = S.n_flips;
+    if (S.n_flips) { u64 lf; ex.download(&lf, S.flip_pos + S.n_flips - 1, 8); counts->last_flip = lf; }
+    counts->first_code = (u8)S.first_code; counts->first_case = (u8)S.first_case; counts->last_case = (u8)S.last_case;
+    counts->format = (u8)S.format;
+    H.active = true; H.finished = false;
+}
+
+void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &link, uint64_t raw[6], uint64_t body[6])
+{
+    Ctx::Shard &H = ctx.shard;
+    const bool packed = H.opts.seq_type < NAFGPU_PROTEIN;
+    // ---- 4-bit stream: global base index of my first base decides who owns the byte it shares with my predecessor
+    if (packed && H.n_bases) {
+        const bool odd_start = link.bases_before & 1;
+        u64 my_bases = H.n_bases;
+        if (odd_start) {                                       // my first base completes my predecessor's last byte
+            my_bases = H.n_bases - 1;
+            const u64 nb = (my_bases + 1) / 2;
+            u8 *shifted = ex.alloc<u8>(nb + 64);
+            ex.zero(shifted + nb, 64);
+            if (nb) { KLAUNCH(ex, "k_nibble_shift", k_nibble_shift<<<(unsigned)((nb + 8 * 256 - 1) / (8 * 256)), 256, 0, ex.stream>>>(H.stream[4], nb, shifted)); }
+            H.stream[4] = shifted; H.raw[4] = nb;
+        }
+        if ((my_bases & 1) && link.next_first_code) {          // my last byte's high nibble is my successor's first base
+            u8 *p = H.stream[4] + H.raw[4] - 1; const u8 code = link.next_first_code;
+            ex.for_each(1, [=] __device__ (size_t) { *p = (u8)((*p & 15) | (code << 4)); }, "shard_nibble");
+        }
+    }
+    // ---- mask: runs that end inside this shard (+ the trailing run if this is the last shard)
+    if (H.store_mask) {
+        // a flip sits at my position 0 iff my first base differs in case from the last base before me
+        const u32 bnd = H.n_bases ? (u32)(H.first_case != (u32)link.prev_last_case) : 0u;
+        u8 *mask = nullptr; u64 n_mask = 0;
+        build_mask_units(ex, H.flip_pos, H.n_flips, H.n_bases, bnd, link.run_carry, link.is_last ? 1u : 0u, &mask, &n_mask);
+        H.stream[3] = mask; H.raw[3] = n_mask;
+    }
+    // ---- zstd blocks of every stream; only the last shard closes the frames
+    ZEncBatch batch; batch.final_shard = link.is_last != 0;
+    const bool present[6] = { true, true, true, (bool)H.store_mask, true, (bool)H.store_qual };
+    int which[6], ns = 0;
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.raw[k], 0); }
+    zstd_compress_batch(ctx, ex, batch);
+    u64 total = 0; std::vector<u64> at(ns);
+    for (int j = 0; j < ns; j++) { at[j] = total; total += (batch.frame_size[j] + 63) & ~63ull; }
+    u8 *blob = ex.alloc<u8>(total + 64);
+    for (int j = 0; j < ns; j++) batch.dest[j] = blob + at[j];
+    zstd_gather_frames(ctx, ex, batch, false);
+    for (int k = 0; k < 6; k++) { H.body[k] = nullptr; H.body_size[k] = 0; raw[k] = 0; body[k] = 0; }
+    for (int j = 0; j < ns; j++) {
+        const int k = which[j];
+        H.body[k] = blob + at[j] + 6; H.body_size[k] = batch.frame_size[j] - 6;      // blocks only: magic, FHD and window byte belong to the merged frame
+        raw[k] = H.raw[k]; body[k] = H.body_size[k];
+    }
+    ex.check();
+    H.finished = true;
 }
 
 }  // namespace nafg

@@ -24,11 +24,11 @@ struct FastArgs {
     int seq_check;           // 0 none here (DNA / RNA: the pack LUT checks), 1 protein, 2 text, 3 text where '>' is unexpected
 };
 
-static const int FAST_TILE_SMEM = PTILE + 64;     // + one padding row: the word-wise copies read one word ahead
+static const int FAST_TILE_SMEM = (PTILE + 64) / 64 * 68;     // fast_pad() layout, + one padding row: the word-wise copies read one word ahead
 
-struct FastRow {
-    const u8 *tile; u32 src0;
-    __device__ __forceinline__ u32 operator()(u32 i) const { return tile[fast_swz(src0 + i)]; }
+struct FastRow {                                  // my 64-byte row of the padded tile
+    const u8 *row;
+    __device__ __forceinline__ u32 operator()(u32 i) const { return row[i]; }
 };
 
 // my 64 bytes -> registers and my row of the swizzled tile; bytes outside [p0, n) read as 'A'
@@ -55,9 +55,9 @@ __device__ __forceinline__ void fast_load(const ParseArgs &A, u64 lo, u32 w[16],
         }
     }
     if (tile) {
-        const u32 src0 = threadIdx.x * 64;
+        u32 *row = (u32 *)(tile + threadIdx.x * 68);
 #pragma unroll
-        for (int k = 0; k < 16; k++) *(u32 *)(tile + fast_swz(src0 + 4 * k)) = w[k];
+        for (int k = 0; k < 16; k++) row[k] = w[k];
     }
 }
 
@@ -95,13 +95,13 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_tiles(const F
     u32 w[16], b0, b1;
     fast_load(A, lo, w, FASTQ ? nullptr : tile, b0, b1);
     u64 nl; u32 bad;
-    fast_chunk_scan(w, nl, bad);
+    fast_chunk_scan<false>(w, nl, bad);
     if (bad) atomicOr(F.flag, (u32)FF_BADBYTE);
     if (FASTQ) {
         u64 total; block_excl_scan((u64)__popcll(nl), &total, sm64);
         if (threadIdx.x == 0) F.tile_elem[blockIdx.x] = (u32)total;
     } else {
-        const FastRow row{tile, threadIdx.x * 64u};
+        const FastRow row{tile + threadIdx.x * 68};
         u32 total; block_excl_scan_fe(fasta_chunk_element(row, nl, b0, b1), &total, sm32);
         if (threadIdx.x == 0) F.tile_elem[blockIdx.x] = total;
     }
@@ -167,15 +167,15 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_count(const F
     const u64 gid = (u64)blockIdx.x * PT + threadIdx.x, lo = gid * PB;
     u32 w[16], b0, b1;
     fast_load(A, lo, w, tile, b0, b1);
-    u64 nl; u32 bad, flag = 0;
-    fast_chunk_scan(w, nl, bad);
-    const FastRow row{tile, threadIdx.x * 64u};
+    u64 nl, sp; u32 bad, flag = 0;
+    fast_chunk_scan<true>(w, nl, bad, &sp);
+    const FastRow row{tile + threadIdx.x * 68};
     FastState st = fast_entry<FASTQ>(F, row, nl, b0, b1, lo, sm64, sm32, flag);
     const u32 entry = st.role | (st.sp << 2) | (st.ls << 3);
     FastEmit n = {0, 0, 0, 0, 0};
     FastLine ln = {0, 0, 0};
     FastNoSink sink;
-    fast_walk<FASTQ, false>(row, nl, b0, b1, st, lo, n, sink, 0, 0, 0, ln, flag);
+    fast_walk<FASTQ, false>(row, nl, sp, b0, b1, st, lo, n, sink, 0, 0, 0, ln, flag);
     if (flag) atomicOr(F.flag, flag);
     ThreadInfo ti; ti.state = (u8)entry; ti.ids = (u8)n.ids; ti.comm = (u8)n.comm; ti.seq = (u8)n.seq; ti.cnt = (u8)n.seq; ti.qual = (u8)n.qual;
     ti.rec = (u8)n.rec; ti.line = (u8)ln.mark;
@@ -198,7 +198,7 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_count(const F
 }
 
 // ------------------------------------------------------------------ pass 3
-static const int FAST_STAGE_SMEM = PTILE + 192;
+static const int FAST_STAGE_SMEM = (PTILE + 256) / 64 * 68;    // fast_pad() layout
 
 // staged bytes of one stream (linear stage offset s0, congruent mod 4 to dst) -> global memory, one word per thread and step
 template <int CHECK>      // 0 none, 1 protein, 2 text, 3 text with '>' unexpected, 4 quality
@@ -210,7 +210,7 @@ __device__ __forceinline__ u32 fast_copy_out(u8 *dst, const u8 *stage, u32 s0, u
     // head / tail bytes: checked as single bytes by the first threads
     if (threadIdx.x < head || (threadIdx.x >= 32 && threadIdx.x - 32 < len - done)) {
         const u32 i = threadIdx.x < head ? threadIdx.x : done + (threadIdx.x - 32);
-        u32 c = stage[fast_swz(s0 + i)];
+        u32 c = stage[fast_pad(s0 + i)];
         const u32 v = c * 0x01010101u;
         if (CHECK == 1) bad |= swar_bad_protein(v); else if (CHECK == 2) bad |= swar_bad_text(v, false); else if (CHECK == 3) bad |= swar_bad_text(v, true);
         else if (CHECK == 4) bad |= swar_bad_qual(v);
@@ -219,7 +219,7 @@ __device__ __forceinline__ u32 fast_copy_out(u8 *dst, const u8 *stage, u32 s0, u
     }
     u32 *dw = (u32 *)(dst + head);
     for (u32 k = threadIdx.x; k < nw; k += blockDim.x) {
-        u32 v = *(const u32 *)(stage + fast_swz(s0 + head + 4 * k));
+        u32 v = *(const u32 *)(stage + fast_pad(s0 + head + 4 * k));
         if (CHECK == 1) bad |= swar_bad_protein(v); else if (CHECK == 2) bad |= swar_bad_text(v, false); else if (CHECK == 3) bad |= swar_bad_text(v, true);
         else if (CHECK == 4) bad |= swar_bad_qual(v);
         if (upper) v = swar_upper(v);
@@ -265,9 +265,9 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_scatter(const
 
     u32 w[16], b0, b1;
     fast_load(A, lo, w, tile, b0, b1);
-    u64 nl; u32 bad, flag = 0;
-    fast_chunk_scan(w, nl, bad);
-    const FastRow row{tile, threadIdx.x * 64u};
+    u64 nl, sp; u32 bad, flag = 0;
+    fast_chunk_scan<true>(w, nl, bad, &sp);
+    const FastRow row{tile + threadIdx.x * 68};
     FastState st; st.role = ti.state & 3; st.sp = (ti.state >> 2) & 1; st.ls = (ti.state >> 3) & 1;
     FastEmit m = {0, 0, 0, 0, 0};
     FastLine ln = {before - 1, 0, 0};
@@ -275,8 +275,9 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_scatter(const
     sink.tile = tile; sink.stage = stage; sink.src0 = threadIdx.x * 64u;
     sink.base[0] = s_ids + l_ids; sink.base[1] = s_comm + l_comm; sink.base[2] = s_seq + l_seq; sink.base[3] = s_qual + l_qual;
     sink.rec_seq_end = A.rec_seq_end; sink.rec_qual_end = A.rec_qual_end; sink.rec_pos = A.rec_pos; sink.fastq = FASTQ;
-    __syncwarp();                                               // my row is only ever read by me (and one word ahead: read-only, unused bytes)
-    fast_walk<FASTQ, true>(row, nl, b0, b1, st, lo, m, sink, o_cnt, o_qual, o_rec, ln, flag);
+    sink.begin();
+    fast_walk<FASTQ, true>(row, nl, sp, b0, b1, st, lo, m, sink, o_cnt, o_qual, o_rec, ln, flag);
+    sink.flush();                                               // the copies, all lanes together
     if (!FASTQ) {
         // pending (unterminated) last line of the input (process.c:417-422)
         if (lo < A.n && lo + PB >= A.n) { const u64 d = o_cnt + m.seq - ln.base; if (d > ln.max) ln.max = d; }

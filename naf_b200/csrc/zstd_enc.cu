@@ -37,6 +37,7 @@ struct ZEncBatch {
     std::vector<u64> frame_size; std::vector<u8 *> dest;
     std::vector<u32> first_block;            // per stream (+1 sentinel)
     ZEncBlock *d_blocks = nullptr; u32 nblocks = 0; u8 *d_slots = nullptr; u64 *d_off = nullptr;
+    bool final_shard = true;                 // false: these frames continue in another shard, no block carries Last_Block
     void add(const u8 *p, u64 bytes, int window_log) { src.push_back(p); n.push_back(bytes); wlog.push_back(window_log); }
 };
 
@@ -442,11 +443,12 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
         for (size_t s = 0; s < ns; s++) { tab.src[s] = b.src[s]; tab.n[s] = b.n[s]; tab.first[s] = b.first_block[s]; }
         tab.first[ns] = b.nblocks; tab.ns = (u32)ns;
         ZEncBlock *blk = b.d_blocks;
+        const u32 fin = b.final_shard ? 1u : 0u;
         ex.for_each(b.nblocks, [=] __device__ (size_t i) {
             u32 s = 0;
             while (s + 1 < tab.ns && (u32)i >= tab.first[s + 1]) s++;
             const u64 k = i - tab.first[s], off = k * ZBS, left = tab.n[s] - (tab.n[s] < off ? tab.n[s] : off);
-            ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < ZBS ? left : ZBS); e.stream = s; e.last = (u32)i + 1 == tab.first[s + 1];
+            ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < ZBS ? left : ZBS); e.stream = s; e.last = ((u32)i + 1 == tab.first[s + 1]) & fin;
             e.type = 0; e.csize = 0;
             blk[i] = e;
         }, "zenc_init_blocks");

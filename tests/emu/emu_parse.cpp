@@ -13,7 +13,7 @@ using namespace nafg;
 
 static const int PT = 256, PB = 64, PTILE = PT * PB;
 
-struct HostRow { const u8 *tile; u32 src0; u32 operator()(u32 i) const { return tile[fast_swz(src0 + i)]; } };
+struct HostRow { const u8 *tile; u32 src0; u32 operator()(u32 i) const { return tile[fast_pad(src0 + i)]; } };
 
 static void load_words(const std::vector<u8> &text, u64 p0, u64 lo, u32 w[16], u32 &b0, u32 &b1)
 {
@@ -33,15 +33,15 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
 {
     const u64 n = text.size(), ntiles = (n + PTILE - 1) / PTILE, nthreads = ntiles * PT;
     u32 flag = 0;
-    std::vector<u64> nls(nthreads); std::vector<u32> elem(nthreads), b0s(nthreads), b1s(nthreads);
-    std::vector<u8> tile(PTILE + 64), stage(PTILE + 192);
+    std::vector<u64> nls(nthreads), sps(nthreads); std::vector<u32> elem(nthreads), b0s(nthreads), b1s(nthreads);
+    std::vector<u8> tile((PTILE + 64) / 64 * 68), stage((PTILE + 256) / 64 * 68);
     // pass 1
     for (u64 t = 0; t < nthreads; t++) {
         u32 w[16], bad; load_words(text, p0, t * PB, w, b0s[t], b1s[t]);
-        fast_chunk_scan(w, nls[t], bad);
+        fast_chunk_scan<true>(w, nls[t], bad, &sps[t]);
         if (bad) flag |= FF_BADBYTE;
         const u32 src0 = (u32)(t % PT) * 64;
-        for (int k = 0; k < 16; k++) *(u32 *)(tile.data() + fast_swz(src0 + 4 * k)) = w[k];
+        for (int k = 0; k < 16; k++) *(u32 *)(tile.data() + fast_pad(src0 + 4 * k)) = w[k];
         HostRow row{tile.data(), src0};
         elem[t] = FASTQ ? (u32)__builtin_popcountll(nls[t]) : fasta_chunk_element(row, nls[t], b0s[t], b1s[t]);
     }
@@ -53,7 +53,7 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
         const u64 lo = t * PB;
         u32 w[16], b0, b1; load_words(text, p0, lo, w, b0, b1);
         const u32 src0 = (u32)(t % PT) * 64;
-        for (int k = 0; k < 16; k++) *(u32 *)(tile.data() + fast_swz(src0 + 4 * k)) = w[k];
+        for (int k = 0; k < 16; k++) *(u32 *)(tile.data() + fast_pad(src0 + 4 * k)) = w[k];
         HostRow row{tile.data(), src0};
         FastState st; st.sp = 0;
         if (FASTQ) { st.role = run_state & 3; st.ls = lo > p0 && b1 > 0 && text[lo - 1] == '\n'; }
@@ -61,7 +61,7 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
         if (b0 < b1 && st.role == FR_HDR && !st.ls) st.sp = fast_lookback_space(text.data(), p0, lo + b0, flag);
         ti[t].st = st;
         FastEmit e = {0, 0, 0, 0, 0}; FastLine ln = {0, 0, 0}; FastNoSink sink;
-        fast_walk<FASTQ, false>(row, nls[t], b0, b1, st, lo, e, sink, 0, 0, 0, ln, flag);
+        fast_walk<FASTQ, false>(row, nls[t], sps[t], b0, b1, st, lo, e, sink, 0, 0, 0, ln, flag);
         ti[t].n = e; ti[t].mark = ln.mark;
         run_state = FASTQ ? run_state + elem[t] : fe_compose(run_state, elem[t]);
     }
@@ -93,7 +93,7 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
         for (int s = 0; s < 4; s++) { s0[s] = ((at + 3) & ~3u) + (u32)((uintptr_t)g[s] & 3); if (s == 0) s0[s] = (u32)((uintptr_t)g[s] & 3); at = s0[s] + (u32)tt[s]; }
         for (int k = 0; k < PT; k++) {            // all rows of the tile first (the kernel's threads load concurrently)
             u32 w[16], b0, b1; load_words(text, p0, (tl * PT + k) * PB, w, b0, b1);
-            for (int q = 0; q < 16; q++) *(u32 *)(tile.data() + fast_swz(k * 64 + 4 * q)) = w[q];
+            for (int q = 0; q < 16; q++) *(u32 *)(tile.data() + fast_pad(k * 64 + 4 * q)) = w[q];
         }
         u64 l[4] = {0, 0, 0, 0}; u64 l_rec = 0;
         for (int k = 0; k < PT; k++) {
@@ -103,7 +103,9 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
             for (int s = 0; s < 4; s++) sink.base[s] = s0[s] + (u32)l[s];
             sink.rec_seq_end = rec_seq_end.data(); sink.rec_qual_end = rec_qual_end.data(); sink.rec_pos = rec_pos.data(); sink.fastq = FASTQ;
             FastState st = ti[t].st; FastEmit m = {0, 0, 0, 0, 0}; FastLine ln = {line_base, 0, 0};
-            fast_walk<FASTQ, true>(row, nls[t], b0s[t], b1s[t], st, lo, m, sink, o_seq + l[2], o_qual + l[3], o_rec + l_rec, ln, flag);
+            sink.begin();
+            fast_walk<FASTQ, true>(row, nls[t], sps[t], b0s[t], b1s[t], st, lo, m, sink, o_seq + l[2], o_qual + l[3], o_rec + l_rec, ln, flag);
+            sink.flush();
             if (m.ids != ti[t].n.ids || m.comm != ti[t].n.comm || m.seq != ti[t].n.seq || m.qual != ti[t].n.qual || m.rec != ti[t].n.rec) { fprintf(stderr, "count/scatter mismatch\n"); return 1; }
             if (!FASTQ) {
                 if (lo < n && lo + PB >= n) { const u64 d = o_seq + l[2] + m.seq - ln.base; if (d > ln.max) ln.max = d; }
@@ -114,7 +116,7 @@ template <bool FASTQ> static int run(const std::vector<u8> &text, u64 p0, int se
         }
         for (int s = 0; s < 4; s++) {
             for (u64 i = 0; i < tt[s]; i++) {
-                u32 c = stage[fast_swz(s0[s] + (u32)i)];
+                u32 c = stage[fast_pad(s0[s] + (u32)i)];
                 const u32 v = c * 0x01010101u;
                 if (s == 2) {
                     if ((seq_check == 1 && swar_bad_protein(v)) || (seq_check == 2 && swar_bad_text(v, false)) || (seq_check == 3 && swar_bad_text(v, true))) flag |= FF_SEQ;
