@@ -168,12 +168,20 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ our arm (GPU)
 ALGO_BYTES_PER_BASE = {
-    # algorithmic HBM bytes per base of each kernel on the config-2 workload (DESIGN.md "Kernels and rooflines")
-    # text = 2.18 B/base (2 x 151 + 25 header bytes per 150-base record), ids+comments 0.14, lengths 0.027
-    "k_fsm_reduce": 2.18, "k_fsm_count": 2.18, "k_fsm_scatter": 2.18 + 1.0 + 1.0 + 0.14 + 0.027,   # scatter: reads text, writes bases + qualities + ids/comments + record ends
-    "k_pack4": 1.0 + 0.5,
-    "k_zenc_block": 2 * (0.5 + 1.0 + 0.17) + 0.92, "k_zenc_gather": 2 * 0.92,
-    "zd_literals": 0.92 + 0.5 + 1.0 + 0.17, "k_write_text": 0.5 + 1.0 + 0.17 + 2.18,
+    # algorithmic HBM bytes per base of each kernel on the config-2 workload (DESIGN.md "Kernels"):
+    # text = 2.185 B/base (2 x 151 + ~25.8 header bytes per 150-base record); streams: 0.5 packed sequence + 1.0 quality
+    # + 0.139 ids/comments + 0.027 lengths = 1.67; bases before packing 1.0; .naf 0.83
+    "k_fast_tiles": 2.185, "k_fast_count": 2.185, "k_fast_scatter": 2.185 + 1.0 + 1.0 + 0.139 + 0.048,   # + per-record arrays
+    "k_fsm_reduce": 2.185, "k_fsm_count": 2.185, "k_fsm_scatter": 2.185 + 1.0 + 1.0 + 0.139 + 0.048,
+    "k_pack4": 1.0 + 0.5 + 0.031,
+    "k_zenc_hist": 1.67, "k_zenc_encode": 1.67 + 0.83, "k_zenc_gather": 2 * 0.83,
+    "zd_literals": 0.83 + 1.67, "k_write_text": 1.67 + 0.19 + 2.185,
+}
+# DRAM bytes per base measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch, 1 M reads:
+# profiles/r1d_top_full_1Mreads.summary.txt, r1e for k_write_text); bench.py scales them to the launch it timed
+NCU_TRAFFIC_PER_BASE = {
+    "k_fast_count": 360.9e6 / 150e6, "k_fast_scatter": 664.8e6 / 150e6, "k_zenc_hist": 258.9e6 / 150e6, "k_zenc_encode": 351.1e6 / 150e6,
+    "zd_literals": 332.9e6 / 150e6, "k_write_text": 638.1e6 / 150e6,
 }
 
 
@@ -307,6 +315,39 @@ def run_ours(args):
         prof[n] = (c0 + c, m0 + ms)
     ctx.profile(False)
 
+    # ---- N > 1: ONE .naf from all ranks' shards (count all-gather, link, gather of zstd blocks over NCCL / NVLink)
+    single = None
+    if world > 1:
+        try:
+            from naf_b200 import sharded
+            enc = sharded.GpuShardEncoder(ctx, device_text=True)
+            dev = torch.device("cuda", local)
+            times, out = [], None
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                out = sharded.encode_sharded(enc, (d_text.data_ptr(), n_text), eopts, device=dev)
+                torch.cuda.synchronize()
+                barrier()
+                times.append(time.perf_counter() - t0)
+            tt = torch.tensor([min(times[1:])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            single = {"encode_gbases_s": bases * world / float(tt.item()) / 1e9, "ms": float(tt.item()) * 1e3, "collectives": "2 x all_gather (9 + 12 int64 per rank), 1 gather of zstd blocks"}
+            if rank == 0:
+                single["naf_bytes"] = int(out.numel())
+                if not args.no_verify:        # rank 0 decodes the merged file: right size, and its own shard comes back bit-exact
+                    hn = out.cpu()
+                    taddr3, tsize3 = ctx.decode_device(out.data_ptr(), out.numel(), (hn.data_ptr(), hn.numel()), dopts)
+                    got = torch.empty(n_text, dtype=torch.uint8, device="cuda")
+                    ctx_copy_d2d(got, taddr3, n_text)
+                    sizes = torch.tensor([n_text], device="cuda", dtype=torch.int64)
+                    single["verified"] = bool(torch.equal(got, d_text[:n_text]))
+                    single["text_bytes"] = int(tsize3)
+                    del got, hn
+            del out
+        except Exception as e:                # the headline numbers above do not depend on this path
+            single = {"error": repr(e)[:300]}
+
     # ---- reduce over ranks: max time
     t = torch.tensor([dev_ms, e2e_ms, enc_ms / args.steps, dec_ms / args.steps, e_enc / args.steps, e_dec / args.steps], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -331,6 +372,9 @@ def run_ours(args):
         if bpb and ms > 0:
             ach = bpb * bases / (ms * 1e-3) / 1e9
             roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_base": bpb})
+        if name in NCU_TRAFFIC_PER_BASE:
+            roofline["traffic"] = NCU_TRAFFIC_PER_BASE[name] * bases
+            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r1d_top_full_1Mreads.summary.txt), scaled per base"
         line = {
             "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -344,6 +388,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(naf_size) + n_text, "encode_gbases_s": total_bases / (e_enc1 * 1e-3) / 1e9,
                     "decode_gbases_s": total_bases / (e_dec1 * 1e-3) / 1e9, "ms_per_step": e2e_ms},
             "gpu_launches": launches_total,
+            "single_file": single,
             "clocks": clocks,
             "roofline": roofline,
         }

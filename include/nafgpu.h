@@ -90,6 +90,10 @@ typedef struct {
     int32_t  no_mask;           /* unnaf --no-mask */
     int32_t  have_line_length;  /* unnaf --line-length N */
     uint64_t line_length;
+    /* record-range decode (one rank of a multi-GPU decode): with n_records != 0 the call returns only the text of
+     * records [first_record, first_record + n_records) -- exactly the bytes they occupy in the full output, so the ranks'
+     * pieces concatenate to it.  Applies to the per-record views (FASTA, FASTQ, --sequences, --ids, --names). */
+    uint64_t first_record, n_records;
 } nafgpu_dec_opts;
 
 /* Facts ennaf prints or needs after encoding (ennaf.c:556,594-596). */
@@ -174,7 +178,7 @@ int nafgpu_split(nafgpu_ctx *ctx, const uint8_t *text, size_t n, const nafgpu_en
  * rank 0 concatenates the zstd *blocks* of all ranks into ONE frame per stream -- the reference unnaf stops after
  * the first frame of the sequence / quality streams (zstd_decompress.c:2129-2140, output.c:640).
  *   nafgpu_shard_begin    parse + split + pack this shard (text: host pointer, or device pointer if text_on_device)
- *   (caller)              all-gather the counts, derive this shard's nafgpu_shard_link (naf_b200/sharded.py: link_for)
+ *   (caller)              all-gather the counts, derive this shard's link record, see naf_b200/sharded.py link_for
  *   nafgpu_shard_finish   nibble shift, boundary mask runs, zstd blocks; raw[k] / body[k] = uncompressed / compressed
  *                         bytes of stream k as this shard contributes them (body = blocks only: no frame header)
  *   nafgpu_shard_fetch    copy the blocks of stream k to dst (host or device memory, cudaMemcpyDefault)

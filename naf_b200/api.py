@@ -33,7 +33,7 @@ class EncOpts(C.Structure):
 
 class DecOpts(C.Structure):
     _fields_ = [("out_type", C.c_int32), ("no_mask", C.c_int32), ("have_line_length", C.c_int32),
-                ("line_length", C.c_uint64)]
+                ("line_length", C.c_uint64), ("first_record", C.c_uint64), ("n_records", C.c_uint64)]
 
 
 class EncInfo(C.Structure):
@@ -145,8 +145,9 @@ def make_enc_opts(seq_type="dna", fmt=0, no_mask=False, strict=False, well_forme
     return o
 
 
-def make_dec_opts(view="default", no_mask=False, line_length=None) -> DecOpts:
+def make_dec_opts(view="default", no_mask=False, line_length=None, first_record=0, n_records=0) -> DecOpts:
     o = DecOpts()
+    o.first_record, o.n_records = int(first_record), int(n_records)
     o.out_type = _VIEWS[view] if isinstance(view, str) else int(view)
     o.no_mask = int(no_mask)
     o.have_line_length = int(line_length is not None)
@@ -220,8 +221,8 @@ class NafGpu:
         self._check(self.lib.nafgpu_decode(self.h, p, n, C.byref(opts), C.byref(out), C.byref(size)))
         return out.value or 0, size.value
 
-    def decode(self, naf, view="default", no_mask=False, line_length=None) -> bytes:
-        addr, size = self.decode_raw(naf, make_dec_opts(view, no_mask, line_length))
+    def decode(self, naf, view="default", no_mask=False, line_length=None, first_record=0, n_records=0) -> bytes:
+        addr, size = self.decode_raw(naf, make_dec_opts(view, no_mask, line_length, first_record, n_records))
         return C.string_at(addr, size) if size else b""
 
     def unnaf(self, naf, view="default", no_mask=False, line_length=None) -> bytes:

@@ -78,6 +78,7 @@ struct TextArgs {
     const u32 *maskbits;             // 1 bit per base or nullptr
     const u64 *out_start;            // per record: first output byte; [N] = total
     u64 N, total, total_bases;
+    u64 rec0;                        // global index of local record 0 (record-range decode): per-record arrays other than out_start are global
     u32 lut[4];                      // code_to_nuc as 16 bytes
     u8 *out;
 };
@@ -99,6 +100,7 @@ __device__ __forceinline__ u32 name_len_of(const TextArgs &A, u32 id_len, u32 cm
 }
 __device__ __forceinline__ void load_rec(const TextArgs &A, u64 i, RecInfo &R)
 {
+    i += A.rec0;
     R.id_s = R.id_len = R.cm_s = R.cm_len = 0;
     if (A.with_name) {
         if (A.has_ids) { R.id_s = i ? A.id_end[i - 1] + 1 : 0; R.id_len = A.id_end[i] - R.id_s; }
@@ -197,13 +199,14 @@ __device__ __forceinline__ void rec_bounds(const TextArgs &A, const RecS &s, Rec
 }
 __device__ __forceinline__ void rec_fetch(const TextArgs &A, u64 i, RecS &s)
 {
+    s.out0 = A.out_start[i];
+    i += A.rec0;
     s.id_s = s.id_len = s.cm_s = s.cm_len = 0;
     if (A.with_name) {
         if (A.has_ids) { s.id_s = i ? A.id_end[i - 1] + 1 : 0; s.id_len = A.id_end[i] - s.id_s; }
         if (A.has_names) { s.cm_s = i ? A.cm_end[i - 1] + 1 : 0; s.cm_len = A.cm_end[i] - s.cm_s; }
     }
     s.L = A.seq_present ? A.L[i] : 0; s.sbase = A.seq_present ? A.seq_start[i] : 0;
-    s.out0 = A.out_start[i];
 }
 
 // The generic composer of one 16-byte chunk of text starting at q0: the chunk is assembled from at most a handful of
@@ -457,11 +460,16 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     if (view == NAFGPU_OUT_LENGTHS && !h.has_lengths) return none;
     if (view == NAFGPU_OUT_MASK && !h.has_mask) return none;
 
-    // ---- entropy stage: all needed streams in one batch
+    // ---- entropy stage: all needed streams in one batch -- or, when only a range of records is wanted (one rank of a
+    // multi-GPU decode), the small streams first and the sequence / quality streams afterwards, restricted to the bytes
+    // the range needs (frames without sequences, i.e. ours, skip every other block; others are decoded whole)
+    const bool ranged = o.n_records != 0 && (view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQUENCES ||
+                                            view == NAFGPU_OUT_IDS || view == NAFGPU_OUT_NAMES);
     nafz::ZDecPlan plan;
     plan.blocks.swap(ctx.zblock_cache);                                   // reuse last call's capacity
     struct GiveBack { nafz::ZDecPlan &p; Ctx &c; ~GiveBack() { p.blocks.swap(c.zblock_cache); } } give_back{plan, ctx};
     int sidx[6]; u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
+    nafz::ZStreamDesc sdesc[6];
     for (int k = 0; k < 6; k++) {
         sidx[k] = -1; sbytes[k] = 0; soff[k] = 0;
         if (!need[k]) continue;
@@ -469,32 +477,43 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         if (k == SEC_DATA && packed) expect = (h.sec[k].orig + 1) / 2;
         sbytes[k] = expect; soff[k] = arena_sz;
         nafz::ZStreamDesc sd; sd.src_off = h.sec[k].off; sd.src_len = h.sec[k].comp; sd.out_off = arena_sz; sd.out_size = expect;
-        sd.one_frame = (k == SEC_DATA || k == SEC_QUAL) ? 1 : 0; sd.no_magic = 1;
-        sidx[k] = (int)plan.streams.size(); plan.streams.push_back(sd);
+        sd.one_frame = (k == SEC_DATA || k == SEC_QUAL) ? 1 : 0; sd.no_magic = 1; sd.need_lo = 0; sd.need_hi = ~0ull;
+        sdesc[k] = sd;
         arena_sz += align256(expect + 64);
     }
     u8 *d_streams = ex.alloc<u8>(arena_sz + 256);
     // padding bytes between streams are read by the 16-byte loaders: keep them defined
     ex.zero(d_streams, arena_sz + 256);
     static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
-    {
+    u64 data_out_size = 0;
+    auto run_batch = [&](bool big_streams) {
+        plan.streams.clear();
+        int in_batch[6], nb = 0;
+        for (int k = 0; k < 6; k++) {
+            const bool big = k == SEC_DATA || k == SEC_QUAL;
+            if (!need[k] || (ranged && big != big_streams)) continue;
+            sidx[k] = (int)plan.streams.size(); plan.streams.push_back(sdesc[k]); in_batch[nb++] = k;
+        }
+        if (!nb) return;
         std::string zerr;
         int rc = nafz::zstd_decode_batch(ex, d_naf, h_naf, d_streams, plan, ctx.d_predef, zerr);
         if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, std::string("can't decompress: ") + zerr + "\n");
-        for (int k = 0; k < 6; k++) {
-            if (sidx[k] < 0) continue;
+        for (int j = 0; j < nb; j++) {
+            const int k = in_batch[j];
             u64 got = plan.results[sidx[k]].out_size;
             bool exact = !(k == SEC_DATA || k == SEC_QUAL);
             if (exact ? got != sbytes[k] : got < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+            if (k == SEC_DATA) data_out_size = got;
         }
-    }
+    };
+    run_batch(false);                       // not ranged: everything
     const u8 *d_ids = d_streams + soff[SEC_IDS], *d_comm = d_streams + soff[SEC_NAMES], *d_mask = d_streams + soff[SEC_MASK];
     const u8 *d_seq = d_streams + soff[SEC_DATA], *d_qual = d_streams + soff[SEC_QUAL];
     const u32 *d_len = (const u32 *)(d_streams + soff[SEC_LEN]);
     const u64 nL = sbytes[SEC_LEN] / 4, nM = sbytes[SEC_MASK], total_bases = h.sec[SEC_DATA].orig;
 
     // raw views
-    if (view == NAFGPU_OUT_4BIT) return DecodeOut{d_seq, plan.results[sidx[SEC_DATA]].out_size};
+    if (view == NAFGPU_OUT_4BIT) return DecodeOut{d_seq, data_out_size};
     if (view == NAFGPU_OUT_LENGTHS) return DecodeOut{(const u8 *)d_len, sbytes[SEC_LEN]};
     if (view == NAFGPU_OUT_MASK) return DecodeOut{d_mask, nM};
 
@@ -607,10 +626,27 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
             return rec_text_size(B.prefix, nl, B.name_nl, B.seq_present, B.seq_nl, B.with_qual, B.W, B.seq_present ? B.L[i] : 0);
         }, NR, d_out_start);
     }
-    A.N = NR; A.out_start = d_out_start;
+    A.N = NR; A.out_start = d_out_start; A.rec0 = 0;
     u64 total; ex.download(&total, d_out_start + NR, 8);
+    if (ranged) {
+        // records [r0, r1) only: their text is the byte range [o0, o1) of the whole output
+        const u64 r0 = o.first_record < NR ? o.first_record : NR, r1 = (o.n_records < NR - r0) ? r0 + o.n_records : NR;
+        u64 o01[2] = { total, total };
+        ex.download(&o01[0], d_out_start + r0, 8); ex.download(&o01[1], d_out_start + r1, 8);
+        if (need[SEC_DATA] || need[SEC_QUAL]) {
+            u64 b01[2]; ex.download(&b01[0], d_seq_start + r0, 8); ex.download(&b01[1], d_seq_start + r1, 8);
+            if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
+            if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
+            run_batch(true);
+        }
+        u64 *local = ex.alloc<u64>(r1 - r0 + 2);
+        const u64 *src = d_out_start + r0; const u64 base = o01[0];
+        ex.for_each(r1 - r0 + 1, [=] __device__ (size_t i) { local[i] = src[i] - base; }, "range_out_start");
+        A.N = NR = r1 - r0; A.out_start = d_out_start = local; A.rec0 = r0;
+        total = o01[1] - o01[0];
+    }
     A.total = total;
-    if (total == 0) return none;
+    if (total == 0 || NR == 0) return none;
     u8 *d_text = ex.alloc<u8>(total + 64);
     A.out = d_text;
     {

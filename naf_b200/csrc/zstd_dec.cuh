@@ -43,6 +43,7 @@ struct ZBlock {
     u8  first_in_frame;
     u8  first_in_stream;
     u8  stream;
+    u8  skip;           // output not wanted (record-range decode): K5 / K6 leave the block alone
     // --- K1 ---
     u32 lit_regen, lit_csize;
     u8  lit_type, lit_streams, lit_hdr, modes;
@@ -74,9 +75,12 @@ struct ZStreamDesc {
     u64 out_off, out_size;      // region of the output arena; out_size = expected regenerated size
     int one_frame;              // 1: stop after the first frame like the reference's streaming loops
     int no_magic;               // 1: the first frame's 4-byte magic was stripped (.naf sections, compressor.c:158)
+    u64 need_lo = 0, need_hi = ~0ull;   // only bytes [need_lo, need_hi) of the regenerated stream are wanted: a stream WITHOUT
+                                // sequences skips the literal decode of every block outside the range
 };
 
 struct ZStreamResult { u64 out_size; u64 nseq; u64 consumed; };
+struct ZNeedTab { u64 lo[8], hi[8]; u32 on[8]; };
 
 static const int HUF_SLOT_ENTRIES = 2048;     // u16 each
 static const int FSE_SLOT_ENTRIES = 1280;     // u32 each: LL 512 | OF 256 | ML 512
@@ -421,7 +425,7 @@ HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr)
 {
     u32 i = t >> 2, k = t & 3;
     const ZBlock &b = a.blk[i];
-    if (b.type != 2 || b.lit_type < 2) return;
+    if (b.type != 2 || b.lit_type < 2 || b.skip) return;
     if (b.lit_streams == 1 && k) return;
     if (b.huf_src < 0) return;
     const ZBlock &hb = a.blk[b.huf_src];
@@ -472,6 +476,7 @@ HD void fill_span(u8 *d, u8 v, u32 n, u32 tid, u32 nt)
 HD void k_copy_block(const ZDecArgs &a, u32 i, u32 tid, u32 nthreads)
 {
     const ZBlock &b = a.blk[i];
+    if (b.skip) return;
     if (b.type == 0) { copy_span(a.out + b.out_off, a.in + b.src, b.rsize, tid, nthreads); return; }
     if (b.type == 1) { fill_span(a.out + b.out_off, a.in[b.src], b.rsize, tid, nthreads); return; }
     if (b.lit_type >= 2) return;
@@ -720,6 +725,24 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         }
     }
 
+    // record-range decode: blocks whose output lies outside the wanted bytes of a sequence-free stream are left alone
+    {
+        ZNeedTab nt; memset(&nt, 0, sizeof nt); bool any = false;
+        for (size_t s = 0; s < plan.streams.size() && s < 8; s++) {
+            const ZStreamDesc &sd = plan.streams[s];
+            nt.on[s] = plan.results[s].nseq == 0 && (sd.need_lo > 0 || sd.need_hi < plan.results[s].out_size);
+            nt.lo[s] = sd.out_off + sd.need_lo; nt.hi[s] = sd.need_hi == ~0ull ? ~0ull : sd.out_off + sd.need_hi;
+            any = any || nt.on[s];
+        }
+        if (any && plan.streams.size() <= 8) {
+            const ZNeedTab t = nt;
+            ex.for_each(nblk, [=] HDN (size_t i) {
+                ZBlock &b = a.blk[i];
+                const u64 lo = b.out_off, hi = lo + blk_out_size(b);
+                if (t.on[b.stream] && (hi <= t.lo[b.stream] || lo >= t.hi[b.stream])) b.skip = 1;
+            }, "zd_need");
+        }
+    }
     if (n_comp) launch_literals(ex, a);
     ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_copy_block(a, (u32)i, tid, nt); }, "zd_copy_block");
 

@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs
         i32 src = -1; u32 need = 0;
         if (i < a.nblk) {
             const ZBlock &b = a.blk[i];
-            if (b.type == 2 && b.lit_type >= 2 && b.huf_src >= 0 && a.blk[b.huf_src].huf_bits) { src = b.huf_src; need = 1u << a.blk[b.huf_src].huf_bits; }
+            if (b.type == 2 && b.lit_type >= 2 && !b.skip && b.huf_src >= 0 && a.blk[b.huf_src].huf_bits) { src = b.huf_src; need = 1u << a.blk[b.huf_src].huf_bits; }
         }
         const i32 prev = __shfl_up_sync(0xFFFFFFFFu, src, 1);
         const bool leader = need && (lane == 0 || prev != src);

@@ -236,3 +236,20 @@ def split_records(text: bytes, pieces: int) -> List[bytes]:
             cuts.append(n if j >= len(nl) else max(int(nl[j]) + 1, cuts[-1]))
     cuts.append(n)
     return [text[cuts[i]:cuts[i + 1]] for i in range(pieces)]
+
+
+def record_range(n_records: int, rank: int, world: int):
+    """records [first, first + count) of rank `rank` when `n_records` are dealt out evenly"""
+    first = n_records * rank // world
+    return first, n_records * (rank + 1) // world - first
+
+
+def decode_shard(ctx, naf, rank: int, world: int, view: str = "default", **kw) -> bytes:
+    """This rank's piece of the text of a .naf file: the ranks' pieces, concatenated in rank order, are the full output
+    (nafgpu_dec_opts.first_record / n_records; sequence and quality blocks outside the range are not decoded when the
+    frames carry no sequences, as ours do).  Every rank needs the whole file (it is the small side: broadcast it)."""
+    n = container.read_header(naf if isinstance(naf, bytes) else bytes(naf)).n_sequences
+    first, count = record_range(n, rank, world)
+    if count == 0:
+        return b""
+    return ctx.decode(naf, view, first_record=first, n_records=count, **kw)

@@ -233,3 +233,29 @@ def test_shards_gpu_bigger(oracle):
         finally:
             for c in ctxs:
                 c.close()
+
+
+@pytest.mark.gpu
+def test_record_range_decode(gpu, oracle):
+    """one rank's piece of a multi-GPU decode: the pieces of any split concatenate to the full output, for files made by
+    us (sequence-free frames: blocks outside the range are skipped) and by the reference (dependent blocks: decoded whole)"""
+    files = []
+    for text, kw in [(synth.fastq(40_001, 150, seed=61), {}), (synth.fasta_softmasked(4_000_001, width=60, seed=62, n_records=11, repeats=True), {}),
+                     (synth.protein_fasta(30_000, 300, seed=63), {"seq_type": "protein"}), (synth.ont_fasta(60, 1000, 50000, seed=64), {})]:
+        files.append(gpu.encode(text, **kw))
+        if helpers.have_ref():
+            args = ["--protein"] if kw.get("seq_type") == "protein" else []
+            rc, naf, err = helpers.ref_run("ennaf", args + ["-c"], text)
+            assert rc == 0, err
+            files.append(naf)
+    for case in helpers.manifest("cases"):
+        files.append(helpers.golden("cases", case["name"] + ".naf"))
+    for naf in files:
+        for view in ("default", "fasta", "ids", "names", "sequences"):
+            try:
+                full = gpu.decode(naf, view)
+            except Exception:
+                continue
+            for world in (1, 2, 3, 8):
+                got = b"".join(sharded.decode_shard(gpu, naf, r, world, view) for r in range(world))
+                assert got == full, (view, world, len(got), len(full))
