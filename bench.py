@@ -344,7 +344,35 @@ def run_ours(args):
                     single["verified"] = bool(torch.equal(got, d_text[:n_text]))
                     single["text_bytes"] = int(tsize3)
                     del got, hn
-            del out
+            # ---- and back: every rank decodes ITS records of that one file (record-range decode; the file is small next to
+            # the text, so every rank holds it -- as it would after reading it from disk: device copy + host mirror, untimed)
+            nbytes = torch.tensor([int(out.numel()) if rank == 0 else 0], device="cuda", dtype=torch.int64)
+            dist.broadcast(nbytes, src=0)
+            d_file = out if rank == 0 else torch.empty(int(nbytes.item()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(d_file, src=0)
+            h_file = d_file.cpu()
+            ropts = api.make_dec_opts(first_record=rank * records, n_records=records)
+            dts = []
+            for rep in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                taddr4, tsize4 = ctx.decode_device(d_file.data_ptr(), d_file.numel(), (h_file.data_ptr(), h_file.numel()), ropts)
+                torch.cuda.synchronize()
+                barrier()
+                dts.append(time.perf_counter() - t0)
+            td = torch.tensor([min(dts[1:])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(td, op=dist.ReduceOp.MAX)
+            okd = torch.tensor([1], device="cuda", dtype=torch.int64)
+            if not args.no_verify:                # my piece of the one file is exactly my shard of the text
+                got = torch.empty(tsize4, dtype=torch.uint8, device="cuda")
+                ctx_copy_d2d(got, taddr4, tsize4)
+                okd[0] = int(tsize4 == n_text and bool(torch.equal(got, d_text[:n_text])))
+                del got
+            dist.all_reduce(okd, op=dist.ReduceOp.MIN)
+            single["decode_gbases_s"] = bases * world / float(td.item()) / 1e9
+            single["decode_ms"] = float(td.item()) * 1e3
+            single["decode_verified_all_ranks"] = bool(okd.item())
+            del out, d_file, h_file
         except Exception as e:                # the headline numbers above do not depend on this path
             single = {"error": repr(e)[:300]}
 
