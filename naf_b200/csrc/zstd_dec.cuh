@@ -26,6 +26,7 @@
 #pragma once
 #include "zstd_hd.cuh"
 #include <string>
+#include <thread>
 #include <vector>
 #include <string.h>
 
@@ -133,6 +134,17 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
             if (bsize > 128 * 1024 && type != 1) { err = "zstd block larger than 128 KB"; return -1; }
             if (pos + b.csize > n) { err = "zstd block truncated"; return -1; }
             pos += b.csize;
+            // The walk is a chain of dependent reads ~10 KB apart: every header is a cache miss in host memory.  Blocks of
+            // one stream have nearly equal sizes, so the headers after the next one are where "same size again" puts
+            // them, give or take a few lines: request those lines now and the misses overlap instead of queueing.
+            {
+                const u64 step = (u64)b.csize + 3;
+                for (u64 k = 1; k <= 3; k++) {
+                    const u64 guess = pos + k * step;
+                    if (guess + 64 * k + 64 >= n) break;
+                    for (u64 d = 0; d <= 2 * k; d++) __builtin_prefetch(p + guess - 64 * k + 64 * d, 0, 0);
+                }
+            }
             blocks.push_back(b);
             first_in_frame = false; first_in_stream = false;
             if (last) break;
@@ -645,11 +657,25 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
 {
     plan.blocks.clear();
     plan.results.assign(plan.streams.size(), ZStreamResult{0, 0, 0});
-    for (size_t s = 0; s < plan.streams.size(); s++) {
-        u64 consumed = 0;
-        if (plan.streams[s].src_len == 0) { err = "empty zstd stream"; return -1; }
-        if (zstd_walk_stream(h_in, plan.streams[s], (int)s, plan.blocks, &consumed, err)) return -1;
-        plan.results[s].consumed = consumed;
+    {
+        // one host thread per big stream (the walks are independent chains of cache misses), the small ones inline
+        const size_t ns = plan.streams.size();
+        std::vector<std::vector<ZBlockHead>> part(ns);
+        std::vector<std::string> errs(ns);
+        std::vector<int> rcs(ns, 0);
+        std::vector<u64> used(ns, 0);
+        std::vector<std::thread> workers;
+        for (size_t s = 0; s < ns; s++) if (plan.streams[s].src_len == 0) { err = "empty zstd stream"; return -1; }
+        auto walk = [&](size_t s) { rcs[s] = zstd_walk_stream(h_in, plan.streams[s], (int)s, part[s], &used[s], errs[s]); };
+        for (size_t s = 0; s < ns; s++) if (ns > 1 && plan.streams[s].src_len > (8u << 20)) workers.emplace_back(walk, s);
+        for (size_t s = 0; s < ns; s++) if (!(ns > 1 && plan.streams[s].src_len > (8u << 20))) walk(s);
+        for (auto &w : workers) w.join();
+        for (size_t s = 0; s < ns; s++) {
+            if (rcs[s]) { err = errs[s]; return -1; }
+            const u32 base = (u32)plan.blocks.size();
+            for (auto &b : part[s]) { ZBlockHead h = b; h.frame_first_blk += base; plan.blocks.push_back(h); }
+            plan.results[s].consumed = used[s];
+        }
     }
     const u32 nblk = (u32)plan.blocks.size();
     if (nblk == 0) return 0;
