@@ -183,7 +183,7 @@ __device__ __forceinline__ u8 base_at(const TextArgs &A, u64 bi)
     return c;
 }
 
-static const int WT_THREADS = 256, WT_ITERS = 2, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 8 KB of text per CTA: two 16-byte chunks per thread
+static const int WT_THREADS = 256, WT_ITERS = 4, WT_TILE = WT_THREADS * 16 * WT_ITERS;   // 16 KB of text per CTA: four 16-byte chunks per thread
 static const int WT_MAXREC = 256;     // records staged in shared memory per tile (more than that: read them from HBM)
 
 struct RecS { u64 out0, L, sbase; u32 id_s, id_len, cm_s, cm_len; };
