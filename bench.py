@@ -178,10 +178,10 @@ ALGO_BYTES_PER_BASE = {
     "zd_literals": 0.83 + 1.67, "k_write_text": 1.67 + 0.19 + 2.185,
 }
 # DRAM bytes per base measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch, 1 M reads:
-# profiles/r1d_top_full_1Mreads.summary.txt, r1e for k_write_text); bench.py scales them to the launch it timed
+# profiles/r1k_top_full_1Mreads.summary.txt); bench.py scales them to the launch it timed
 NCU_TRAFFIC_PER_BASE = {
-    "k_fast_count": 360.9e6 / 150e6, "k_fast_scatter": 664.8e6 / 150e6, "k_zenc_hist": 258.9e6 / 150e6, "k_zenc_encode": 351.1e6 / 150e6,
-    "zd_literals": 332.9e6 / 150e6, "k_write_text": 638.1e6 / 150e6,
+    "k_fast_tiles": 329.9e6 / 150e6, "k_fast_count": 363.9e6 / 150e6, "k_fast_scatter": 664.9e6 / 150e6, "k_pack4": 213.4e6 / 150e6,
+    "k_zenc_hist": 257.5e6 / 150e6, "k_zenc_encode": 351.2e6 / 150e6, "zd_literals": 332.5e6 / 150e6, "k_write_text": 587.9e6 / 150e6,
 }
 
 
@@ -402,7 +402,7 @@ def run_ours(args):
             roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_base": bpb})
         if name in NCU_TRAFFIC_PER_BASE:
             roofline["traffic"] = NCU_TRAFFIC_PER_BASE[name] * bases
-            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r1d_top_full_1Mreads.summary.txt), scaled per base"
+            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r1k_top_full_1Mreads.summary.txt), scaled per base"
         line = {
             "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--configs", default="c2,c3,c4,c5")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--ref", action="store_true", help="also: the UNMODIFIED reference ennaf (oracle/_ref) makes the .naf on the host, "
+                    "the GPU decodes it; must be byte-identical to what the reference unnaf prints (= the input here)")
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -65,7 +67,36 @@ def main():
             naf_size = size
             del out, d_naf
         e, d = min(enc_ms), min(dec_ms)
-        print(json.dumps({"config": name, "workload": what, "text_bytes": n, "bases": bases, "naf_bytes": naf_size, "ratio": round(naf_size / n, 4),
+        ref = None
+        ref_ennaf = os.path.join(ROOT, "oracle", "_ref", "ennaf")
+        if a.ref and os.access(ref_ennaf, os.X_OK):
+            import subprocess
+            work = f"/dev/shm/nafsweep_{os.getpid()}"
+            os.makedirs(work, exist_ok=True)
+            d_text[:n].cpu().numpy().tofile(os.path.join(work, "in.txt"))
+            t1 = time.time()
+            args = [ref_ennaf] + (["--protein"] if kw.get("seq_type") == "protein" else []) + [os.path.join(work, "in.txt"), "-o", os.path.join(work, "ref.naf")]
+            subprocess.run(args, check=True, env=dict(os.environ, TMPDIR=work))
+            ref_enc_s = time.time() - t1
+            rnaf = np.fromfile(os.path.join(work, "ref.naf"), dtype=np.uint8)
+            d_rnaf = torch.zeros(rnaf.size + 64, dtype=torch.uint8, device="cuda")
+            d_rnaf[:rnaf.size] = torch.from_numpy(rnaf).cuda()
+            h_rnaf = torch.from_numpy(rnaf)
+            rms, rok = [], True
+            for rep in range(a.reps):
+                taddr, tsize = ctx.decode_device(d_rnaf.data_ptr(), rnaf.size, (h_rnaf.data_ptr(), rnaf.size), do)
+                rms.append(ctx.timing().kernels_ms)
+                out = torch.empty(tsize, dtype=torch.uint8, device="cuda")
+                cudart.cudaMemcpy(out.data_ptr(), taddr, tsize, 3)
+                rok = rok and tsize == n and bool(torch.equal(out, d_text[:n]))
+                del out
+            ref = {"reference_naf_bytes": int(rnaf.size), "reference_ennaf_s": round(ref_enc_s, 1), "gpu_decode_of_reference_naf_bit_exact": rok,
+                   "gpu_decode_of_reference_naf_ms": round(min(rms), 3), "gpu_decode_of_reference_naf_gbases_s": round(bases / min(rms) / 1e6, 2)}
+            for f in os.listdir(work):
+                os.remove(os.path.join(work, f))
+            os.rmdir(work)
+            del d_rnaf
+        print(json.dumps({"config": name, "workload": what, "reference_made_file": ref, "text_bytes": n, "bases": bases, "naf_bytes": naf_size, "ratio": round(naf_size / n, 4),
                           "round_trip_bit_exact": ok, "fast_parser": not fallback, "encode_ms": round(e, 3), "decode_ms": round(d, 3),
                           "encode_gbases_s": round(bases / e / 1e6, 2), "decode_gbases_s": round(bases / d / 1e6, 2),
                           "host_generation_s": round(gen_s, 1)}), flush=True)
