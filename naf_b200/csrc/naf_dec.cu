@@ -482,8 +482,10 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         arena_sz += align256(expect + 64);
     }
     u8 *d_streams = ex.alloc<u8>(arena_sz + 256);
-    // padding bytes between streams are read by the 16-byte loaders: keep them defined
-    ex.zero(d_streams, arena_sz + 256);
+    // padding bytes between streams are read by the 16-byte loaders: keep them defined (the streams themselves are
+    // written by the decoder; bytes of blocks a record-range decode skips are never used)
+    for (int k = 0; k < 6; k++) if (need[k]) ex.zero(d_streams + soff[k] + sbytes[k], align256(sbytes[k] + 64) - sbytes[k]);
+    ex.zero(d_streams + arena_sz, 256);
     static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
     u64 data_out_size = 0;
     auto run_batch = [&](bool big_streams) {

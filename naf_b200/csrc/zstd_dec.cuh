@@ -317,7 +317,8 @@ HD const u32 *fse_table_for(const ZDecArgs &a, i32 src, int kind, int *log)
 
 // K4 — decode the sequences of one block (spec "Sequences_Section": bitstream, state update order)
 // Replaces zstd_decompress_block.c:937 ZSTD_decodeSequence, minus offset resolution (done in K7).
-HD void k_seq_decode(const ZDecArgs &a, u32 i)
+// `stl/sto/stm`: the block's three decode tables already copied next to the thread (shared memory on the GPU), or nullptr
+HD void k_seq_decode(const ZDecArgs &a, u32 i, const u32 *stl = nullptr, const u32 *sto = nullptr, const u32 *stm = nullptr)
 {
     ZBlock &b = a.blk[i];
     b.repfn = repfn_identity(); b.match_total = 0;
@@ -325,6 +326,7 @@ HD void k_seq_decode(const ZDecArgs &a, u32 i)
     if (b.ll_src < 0 || b.of_src < 0 || b.ml_src < 0) { b.nseq = 0; return; }
     int ll_log, of_log, ml_log;
     const u32 *tl = fse_table_for(a, b.ll_src, 0, &ll_log), *to = fse_table_for(a, b.of_src, 1, &of_log), *tm = fse_table_for(a, b.ml_src, 2, &ml_log);
+    if (stl) { tl = stl; to = sto; tm = stm; }
     BackBits bs;
     if (!bs.init(a.in + b.src + b.bits_off, b.csize - b.bits_off)) { zerr(a, Z_ERR_SEQ_STREAM, i); b.nseq = 0; return; }
     u32 sl = bs.read(ll_log), so = bs.read(of_log), sm = bs.read(ml_log);
@@ -632,6 +634,21 @@ HD void k_jump(const ZDecArgs &a, u64 w)
     if (clear != bits) a.status[2] = 1;
 }
 
+// K4 / K7 / K8-big launches: generic executors run the HD bodies as they are; the CUDA executor overloads them
+// (zstd_dec_cuda.cuh) with kernels that stage tables / sequence fields in shared memory.
+template <class Exec> void launch_seq_decode(Exec &ex, const ZDecArgs &a)
+{
+    ex.for_each(a.nblk, [=] HDN (size_t i) { k_seq_decode(a, (u32)i); }, "zd_seq_decode", 32);
+}
+template <class Exec> void launch_seq_resolve(Exec &ex, const ZDecArgs &a)
+{
+    ex.for_each(a.nblk, [=] HDN (size_t i) { k_seq_resolve(a, (u32)i); }, "zd_seq_resolve", 32);
+}
+template <class Exec> void launch_seq_exec_big(Exec &ex, const ZDecArgs &a)
+{
+    ex.for_each_group(a.nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_seq_exec_big(a, (u32)i, tid, nt); }, "zd_seq_exec_big");
+}
+
 // K5 launch: generic executors run one thread per Huffman stream straight from the table pool; the CUDA
 // executor overloads this (zstd_dec_cuda.cuh) with a kernel that first stages the tables in shared memory.
 template <class Exec> void launch_literals(Exec &ex, const ZDecArgs &a)
@@ -730,7 +747,7 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
     if (tot_huf) ex.for_each(nblk, [=] HDN (size_t i) { k_huf_table(a, (u32)i); }, "zd_huf_table", 64);
     if (tot_seq) {
         ex.for_each(nblk, [=] HDN (size_t i) { k_fse_tables(a, (u32)i); }, "zd_fse_tables", 32);
-        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_decode(a, (u32)i); }, "zd_seq_decode", 32);
+        launch_seq_decode(ex, a);
     }
     ex.for_each(a.nchunks, [=] HDN (size_t c) { k_scan2_phase1(a, (u32)c); }, "zd_scan2");
     ex.for_each(1, [=] HDN (size_t) { k_scan2_phase2(a); }, "zd_scan2");
@@ -787,9 +804,9 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         a.link = ex.template alloc<u32>(span + 1);
         a.bitmap = ex.template alloc<u32>(words + 1);
         ex.zero(a.bitmap, (words + 1) * 4);
-        ex.for_each(nblk, [=] HDN (size_t i) { k_seq_resolve(a, (u32)i); }, "zd_seq_resolve", 32);
+        launch_seq_resolve(ex, a);
         ex.for_each(tot_seq, [=] HDN (size_t j) { k_seq_exec_small(a, j); }, "zd_seq_exec_small");
-        ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_seq_exec_big(a, (u32)i, tid, nt); }, "zd_seq_exec_big");
+        launch_seq_exec_big(ex, a);
         for (int round = 0; round < 40; round++) {
             ex.zero(a.status + 2, 4);
             for (int k = 0; k < 4; k++) ex.for_each(words, [=] HDN (size_t w) { k_jump(a, w); }, "zd_jump");

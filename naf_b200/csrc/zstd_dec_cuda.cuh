@@ -67,4 +67,140 @@ inline void launch_literals(nafg::CudaExec &ex, const ZDecArgs &a)
     ex.prof_end();
 }
 
+
+// ---- sequences of reference-made frames: the three serial-per-block kernels, with their working sets in shared memory.
+// One block of ids / comments can carry tens of thousands of sequences and the kernel takes as long as its longest
+// block, so what counts is the latency per sequence: FSE states walk 5 KB of tables (L2-latency loads when left in
+// HBM), repeat offsets are a serial recurrence over fields scattered 24 bytes apart.
+
+static const int SD_BLOCKS = 16;                                 // blocks per CTA of k_seq_decode_smem (one lane each)
+static const u32 SD_MIN_SEQ = 64;                                // below that the tables are not worth staging
+
+__global__ void __launch_bounds__(32) k_seq_decode_smem(const ZDecArgs a)
+{
+    extern __shared__ u32 sd_tabs[];                             // SD_BLOCKS x FSE_SLOT_ENTRIES
+    __shared__ u8 staged[SD_BLOCKS];
+    const u32 lane = threadIdx.x, first = blockIdx.x * SD_BLOCKS;
+    for (int j = 0; j < SD_BLOCKS; j++) {
+        const u32 i = first + j;
+        bool st = false;
+        if (i < a.nblk) {
+            const ZBlock &b = a.blk[i];
+            st = b.type == 2 && b.nseq >= SD_MIN_SEQ && b.ll_src >= 0 && b.of_src >= 0 && b.ml_src >= 0;
+            if (st) {
+                int l0, l1, l2;
+                const u32 *t0 = fse_table_for(a, b.ll_src, 0, &l0), *t1 = fse_table_for(a, b.of_src, 1, &l1), *t2 = fse_table_for(a, b.ml_src, 2, &l2);
+                u32 *d = sd_tabs + (size_t)j * FSE_SLOT_ENTRIES;
+                for (u32 k = lane; k < (1u << l0); k += 32) d[k] = t0[k];
+                for (u32 k = lane; k < (1u << l1); k += 32) d[FSE_OF_AT + k] = t1[k];
+                for (u32 k = lane; k < (1u << l2); k += 32) d[FSE_ML_AT + k] = t2[k];
+            }
+        }
+        if (lane == 0) staged[j] = st;
+    }
+    __syncwarp();
+    if (lane < SD_BLOCKS && first + lane < a.nblk) {
+        const u32 *d = sd_tabs + (size_t)lane * FSE_SLOT_ENTRIES;
+        if (staged[lane]) k_seq_decode(a, first + lane, d, d + FSE_OF_AT, d + FSE_ML_AT);
+        else k_seq_decode(a, first + lane);
+    }
+}
+
+// one warp per block: 32 sequences' fields at a time into shared memory, lane 0 runs the repeat-offset recurrence over
+// them, then every lane validates and stores its own sequence
+__global__ void __launch_bounds__(128) k_seq_resolve_warp(const ZDecArgs a)
+{
+    __shared__ u32 s_of[4][32], s_ll[4][32];
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * 4 + w;
+    if (i >= a.nblk) return;
+    const ZBlock &b = a.blk[i];
+    if (b.type != 2 || b.nseq == 0) return;
+    u32 r0 = b.rep_in[0], r1 = b.rep_in[1], r2 = b.rep_in[2];
+    ZSeq *seq = a.seq + b.seq_base;
+    const u64 out_off = b.out_off, frame_out = b.frame_out;
+    bool bad = false;
+    for (u32 k0 = 0; k0 < b.nseq; k0 += 32) {
+        const u32 m = b.nseq - k0 < 32 ? b.nseq - k0 : 32;
+        u32 ofv = 0, ll = 0, dr = 0;
+        if (lane < m) { const ZSeq s = seq[k0 + lane]; ofv = s.of; ll = s.ll; dr = s.dst_rel; }
+        s_of[w][lane] = ofv; s_ll[w][lane] = ll;
+        __syncwarp();
+        if (lane == 0) {
+            for (u32 j = 0; j < m; j++) {
+                const u32 v = s_of[w][j]; u32 off;
+                if (v > 3) { off = v - 3; r2 = r1; r1 = r0; r0 = off; }
+                else {
+                    const u32 idx = v - 1 + (s_ll[w][j] == 0 ? 1u : 0u);
+                    if (idx == 0) off = r0;
+                    else {
+                        off = idx == 1 ? r1 : (idx == 2 ? r2 : r0 - 1);
+                        if (idx != 1) r2 = r1;
+                        r1 = r0; r0 = off;
+                    }
+                }
+                s_of[w][j] = off;
+            }
+        }
+        __syncwarp();
+        if (lane < m) {
+            u32 off = s_of[w][lane];
+            const u64 match_pos = out_off + dr + ll;
+            if (off == 0 || off > match_pos - frame_out) { bad = true; off = 0; seq[k0 + lane].ml = 0; }
+            seq[k0 + lane].of = off;
+        }
+        __syncwarp();
+    }
+    if (bad) zerr(a, Z_ERR_OFFSET, i);
+}
+
+// one CTA per block: find the long sequences in parallel, then copy each with the whole CTA; tail literals
+__global__ void __launch_bounds__(256) k_seq_exec_big_cta(const ZDecArgs a)
+{
+    __shared__ u32 big[256];
+    __shared__ u32 nbig;
+    const u32 i = blockIdx.x, tid = threadIdx.x;
+    const ZBlock &b = a.blk[i];
+    if (b.type != 2 || b.nseq == 0) return;
+    const ZSeq *seq = a.seq + b.seq_base;
+    for (u32 base = 0; base < b.nseq; base += 256) {
+        if (tid == 0) nbig = 0;
+        __syncthreads();
+        const u32 k = base + tid;
+        if (k < b.nseq && seq[k].ll + seq[k].ml > BIG_SEQ) big[atomicAdd(&nbig, 1u)] = k;
+        __syncthreads();
+        const u32 n = nbig;
+        for (u32 j = 0; j < n; j++) k_seq_exec_one(a, seq[big[j]], tid, 256);
+        __syncthreads();
+    }
+    const ZSeq &last = seq[b.nseq - 1];
+    const u32 lit_used = last.lit_rel + last.ll, out_used = last.dst_rel + last.ll + last.ml;
+    const u8 *lit = a.lit_scratch + b.lit_off + lit_used; u8 *o = a.out + b.out_off + out_used;
+    for (u32 k = tid; k + lit_used < b.lit_regen; k += 256) o[k] = lit[k];
+}
+
+inline void launch_seq_decode(nafg::CudaExec &ex, const ZDecArgs &a)
+{
+    if (!a.nblk) return;
+    static bool attr = false;
+    const int smem = SD_BLOCKS * FSE_SLOT_ENTRIES * 4;
+    if (!attr) { cudaFuncSetAttribute(k_seq_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    ex.prof_begin("zd_seq_decode");
+    k_seq_decode_smem<<<(a.nblk + SD_BLOCKS - 1) / SD_BLOCKS, 32, smem, ex.stream>>>(a);
+    ex.prof_end();
+}
+inline void launch_seq_resolve(nafg::CudaExec &ex, const ZDecArgs &a)
+{
+    if (!a.nblk) return;
+    ex.prof_begin("zd_seq_resolve");
+    k_seq_resolve_warp<<<(a.nblk + 3) / 4, 128, 0, ex.stream>>>(a);
+    ex.prof_end();
+}
+inline void launch_seq_exec_big(nafg::CudaExec &ex, const ZDecArgs &a)
+{
+    if (!a.nblk) return;
+    ex.prof_begin("zd_seq_exec_big");
+    k_seq_exec_big_cta<<<a.nblk, 256, 0, ex.stream>>>(a);
+    ex.prof_end();
+}
+
 }  // namespace nafz
