@@ -483,18 +483,20 @@ HD RepSlot repslot_concrete(u32 v) { RepSlot r; r.src = -1; r.delta = 0; r.value
 // describing the actual offset used by this sequence.
 HD RepSlot repfn_step(RepFn &f, u32 ofv, u32 ll)
 {
+    // (no f.s[idx] with a run-time idx: that would put the whole history in local memory on the GPU, and this runs once
+    // per sequence in a single thread per block)
     RepSlot used;
     if (ofv > 3) {
         used = repslot_concrete(ofv - 3);
         f.s[2] = f.s[1]; f.s[1] = f.s[0]; f.s[0] = used;
         return used;
     }
-    u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
+    const u32 idx = ofv - 1 + (ll == 0 ? 1u : 0u);
     if (idx == 0) return f.s[0];
-    if (idx == 3) { used = f.s[0]; if (used.src < 0) used.value -= 1; else used.delta -= 1; }
-    else used = f.s[idx];
-    if (idx != 1) f.s[2] = f.s[1];
-    f.s[1] = f.s[0]; f.s[0] = used;
+    if (idx == 1) { used = f.s[1]; f.s[1] = f.s[0]; f.s[0] = used; return used; }
+    if (idx == 2) used = f.s[2];
+    else { used = f.s[0]; if (used.src < 0) used.value -= 1; else used.delta -= 1; }
+    f.s[2] = f.s[1]; f.s[1] = f.s[0]; f.s[0] = used;
     return used;
 }
 
