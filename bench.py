@@ -335,7 +335,7 @@ def run_ours(args):
             single = {"encode_gbases_s": bases * world / float(tt.item()) / 1e9, "ms": float(tt.item()) * 1e3, "collectives": "2 x all_gather (9 + 12 int64 per rank), 1 gather of zstd blocks"}
             if rank == 0:
                 single["naf_bytes"] = int(out.numel())
-                if not args.no_verify:        # rank 0 decodes the merged file: right size, and its own shard comes back bit-exact
+                if not args.no_verify and world <= 2:   # rank 0 decodes the WHOLE merged file (beyond 2 ranks the per-rank range decodes below check every record anyway)
                     hn = out.cpu()
                     taddr3, tsize3 = ctx.decode_device(out.data_ptr(), out.numel(), (hn.data_ptr(), hn.numel()), dopts)
                     got = torch.empty(n_text, dtype=torch.uint8, device="cuda")
