@@ -199,7 +199,8 @@ typedef struct {
     uint8_t  prev_last_case;    /* case of the last base before this shard (0 if there is none) */
     uint8_t  next_first_code;   /* 4-bit code of the first base after this shard (0 if there is none) */
     uint8_t  is_last;           /* last shard: sets Last_Block and writes the trailing mask run */
-    uint8_t  pad[5];
+    uint8_t  store_qual;        /* some shard is FASTQ: the file has a quality stream, and every shard (an empty one too) contributes to it */
+    uint8_t  pad[4];
 } nafgpu_shard_link;
 
 int nafgpu_shard_begin(nafgpu_ctx *ctx, const uint8_t *text, size_t n, int text_on_device, const nafgpu_enc_opts *opts,

@@ -55,7 +55,7 @@ class ShardCounts(C.Structure):
 
 class ShardLink(C.Structure):
     _fields_ = [("bases_before", C.c_uint64), ("run_carry", C.c_uint64), ("prev_last_case", C.c_uint8),
-                ("next_first_code", C.c_uint8), ("is_last", C.c_uint8), ("pad", C.c_uint8 * 5)]
+                ("next_first_code", C.c_uint8), ("is_last", C.c_uint8), ("store_qual", C.c_uint8), ("pad", C.c_uint8 * 4)]
 
 
 # every symbol include/nafgpu.h declares (tests check the .so exports exactly these)

@@ -613,9 +613,10 @@ void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &lin
     }
     // ---- zstd blocks of every stream; only the last shard closes the frames
     ZEncBatch batch; batch.final_shard = link.is_last != 0;
-    const bool present[6] = { true, true, true, (bool)H.store_mask, true, (bool)H.store_qual };
+    // (a shard that is empty, or FASTA-empty among FASTQ shards, still adds its -- empty -- block to every stream of the file)
+    const bool present[6] = { true, true, true, (bool)H.store_mask, true, (bool)(H.store_qual || link.store_qual) };
     int which[6], ns = 0;
-    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.raw[k], 0); }
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.stream[k] ? H.raw[k] : 0, 0); }
     zstd_compress_batch(ctx, ex, batch);
     u64 total = 0; std::vector<u64> at(ns);
     for (int j = 0; j < ns; j++) { at[j] = total; total += (batch.frame_size[j] + 63) & ~63ull; }

@@ -58,6 +58,7 @@ class Link:
     prev_last_case: int
     next_first_code: int
     is_last: int
+    store_qual: int = 0          # some shard is FASTQ: every shard contributes (possibly empty) blocks to the quality stream
 
 
 def link_for(all_counts: Sequence[Counts], rank: int) -> Link:
@@ -73,7 +74,8 @@ def link_for(all_counts: Sequence[Counts], rank: int) -> Link:
         bases_before += c.n_bases
     nxt = [c for c in all_counts[rank + 1:] if c.n_bases]
     return Link(bases_before=bases_before, run_carry=bases_before - (last_flip or 0), prev_last_case=prev_case,
-                next_first_code=nxt[0].first_code if nxt else 0, is_last=int(rank == len(all_counts) - 1))
+                next_first_code=nxt[0].first_code if nxt else 0, is_last=int(rank == len(all_counts) - 1),
+                store_qual=int(any(c.format == 2 for c in all_counts)))
 
 
 def container_layout(seq_type: int, title: Optional[bytes], line_length: Optional[int], all_counts: Sequence[Counts],
@@ -131,7 +133,7 @@ class GpuShardEncoder:
         from . import api
         l = api.ShardLink()
         l.bases_before, l.run_carry, l.prev_last_case = link.bases_before, link.run_carry, link.prev_last_case
-        l.next_first_code, l.is_last = link.next_first_code, link.is_last
+        l.next_first_code, l.is_last, l.store_qual = link.next_first_code, link.is_last, link.store_qual
         return self.ctx.shard_finish(l)
 
     def fetch(self, stream: int, dst):

@@ -90,7 +90,7 @@ class OracleShardEncoder:
                 h = last | (0 << 1) | (len(piece) << 3)
                 body += bytes([h & 255, (h >> 8) & 255, (h >> 16) & 255]) + piece
             self.bodies.append(bytes(body))
-        present = [True, True, True, bool(self.info["store_mask"]) or self.packed and not self.kw.get("no_mask"), True, bool(self.info["store_qual"])]
+        present = [True, True, True, self.packed and not self.kw.get("no_mask"), True, bool(self.info["store_qual"]) or bool(link.store_qual)]
         raw = [len(s[k]) if present[k] else 0 for k in range(6)]
         return raw, [len(self.bodies[k]) if present[k] else 0 for k in range(6)]
 
@@ -127,13 +127,15 @@ CASES = [
     ("nomask", lambda: synth.fasta_softmasked(50_000, width=60, seed=8, n_records=5), {"no_mask": True}),
     ("all_lower", lambda: synth.fasta_reads(40, 150, seed=9).lower().replace(b">read", b">READ"), {}),
     ("empty_records", lambda: b">a\n>b\nACGTacgt\n>c\n>d x y\nacgtN\n>e\n", {}),
+    ("fewer_records_than_ranks_fq", lambda: synth.fastq(3, 31, seed=10, lowercase=True), {}),
+    ("one_record_fa", lambda: b">only\n" + b"acgtN" * 1001 + b"\n", {}),
 ]
 
 
 @pytest.mark.parametrize("name,make,kw", CASES, ids=[c[0] for c in CASES])
 def test_shards_local_oracle(oracle, name, make, kw):
     text = make()
-    for world in (1, 2, 3, 5):
+    for world in (1, 2, 3, 5, 8):
         pieces = sharded.split_records(text, world)
         assert b"".join(pieces) == text and len(pieces) == world
         encs = [OracleShardEncoder(oracle, **kw) for _ in pieces]
@@ -149,7 +151,7 @@ def test_link_math():
           C_(n_records=1, n_bases=4, first_case=1, last_case=1, first_code=2),
           C_(n_records=1, n_bases=3, first_case=0, last_case=0, first_code=4)]
     l0, l1, l2, l3 = (sharded.link_for(cs, r) for r in range(4))
-    assert (l0.bases_before, l0.run_carry, l0.prev_last_case, l0.next_first_code, l0.is_last) == (0, 0, 0, 2, 0)
+    assert (l0.bases_before, l0.run_carry, l0.prev_last_case, l0.next_first_code, l0.is_last, l0.store_qual) == (0, 0, 0, 2, 0, 0)
     assert (l1.bases_before, l1.run_carry, l1.prev_last_case, l1.next_first_code) == (5, 2, 1, 2)
     assert (l2.bases_before, l2.run_carry, l2.prev_last_case, l2.next_first_code) == (5, 2, 1, 4)
     assert (l3.bases_before, l3.run_carry, l3.prev_last_case, l3.next_first_code, l3.is_last) == (9, 6, 1, 0, 1)
@@ -200,7 +202,7 @@ def test_shards_local_gpu(oracle, name, make, kw):
     import naf_b200
     text = make()
     seq_type = helpers.SEQ_TYPES[kw.get("seq_type", "dna")]
-    for world in (1, 2, 3, 5):
+    for world in (1, 2, 3, 5, 8):
         pieces = sharded.split_records(text, world)
         ctxs = [naf_b200.NafGpu(0) for _ in pieces]
         try:
