@@ -162,7 +162,7 @@ def test_zstd_compress_roundtrip(gpu, oracle):
     """our frames are valid zstd: the oracle decoder (pinned to libzstd) regenerates the input"""
     rng = np.random.default_rng(3)
     datasets = [b"", b"A", b"AB", b"A" * 70000, bytes(range(256)) * 300]
-    for n in [2, 3, 15, 16, 17, 255, 256, 1023, 1024, 1025, 5000, 65535, 65536, 65537, 200000]:
+    for n in [2, 3, 15, 16, 17, 255, 256, 1023, 1024, 1025, 5000, 32767, 32768, 32769, 65535, 65536, 65537, 200000]:
         datasets.append(bytes(rng.choice(np.frombuffer(b"\x11\x12\x14\x18\x21\x22\x24\x28\x41\x42\x44\x48\x81\x82\x84\x88", dtype=np.uint8), n)))
         datasets.append((np.clip(np.round(rng.normal(34, 6, n)), 2, 40).astype(np.uint8) + 33).tobytes())
     datasets.append(b"".join(b"SRR1.%d\0" % i for i in range(30000)))
@@ -229,3 +229,23 @@ def test_error_messages_match_reference_strings(gpu, oracle):
     for text, kw in [(b"ACGT\n", {}), (b"x>a\nAC\n", {}), (b"@r\nACGT\n+\nII\n", {}), (b"@r\nACGT\n", {}), (b"@r", {}),
                      (b"@r\nAC\nXX\nII\n", {}), (b"@r\nAC\n+\nII\nzz\n", {}), (b">a\nACZT\n", {"strict": True})]:
         check_split(gpu, oracle, text, **kw)
+
+
+def test_roundtrip_tiny_records(gpu, oracle):
+    """thousands of records per 16 KB of text: more records than a tile of the text writer stages in shared memory, more
+    runs than the fast parser lists per tile -- both directions must still be exact"""
+    rng = np.random.default_rng(71)
+    texts = []
+    for L in (1, 2, 5, 31):
+        texts.append(b"".join(b"@%d\n" % i + bytes(np.frombuffer(b"ACGTN", dtype=np.uint8)[rng.integers(0, 5, L)]) + b"\n+\n" +
+                              bytes(rng.integers(33, 127, L).astype(np.uint8)) + b"\n" for i in range(20000)))
+    texts.append(b"".join(b">s%d\n" % i + b"\n".join(bytes(np.frombuffer(b"ACGTacgt", dtype=np.uint8)[rng.integers(0, 8, 3)]) for _ in range(4)) + b"\n" for i in range(20000)))
+    texts.append(b"".join(b">%d\n" % i for i in range(50000)))                      # names only, no sequence at all
+    for text in texts:
+        naf = gpu.encode(text)
+        want = oracle.decode(oracle.encode(text)[0])
+        assert gpu.decode(naf) == want
+        assert oracle.decode(naf) == want
+        assert gpu.decode(oracle.encode(text)[0]) == want
+        for view in ("fasta", "ids", "sequences", "seq"):
+            assert gpu.decode(naf, view) == oracle.decode(naf, view), view
