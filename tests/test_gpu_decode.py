@@ -79,3 +79,38 @@ def test_oracle_roundtrip_property(gpu, oracle):
     naf, _ = oracle.encode(text)
     assert gpu.decode(naf) == text
     assert gpu.decode(naf, "fasta", line_length=0) == oracle.decode(naf, "fasta", line_length=0)
+
+
+def test_corrupt_input_never_crashes(gpu, oracle, tmp_path):
+    """bit flips, truncation and overwritten spans in .naf files made by us, by the oracle and by the reference: every
+    call returns (an error like the reference's die(), or some text -- zstd frames here carry no checksum), nothing hangs,
+    and the context keeps working (cf. unnaf/src/utils.c:52 "incomplete or truncated input")"""
+    import random
+    import naf_b200
+    rng = random.Random(7)
+    texts = [synth.fastq(3000, 150, seed=1, lowercase=True), synth.fasta_softmasked(300000, 60, seed=2, n_records=3, repeats=True)]
+    files = []
+    for t in texts:
+        files += [gpu.encode(t), oracle.encode(t)[0]]
+        if helpers.have_ref():
+            rc, naf, err = helpers.ref_run("ennaf", ["-c"], t, tmp=str(tmp_path))
+            assert rc == 0, err
+            files.append(naf)
+    errors = 0
+    for it in range(300):
+        naf = bytearray(rng.choice(files))
+        kind = rng.random()
+        if kind < 0.5:
+            for _ in range(rng.randint(1, 3)):
+                naf[rng.randrange(len(naf))] ^= 1 << rng.randrange(8)
+        elif kind < 0.75:
+            naf = naf[:rng.randrange(1, len(naf))]
+        else:
+            at = rng.randrange(len(naf))
+            naf[at:at + rng.randint(1, 64)] = bytes(rng.randrange(256) for _ in range(rng.randint(1, 64)))
+        try:
+            gpu.decode(bytes(naf))
+        except naf_b200.NafGpuError:
+            errors += 1
+    assert errors > 50
+    assert gpu.decode(files[0]) == oracle.decode(files[0])
