@@ -615,7 +615,9 @@ __global__ void __launch_bounds__(PT) k_fsm_scatter(const ParseArgs A)
     if (!A.cfg.fastq) {
         // pending (unterminated) last line of the input: counted bytes after the last line end (process.c:417-422)
         if (lo < A.n && lo + PB >= A.n) { const u64 d = o_cnt + m.cnt - line_base; if (d > line_max) line_max = d; }
-        if (line_max) atomicMax(A.longest, (unsigned long long)line_max);
+        // (skip the atomic unless this thread beats the current maximum: lines are mostly equally long, and an atomicMax per
+        // thread on one address serialises in L2)
+        if (line_max > *(volatile unsigned long long *)A.longest) atomicMax(A.longest, (unsigned long long)line_max);
     }
     __syncthreads();
     tile_copy_out(g_ids, s_ids, (u32)t_ids);

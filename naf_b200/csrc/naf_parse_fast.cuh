@@ -281,9 +281,22 @@ template <bool FASTQ> __global__ void __launch_bounds__(PT) k_fast_scatter(const
     if (!FASTQ) {
         // pending (unterminated) last line of the input (process.c:417-422)
         if (lo < A.n && lo + PB >= A.n) { const u64 d = o_cnt + m.seq - ln.base; if (d > ln.max) ln.max = d; }
-        if (ln.max) atomicMax(A.longest, (unsigned long long)ln.max);
     }
     __syncthreads();
+    if (!FASTQ) {
+        // one atomic per CTA at most, and none once the global maximum is at least ours (lines are mostly equally long:
+        // an atomicMax per thread on one address serialises in L2 -- 10 ms on a 1 GB FASTA)
+        u64 v = ln.max;
+        for (int d = 16; d; d >>= 1) { const u64 o = __shfl_xor_sync(0xFFFFFFFFu, v, d); if (o > v) v = o; }
+        if (lane == 0) sm64[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            u64 mx = 0;
+            for (int k = 0; k < PT / 32; k++) if (sm64[k] > mx) mx = sm64[k];
+            if (mx > *(volatile unsigned long long *)A.longest) atomicMax(A.longest, (unsigned long long)mx);
+        }
+        __syncthreads();
+    }
     fast_copy_out<0>(g_ids, stage, s_ids, t_ids, false);
     fast_copy_out<0>(g_comm, stage, s_comm, t_comm, false);
     u32 sbad;

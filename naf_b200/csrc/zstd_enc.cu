@@ -216,14 +216,22 @@ __global__ void __launch_bounds__(64) k_zenc_tables(const ZEncArgs A, u32 nblock
     const u16 *hist = hists + (size_t)b * 256;
     M.mode = 2; M.tree_len = 0; M.rle_sym = 0;
     if (A.blk[b].n == 0) { M.mode = 0; return; }
-    // symbols that occur, sorted by (count, symbol): insertion sort (alphabets here are tens of symbols)
+    // symbols that occur, sorted by (count, symbol): shell sort of the keys count << 8 | symbol (a mask or length stream can
+    // have all 256 symbols, and this thread is alone with its block)
     u8 sorted[256]; u16 cnt[256]; u32 nsym = 0;
-    for (u32 s = 0; s < 256; s++) {
-        const u16 h = hist[s];
-        if (!h) continue;
-        u32 j = nsym++;
-        while (j > 0 && cnt[j - 1] > h) { cnt[j] = cnt[j - 1]; sorted[j] = sorted[j - 1]; j--; }      // equal counts keep symbol order
-        cnt[j] = h; sorted[j] = (u8)s;
+    {
+        u32 key[256];
+        for (u32 s = 0; s < 256; s++) { const u32 h = hist[s]; if (h) key[nsym++] = (h << 8) | s; }
+        const int gaps[6] = { 132, 57, 23, 10, 4, 1 };
+        for (int gi = 0; gi < 6; gi++) {
+            const u32 gap = (u32)gaps[gi];
+            for (u32 i = gap; i < nsym; i++) {
+                const u32 v = key[i]; u32 j = i;
+                while (j >= gap && key[j - gap] > v) { key[j] = key[j - gap]; j -= gap; }
+                key[j] = v;
+            }
+        }
+        for (u32 i = 0; i < nsym; i++) { cnt[i] = (u16)(key[i] >> 8); sorted[i] = (u8)key[i]; }
     }
     for (u32 s = 0; s < 256; s++) M.ctab[s] = 0;
     if (nsym == 1) { M.mode = 1; M.rle_sym = sorted[0]; return; }
