@@ -717,7 +717,12 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         }, "zd_block_headers");
     }
     ex.zero(a.status, 16);
-    a.nchunks = nblk < 4096 ? (nblk + 7) / 8 : 1024; if (a.nchunks == 0) a.nchunks = 1;
+    // Two block scans in three phases: per-chunk serial (~1.1 us per block, measured on B200), ONE thread over the chunk
+    // aggregates (~0.66 us per chunk), per-chunk serial again.  2 * 1.1 * nblk / c + 0.66 * c is least at c = sqrt(3.3 nblk).
+    {
+        u32 c = 1; while ((u64)c * c < (u64)nblk * 33 / 10) c++;
+        a.nchunks = nblk < 256 ? (nblk + 7) / 8 : (c > 1024 ? 1024 : c); if (a.nchunks == 0) a.nchunks = 1;
+    }
     a.scan_a = ex.template alloc<ScanA>(a.nchunks + 1);
     a.scan_b = ex.template alloc<ScanB>(a.nchunks);
     ZStreamResult *d_res = ex.template alloc<ZStreamResult>(plan.streams.size());
