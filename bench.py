@@ -15,6 +15,9 @@ naturally; no data-path collective) and `value` is all ranks' bases / max-over-r
   cpu_baseline  the UNMODIFIED reference (oracle/_ref ennaf + unnaf, 1 thread: that is all it has) on a
           bounded sample of the same workload, timed on this box's host cores
 
+  single_file  (N > 1 only, extra to the contract) ONE .naf from all ranks' shards -- count all-gather, link, gather of zstd
+          blocks over NCCL (naf_b200/sharded.py) -- and every rank decoding its record range of that one file; verified
+
 `--impl reference` times the reference's own CPU implementation on all host cores (record-aligned pieces,
 one ennaf/unnaf process per core) and prints the same JSON line with "impl": "reference".
 """

@@ -3,8 +3,8 @@
 // Same three passes and the same per-thread / per-tile records as the general parser (naf_parse.cuh), so
 // everything downstream of the scatter (lengths, quality-length check, 4-bit pack, mask RLE, end-of-input
 // handling, error reporting) is shared.  What differs is the cost per byte: no action tables, no state-map
-// algebra — '\n' positions from three SWAR operations per word, a handful of instructions per *line*, and
-// word-wise copies between bank-conflict-free (XOR-swizzled) shared-memory tiles.
+// algebra — '\n' and ' ' positions from a few SWAR operations per word, a handful of instructions per *line*, and
+// word-wise copies between bank-conflict-free (one pad word per 16: fast_pad()) shared-memory tiles.
 //   k_fast_tiles    per tile: number of '\n' (FASTQ) / line-kind element (FASTA); C1 check
 //   k_fast_scan     one CTA: line index (mod 4) / line kind entering every tile; parser state at end of input
 //   k_fast_count    per thread: bytes emitted per stream, records ended (ThreadInfo), per tile TileCounts

@@ -1,5 +1,5 @@
 // emu_parse — TEST-ONLY: runs the per-chunk logic of the canonical-input parser (naf_b200/csrc/naf_fast_hd.cuh:
-// chunk scan, FASTA element algebra, line walk, swizzled staging sink, SWAR byte checks) on the CPU, with the
+// chunk scan, FASTA element algebra, line walk, padded staging sink, SWAR byte checks) on the CPU, with the
 // kernels' tile / thread plumbing restated as serial loops, and writes the raw streams for comparison with the oracle.
 //   emu_parse IN OUTPREFIX seq_type(0..3) no_mask(0/1)
 // exit 0: ok (streams written), 3: input is not canonical (the library would fall back to the general parser), 2: usage
