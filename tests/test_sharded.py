@@ -261,3 +261,30 @@ def test_record_range_decode(gpu, oracle):
             for world in (1, 2, 3, 8):
                 got = b"".join(sharded.decode_shard(gpu, naf, r, world, view) for r in range(world))
                 assert got == full, (view, world, len(got), len(full))
+
+
+def test_split_records_is_exact_on_ambiguous_fastq(oracle):
+    """quality lines that begin with '@' (and '+' lines that repeat the name) must not fool the record splitter: it counts
+    lines from the top instead of sniffing characters"""
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(997):
+        L = int(rng.integers(20, 90))
+        seq = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)])
+        qual = b"@" + bytes(rng.choice(np.frombuffer(b"@+IJ#", dtype=np.uint8), L - 1))
+        recs.append(b"@r%d x\n" % i + seq + b"\n+r%d x\n" % i + qual + b"\n")
+    text = b"".join(recs)
+    for world in (2, 3, 7, 16):
+        pieces = sharded.split_records(text, world)
+        assert b"".join(pieces) == text and len(pieces) == world
+        starts = set()
+        off = 0
+        for r in recs:
+            starts.add(off); off += len(r)
+        starts.add(len(text))
+        off = 0
+        for p in pieces:
+            assert off in starts, "a piece does not start at a record boundary"
+            off += len(p)
+        naf = sharded.encode_shards_local([OracleShardEncoder(oracle) for _ in pieces], pieces, _opts())
+        _check_merged(oracle, naf, text)
