@@ -113,6 +113,15 @@ def load_library():
     return lib
 
 
+def _bytes_at(addr: int, size: int) -> bytes:
+    """copy `size` bytes at `addr` into a bytes object (ctypes.string_at takes a C int: not for texts beyond 2 GB)"""
+    if not size:
+        return b""
+    if size < (1 << 31):
+        return C.string_at(addr, size)
+    return memoryview((C.c_ubyte * size).from_address(addr)).tobytes()
+
+
 def _as_ptr(buf):
     """(address, length, keepalive) for bytes / bytearray / memoryview / numpy / torch CPU tensors / int address."""
     if isinstance(buf, tuple):          # (address, nbytes): caller-managed memory (pinned or device)
@@ -209,11 +218,11 @@ class NafGpu:
 
     def encode(self, text, **kw) -> bytes:
         addr, size, _ = self.encode_raw(text, make_enc_opts(**kw))
-        return C.string_at(addr, size) if size else b""
+        return _bytes_at(addr, size)
 
     def encode_with_info(self, text, **kw):
         addr, size, info = self.encode_raw(text, make_enc_opts(**kw))
-        return (C.string_at(addr, size) if size else b""), info
+        return _bytes_at(addr, size), info
 
     def decode_raw(self, naf, opts: DecOpts):
         p, n, keep = _as_ptr(naf)
@@ -223,7 +232,7 @@ class NafGpu:
 
     def decode(self, naf, view="default", no_mask=False, line_length=None, first_record=0, n_records=0) -> bytes:
         addr, size = self.decode_raw(naf, make_dec_opts(view, no_mask, line_length, first_record, n_records))
-        return C.string_at(addr, size) if size else b""
+        return _bytes_at(addr, size)
 
     def unnaf(self, naf, view="default", no_mask=False, line_length=None) -> bytes:
         """Every unnaf output type, byte-identical to the reference CLI's stdout (unnaf.c:395-447)."""
@@ -280,13 +289,13 @@ class NafGpu:
         p, n, keep = _as_ptr(frame)
         out, size = C.c_void_p(), C.c_size_t()
         self._check(self.lib.nafgpu_zstd_decompress(self.h, p, n, expected_size, int(one_frame), C.byref(out), C.byref(size)))
-        return C.string_at(out.value, size.value) if size.value else b""
+        return _bytes_at(out.value, size.value)
 
     def zstd_compress(self, data, window_log: int = 0) -> bytes:
         p, n, keep = _as_ptr(data)
         out, size = C.c_void_p(), C.c_size_t()
         self._check(self.lib.nafgpu_zstd_compress(self.h, p, n, window_log, C.byref(out), C.byref(size)))
-        return C.string_at(out.value, size.value) if size.value else b""
+        return _bytes_at(out.value, size.value)
 
     def split(self, text, **kw):
         """-> (list of six stream byte strings, EncInfo)"""
@@ -294,7 +303,7 @@ class NafGpu:
         ptrs, sizes, info = (C.c_void_p * 6)(), (C.c_size_t * 6)(), EncInfo()
         opts = make_enc_opts(**kw)
         self._check(self.lib.nafgpu_split(self.h, p, n, C.byref(opts), C.byref(ptrs), C.byref(sizes), C.byref(info)))
-        return [C.string_at(ptrs[k], sizes[k]) if sizes[k] else b"" for k in range(6)], info
+        return [_bytes_at(ptrs[k], sizes[k]) for k in range(6)], info
 
 
 _default: Optional[NafGpu] = None
