@@ -62,7 +62,7 @@ class ShardLink(C.Structure):
 EXPORTS = [
     "nafgpu_create", "nafgpu_destroy", "nafgpu_last_error", "nafgpu_version", "nafgpu_get_timing", "nafgpu_stream",
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
-    "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_split", "nafgpu_profile",
+    "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_zstd_compress_level", "nafgpu_split", "nafgpu_profile",
     "nafgpu_profile_report", "nafgpu_shard_begin", "nafgpu_shard_finish", "nafgpu_shard_fetch",
 ]
 
@@ -105,6 +105,7 @@ def load_library():
     lib.nafgpu_decode_device.argtypes = [vp, vp, sz, vp, C.POINTER(DecOpts), C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_zstd_decompress.argtypes = [vp, vp, sz, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_zstd_compress.argtypes = [vp, vp, sz, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    lib.nafgpu_zstd_compress_level.argtypes = [vp, vp, sz, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_split.argtypes = [vp, vp, sz, C.POINTER(EncOpts), C.POINTER(vp * 6), C.POINTER(sz * 6), C.POINTER(EncInfo)]
     lib.nafgpu_shard_begin.argtypes = [vp, vp, sz, C.c_int, C.POINTER(EncOpts), C.POINTER(ShardCounts), C.POINTER(EncInfo)]
     lib.nafgpu_shard_finish.argtypes = [vp, C.POINTER(ShardLink), C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64 * 6)]
@@ -291,10 +292,10 @@ class NafGpu:
         self._check(self.lib.nafgpu_zstd_decompress(self.h, p, n, expected_size, int(one_frame), C.byref(out), C.byref(size)))
         return _bytes_at(out.value, size.value)
 
-    def zstd_compress(self, data, window_log: int = 0) -> bytes:
+    def zstd_compress(self, data, window_log: int = 0, level: int = 0) -> bytes:
         p, n, keep = _as_ptr(data)
         out, size = C.c_void_p(), C.c_size_t()
-        self._check(self.lib.nafgpu_zstd_compress(self.h, p, n, window_log, C.byref(out), C.byref(size)))
+        self._check(self.lib.nafgpu_zstd_compress_level(self.h, p, n, window_log, level, C.byref(out), C.byref(size)))
         return _bytes_at(out.value, size.value)
 
     def split(self, text, **kw):

@@ -8,7 +8,7 @@ namespace nafg {
 DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o);
 EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
 SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
-EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log);
+EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log, int level);
 void shard_begin_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_shard_counts *counts, nafgpu_enc_info *info);
 void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &link, uint64_t raw[6], uint64_t body[6]);
 }
@@ -253,6 +253,11 @@ int nafgpu_encode_device(nafgpu_ctx *c, const uint8_t *d_text, size_t n, const n
 
 int nafgpu_zstd_compress(nafgpu_ctx *c, const uint8_t *src, size_t n, int window_log, const uint8_t **out, size_t *out_size)
 {
+    return nafgpu_zstd_compress_level(c, src, n, window_log, 0, out, out_size);
+}
+
+int nafgpu_zstd_compress_level(nafgpu_ctx *c, const uint8_t *src, size_t n, int window_log, int level, const uint8_t **out, size_t *out_size)
+{
     if ((!src && n) || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
@@ -260,7 +265,7 @@ int nafgpu_zstd_compress(nafgpu_ctx *c, const uint8_t *src, size_t n, int window
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
-        EncodeOut r = zstd_compress_on_device(*c, ex, d_in, n, window_log);
+        EncodeOut r = zstd_compress_on_device(*c, ex, d_in, n, window_log, level);
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
         *out = to_pinned(*c, r.d_naf, r.size); *out_size = r.size;
         finish_timing(*c, ex);

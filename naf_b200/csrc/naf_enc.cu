@@ -476,6 +476,16 @@ SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, con
 
 namespace nafg {
 
+// ennaf -# (ennaf.c:222-223, compressor.c:7): level >= 1 (the tools' default is 1) adds LZ77 matches and FSE-coded sequences to
+// the text-like streams; level <= 0 (zstd's "fast" negative levels) keeps the entropy-only parse for every stream.
+// NAFGPU_LZ=0/1 in the environment overrides the level (A/B measurements).
+static bool lz_for_level(int level)
+{
+    static const char *env = getenv("NAFGPU_LZ");
+    if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
+    return level >= 1;
+}
+
 // ennaf.c:538-589: header, then per stream VLE(original size) VLE(compressed size - 4) frame-without-magic
 EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)
 {
@@ -488,7 +498,8 @@ EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
 
     ZEncBatch batch;
     int which[6], ns = 0;
-    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(sp[k], ss[k], k == 4 ? o.window_log : 0); }
+    const bool lz = lz_for_level(o.level);                     // ids, comments, lengths, mask: LZ77 + FSE-coded sequences
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(sp[k], ss[k], k == 4 ? o.window_log : 0, lz && k < 4); }
     zstd_compress_batch(ctx, ex, batch);                       // sizes known on the host afterwards
 
     std::vector<u8> hdr;
@@ -524,10 +535,10 @@ EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
     return EncodeOut{d_naf, total};
 }
 
-EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log)
+EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log, int level)
 {
     ZEncBatch batch;
-    batch.add(d_src, n, window_log);
+    batch.add(d_src, n, window_log, lz_for_level(level));
     zstd_compress_batch(ctx, ex, batch);
     u8 *out = ex.alloc<u8>(batch.frame_size[0] + 64);
     batch.dest[0] = out;
@@ -616,7 +627,8 @@ void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &lin
     // (a shard that is empty, or FASTA-empty among FASTQ shards, still adds its -- empty -- block to every stream of the file)
     const bool present[6] = { true, true, true, (bool)H.store_mask, true, (bool)(H.store_qual || link.store_qual) };
     int which[6], ns = 0;
-    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.stream[k] ? H.raw[k] : 0, 0); }
+    const bool lz = lz_for_level(H.opts.level);
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.stream[k] ? H.raw[k] : 0, 0, lz && k < 4); }
     zstd_compress_batch(ctx, ex, batch);
     u64 total = 0; std::vector<u64> at(ns);
     for (int j = 0; j < ns; j++) { at[j] = total; total += (batch.frame_size[j] + 63) & ~63ull; }

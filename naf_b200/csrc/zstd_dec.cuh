@@ -45,6 +45,7 @@ struct ZBlock {
     u8  first_in_stream;
     u8  stream;
     u8  skip;           // output not wanted (record-range decode): K5 / K6 leave the block alone
+    u8  local;          // K7b executed this block's sequences itself (every match starts inside the block): K8 / K9 leave it alone
     // --- K1 ---
     u32 lit_regen, lit_csize;
     u8  lit_type, lit_streams, lit_hdr, modes;
@@ -533,6 +534,31 @@ HD void k_seq_resolve(const ZDecArgs &a, u32 i)
     }
 }
 
+// K7b — a block whose matches all start inside the block itself needs neither back-pointers nor pointer jumping: one
+// thread runs its sequences in order (zstd_decompress_block.c:804 ZSTD_execSequence as it stands).  That is every block
+// our own encoder writes (blocks are kept independent of each other; 8 KB when they carry sequences), so a
+// file of ours never enters K9.  Bigger blocks (a reference-made 128 KB first block qualifies too) stay on the
+// parallel path: a serial walk over them would take longer than the jumps it saves.
+static const u32 LOCAL_MAX_OUT = 16 * 1024;
+HD void k_block_local(const ZDecArgs &a, u32 i)
+{
+    ZBlock &b = a.blk[i];
+    if (b.type != 2 || b.nseq == 0 || b.skip || b.lit_regen + b.match_total > LOCAL_MAX_OUT) return;
+    const ZSeq *seq = a.seq + b.seq_base;
+    for (u32 k = 0; k < b.nseq; k++) if (seq[k].ml && seq[k].of > seq[k].dst_rel + seq[k].ll) return;
+    u8 *o = a.out + b.out_off; const u8 *lit = a.lit_scratch + b.lit_off;
+    u32 d = 0, l = 0;
+    for (u32 k = 0; k < b.nseq; k++) {
+        const u32 ll = seq[k].ll, ml = seq[k].ml, of = seq[k].of;
+        for (u32 j = 0; j < ll; j++) o[d + j] = lit[l + j];
+        d += ll; l += ll;
+        for (u32 j = 0; j < ml; j++) o[d + j] = o[d + j - of];         // forward byte order: overlapping (periodic) matches come out right
+        d += ml;
+    }
+    for (; l < b.lit_regen; l++) o[d++] = lit[l];
+    b.local = 1;
+}
+
 HD void set_bits(u32 *bitmap, u64 lo, u64 hi)     // [lo, hi) in bit coordinates
 {
     while (lo < hi) {
@@ -571,14 +597,14 @@ static const u32 BIG_SEQ = 512;
 HD void k_seq_exec_small(const ZDecArgs &a, u64 j)
 {
     const ZSeq s = a.seq[j];
-    if (s.ll + s.ml > BIG_SEQ) return;
+    if (s.ll + s.ml > BIG_SEQ || a.blk[s.blk].local) return;
     k_seq_exec_one(a, s, 0, 1);
 }
 // one thread group per block: long sequences + the literals after the last sequence
 HD void k_seq_exec_big(const ZDecArgs &a, u32 i, u32 tid, u32 nthreads)
 {
     const ZBlock &b = a.blk[i];
-    if (b.type != 2 || b.nseq == 0) return;
+    if (b.type != 2 || b.nseq == 0 || b.local) return;
     const ZSeq *seq = a.seq + b.seq_base;
     for (u32 k = 0; k < b.nseq; k++) if (seq[k].ll + seq[k].ml > BIG_SEQ) k_seq_exec_one(a, seq[k], tid, nthreads);
     const ZSeq &last = seq[b.nseq - 1];
@@ -810,6 +836,7 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
         a.bitmap = ex.template alloc<u32>(words + 1);
         ex.zero(a.bitmap, (words + 1) * 4);
         launch_seq_resolve(ex, a);
+        ex.for_each(nblk, [=] HDN (size_t i) { k_block_local(a, (u32)i); }, "zd_block_local", 32);
         ex.for_each(tot_seq, [=] HDN (size_t j) { k_seq_exec_small(a, j); }, "zd_seq_exec_small");
         launch_seq_exec_big(ex, a);
         for (int round = 0; round < 40; round++) {

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) k_seq_exec_big_cta(const ZDecArgs a)
     __shared__ u32 nbig;
     const u32 i = blockIdx.x, tid = threadIdx.x;
     const ZBlock &b = a.blk[i];
-    if (b.type != 2 || b.nseq == 0) return;
+    if (b.type != 2 || b.nseq == 0 || b.local) return;           // local: K7b has written the whole block already
     const ZSeq *seq = a.seq + b.seq_base;
     for (u32 base = 0; base < b.nseq; base += 256) {
         if (tid == 0) nbig = 0;

@@ -14,120 +14,48 @@
 // Per block: histogram -> code lengths -> tree description -> bit-exact sizes -> encode into a fixed slot
 // (k_zenc_hist / k_zenc_tables / k_zenc_encode); a scan over block sizes then lets k_zenc_gather lay the blocks
 // out as frames.
+//   * the small, text-like streams (ids, comments, lengths, mask) at level >= 1: 8 KB blocks with LZ77 matches
+//     (compress/zstd_fast.c:186 ZSTD_compressBlock_fast) and FSE-coded sequences (compress/zstd_compress_sequences.c:418),
+//     one thread per block (k_zenc_lz; the body is HD code in zstd_enc_hd.cuh, validated on the CPU against libzstd);
+//     still independent blocks — matches stay inside the block, repeat-offset codes only name offsets the block itself pushed
 //
 // Format: zstd/doc/zstd_compression_format.md ("Huffman Tree Description", "Huffman-coded streams",
 // "FSE Table Description"); reference counterparts: compress/huf_compress.c:513 HUF_buildCTable_wksp,
 // :116 HUF_writeCTable_wksp, compress/fse_compress.c:437 FSE_normalizeCount, :292 FSE_writeNCount,
 // compress/zstd_compress_literals.c:70 ZSTD_compressLiterals, zstd_compress.c:3967 ZSTD_writeFrameHeader.
 
+#include "zstd_enc_hd.cuh"
+
 namespace nafg {
 
-static const u32 ZBS = 32 * 1024;            // uncompressed bytes per block
+using nafz::ZEncMeta; using nafz::BitW;
+
+static const u32 ZBS = 32 * 1024;            // uncompressed bytes per block (Huffman-only streams)
 static const u32 ZSLOT = ZBS + 512;          // bytes reserved per block for its compressed content
+static const u32 ZLB = 8 * 1024;             // uncompressed bytes per block of an LZ stream (one thread encodes a block)
+static const u32 ZLSLOT = ZLB + 512;
+static const u32 ZLZ_MAXSEQ = ZLB / 4;
 static const int ZWINDOW_LOG = 17;
 
 struct ZEncBlock {
     const u8 *src; u32 n; u32 stream; u32 last;
     u32 type;      // 0 raw (content = src bytes), 1 RLE, 2 compressed (content in slot)
     u32 csize;     // content bytes
+    u32 lz;        // block of an LZ stream: k_zenc_lz does everything, the three Huffman kernels pass
+    u64 slot_off;  // where my slot starts in the slot pool
 };
 
 struct ZEncBatch {
-    std::vector<const u8 *> src; std::vector<u64> n; std::vector<int> wlog;
+    std::vector<const u8 *> src; std::vector<u64> n; std::vector<int> wlog; std::vector<int> lz;
     std::vector<u64> frame_size; std::vector<u8 *> dest;
     std::vector<u32> first_block;            // per stream (+1 sentinel)
     ZEncBlock *d_blocks = nullptr; u32 nblocks = 0; u8 *d_slots = nullptr; u64 *d_off = nullptr;
     bool final_shard = true;                 // false: these frames continue in another shard, no block carries Last_Block
-    void add(const u8 *p, u64 bytes, int window_log) { src.push_back(p); n.push_back(bytes); wlog.push_back(window_log); }
+    void add(const u8 *p, u64 bytes, int window_log, bool with_lz = false) { src.push_back(p); n.push_back(bytes); wlog.push_back(window_log); lz.push_back(with_lz ? 1 : 0); }
 };
-
-// ---- forward LSB-first bit writer into a small local buffer (FSE weights)
-struct BitW {
-    u8 *p; u32 cap; u32 pos; u64 acc; u32 fill; bool ok;
-    __device__ void init(u8 *dst, u32 c) { p = dst; cap = c; pos = 0; acc = 0; fill = 0; ok = true; }
-    __device__ void put(u32 v, u32 nb)
-    {
-        acc |= (u64)(v & ((1u << nb) - 1)) << fill; fill += nb;
-        while (fill >= 8) { if (pos < cap) p[pos++] = (u8)acc; else ok = false; acc >>= 8; fill -= 8; }
-    }
-    __device__ u32 finish_with_mark() { put(1, 1); if (fill) { if (pos < cap) p[pos++] = (u8)acc; else ok = false; fill = 0; acc = 0; } return pos; }
-    __device__ u32 finish_aligned() { if (fill) { if (pos < cap) p[pos++] = (u8)acc; else ok = false; fill = 0; acc = 0; } return pos; }
-};
-
-// FSE-compress the Huffman weights w[0..n).  Returns the number of bytes written (table description +
-// bitstream), or 0 when not representable / not worthwhile.  Mirrors compress/huf_compress.c:76 HUF_compressWeights.
-__device__ u32 fse_compress_weights(const u8 *w, int n, u8 *dst, u32 cap)
-{
-    const int LOG = 6, SIZE = 64;
-    if (n <= 1) return 0;
-    int count[13]; for (int i = 0; i < 13; i++) count[i] = 0;
-    int maxw = 0, maxc = 0;
-    for (int i = 0; i < n; i++) { count[w[i]]++; if (w[i] > maxw) maxw = w[i]; }
-    for (int s = 0; s <= maxw; s++) if (count[s] > maxc) maxc = count[s];
-    if (maxc == n || maxc == 1) return 0;                 // one symbol only / all distinct: not compressible
-    // normalise to SIZE slots, every present symbol >= 1
-    int norm[13], sum = 0;
-    for (int s = 0; s <= maxw; s++) { norm[s] = count[s] ? (count[s] * SIZE + n / 2) / n : 0; if (count[s] && norm[s] < 1) norm[s] = 1; sum += norm[s]; }
-    while (sum != SIZE) {
-        int best = -1;
-        for (int s = 0; s <= maxw; s++) if (norm[s] > (sum > SIZE ? 1 : 0) && (best < 0 || norm[s] > norm[best])) best = s;
-        if (best < 0) return 0;
-        if (sum > SIZE) { norm[best]--; sum--; } else { norm[best]++; sum++; }
-    }
-    // table description (spec "FSE Table Description")
-    BitW bw; bw.init(dst, cap);
-    bw.put(LOG - 5, 4);
-    int remaining = SIZE, s = 0;
-    while (remaining > 0 && s <= maxw) {
-        int bits = nafz::hibit((u32)remaining + 1) + 1;
-        u32 lower = (1u << (bits - 1)) - 1, thresh = (1u << bits) - 1 - (u32)(remaining + 1);
-        u32 v = (u32)(norm[s] + 1);
-        if (v < thresh) bw.put(v, bits - 1);
-        else bw.put(v > lower ? v + thresh : v, bits);
-        remaining -= norm[s];
-        bool zero = norm[s] == 0;
-        s++;
-        if (zero) {
-            int run = 0;
-            while (s <= maxw && norm[s] == 0 && remaining > 0) { run++; s++; }
-            while (run >= 3) { bw.put(3, 2); run -= 3; }
-            bw.put((u32)run, 2);
-        }
-    }
-    if (remaining != 0) return 0;
-    u32 hdr = bw.finish_aligned();
-    if (!bw.ok) return 0;
-    // state table: positions of every symbol in increasing order (the decoder's spread, spec "From normalized distribution...")
-    u8 tsym[SIZE], spos[SIZE]; int cum[14];
-    cum[0] = 0; for (int k = 0; k <= maxw; k++) cum[k + 1] = cum[k] + norm[k];
-    {
-        int pos = 0; const int step = (SIZE >> 1) + (SIZE >> 3) + 3, mask = SIZE - 1;
-        for (int k = 0; k <= maxw; k++) for (int i = 0; i < norm[k]; i++) { tsym[pos] = (u8)k; pos = (pos + step) & mask; }
-        int occ[13]; for (int k = 0; k < 13; k++) occ[k] = 0;
-        for (int p = 0; p < SIZE; p++) { int k = tsym[p]; spos[cum[k] + occ[k]++] = (u8)p; }
-    }
-    BitW bs; bs.init(dst + hdr, cap - hdr);
-    int last = n - 1, prev = n - 2;
-    u32 st[2];                                               // st[parity of the weight index]
-    st[last & 1] = spos[cum[w[last]]];
-    st[prev & 1] = spos[cum[w[prev]]];
-    for (int i = n - 3; i >= 0; i--) {
-        int sym = w[i], p = norm[sym];
-        u32 y = st[i & 1] + SIZE;
-        int nb = LOG - nafz::hibit((u32)p);
-        u32 nn = y >> nb;
-        if (nn < (u32)p) { nb--; nn = y >> nb; }
-        bs.put(y, nb);                                       // low nb bits of y
-        st[i & 1] = spos[cum[sym] + (nn - p)];
-    }
-    bs.put(st[1], LOG); bs.put(st[0], LOG);                  // decoder reads state1 (even chain) first
-    u32 body = bs.finish_with_mark();
-    if (!bs.ok) return 0;
-    return hdr + body;
-}
 
 struct ZEncArgs { ZEncBlock *blk; u8 *slots; };
-struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u32 first[9]; u32 ns; };
+struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u64 slot_base[8]; u32 first[9]; u32 bs[8]; u32 lz[8]; u32 ns; };
 struct ZEncFirstBlocks { u32 v[9]; };
 
 // Three kernels per batch of 32 KB blocks.  Shared-memory atomics cost 32-64 cycles per warp instruction on this
@@ -144,13 +72,6 @@ static const u32 ZET = 256, ZEPER = ZBS / ZET;                    // threads per
 static const u32 ZHIST_SMEM = 65536;
 static const u32 ZENC_SMEM = ZBS + 1024;
 
-struct ZEncMeta {            // k_zenc_tables -> k_zenc_encode
-    u16 ctab[256];           // code | len << 12 (len 0 = symbol absent)
-    u8  tree[132];           // Huffman tree description
-    u8  mode;                // 0 raw (tree not describable), 1 RLE, 2 Huffman
-    u8  rle_sym;
-    u16 tree_len;
-};
 
 // A full block's thread range is 128 aligned bytes: read with 128-bit loads; ragged tail blocks go byte by byte.
 template <class F> __device__ __forceinline__ void zenc_each(bool full, const u8 *src, u32 t0, u32 t1, F f)
@@ -184,6 +105,7 @@ __global__ void __launch_bounds__(256, 3) k_zenc_hist(const ZEncArgs A, u16 *his
 {
     extern __shared__ __align__(16) u8 R[];
     const ZEncBlock &B = A.blk[blockIdx.x];
+    if (B.lz) return;
     const u8 *src = B.src; const u32 n = B.n;
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     {
@@ -212,91 +134,10 @@ __global__ void __launch_bounds__(64) k_zenc_tables(const ZEncArgs A, u32 nblock
 {
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
+    if (A.blk[b].lz) return;
     ZEncMeta &M = metas[b];
-    const u16 *hist = hists + (size_t)b * 256;
-    M.mode = 2; M.tree_len = 0; M.rle_sym = 0;
-    if (A.blk[b].n == 0) { M.mode = 0; return; }
-    // symbols that occur, sorted by (count, symbol): shell sort of the keys count << 8 | symbol (a mask or length stream can
-    // have all 256 symbols, and this thread is alone with its block)
-    u8 sorted[256]; u16 cnt[256]; u32 nsym = 0;
-    {
-        u32 key[256];
-        for (u32 s = 0; s < 256; s++) { const u32 h = hist[s]; if (h) key[nsym++] = (h << 8) | s; }
-        const int gaps[6] = { 132, 57, 23, 10, 4, 1 };
-        for (int gi = 0; gi < 6; gi++) {
-            const u32 gap = (u32)gaps[gi];
-            for (u32 i = gap; i < nsym; i++) {
-                const u32 v = key[i]; u32 j = i;
-                while (j >= gap && key[j - gap] > v) { key[j] = key[j - gap]; j -= gap; }
-                key[j] = v;
-            }
-        }
-        for (u32 i = 0; i < nsym; i++) { cnt[i] = (u16)(key[i] >> 8); sorted[i] = (u8)key[i]; }
-    }
-    for (u32 s = 0; s < 256; s++) M.ctab[s] = 0;
-    if (nsym == 1) { M.mode = 1; M.rle_sym = sorted[0]; return; }
-    // code lengths: two-queue Huffman over the sorted counts, then limit to 11 bits
-    u8 len_of[256], weight[257];
-    for (u32 s = 0; s < 256; s++) { len_of[s] = 0; weight[s] = 0; }
-    weight[256] = 0;
-    u32 maxbits = 0;
-    {
-        u32 iw[256]; u16 lp[256], ip[256]; u8 idp[256];
-        u32 li = 0, ii = 0;
-        for (u32 m = 0; m + 1 < nsym; m++) {
-            u32 wsum = 0;
-            for (int t = 0; t < 2; t++) {
-                const bool take_leaf = li < nsym && (ii >= m || cnt[li] <= iw[ii]);
-                if (take_leaf) { wsum += cnt[li]; lp[li++] = (u16)m; } else { wsum += iw[ii]; ip[ii++] = (u16)m; }
-            }
-            iw[m] = wsum;
-        }
-        const u32 root = nsym - 2;
-        idp[root] = 0;
-        for (int m = (int)root - 1; m >= 0; m--) { const u32 d = idp[ip[m]] + 1u; idp[m] = (u8)(d > 60 ? 60 : d); }
-        u32 num[40]; for (int i = 0; i < 40; i++) num[i] = 0;
-        for (u32 i = 0; i < nsym; i++) { u32 d = idp[lp[i]] + 1u; if (d > 39) d = 39; num[d]++; }
-        const u32 MAXB = 11;
-        for (u32 i = MAXB + 1; i < 40; i++) { num[MAXB] += num[i]; num[i] = 0; }
-        u32 total = 0;
-        for (u32 i = 1; i <= MAXB; i++) total += num[i] << (MAXB - i);
-        while (total != (1u << MAXB)) {
-            num[MAXB]--;
-            for (u32 i = MAXB - 1; i > 0; i--) if (num[i]) { num[i]--; num[i + 1] += 2; break; }
-            total--;
-        }
-        u32 idx = 0;
-        for (u32 l = MAXB; l >= 1; l--) { if (num[l] && !maxbits) maxbits = l; for (u32 c = 0; c < num[l]; c++) len_of[sorted[idx++]] = (u8)l; }
-    }
-    // canonical codes exactly as the decoder rebuilds them: longer codes take the numerically lower values, equal
-    // lengths in symbol order
-    {
-        u32 next[13];                                         // next code value (at full maxbits resolution) per length
-        u32 acc = 0;
-        u32 count_len[13]; for (int i = 0; i < 13; i++) count_len[i] = 0;
-        for (u32 s = 0; s < 256; s++) count_len[len_of[s]]++;
-        for (u32 l = maxbits; l >= 1; l--) { next[l] = acc; acc += count_len[l] << (maxbits - l); }
-        for (u32 s = 0; s < 256; s++) {
-            const u32 l = len_of[s];
-            if (!l) continue;
-            M.ctab[s] = (u16)((next[l] >> (maxbits - l)) | (l << 12));
-            next[l] += 1u << (maxbits - l);
-            weight[s] = (u8)(maxbits + 1 - l);
-        }
-    }
-    // tree description
-    int last_sym = 255; while (last_sym > 0 && !weight[last_sym]) last_sym--;
-    const int nlisted = last_sym;                             // weights of symbols 0 .. last_sym-1; the last one is implied
-    u8 tmp[132];
-    const u32 fse = fse_compress_weights(weight, nlisted, tmp + 1, 127);
-    const u32 direct = nlisted <= 128 ? 1 + (nlisted + 1) / 2 : 0xFFFFFFFFu;
-    if (fse && fse < 128 && 1 + fse < direct) { tmp[0] = (u8)fse; M.tree_len = (u16)(1 + fse); }
-    else if (direct != 0xFFFFFFFFu) {
-        tmp[0] = (u8)(127 + nlisted);
-        for (int i = 0; i < nlisted; i += 2) tmp[1 + i / 2] = (u8)((weight[i] << 4) | (i + 1 < nlisted ? weight[i + 1] : 0));
-        M.tree_len = (u16)direct;
-    } else { M.mode = 0; return; }                            // cannot describe the tree: raw block
-    for (u32 i = 0; i < M.tree_len; i++) M.tree[i] = tmp[i];
+    if (A.blk[b].n == 0) { M.mode = 0; M.tree_len = 0; M.rle_sym = 0; return; }
+    nafz::zenc_huf_build(hists + (size_t)b * 256, M);
 }
 
 __global__ void __launch_bounds__(256) k_zenc_encode(const ZEncArgs A, const ZEncMeta *metas)
@@ -309,9 +150,10 @@ __global__ void __launch_bounds__(256) k_zenc_encode(const ZEncArgs A, const ZEn
     __shared__ u32 s_stream_bytes[4];
 
     ZEncBlock &B = A.blk[blockIdx.x];
+    if (B.lz) return;                          // k_zenc_lz's block
     const ZEncMeta &M = metas[blockIdx.x];
     const u8 *src = B.src; const u32 n = B.n;
-    u8 *slot = A.slots + (size_t)blockIdx.x * ZSLOT;
+    u8 *slot = A.slots + B.slot_off;
     const u32 tid = threadIdx.x;
 
     if (n == 0 || M.mode == 0) { if (tid == 0) { B.type = 0; B.csize = n; } return; }
@@ -426,7 +268,7 @@ __global__ void __launch_bounds__(256) k_zenc_gather(const ZGatherArgs A)
         dst[0] = (u8)bh; dst[1] = (u8)(bh >> 8); dst[2] = (u8)(bh >> 16);
     }
     // content: 128-bit stores aligned to the destination, each fed by one unaligned 16-byte read (load_bytes16, naf_dec.cu)
-    const u8 *from = B.type == 0 ? B.src : A.slots + (size_t)blockIdx.x * ZSLOT;
+    const u8 *from = B.type == 0 ? B.src : A.slots + B.slot_off;
     u8 *d0 = dst + 3; const u32 nbytes = B.csize;
     const u32 head = min(nbytes, (u32)((16 - ((uintptr_t)d0 & 15)) & 15));
     if (threadIdx.x < head) d0[threadIdx.x] = from[threadIdx.x];
@@ -435,31 +277,74 @@ __global__ void __launch_bounds__(256) k_zenc_gather(const ZGatherArgs A)
     if (threadIdx.x < nbytes - done) d0[done + threadIdx.x] = from[done + threadIdx.x];
 }
 
+// ---- LZ streams: one thread per 8 KB block runs nafz::zlz_encode_block (match finder, literal Huffman, FSE-coded sequences).
+// The 32 hash tables of a CTA live in shared memory, interleaved so that entry e of lane l sits in bank l; the rest of a
+// block's scratch (literals, sequence arrays, symbol codes, FSE state tables) is a private slice of one HBM workspace.
+static const u32 ZLZ_WORK_LIT = ZLB + 64, ZLZ_WORK_SEQ = ZLZ_MAXSEQ * 2, ZLZ_WORK_SPOS = 1280 * 2, ZLZ_WORK_TSYM = 512,
+                 ZLZ_WORK_CODES = 3 * ZLZ_MAXSEQ;
+static const u32 ZLZ_WORK = ZLZ_WORK_LIT + 3 * ZLZ_WORK_SEQ + ZLZ_WORK_SPOS + ZLZ_WORK_TSYM + ZLZ_WORK_CODES;
+static const u32 ZLZ_SMEM = 32 * (1u << nafz::ZLZ_HLOG) * 2;
+struct ZLzArgs { ZEncBlock *blk; u8 *slots; u8 *work; u32 first[9]; u32 lzfirst[9]; u32 ns; u32 nlz; };
+
+__global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
+{
+    extern __shared__ __align__(16) u16 htabs[];               // 32 interleaved tables of 1 << ZLZ_HLOG entries
+    const u32 j = blockIdx.x * 32 + threadIdx.x;               // j-th LZ block of the batch
+    if (j >= A.nlz) return;
+    u32 s = 0;
+    while (s + 1 < A.ns && j >= A.lzfirst[s + 1]) s++;
+    ZEncBlock &B = A.blk[A.first[s] + (j - A.lzfirst[s])];
+    u8 *w = A.work + (size_t)j * ZLZ_WORK;
+    u8 *lit = w; w += ZLZ_WORK_LIT;
+    nafz::ZLzSeqs S; S.ll = (u16 *)w; w += ZLZ_WORK_SEQ; S.ml = (u16 *)w; w += ZLZ_WORK_SEQ; S.ov = (u16 *)w; w += ZLZ_WORK_SEQ; S.n = 0;
+    nafz::ZLzWork W; W.spos = (u16 *)w; w += ZLZ_WORK_SPOS; W.tsym = w; w += ZLZ_WORK_TSYM; W.codes = w;
+    u8 *slot = A.slots + B.slot_off;
+    bool rle = false;
+    const u32 cs = nafz::zlz_encode_block(B.src, B.n, true, htabs + threadIdx.x, 32, lit, S, ZLZ_MAXSEQ, W, slot, ZLSLOT, &rle);
+    if (cs) { B.type = 2; B.csize = cs; }
+    else if (rle) { slot[0] = B.src[0]; B.type = 1; B.csize = 1; }
+    else { B.type = 0; B.csize = B.n; }
+}
+
 static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
 {
     const size_t ns = b.src.size();
-    // block list: stream s contributes ceil(n / ZBS) blocks (an empty stream: one empty raw last block); built on the device
+    if (ns > 8) fail(NAFGPU_E_ARG, "too many streams in one compression batch\n");
+    // block list: stream s contributes ceil(n / block size) blocks (an empty stream: one empty raw last block); built on the device
+    ZEncStreamTab tab; memset(&tab, 0, sizeof tab);
+    ZLzArgs L; memset(&L, 0, sizeof L);
     b.first_block.assign(ns + 1, 0);
-    for (size_t s = 0; s < ns; s++) b.first_block[s + 1] = b.first_block[s] + (u32)(b.n[s] ? (b.n[s] + ZBS - 1) / ZBS : 1);
+    u64 slot_total = 0; u32 nlz = 0;
+    for (size_t s = 0; s < ns; s++) {
+        const u32 bs = b.lz[s] ? ZLB : ZBS, slot = b.lz[s] ? ZLSLOT : ZSLOT;
+        const u32 nb = (u32)(b.n[s] ? (b.n[s] + bs - 1) / bs : 1);
+        b.first_block[s + 1] = b.first_block[s] + nb;
+        tab.src[s] = b.src[s]; tab.n[s] = b.n[s]; tab.first[s] = b.first_block[s]; tab.bs[s] = bs; tab.lz[s] = (u32)b.lz[s];
+        tab.slot_base[s] = slot_total; slot_total += (u64)nb * slot;
+        L.first[s] = b.first_block[s]; L.lzfirst[s] = nlz; if (b.lz[s]) nlz += nb;
+    }
     b.nblocks = b.first_block[ns];
+    tab.first[ns] = b.nblocks; tab.ns = (u32)ns;
+    L.first[ns] = b.nblocks; L.lzfirst[ns] = nlz; L.ns = (u32)ns; L.nlz = nlz;
     b.d_blocks = ex.alloc<ZEncBlock>(b.nblocks);
-    b.d_slots = ex.alloc<u8>((size_t)b.nblocks * ZSLOT);
+    b.d_slots = ex.alloc<u8>(slot_total + 64);
     {
-        ZEncStreamTab tab;
-        if (ns > 8) fail(NAFGPU_E_ARG, "too many streams in one compression batch\n");
-        memset(&tab, 0, sizeof tab);
-        for (size_t s = 0; s < ns; s++) { tab.src[s] = b.src[s]; tab.n[s] = b.n[s]; tab.first[s] = b.first_block[s]; }
-        tab.first[ns] = b.nblocks; tab.ns = (u32)ns;
         ZEncBlock *blk = b.d_blocks;
         const u32 fin = b.final_shard ? 1u : 0u;
         ex.for_each(b.nblocks, [=] __device__ (size_t i) {
             u32 s = 0;
             while (s + 1 < tab.ns && (u32)i >= tab.first[s + 1]) s++;
-            const u64 k = i - tab.first[s], off = k * ZBS, left = tab.n[s] - (tab.n[s] < off ? tab.n[s] : off);
-            ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < ZBS ? left : ZBS); e.stream = s; e.last = ((u32)i + 1 == tab.first[s + 1]) & fin;
-            e.type = 0; e.csize = 0;
+            const u32 bs = tab.bs[s];
+            const u64 k = i - tab.first[s], off = k * bs, left = tab.n[s] - (tab.n[s] < off ? tab.n[s] : off);
+            ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < bs ? left : bs); e.stream = s; e.last = ((u32)i + 1 == tab.first[s + 1]) & fin;
+            e.type = 0; e.csize = 0; e.lz = tab.lz[s]; e.slot_off = tab.slot_base[s] + k * (tab.lz[s] ? ZLSLOT : ZSLOT);
             blk[i] = e;
         }, "zenc_init_blocks");
+    }
+    if (nlz) {
+        L.blk = b.d_blocks; L.slots = b.d_slots; L.work = ex.alloc<u8>((size_t)nlz * ZLZ_WORK);
+        CUDA_TRY(cudaFuncSetAttribute(k_zenc_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZLZ_SMEM));
+        KLAUNCH(ex, "k_zenc_lz", k_zenc_lz<<<(nlz + 31) / 32, 32, ZLZ_SMEM, ex.stream>>>(L));
     }
     ZEncArgs A{b.d_blocks, b.d_slots};
     u16 *d_hists = ex.alloc<u16>((size_t)b.nblocks * 256);

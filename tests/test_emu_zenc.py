@@ -1,0 +1,178 @@
+"""not-gpu: the block encoder's HD bodies (naf_b200/csrc/zstd_enc_hd.cuh: LZ77 match finder, Huffman literals, FSE-coded
+sequences, repeat-offset codes) run on the CPU by tests/emu/emu_zenc.cpp.  Every frame must be decoded back to the input
+by (a) the oracle's from-spec decoder, (b) the unmodified libzstd 1.5.0 built from the reference's sources (when
+present), (c) our own decoder's HD bodies (tests/emu/emu_zstd).  The encoder is free-parse, so parity on this side IS
+decodability; the ratio checks only guard against the match finder silently finding nothing."""
+import ctypes as C
+import os
+import random
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from naf_b200 import synth
+
+ROOT = helpers.ROOT
+BUILD = os.path.join(ROOT, "tests", "_build")
+CSRC = os.path.join(ROOT, "naf_b200", "csrc")
+
+
+def _build(name, deps):
+    os.makedirs(BUILD, exist_ok=True)
+    exe, src = os.path.join(BUILD, name), os.path.join(ROOT, "tests", "emu", name + ".cpp")
+    deps = [src] + [os.path.join(CSRC, d) for d in deps]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unused-function", "-o", exe, src], check=True)
+    return exe
+
+
+@pytest.fixture(scope="module")
+def enc():
+    return _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+
+
+@pytest.fixture(scope="module")
+def dec():
+    return _build("emu_zstd", ["zstd_dec.cuh", "zstd_hd.cuh"])
+
+
+@pytest.fixture(scope="module")
+def libzstd():
+    so = os.path.join(helpers.REF_BIN, "libzstd.so")
+    if not os.path.exists(so):
+        return None
+    lib = C.CDLL(so)
+    lib.ZSTD_decompress.restype = C.c_size_t
+    lib.ZSTD_decompress.argtypes = [C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.ZSTD_isError.argtypes = [C.c_size_t]
+    # frames without a content size: streaming API
+    lib.ZSTD_createDStream.restype = C.c_void_p
+    lib.ZSTD_freeDStream.argtypes = [C.c_void_p]
+    lib.ZSTD_decompressStream.restype = C.c_size_t
+    lib.ZSTD_decompressStream.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ZSTD_getErrorName.restype = C.c_char_p
+    lib.ZSTD_getErrorName.argtypes = [C.c_size_t]
+    return lib
+
+
+class _Buf(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("size", C.c_size_t), ("pos", C.c_size_t)]
+
+
+def libzstd_decode(lib, frame, expect):
+    ds = lib.ZSTD_createDStream()
+    src = C.create_string_buffer(frame, len(frame))
+    dst = C.create_string_buffer(expect + 64)
+    i, o = _Buf(C.cast(src, C.c_void_p), len(frame), 0), _Buf(C.cast(dst, C.c_void_p), expect + 64, 0)
+    while True:
+        r = lib.ZSTD_decompressStream(ds, C.byref(o), C.byref(i))
+        assert not lib.ZSTD_isError(r), lib.ZSTD_getErrorName(r)
+        if r == 0 or i.pos == i.size:
+            break
+    lib.ZSTD_freeDStream(ds)
+    assert r == 0, "libzstd wants more input"
+    return dst.raw[:o.pos]
+
+
+def roundtrip(enc, dec, libzstd, tmp_path, data, block=8192, lz=1, hstride=1, own_decoder=True):
+    inp, z, back = str(tmp_path / "in.bin"), str(tmp_path / "f.zst"), str(tmp_path / "back.bin")
+    with open(inp, "wb") as f:
+        f.write(data)
+    p = subprocess.run([enc, inp, z, str(block), str(lz), str(hstride)], capture_output=True)
+    assert p.returncode == 0, p.stderr
+    frame = open(z, "rb").read()
+    assert helpers.load_oracle().zstd_decompress(frame) == data, "oracle decoder"
+    if libzstd is not None:
+        assert libzstd_decode(libzstd, frame, len(data)) == data, "libzstd 1.5.0"
+    if own_decoder:
+        q = subprocess.run([dec, z, back], capture_output=True)
+        assert q.returncode == 0, q.stderr
+        assert open(back, "rb").read() == data, "own decoder (HD bodies)"
+    return len(frame)
+
+
+def ids_stream(n, start=1):
+    return b"".join(b"SRR1.%d\0" % i for i in range(start, start + n))
+
+
+def test_ids_comments_lengths(enc, dec, libzstd, tmp_path):
+    ids = ids_stream(20000, 999000)
+    z = roundtrip(enc, dec, libzstd, tmp_path, ids)
+    assert z < 0.2 * len(ids), (z, len(ids))           # Huffman-only gets ~0.45; zstd -1 ~0.1
+    comm = b"".join(b"%d/1\0" % i for i in range(1, 20001))
+    assert roundtrip(enc, dec, libzstd, tmp_path, comm) < 0.25 * len(comm)
+    lens = struct.pack("<I", 150) * 50000
+    assert roundtrip(enc, dec, libzstd, tmp_path, lens) < 0.005 * len(lens)
+    illumina = b"".join(b"A00123:45:HXXXX:1:%d:%d:%d\0" % (1101 + i // 500, 1000 + (i * 37) % 9000, 2000 + (i * 91) % 30000) for i in range(8000))
+    assert roundtrip(enc, dec, libzstd, tmp_path, illumina) < 0.45 * len(illumina)
+    ont = b"".join(b"ont_%d len=%d\0" % (i, 10000 + (i * 7919) % 40000) for i in range(10000))
+    roundtrip(enc, dec, libzstd, tmp_path, ont)
+
+
+@pytest.mark.parametrize("block", [8192, 32768, 1024, 100])
+def test_block_sizes_and_modes(enc, dec, libzstd, tmp_path, block):
+    rng = np.random.default_rng(block)
+    cases = [
+        b"", b"a", b"ab" * 7, b"x" * 15, b"x" * 16, b"x" * 100000,                       # empty / raw / RLE blocks
+        bytes(rng.integers(0, 256, 50000, dtype=np.uint8)),                             # incompressible: raw blocks
+        bytes(rng.integers(0, 4, 70000, dtype=np.uint8)),                               # Huffman, few matches
+        bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 40001)),
+        b"abcdefgh" * 5000 + b"tail",                                                   # one long periodic match per block
+        b"0123456789" * 3 + bytes(rng.integers(0, 256, 30, dtype=np.uint8)) + b"0123456789" * 900,
+        ids_stream(3000) + bytes(rng.integers(0, 256, 3000, dtype=np.uint8)) + ids_stream(3000, 5),
+        b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(3000)),        # runs: offset-1 matches, ll == 0 cases
+        b"".join(struct.pack("<I", int(v)) for v in rng.integers(10000, 50000, 9000)),  # ONT-like length units
+        bytes([255]) * 30000 + bytes(rng.integers(0, 255, 5000, dtype=np.uint8)),       # mask units
+    ]
+    for data in cases:
+        roundtrip(enc, dec, libzstd, tmp_path, data, block=block)
+        roundtrip(enc, dec, libzstd, tmp_path, data, block=block, lz=0, own_decoder=False)   # literals-only path of the same coder
+
+
+def test_interleaved_hash_table_is_the_same_parse(enc, dec, libzstd, tmp_path):
+    """the kernel interleaves the hash tables of a warp's lanes (stride 32): same frame as stride 1"""
+    data = ids_stream(5000, 12345)
+    inp = str(tmp_path / "i.bin")
+    open(inp, "wb").write(data)
+    outs = []
+    for stride in (1, 32):
+        z = str(tmp_path / f"s{stride}.zst")
+        assert subprocess.run([enc, inp, z, "8192", "1", str(stride)], capture_output=True).returncode == 0
+        outs.append(open(z, "rb").read())
+    assert outs[0] == outs[1]
+
+
+def test_fuzz_structured(enc, dec, libzstd, tmp_path):
+    """random mixtures of copies, runs and noise: every repeat-offset / literal-length-0 / mode combination gets hit"""
+    rnd = random.Random(7)
+    for it in range(60):
+        n = rnd.choice([17, 200, 5000, 8192, 8193, 20000, 40000])
+        out = bytearray()
+        alpha = rnd.choice([2, 4, 16, 64, 256])
+        while len(out) < n:
+            k = rnd.random()
+            if k < 0.45 and len(out) > 8:
+                off = rnd.choice([1, 2, 3, 4, 13, rnd.randint(1, len(out))])
+                off = min(off, len(out))
+                ln = rnd.choice([3, 4, 5, 8, 20, 300, rnd.randint(3, 2000)])
+                for _ in range(ln):
+                    out.append(out[-off])
+            elif k < 0.55:
+                out += bytes([rnd.randrange(alpha)]) * rnd.randint(1, 50)
+            else:
+                out += bytes(rnd.randrange(alpha) for _ in range(rnd.randint(1, 30)))
+        data = bytes(out[:n])
+        roundtrip(enc, dec, libzstd, tmp_path, data, block=rnd.choice([8192, 8192, 4096, 32768, 333]))
+
+
+def test_golden_texts(enc, dec, libzstd, tmp_path):
+    """the six streams of real-shaped inputs (oracle split of synthetic FASTQ / soft-masked FASTA)"""
+    oracle = helpers.load_oracle()
+    for text in (synth.fastq(3000, 150, seed=3), synth.ont_fasta(40, 1000, 5000, seed=4), synth.protein_fasta(500, 300, seed=5)):
+        kw = {"seq_type": "protein"} if text.startswith(b">sp|") else {}
+        streams, _ = oracle.split(text, **kw)
+        for s in streams:
+            roundtrip(enc, dec, libzstd, tmp_path, s)

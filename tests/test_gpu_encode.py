@@ -169,11 +169,37 @@ def test_zstd_compress_roundtrip(gpu, oracle):
     datasets.append(np.tile(np.array([150, 0, 0, 0], dtype=np.uint8), 50000).tobytes())
     datasets.append(rng.integers(0, 256, 300000, dtype=np.uint8).tobytes())
     datasets.append(bytes(rng.choice(np.arange(200, dtype=np.uint8), 100000, p=np.r_[[0.5], np.full(199, 0.5 / 199)])))
-    for d in datasets:
-        z = gpu.zstd_compress(d)
-        assert z[:4] == b"\x28\xb5\x2f\xfd"
-        assert oracle.zstd_decompress(z) == d, len(d)
-        assert gpu.zstd_decompress(z) == d, len(d)
+    datasets.append(b"".join(b"%d/1\0" % i for i in range(1, 40000)))
+    datasets.append(b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(6000)))      # runs: offset-1 matches, literal length 0
+    datasets.append(b"abcdefgh" * 9000 + b"tail")
+    for level in (0, 1):                      # 0: Huffman-only 32 KB blocks; 1: 8 KB blocks with LZ77 matches + FSE-coded sequences
+        for d in datasets:
+            z = gpu.zstd_compress(d, level=level)
+            assert z[:4] == b"\x28\xb5\x2f\xfd"
+            assert oracle.zstd_decompress(z) == d, (level, len(d))
+            assert gpu.zstd_decompress(z) == d, (level, len(d))
+    ids = datasets[-7]
+    assert ids.startswith(b"SRR1.0")
+    assert len(gpu.zstd_compress(ids, level=1)) < 0.4 * len(gpu.zstd_compress(ids, level=0))
+
+
+def test_levels_lz_on_text_streams(gpu, oracle):
+    """ennaf -# : level >= 1 parses ids / comments / lengths / mask with matches, level <= 0 does not; both files are valid
+    for every decoder, and the sequence / quality streams do not depend on the level"""
+    for text, kw in [(synth.fastq(60_000, 150, seed=11), {}), (synth.ont_fasta(200, 10000, 30000, seed=12), {}),
+                     (synth.protein_fasta(30_000, 300, seed=13), {"seq_type": "protein"})]:
+        naf0, i0 = gpu.encode_with_info(text, level=-1, **kw)
+        naf1, i1 = gpu.encode_with_info(text, level=1, **kw)
+        for naf in (naf0, naf1):
+            assert gpu.decode(naf) == text
+            assert oracle.decode(naf) == text
+            if helpers.have_ref():
+                rc, out, err = helpers.ref_run("unnaf", [], naf)
+                assert rc == 0 and out == text, err
+        assert list(i0.stream_raw) == list(i1.stream_raw)
+        assert i0.stream_comp[4] == i1.stream_comp[4] and i0.stream_comp[5] == i1.stream_comp[5]
+        assert i1.stream_comp[0] + i1.stream_comp[1] < 0.6 * (i0.stream_comp[0] + i0.stream_comp[1])
+        assert len(naf1) < len(naf0)
 
 
 def test_encode_reference_suite(gpu, oracle):
