@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-records", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--level", type=int, default=1, help="ennaf -# (1 = the tools' default: LZ77 + FSE sequences on ids/comments/lengths/mask; <= 0 entropy-only)")
     return ap.parse_args()
 
 
@@ -217,7 +218,7 @@ def run_ours(args):
     d_text[n_text:].zero_()
     torch.cuda.synchronize()
 
-    eopts, dopts = api.make_enc_opts(), api.make_dec_opts()
+    eopts, dopts = api.make_enc_opts(level=args.level), api.make_dec_opts()
     stream = torch.cuda.ExternalStream(ctx.lib.nafgpu_stream(ctx.h))
 
     def barrier():
@@ -411,7 +412,7 @@ def run_ours(args):
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{records} x {READ_LEN} bp synthetic Illumina FASTQ per GPU (BASELINE configs[1])", "records_per_gpu": records,
-                       "read_len": READ_LEN, "text_bytes_per_gpu": n_text, "naf_bytes_per_gpu": int(naf_size),
+                       "read_len": READ_LEN, "level": args.level, "text_bytes_per_gpu": n_text, "naf_bytes_per_gpu": int(naf_size),
                        "l2": "inputs (3.3 GB text, 1.3 GB .naf at 10 M reads) are larger than the 126 MB L2; no explicit flush",
                        "parallelism": f"{world} x independent record shards, no data-path collective"},
             "encode_gbases_s": total_bases / (enc_ms1 * 1e-3) / 1e9, "decode_gbases_s": total_bases / (dec_ms1 * 1e-3) / 1e9,
