@@ -3,7 +3,8 @@
 // to nafgpu_encode() in libnafgpu.so (B200).  Same flags, same defaults, same messages and exit codes.
 // Deliberate differences: no temporary files are ever needed, so --temp-dir / --name / --keep-temp-files
 // are accepted and ignored and a missing TMPDIR is not an error (reference quirk);
-// -# / --level is accepted but the GPU encoder has a single parse; --version names this implementation.
+// -# / --level selects between the two parses the GPU encoder has (1: entropy-only, >= 2: + LZ77 on the text-like streams);
+// --version names this implementation.
 #include "cli_common.hpp"
 
 static bool verbose = false, force_stdout = false, no_mask = false, strict_mode = false, well_formed = false;
@@ -46,7 +47,7 @@ static void show_help()
         "Options:\n"
         "  -o FILE            - Write compressed output to FILE\n"
         "  -c                 - Write to standard output\n"
-        "  -#, --level #      - Accepted for compatibility (the GPU encoder has one parse; default: 1)\n"
+        "  -#, --level #      - 1 (default): fastest parse; 2 and above: also LZ77-match names, lengths and mask\n"
         "  --long N           - Accepted for compatibility (window of size 2^N for sequence stream)\n"
         "  --temp-dir DIR     - Accepted for compatibility (no temporary files are used)\n"
         "  --name NAME        - Accepted for compatibility\n"

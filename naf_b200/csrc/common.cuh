@@ -37,15 +37,19 @@ struct Arena {
     {
         n = (n + 255) & ~(size_t)255;
         if (n == 0) n = 256;
+        void *r = nullptr;
+        for (auto &s : slabs)
+            if (s.cap - s.used >= n) { r = s.p + s.used; s.used += n; break; }
+        if (!r) {
+            size_t cap = n > (size_t)(256u << 20) ? n : (size_t)(256u << 20);
+            Slab s; s.cap = cap; s.used = n;
+            CUDA_TRY(cudaMalloc(&s.p, cap));                     // a request the device cannot satisfy (a corrupt file claiming
+            slabs.push_back(s);                                  // terabytes) fails HERE, before it can enter the high-water mark
+            r = s.p;
+        }
         cur_total += n;
         if (cur_total > high_water) high_water = cur_total;
-        for (auto &s : slabs)
-            if (s.cap - s.used >= n) { void *r = s.p + s.used; s.used += n; return r; }
-        size_t cap = n > (size_t)(256u << 20) ? n : (size_t)(256u << 20);
-        Slab s; s.cap = cap; s.used = n;
-        CUDA_TRY(cudaMalloc(&s.p, cap));
-        slabs.push_back(s);
-        return s.p;
+        return r;
     }
     void reset()
     {
@@ -53,8 +57,8 @@ struct Arena {
             for (auto &s : slabs) cudaFree(s.p);
             slabs.clear();
             Slab s; s.cap = high_water + (high_water >> 3) + (1u << 20); s.used = 0;
-            CUDA_TRY(cudaMalloc(&s.p, s.cap));
-            slabs.push_back(s);
+            if (cudaMalloc(&s.p, s.cap) == cudaSuccess) slabs.push_back(s);
+            else { cudaGetLastError(); high_water = 0; }         // no room for the merged slab: start over with on-demand slabs
         }
         for (auto &s : slabs) s.used = 0;
         cur_total = 0;

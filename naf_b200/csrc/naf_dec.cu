@@ -468,6 +468,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     nafz::ZDecPlan plan;
     plan.blocks.swap(ctx.zblock_cache);                                   // reuse last call's capacity
     struct GiveBack { nafz::ZDecPlan &p; Ctx &c; ~GiveBack() { p.blocks.swap(c.zblock_cache); } } give_back{plan, ctx};
+    static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
     int sidx[6]; u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
     nafz::ZStreamDesc sdesc[6];
     for (int k = 0; k < 6; k++) {
@@ -475,6 +476,9 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         if (!need[k]) continue;
         u64 expect = h.sec[k].orig;
         if (k == SEC_DATA && packed) expect = (h.sec[k].orig + 1) / 2;
+        // no zstd frame regenerates more than 128 KB from the 4 bytes of an RLE block: a header that claims more is
+        // damaged, and must fail here rather than as a failed multi-terabyte allocation
+        if (expect > (h.sec[k].comp + 4) * 32768 + (128u << 10)) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
         sbytes[k] = expect; soff[k] = arena_sz;
         nafz::ZStreamDesc sd; sd.src_off = h.sec[k].off; sd.src_len = h.sec[k].comp; sd.out_off = arena_sz; sd.out_size = expect;
         sd.one_frame = (k == SEC_DATA || k == SEC_QUAL) ? 1 : 0; sd.no_magic = 1; sd.need_lo = 0; sd.need_hi = ~0ull;
@@ -486,7 +490,6 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     // written by the decoder; bytes of blocks a record-range decode skips are never used)
     for (int k = 0; k < 6; k++) if (need[k]) ex.zero(d_streams + soff[k] + sbytes[k], align256(sbytes[k] + 64) - sbytes[k]);
     ex.zero(d_streams + arena_sz, 256);
-    static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
     u64 data_out_size = 0;
     auto run_batch = [&](bool big_streams) {
         plan.streams.clear();

@@ -476,14 +476,16 @@ SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, con
 
 namespace nafg {
 
-// ennaf -# (ennaf.c:222-223, compressor.c:7): level >= 1 (the tools' default is 1) adds LZ77 matches and FSE-coded sequences to
-// the text-like streams; level <= 0 (zstd's "fast" negative levels) keeps the entropy-only parse for every stream.
-// NAFGPU_LZ=0/1 in the environment overrides the level (A/B measurements).
+// ennaf -# (ennaf.c:222-223, compressor.c:7).  Level 1 -- the tools' default -- is the fastest parse: every stream entropy-coded
+// in independent 32 KB blocks.  Level >= 2 adds LZ77 matches and FSE-coded sequences to the text-like streams (ids, comments,
+// lengths, mask): the file shrinks to what `ennaf -1` writes, at (measured on B200, profiles/r1q_ab_level.json) about twice
+// the encode and decode time of level 1 while that path is one thread per 8 KB block.  NAFGPU_LZ=0/1 in the environment
+// overrides the level (A/B measurements).
 static bool lz_for_level(int level)
 {
     static const char *env = getenv("NAFGPU_LZ");
     if (env && (env[0] == '0' || env[0] == '1')) return env[0] == '1';
-    return level >= 1;
+    return level >= 2;
 }
 
 // ennaf.c:538-589: header, then per stream VLE(original size) VLE(compressed size - 4) frame-without-magic

@@ -540,6 +540,18 @@ HD void k_seq_resolve(const ZDecArgs &a, u32 i)
 // file of ours never enters K9.  Bigger blocks (a reference-made 128 KB first block qualifies too) stay on the
 // parallel path: a serial walk over them would take longer than the jumps it saves.
 static const u32 LOCAL_MAX_OUT = 16 * 1024;
+// Forward copy by one thread, up to 16 bytes per step: all loads of a step are issued before its stores, so the thread
+// waits for memory once per step instead of once per byte (a byte loop costs one L2 round trip per byte: measured
+// 3.8 ms for 0.25 GB of ids on B200).  `dist` = distance from source to destination when they overlap (16 = apart).
+HD void copy_fwd16(u8 *dst, const u8 *src, u32 n, u32 dist)
+{
+    const u32 step = dist >= 16 ? 16 : (dist >= 8 ? 8 : (dist >= 4 ? 4 : 1));
+    u32 i = 0;
+    if (step == 16) for (; i + 16 <= n; i += 16) { u8 t[16]; for (int k = 0; k < 16; k++) t[k] = src[i + k]; for (int k = 0; k < 16; k++) dst[i + k] = t[k]; }
+    else if (step == 8) for (; i + 8 <= n; i += 8) { u8 t[8]; for (int k = 0; k < 8; k++) t[k] = src[i + k]; for (int k = 0; k < 8; k++) dst[i + k] = t[k]; }
+    else if (step == 4) for (; i + 4 <= n; i += 4) { u8 t[4]; for (int k = 0; k < 4; k++) t[k] = src[i + k]; for (int k = 0; k < 4; k++) dst[i + k] = t[k]; }
+    for (; i < n; i++) dst[i] = src[i];
+}
 HD void k_block_local(const ZDecArgs &a, u32 i)
 {
     ZBlock &b = a.blk[i];
@@ -550,12 +562,12 @@ HD void k_block_local(const ZDecArgs &a, u32 i)
     u32 d = 0, l = 0;
     for (u32 k = 0; k < b.nseq; k++) {
         const u32 ll = seq[k].ll, ml = seq[k].ml, of = seq[k].of;
-        for (u32 j = 0; j < ll; j++) o[d + j] = lit[l + j];
+        copy_fwd16(o + d, lit + l, ll, 16);
         d += ll; l += ll;
-        for (u32 j = 0; j < ml; j++) o[d + j] = o[d + j - of];         // forward byte order: overlapping (periodic) matches come out right
+        copy_fwd16(o + d, o + d - of, ml, of);                  // a match may overlap its own output (offset < length)
         d += ml;
     }
-    for (; l < b.lit_regen; l++) o[d++] = lit[l];
+    copy_fwd16(o + d, lit + l, b.lit_regen - l, 16);
     b.local = 1;
 }
 

@@ -14,7 +14,7 @@
 // Per block: histogram -> code lengths -> tree description -> bit-exact sizes -> encode into a fixed slot
 // (k_zenc_hist / k_zenc_tables / k_zenc_encode); a scan over block sizes then lets k_zenc_gather lay the blocks
 // out as frames.
-//   * the small, text-like streams (ids, comments, lengths, mask) at level >= 1: 8 KB blocks with LZ77 matches
+//   * the small, text-like streams (ids, comments, lengths, mask) at level >= 2: 8 KB blocks with LZ77 matches
 //     (compress/zstd_fast.c:186 ZSTD_compressBlock_fast) and FSE-coded sequences (compress/zstd_compress_sequences.c:418),
 //     one thread per block (k_zenc_lz; the body is HD code in zstd_enc_hd.cuh, validated on the CPU against libzstd);
 //     still independent blocks — matches stay inside the block, repeat-offset codes only name offsets the block itself pushed

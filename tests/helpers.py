@@ -199,3 +199,14 @@ def parse_unnaf_args(args):
             kw["view"] = a[2:]
         i += 1
     return kw
+
+
+def claim_huge_ids(naf: bytes) -> bytes:
+    """the same .naf with the ids section's original-size field rewritten to 2^40 + 1 (a damaged header)"""
+    from naf_b200 import container
+    h = container.read_header(naf)
+    orig, comp, off = h.sections[0]                      # ids: VLE(orig) VLE(comp) payload at `off`
+    head = container.put_vle(orig) + container.put_vle(comp)
+    at = off - len(head)
+    assert naf[at:off] == head
+    return naf[:at] + container.put_vle((1 << 40) + 1) + container.put_vle(comp) + naf[off:]

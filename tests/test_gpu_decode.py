@@ -91,7 +91,7 @@ def test_corrupt_input_never_crashes(gpu, oracle, tmp_path):
     texts = [synth.fastq(3000, 150, seed=1, lowercase=True), synth.fasta_softmasked(300000, 60, seed=2, n_records=3, repeats=True)]
     files = []
     for t in texts:
-        files += [gpu.encode(t), oracle.encode(t)[0]]
+        files += [gpu.encode(t), gpu.encode(t, level=3), oracle.encode(t)[0]]
         if helpers.have_ref():
             rc, naf, err = helpers.ref_run("ennaf", ["-c"], t, tmp=str(tmp_path))
             assert rc == 0, err
@@ -113,4 +113,19 @@ def test_corrupt_input_never_crashes(gpu, oracle, tmp_path):
         except naf_b200.NafGpuError:
             errors += 1
     assert errors > 50
-    assert gpu.decode(files[0]) == oracle.decode(files[0])
+    for f in files[:3]:
+        assert gpu.decode(f) == oracle.decode(f)
+
+
+def test_absurd_sizes_fail_cleanly_and_leave_the_context_usable(gpu, oracle):
+    """a header that claims terabytes (one flipped VLE byte) is refused like any damaged file -- and the calls after it work
+    (a failed giant allocation used to stay in the arena's high-water mark and made every second call fail)"""
+    import naf_b200
+    text = synth.fastq(2000, 150, seed=5)
+    naf = gpu.encode(text)
+    bad = helpers.claim_huge_ids(naf)
+    for _ in range(3):
+        with pytest.raises(naf_b200.NafGpuError):
+            gpu.decode(bad)
+        assert gpu.decode(naf) == text
+        assert gpu.encode(text) == naf

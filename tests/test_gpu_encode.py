@@ -2,6 +2,7 @@
 to the oracle's restatement of process.c/encoders.c.  File level: the .naf we emit is decoded by the
 oracle and by the UNMODIFIED reference unnaf back to the reference's pinned output (north_star: "the
 encode path emits a format-valid .naf that the reference unnaf decodes back to the byte-identical input")."""
+import os
 import random
 
 import numpy as np
@@ -172,7 +173,7 @@ def test_zstd_compress_roundtrip(gpu, oracle):
     datasets.append(b"".join(b"%d/1\0" % i for i in range(1, 40000)))
     datasets.append(b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(6000)))      # runs: offset-1 matches, literal length 0
     datasets.append(b"abcdefgh" * 9000 + b"tail")
-    for level in (0, 1):                      # 0: Huffman-only 32 KB blocks; 1: 8 KB blocks with LZ77 matches + FSE-coded sequences
+    for level in (1, 3):                      # 1: Huffman-only 32 KB blocks; >= 2: 8 KB blocks with LZ77 matches + FSE-coded sequences
         for d in datasets:
             z = gpu.zstd_compress(d, level=level)
             assert z[:4] == b"\x28\xb5\x2f\xfd"
@@ -180,16 +181,37 @@ def test_zstd_compress_roundtrip(gpu, oracle):
             assert gpu.zstd_decompress(z) == d, (level, len(d))
     ids = datasets[-7]
     assert ids.startswith(b"SRR1.0")
-    assert len(gpu.zstd_compress(ids, level=1)) < 0.4 * len(gpu.zstd_compress(ids, level=0))
+    assert len(gpu.zstd_compress(ids, level=3)) < 0.4 * len(gpu.zstd_compress(ids, level=1))
+
+
+def test_lz_frames_equal_cpu_emulation(gpu, tmp_path):
+    """the GPU runs the same HD block encoder the not-gpu tests run on the CPU (tests/emu/emu_zenc.cpp): same bytes out"""
+    import shutil
+    import subprocess
+    exe = os.path.join(helpers.ROOT, "tests", "_build", "emu_zenc")
+    if shutil.which("g++"):                                  # build from the sources of this snapshot; else the binary that travelled
+        exe = str(tmp_path / "emu_zenc")
+        subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(helpers.ROOT, "tests", "emu", "emu_zenc.cpp")], check=True)
+    elif not os.path.exists(exe):
+        pytest.skip("no emu_zenc binary and no g++ on this box")
+    rng = np.random.default_rng(9)
+    for d in [b"".join(b"SRR1.%d\0" % i for i in range(70000, 90000)), b"".join(b"%d/1\0" % i for i in range(1, 30000)),
+              np.tile(np.array([150, 0, 0, 0], dtype=np.uint8), 30000).tobytes(), bytes(rng.integers(0, 5, 100000, dtype=np.uint8)),
+              b"abcdefgh" * 9000 + b"tail", b"", b"q" * 20000]:
+        inp, z = str(tmp_path / "i.bin"), str(tmp_path / "o.zst")
+        with open(inp, "wb") as f:
+            f.write(d)
+        assert subprocess.run([exe, inp, z, "8192", "1", "32"], capture_output=True).returncode == 0
+        assert gpu.zstd_compress(d, level=3) == open(z, "rb").read(), len(d)
 
 
 def test_levels_lz_on_text_streams(gpu, oracle):
-    """ennaf -# : level >= 1 parses ids / comments / lengths / mask with matches, level <= 0 does not; both files are valid
-    for every decoder, and the sequence / quality streams do not depend on the level"""
+    """ennaf -# : level >= 2 parses ids / comments / lengths / mask with matches, level 1 (the default) does not; both files
+    are valid for every decoder, and the sequence / quality streams do not depend on the level"""
     for text, kw in [(synth.fastq(60_000, 150, seed=11), {}), (synth.ont_fasta(200, 10000, 30000, seed=12), {}),
                      (synth.protein_fasta(30_000, 300, seed=13), {"seq_type": "protein"})]:
-        naf0, i0 = gpu.encode_with_info(text, level=-1, **kw)
-        naf1, i1 = gpu.encode_with_info(text, level=1, **kw)
+        naf0, i0 = gpu.encode_with_info(text, level=1, **kw)
+        naf1, i1 = gpu.encode_with_info(text, level=3, **kw)
         for naf in (naf0, naf1):
             assert gpu.decode(naf) == text
             assert oracle.decode(naf) == text
@@ -198,7 +220,7 @@ def test_levels_lz_on_text_streams(gpu, oracle):
                 assert rc == 0 and out == text, err
         assert list(i0.stream_raw) == list(i1.stream_raw)
         assert i0.stream_comp[4] == i1.stream_comp[4] and i0.stream_comp[5] == i1.stream_comp[5]
-        assert i1.stream_comp[0] + i1.stream_comp[1] < 0.6 * (i0.stream_comp[0] + i0.stream_comp[1])
+        assert i1.stream_comp[0] + i1.stream_comp[1] < 0.75 * (i0.stream_comp[0] + i0.stream_comp[1])
         assert len(naf1) < len(naf0)
 
 
