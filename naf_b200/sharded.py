@@ -255,3 +255,136 @@ def decode_shard(ctx, naf, rank: int, world: int, view: str = "default", **kw) -
     if count == 0:
         return b""
     return ctx.decode(naf, view, first_record=first, n_records=count, **kw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One GPU working through a file that does not fit in HBM: the shard protocol run sequentially.
+#
+# The reference streams its input through 16 KB / 128 KB windows into one temp file per stream and concatenates them at
+# the end (ennaf.c:538-589, compressor.c:150).  Here a "window" is a record-aligned piece of a few hundred MB: piece i is
+# begun on one context while piece i-1 -- which needs piece i's first base code for its last nibble -- is finished on
+# the other; the zstd blocks of each stream accumulate on the host (``sink``) and the container is laid out at the end.
+
+def iter_record_pieces(chunks, piece_bytes: int):
+    """Record-aligned pieces of roughly `piece_bytes` from an iterable of byte chunks (a file read in order).
+    FASTA: cut before a '>' at a line start.  FASTQ: cut after every 4th line, counted from the top of the file (a
+    quality line may begin with '@'), i.e. 4-line records without blank lines -- what split_records accepts too."""
+    import numpy as np
+    buf, fmt, lines = bytearray(), None, 0              # lines: newlines in the pieces already yielded (FASTQ)
+    for chunk in chunks:
+        buf += chunk
+        if fmt is None:
+            head = bytes(buf[:4096]).lstrip()
+            if not head:
+                continue
+            fmt = ">" if head[:1] == b">" else "@"
+        while len(buf) >= piece_bytes:
+            if fmt == ">":
+                at = buf.rfind(b"\n>", 0, len(buf))
+                cut = at + 1 if at >= 0 else 0
+            else:
+                nl = np.flatnonzero(np.frombuffer(buf, dtype=np.uint8) == 10)
+                ends = nl[(lines + np.arange(1, len(nl) + 1)) % 4 == 0]       # newlines that end a record
+                cut = int(ends[-1]) + 1 if len(ends) else 0
+                if cut:
+                    lines += int(np.searchsorted(nl, cut))
+            if cut == 0:
+                break                                   # one record longer than a piece: keep reading
+            yield bytes(buf[:cut])
+            del buf[:cut]
+    if buf or fmt is None:
+        yield bytes(buf)
+
+
+class MemorySink:
+    """Per-stream accumulation of zstd blocks in host memory (the reference uses one temp file per stream)."""
+
+    def __init__(self):
+        self.parts = [[] for _ in range(6)]
+
+    def buffer(self, k: int, n: int):
+        import torch
+        t = torch.empty(n, dtype=torch.uint8)
+        self.parts[k].append(t)
+        return t
+
+    def stream(self, k: int) -> bytes:
+        return b"".join(p.numpy().tobytes() for p in self.parts[k])
+
+
+def encode_stream(encoders, pieces, opts, *, seq_type: int = 0, title: Optional[bytes] = None, line_length: Optional[int] = None,
+                  sink=None) -> bytes:
+    """Sequential form of encode_sharded for ONE device: `encoders` are two shard encoders (two contexts on the same GPU)
+    used alternately, `pieces` an iterable of record-aligned texts (iter_record_pieces).  At most two pieces are resident
+    at any time.  Returns the .naf."""
+    sink = sink or MemorySink()
+    all_counts: List[Counts] = []
+    raws: List[List[int]] = []
+    bodies: List[List[int]] = []
+    pending = None                                      # (encoder, index into all_counts) begun, not finished
+    carry = b""
+    turn = 0
+
+    def finish(enc, idx, is_last):
+        link = link_for(all_counts, idx)
+        link.is_last = int(is_last)
+        raw, body = enc.finish(link)
+        raws.append(list(raw)); bodies.append(list(body))
+        for k in range(6):
+            if body[k]:
+                enc.fetch(k, sink.buffer(k, body[k]))
+
+    for piece in pieces:
+        piece = carry + piece
+        carry = b""
+        enc = encoders[turn]
+        c = enc.begin(piece, opts)
+        if pending is not None and c.n_bases == 0 and (sum(x.n_bases for x in all_counts) & 1):
+            # the piece before this one ends on a low nibble and this piece has no base to complete it with: take the
+            # next piece into this one and begin again (begin on the same context drops the abandoned shard)
+            carry = piece
+            continue
+        formats = {x.format for x in all_counts + [c] if x.format}
+        if len(formats) > 1:
+            raise ValueError("pieces disagree about the input format (FASTA / FASTQ)")
+        all_counts.append(c)
+        if pending is not None:
+            finish(pending[0], pending[1], False)
+        pending = (enc, len(all_counts) - 1)
+        turn ^= 1
+    if carry:                                           # trailing pieces without bases: one last shard
+        enc = encoders[turn]
+        all_counts.append(enc.begin(carry, opts))
+        if pending is not None:
+            finish(pending[0], pending[1], False)
+        pending = (enc, len(all_counts) - 1)
+    if pending is None:                                 # no input at all: one empty shard
+        all_counts.append(encoders[0].begin(b"", opts))
+        pending = (encoders[0], 0)
+    finish(pending[0], pending[1], True)
+
+    formats = {c.format for c in all_counts if c.format}
+    store_qual = 2 in formats
+    store_mask = seq_type < 2 and not bool(getattr(opts, "no_mask", 0))
+    total, pieces_hdr, at = container_layout(seq_type, title, line_length, all_counts, raws, bodies, store_mask, store_qual)
+    out = bytearray(total)
+    for pos, data in pieces_hdr:
+        out[pos:pos + len(data)] = data
+    present = [True, True, True, store_mask, True, store_qual]
+    for k in range(6):
+        if present[k]:
+            s = sink.stream(k)
+            assert len(s) == sum(b[k] for b in bodies)
+            out[at[0][k]:at[0][k] + len(s)] = s         # the shards' blocks of a stream are contiguous, in order
+    return bytes(out)
+
+
+def decode_stream(ctx, naf, write, pieces: int, view: str = "default", **kw) -> int:
+    """unnaf for outputs larger than HBM: the records in `pieces` consecutive ranges, each decoded by one call and handed to
+    `write(bytes)` in order.  Returns the number of bytes written."""
+    n = 0
+    for r in range(max(1, pieces)):
+        part = decode_shard(ctx, naf, r, max(1, pieces), view, **kw)
+        write(part)
+        n += len(part)
+    return n

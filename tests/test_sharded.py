@@ -288,3 +288,66 @@ def test_split_records_is_exact_on_ambiguous_fastq(oracle):
             off += len(p)
         naf = sharded.encode_shards_local([OracleShardEncoder(oracle) for _ in pieces], pieces, _opts())
         _check_merged(oracle, naf, text)
+
+
+# ---- one device, file in pieces (sharded.encode_stream / iter_record_pieces / decode_stream)
+
+def _chunks(text, size):
+    return (text[i:i + size] for i in range(0, len(text), size))
+
+
+@pytest.mark.parametrize("name,make,kw", CASES, ids=[c[0] for c in CASES])
+def test_stream_pieces_and_encode_oracle(oracle, name, make, kw):
+    """the piece cutter is exact (pieces concatenate to the input, every piece starts at a record), and the sequential
+    two-encoder protocol gives a file indistinguishable from a one-piece encode"""
+    text = make()
+    seq_type = helpers.SEQ_TYPES[kw.get("seq_type", "dna")]
+    for piece_bytes, chunk in ((700, 333), (5000, 4096), (len(text) // 3 + 1, 1 << 16), (1 << 30, 1000)):
+        pieces = list(sharded.iter_record_pieces(_chunks(text, chunk), piece_bytes))
+        assert b"".join(pieces) == text
+        total = 0
+        for p in pieces:
+            assert p[:1] in (b">", b"@") or not p.strip()
+            total += oracle.split(p, **kw)[1]["n_sequences"]
+        assert total == oracle.split(text, **kw)[1]["n_sequences"]
+        encs = [OracleShardEncoder(oracle, **kw) for _ in range(2)]
+        naf = sharded.encode_stream(encs, iter(pieces), _opts(**kw), seq_type=seq_type)
+        _check_merged(oracle, naf, text, **kw)
+
+
+def test_stream_piece_without_bases(oracle):
+    """a piece that holds only names (no base to complete the previous piece's last nibble) is merged into the next one"""
+    text = b">a\nACG\n" + b">n1\n>n2\n>n3\n" * 40 + b">b\nTTGCA\n>c\n" + b">z\n" * 30
+    for piece_bytes in (8, 20, 64):
+        pieces = list(sharded.iter_record_pieces(_chunks(text, 7), piece_bytes))
+        assert b"".join(pieces) == text and len(pieces) > 3
+        naf = sharded.encode_stream([OracleShardEncoder(oracle) for _ in range(2)], iter(pieces), _opts())
+        _check_merged(oracle, naf, text)
+    assert oracle.decode(sharded.encode_stream([OracleShardEncoder(oracle) for _ in range(2)], iter([]), _opts())) == b""
+
+
+@pytest.mark.gpu
+def test_stream_gpu(oracle):
+    """config-2 / config-5 shapes through two contexts on one GPU, ~1 MB pieces; decode_stream returns the text in ranges"""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import naf_b200
+    ctxs = [naf_b200.NafGpu(0) for _ in range(2)]
+    try:
+        for text in (synth.fastq(40_001, 150, seed=61, lowercase=True), synth.fasta_softmasked(5_000_001, width=60, seed=62, n_records=5, repeats=True, n_gaps=2)):
+            pieces = list(sharded.iter_record_pieces(_chunks(text, 1 << 18), 1 << 20))
+            assert b"".join(pieces) == text and len(pieces) >= 4
+            naf = sharded.encode_stream([sharded.GpuShardEncoder(c) for c in ctxs], iter(pieces), _opts())
+            want = oracle.decode(naf)
+            assert want == oracle.decode(oracle.encode(text)[0])
+            assert ctxs[0].decode(naf) == want
+            if helpers.have_ref():
+                rc, out, err = helpers.ref_run("unnaf", [], naf)
+                assert rc == 0 and out == want, err
+            got = []
+            assert sharded.decode_stream(ctxs[1], naf, got.append, 5) == len(want)
+            assert b"".join(got) == want
+    finally:
+        for c in ctxs:
+            c.close()
