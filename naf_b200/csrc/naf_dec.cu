@@ -558,6 +558,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     // ---- lengths: merge 0xFFFFFFFF continuation units (output.c:390-393), prefix-sum into base offsets
     u64 *d_L = nullptr, *d_seq_start = nullptr;
     u64 NR = N;      // records in the text
+    u64 len_sum = 0; // bases the length units add up to
     const bool rec_views = view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQUENCES;
     if (rec_views) {
         if (nL == 0) fail(NAFGPU_E_FORMAT, "can't decompress lengths\n");
@@ -575,6 +576,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         // clamp to the bases actually present (print_dna_buffer_as_fasta never prints past total_seq_length)
         u64 sum; ex.download(&sum, d_seq_start + NR, 8);
         if (sum > total_bases) fail(NAFGPU_E_FORMAT, "corrupted lengths - sum exceeds the sequence size\n");
+        len_sum = sum;
     }
     A.L = d_L; A.seq_start = d_seq_start;
 
@@ -652,7 +654,34 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     A.total = total;
     if (total == 0 || NR == 0) return none;
-    u8 *d_text = ex.alloc<u8>(total + 64);
+    // ---- FASTA: sequence data beyond what the length units add up to.  ennaf's id-byte bug (an unexpected byte in an id puts
+    // its '?' into the SEQUENCE buffer, process.c:366,485) writes such files, and print_dna_buffer_as_fasta
+    // (output.c:420-427) prints the surplus after the last record: first into whatever is left of that record's last line,
+    // then in lines of W, with no newline at the end.  Rare and tiny, so it is laid out on the host: the surplus bases are
+    // produced by the text kernel as one bare pseudo-record, fetched, wrapped, and put behind the text.
+    u64 surplus = 0, surplus_text = 0, line_rem = 0;
+    if (view == NAFGPU_OUT_FASTA && !ranged && len_sum < total_bases) {
+        surplus = total_bases - len_sum;
+        if (surplus > (64u << 20)) fail(NAFGPU_E_UNSUPPORTED, "more than 64 MB of sequence beyond the recorded lengths is not supported by this build\n");
+        // length of the last non-empty record: its last line decides the budget (empty records do not touch it)
+        u64 last_len = 0;
+        for (u64 win = 4096; last_len == 0; win *= 16) {
+            const u64 cnt = win < NR ? win : NR;
+            std::vector<u64> tail(cnt);
+            ex.download(tail.data(), d_L + (NR - cnt), cnt * 8);
+            for (u64 i = cnt; i > 0 && last_len == 0; i--) last_len = tail[i - 1];
+            if (cnt == NR) break;
+        }
+        if (last_len == 0) surplus = 0;                                  // no record has bases: print_fasta returns before any sequence (output.c:629)
+        else if (W == 0) surplus_text = surplus;
+        else {
+            line_rem = W - ((last_len - 1) % W + 1);
+            u64 sz = surplus, lr = line_rem;
+            while (sz > lr) { surplus_text += lr + 1; sz -= lr; lr = W; }
+            surplus_text += sz;
+        }
+    }
+    u8 *d_text = ex.alloc<u8>(total + surplus_text + 64);
     A.out = d_text;
     {
         if (NR >= 0xFFFFFFFFull) fail(NAFGPU_E_UNSUPPORTED, "more than 2^32 - 1 records in one file are not supported by this build\n");
@@ -660,6 +689,32 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         u32 *tile_first = ex.alloc<u32>(ntiles + 2);
         KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(d_out_start, NR, ntiles, tile_first));
         KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A, tile_first));
+    }
+    if (surplus) {
+        TextArgs S = A;
+        S.prefix = 0; S.with_name = 0; S.name_nl = 0; S.seq_present = 1; S.seq_nl = 0; S.with_qual = 0; S.W = 0; S.rec0 = 0;
+        u64 hl[2] = { surplus, 0 }, hs[3] = { len_sum, total_bases, 0 }, ho[3] = { 0, surplus, 0 };
+        u64 *sL = ex.alloc<u64>(2), *sS = ex.alloc<u64>(3), *sO = ex.alloc<u64>(3);
+        ex.upload(sL, hl, 16); ex.upload(sS, hs, 24); ex.upload(sO, ho, 24);
+        u8 *d_sur = ex.alloc<u8>(surplus + 64);
+        S.L = sL; S.seq_start = sS; S.out_start = sO; S.N = 1; S.total = surplus; S.out = d_sur;
+        const u64 ntiles = (surplus + WT_TILE - 1) / WT_TILE;
+        u32 *tile_first = ex.alloc<u32>(ntiles + 2);
+        KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(sO, 1, ntiles, tile_first));
+        KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(S, tile_first));
+        std::vector<u8> raw(surplus), wrapped;
+        ex.download(raw.data(), d_sur, surplus);
+        wrapped.reserve(surplus_text);
+        if (W == 0) wrapped = raw;
+        else {
+            u64 pos = 0, sz = surplus, lr = line_rem;
+            while (sz > lr) { wrapped.insert(wrapped.end(), raw.begin() + pos, raw.begin() + pos + lr); wrapped.push_back('\n'); pos += lr; sz -= lr; lr = W; }
+            wrapped.insert(wrapped.end(), raw.begin() + pos, raw.begin() + pos + sz);
+        }
+        if (wrapped.size() != surplus_text) fail(NAFGPU_E_CUDA, "internal error: surplus layout\n");
+        ex.upload(d_text + total, wrapped.data(), wrapped.size());
+        CUDA_TRY(cudaStreamSynchronize(ex.stream));                      // `wrapped` is on this frame
+        total += surplus_text;
     }
     if (view == NAFGPU_OUT_CHARCOUNT) {
         unsigned long long *counts = ex.alloc<unsigned long long>(256);

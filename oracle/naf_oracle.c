@@ -692,33 +692,53 @@ int onaf_decode(const uint8_t *naf, size_t n, const onaf_dec_opts *o, obuf_t *ou
         LOAD_LEN();
         if (load_bases(&h, o, 1, &bases, err)) { rc = -1; break; }
         if (bases.size == 0) break;                                     /* nothing is flushed when there are no bases */
+        /* output-sequences.c:7 as it stands: a length unit at a time; data beyond the last unit is printed bare */
+        uint64_t n = bases.size < h.sec[4].orig ? bases.size : h.sec[4].orig, rec_rem = nL ? L[0] : 0, idx = 0;
         size_t pos = 0;
-        for (uint64_t k = 0; k < nL; k++) {
-            size_t take = L[k]; if (take > bases.size - pos) take = bases.size - pos;
-            obuf_put(out, bases.data + pos, take); pos += take;
-            if (L[k] != 0xFFFFFFFFu) obuf_putc(out, '\n');
+        while (nL && n >= rec_rem) {
+            if (rec_rem > 0) { obuf_put(out, bases.data + pos, rec_rem); pos += rec_rem; n -= rec_rem; }
+            if (L[idx] != 0xFFFFFFFFu) obuf_putc(out, '\n');
+            idx++;
+            if (idx >= nL) break;
+            rec_rem = L[idx];
         }
+        if (n > 0) obuf_put(out, bases.data + pos, n);
         break;
     }
-    case ONAF_OUT_FASTA: {                                              /* output.c:608 + :369 */
+    case ONAF_OUT_FASTA: {                                              /* output.c:608 print_fasta + :369 print_dna_buffer_as_fasta */
         if (!h.has_data) break;
         LOAD_IDS(); LOAD_NAMES(); LOAD_LEN();
         if (load_bases(&h, o, 1, &bases, err)) { rc = -1; break; }
-        size_t pos = 0; uint64_t k = 0;
-        for (uint64_t i = 0; i < N && k < nL; i++) {
-            obuf_putc(out, '>'); put_name(out, &h, idv ? idv[i] : "", cmv ? cmv[i] : ""); obuf_putc(out, '\n');
-            uint64_t reclen = 0;
-            while (k < nL && L[k] == 0xFFFFFFFFu) { reclen += L[k]; k++; }   /* continuation units, output.c:390 */
-            if (k < nL) { reclen += L[k]; k++; }
-            if (reclen > bases.size - pos) reclen = bases.size - pos;
-            if (reclen == 0) continue;                                  /* no blank line for empty sequences */
-            if (W == 0) { obuf_put(out, bases.data + pos, reclen); obuf_putc(out, '\n'); }
-            else for (uint64_t d = 0; d < reclen; d += W) {
-                uint64_t w = reclen - d < W ? reclen - d : W;
-                obuf_put(out, bases.data + pos + d, w); obuf_putc(out, '\n');
+        /* The reference's state machine as it stands, over the whole sequence at once: a length unit at a time, the line
+         * budget carried across continuation units, and -- output.c:420-427 -- whatever sequence data is left once the
+         * length units are used up (ennaf's id-byte bug, SURVEY A.4 #7, makes such files) printed with the line budget the
+         * last record left behind and no newline after it. */
+        uint64_t n = bases.size < h.sec[4].orig ? bases.size : h.sec[4].orig;      /* total_seq_n_bp_remaining */
+        uint64_t idx = 0, seq = 0, line_rem, rec_rem; size_t pos = 0;
+#define NAME(i) do { obuf_putc(out, '>'); put_name(out, &h, idv ? idv[i] : "", cmv ? cmv[i] : ""); obuf_putc(out, '\n'); } while (0)
+#define SPLIT(size_) do { uint64_t sz_ = (size_);                                                       \
+            if (W == 0) { obuf_put(out, bases.data + pos, sz_); pos += sz_; }                             \
+            else {                                                                                        \
+                while (sz_ > line_rem) { obuf_put(out, bases.data + pos, line_rem); obuf_putc(out, '\n'); pos += line_rem; sz_ -= line_rem; line_rem = W; } \
+                obuf_put(out, bases.data + pos, sz_); pos += sz_; line_rem -= sz_;                        \
+            } } while (0)
+        while (idx < nL && seq < N && L[idx] == 0) { NAME(seq); idx++; seq++; }
+        if (seq >= N || idx >= nL) break;
+        NAME(seq); line_rem = W; rec_rem = L[idx];
+        while (n >= rec_rem) {
+            if (rec_rem > 0) { SPLIT(rec_rem); n -= rec_rem; }
+            if (L[idx] == 0xFFFFFFFFu) idx++;
+            else {
+                obuf_putc(out, '\n'); idx++; seq++;
+                while (idx < nL && seq < N && L[idx] == 0) { NAME(seq); idx++; seq++; }   /* empty sequences: no empty lines */
+                if (seq < N) { NAME(seq); line_rem = W; }
             }
-            pos += reclen;
+            if (idx >= nL) break;
+            rec_rem = L[idx];
         }
+        if (n > 0) SPLIT(n);
+#undef NAME
+#undef SPLIT
         break;
     }
     case ONAF_OUT_FASTQ: {                                              /* output-fastq.c:100; mask never applied (unnaf.c:442) */

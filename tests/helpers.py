@@ -136,10 +136,10 @@ def have_ref():
     return all(os.access(os.path.join(REF_BIN, b), os.X_OK) for b in ("ennaf", "unnaf"))
 
 
-def ref_run(tool, args, stdin=b"", tmp="/tmp"):
+def ref_run(tool, args, stdin=b"", tmp="/tmp", timeout=None):
     env = dict(os.environ, TMPDIR=tmp)
     extra = ["--binary-stderr"] + (["--binary-stdout"] if tool == "unnaf" else [])
-    p = subprocess.run([os.path.join(REF_BIN, tool), *extra, *args], input=stdin, capture_output=True, env=env)
+    p = subprocess.run([os.path.join(REF_BIN, tool), *extra, *args], input=stdin, capture_output=True, env=env, timeout=timeout)
     return p.returncode, p.stdout, p.stderr
 
 

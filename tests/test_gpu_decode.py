@@ -129,3 +129,26 @@ def test_absurd_sizes_fail_cleanly_and_leave_the_context_usable(gpu, oracle):
             gpu.decode(bad)
         assert gpu.decode(naf) == text
         assert gpu.encode(text) == naf
+
+
+def test_fasta_surplus_sequence_is_printed_like_the_reference(gpu, oracle, tmp_path):
+    """ennaf's id-byte bug (an unexpected byte in an id puts its replacement into the SEQUENCE) makes files whose
+    sequence is longer than their lengths add up to; unnaf prints the surplus after the last record, into what is left of its
+    last line, without a final newline (output.c:420-427).  Same bytes from us, for every maker of the file."""
+    cases = [(b">>\na", "text"), (b">a\x01b\nACGTAC\nGG\n>c\x02\x03\nTTTTTTT\n", "dna"),
+             (b">a\x01b x\nacgtnnac\nGG\n>c\x02\x03\nTTTTTTT\n>e\n>f\n", "dna"), (b">p\x01\nMKV\nLLA\n>q\x7f\x01\x01\nMM\n", "protein"),
+             (b"@r\x01\nACGT\n+\nIIII\n", "dna"), (b">u\x01\x01\x01\nACGU\n" + b">v\x02\nacguACGU\n" * 300, "rna")]
+    for text, st in cases:
+        files = [oracle.encode(text, seq_type=st)[0], gpu.encode(text, seq_type=st), gpu.encode(text, seq_type=st, level=3)]
+        if helpers.have_ref():
+            rc, naf, err = helpers.ref_run("ennaf", ["--" + st, "-c"], text, tmp=str(tmp_path))
+            assert rc == 0, err
+            files.append(naf)
+        for naf in files:
+            for kw, args in (({}, []), ({"line_length": 3}, ["--line-length", "3"]), ({"line_length": 0}, ["--line-length", "0"]),
+                             ({"no_mask": True}, ["--no-mask"])):
+                want = oracle.decode(naf, "fasta", **kw)
+                assert gpu.decode(naf, "fasta", **kw) == want, (text, st, kw)
+                if helpers.have_ref():
+                    rc, out, err = helpers.ref_run("unnaf", ["--fasta"] + args, naf, timeout=20)
+                    assert rc == 0 and out == want, (text, st, kw, err)
