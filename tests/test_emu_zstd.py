@@ -29,3 +29,27 @@ def test_emu_decoder_on_golden_frames(emu, tmp_path):
         p = subprocess.run([emu, os.path.join(helpers.GOLDEN, "zstd", e["frame"]), out], capture_output=True)
         assert p.returncode == 0, (e["frame"], p.stderr)
         assert helpers.sha(open(out, "rb").read()) == e["sha256"], e["frame"]
+
+
+@pytest.mark.skipif(not os.access(os.path.join(helpers.REF_BIN, "decodecorpus"), os.X_OK), reason="oracle/_ref/decodecorpus not built")
+def test_fresh_decodecorpus_frames(emu, tmp_path):
+    """frames the committed goldens have not seen: zstd's own generator of valid frames (every block / literal / sequence mode,
+    repeat offsets, treeless literals, Repeat_Mode tables) with a different seed, including the large ones the goldens leave out
+    for size; the oracle's from-spec decoder and our decoder's HD bodies must both regenerate the originals"""
+    dc, dco = tmp_path / "dc", tmp_path / "dco"
+    dc.mkdir(); dco.mkdir()
+    seed = int(os.environ.get("NAF_DC_SEED", "77"))
+    subprocess.run([os.path.join(helpers.REF_BIN, "decodecorpus"), "-n120", f"-s{seed}", f"-p{dc}", f"-o{dco}"], capture_output=True, check=True)
+    oracle = helpers.load_oracle()
+    out, n = str(tmp_path / "o.bin"), 0
+    for f in sorted(os.listdir(dc)):
+        z = open(dc / f, "rb").read()
+        raw = open(dco / f[:-4], "rb").read()
+        if len(raw) > (8 << 20):
+            continue
+        assert oracle.zstd_decompress(z) == raw, f
+        p = subprocess.run([emu, str(dc / f), out], capture_output=True)
+        assert p.returncode == 0, (f, p.stderr)
+        assert open(out, "rb").read() == raw, f
+        n += 1
+    assert n > 60

@@ -101,6 +101,10 @@ def test_oracle_vs_reference_on_non_well_formed_input(oracle, tmp_path):
             args.append("--no-mask"); kw["no_mask"] = True
         if rng.random() < 0.1:
             args.append("--strict"); kw["strict"] = True
+        if rng.random() < 0.15:
+            kw["line_length"] = rng.choice([1, 5, 60, 1000]); args += ["--line-length", str(kw["line_length"])]
+        if rng.random() < 0.1:
+            kw["title"] = rng.choice(["t", "a title with spaces", "x" * 200]); args += ["--title", kw["title"]]
         rc, refnaf, referr = helpers.ref_run("ennaf", args + ["-c"], text, tmp=str(tmp_path))
         try:
             naf, report = oracle.encode(text, **kw)
@@ -115,7 +119,7 @@ def test_oracle_vs_reference_on_non_well_formed_input(oracle, tmp_path):
         # --sequences then reads lengths_buffer[] past its end (output-sequences.c:27-35, once per ZSTD_decompressStream
         # call): undefined, not comparable.  Its FASTA printer treats the surplus deterministically and is compared.
         consistent = sum(int(x) for x in oracle.decode(naf, "lengths").split()) == int(oracle.decode(naf, "total-length") or b"0")
-        for view in ("default", "ids", "names", "lengths", "mask", "seq", "sequences", "fasta", "fastq", "number", "total-length", "charcount", "ll7"):
+        for view in ("default", "ids", "names", "lengths", "mask", "seq", "sequences", "fasta", "fastq", "number", "total-length", "charcount", "title", "ll7"):
             if view == "sequences" and not consistent:
                 continue
             uargs, ukw = ([] if view == "default" else ["--" + view]), {"view": view}
