@@ -293,7 +293,10 @@ HD u32 fse_cost256(u32 p, int log)
 }
 
 // ------------------------------------------------------------------ LZ77 over one block
-static const u32 ZLZ_HLOG = 10, ZLZ_EMPTY = 0xFFFF;
+// 128 entries: on the streams this parse is for (ids, comments, lengths, mask in 8 KB blocks) a 128-, 256- or 1024-entry table
+// give the same sizes within 1 % (emulation) -- candidates are recent -- and 256 B per thread instead of 2 KB
+// lets 16 CTAs share an SM instead of 3.
+static const u32 ZLZ_HLOG = 7, ZLZ_EMPTY = 0xFFFF;
 static const u32 ZLZ_MAX_BLOCK = 32768;                       // positions are kept in u16
 
 HD u32 zlz_read32(const u8 *p) { return (u32)p[0] | ((u32)p[1] << 8) | ((u32)p[2] << 16) | ((u32)p[3] << 24); }
