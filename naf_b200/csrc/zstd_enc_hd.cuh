@@ -39,6 +39,16 @@ struct BitW {
     HD u32 finish_aligned() { if (fill) { if (pos < cap) p[pos++] = (u8)acc; else ok = false; fill = 0; acc = 0; } return pos; }
 };
 
+// K consecutive elements into registers: the loads are independent of each other, so a thread waits for memory once per
+// group instead of once per element (the thread-per-block kernels are bound by exactly that wait)
+template <int K, class T> HD void ld_group(const T *p, T *t)
+{
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k < K; k++) t[k] = p[k];
+}
+
 // FSE-compress the Huffman weights w[0..n).  Returns the number of bytes written (table description +
 // bitstream), or 0 when not representable / not worthwhile.  Mirrors compress/huf_compress.c:76 HUF_compressWeights.
 HDN inline u32 fse_compress_weights(const u8 *w, int n, u8 *dst, u32 cap)
@@ -383,7 +393,11 @@ HDN inline u32 zlz_put_literals(const u8 *lit, u32 nlit, u8 *out, u32 cap)
     };
     if (nlit == 0) return raw_or_rle(0, 0);
     u16 hist[256]; for (int s = 0; s < 256; s++) hist[s] = 0;
-    for (u32 i = 0; i < nlit; i++) hist[lit[i]]++;
+    {
+        u32 i = 0;
+        for (; i + 8 <= nlit; i += 8) { u8 t[8]; ld_group<8>(lit + i, t); for (int k = 0; k < 8; k++) hist[t[k]]++; }
+        for (; i < nlit; i++) hist[lit[i]]++;
+    }
     ZEncMeta M; zenc_huf_build(hist, M);
     if (M.mode == 1) return raw_or_rle(1, 1);
     if (M.mode != 2 || nlit < 8) return raw_or_rle(0, nlit);
@@ -392,8 +406,9 @@ HDN inline u32 zlz_put_literals(const u8 *lit, u32 nlit, u8 *out, u32 cap)
     u32 sbytes[4] = {0, 0, 0, 0}, payload = M.tree_len + (nstreams == 4 ? 6u : 0u);
     for (u32 k = 0; k < nstreams; k++) {
         const u32 a = k * seg, b = k == nstreams - 1 ? nlit : (a + seg < nlit ? a + seg : nlit);
-        u32 bits = 0;
-        for (u32 i = a; i < b && i < nlit; i++) bits += M.ctab[lit[i]] >> 12;
+        u32 bits = 0, i = a;
+        for (; i + 8 <= b; i += 8) { u8 t[8]; ld_group<8>(lit + i, t); for (int k = 0; k < 8; k++) bits += M.ctab[t[k]] >> 12; }
+        for (; i < b; i++) bits += M.ctab[lit[i]] >> 12;
         sbytes[k] = bits / 8 + 1; payload += sbytes[k];
     }
     const u32 lh = nstreams == 1 ? 3 : ((nlit <= 16383 && payload <= 16383) ? 4 : 5);
@@ -408,7 +423,9 @@ HDN inline u32 zlz_put_literals(const u8 *lit, u32 nlit, u8 *out, u32 cap)
     for (u32 k = 0; k < nstreams; k++) {
         const u32 a = k * seg, b = k == nstreams - 1 ? nlit : (a + seg < nlit ? a + seg : nlit);
         BitW bw; bw.init(out + at, sbytes[k]);
-        for (u32 i = b; i > a; i--) { const u32 e = M.ctab[lit[i - 1]]; bw.put(e & 0xFFF, e >> 12); }   // the last symbol sits at the lowest bits
+        u32 i = b;                                            // the last symbol sits at the lowest bits
+        for (; i >= a + 8; i -= 8) { u8 t[8]; ld_group<8>(lit + i - 8, t); for (int k = 7; k >= 0; k--) { const u32 e = M.ctab[t[k]]; bw.put(e & 0xFFF, e >> 12); } }
+        for (; i > a; i--) { const u32 e = M.ctab[lit[i - 1]]; bw.put(e & 0xFFF, e >> 12); }
         bw.finish_with_mark();
         at += sbytes[k];
     }
@@ -422,7 +439,11 @@ HDN inline int zlz_put_table(const u8 *codes, u32 n, int nsym_max, int max_log, 
 {
     u32 count[64]; for (int s = 0; s < 64; s++) count[s] = 0;
     int top = 0, npresent = 0;
-    for (u32 i = 0; i < n; i++) count[codes[i]]++;
+    {
+        u32 i = 0;
+        for (; i + 8 <= n; i += 8) { u8 t[8]; ld_group<8>(codes + i, t); for (int k = 0; k < 8; k++) count[t[k]]++; }
+        for (; i < n; i++) count[codes[i]]++;
+    }
     for (int s = 0; s < nsym_max; s++) if (count[s]) { top = s; npresent++; }
     E.norm = norm; E.cum = cum; E.spos = spos; E.st = 0; E.rle_sym = 0;
     if (npresent == 1) {                                      // RLE mode: one byte, no state bits at all
@@ -488,7 +509,14 @@ HDN inline u32 zlz_encode_block(const u8 *src, u32 n, bool use_lz, u16 *htab, u3
     const u32 modes_at = at++;
     // codes
     u8 *cl = W.codes, *co = W.codes + max_seq, *cm = W.codes + 2 * max_seq;
-    for (u32 i = 0; i < nseq; i++) { cl[i] = (u8)zlz_ll_code(S.ll[i]); co[i] = (u8)hibit(S.ov[i]); cm[i] = (u8)zlz_ml_code(S.ml[i]); }
+    {
+        u32 i = 0;
+        for (; i + 4 <= nseq; i += 4) {
+            u16 a[4], b[4], c[4]; ld_group<4>(S.ll + i, a); ld_group<4>(S.ov + i, b); ld_group<4>(S.ml + i, c);
+            for (int k = 0; k < 4; k++) { cl[i + k] = (u8)zlz_ll_code(a[k]); co[i + k] = (u8)hibit(b[k]); cm[i + k] = (u8)zlz_ml_code(c[k]); }
+        }
+        for (; i < nseq; i++) { cl[i] = (u8)zlz_ll_code(S.ll[i]); co[i] = (u8)hibit(S.ov[i]); cm[i] = (u8)zlz_ml_code(S.ml[i]); }
+    }
     SeqConsts C; seq_consts_init(C);
     short nl[36], no[32], nm[53]; u16 cuml[37], cumo[33], cumm[54];
     FseEnc EL, EO, EM;
@@ -508,12 +536,20 @@ HDN inline u32 zlz_encode_block(const u8 *src, u32 n, bool use_lz, u16 *htab, u3
         bw.put(S.ml[i] - ml_base_of(cm[i]), ml_bits_of(cm[i]));
         bw.put(S.ov[i] - (1u << co[i]), co[i]);
     }
-    for (u32 i = nseq - 1; i-- > 0;) {
-        EO.put(bw, co[i]); EM.put(bw, cm[i]); EL.put(bw, cl[i]);
-        bw.put(S.ll[i] - ll_base_of(cl[i]), ll_bits_of(cl[i]));
-        bw.put(S.ml[i] - ml_base_of(cm[i]), ml_bits_of(cm[i]));
-        bw.put(S.ov[i] - (1u << co[i]), co[i]);
+    auto one = [&](u32 c_l, u32 c_o, u32 c_m, u32 ll, u32 ml, u32 ov) {
+        EO.put(bw, c_o); EM.put(bw, c_m); EL.put(bw, c_l);
+        bw.put(ll - ll_base_of(c_l), ll_bits_of(c_l));
+        bw.put(ml - ml_base_of(c_m), ml_bits_of(c_m));
+        bw.put(ov - (1u << c_o), c_o);
+    };
+    u32 i = nseq - 1;                                         // sequences i-1, i-2, ... 0 remain
+    for (; i >= 4; i -= 4) {
+        u8 x[4], y[4], z[4]; u16 a[4], b[4], c[4];
+        ld_group<4>(cl + i - 4, x); ld_group<4>(co + i - 4, y); ld_group<4>(cm + i - 4, z);
+        ld_group<4>(S.ll + i - 4, a); ld_group<4>(S.ml + i - 4, b); ld_group<4>(S.ov + i - 4, c);
+        for (int k = 3; k >= 0; k--) one(x[k], y[k], z[k], a[k], b[k], c[k]);
     }
+    for (; i > 0; i--) one(cl[i - 1], co[i - 1], cm[i - 1], S.ll[i - 1], S.ml[i - 1], S.ov[i - 1]);
     EM.flush(bw); EO.flush(bw); EL.flush(bw);
     bw.finish_with_mark();
     if (!bw.ok) return 0;
