@@ -487,18 +487,10 @@ HDN inline int zlz_put_table(const u8 *codes, u32 n, int nsym_max, int max_log, 
     return 2;
 }
 
-// A complete Compressed_Block for src[0..n) at out (capacity cap >= n).  Returns its size, or 0 when the block should
-// be stored raw (no gain) — the caller emits a Raw_Block (or an RLE_Block when *rle is set).
-HDN inline u32 zlz_encode_block(const u8 *src, u32 n, bool use_lz, u16 *htab, u32 hstride, u8 *lit, ZLzSeqs S, u32 max_seq,
-                                ZLzWork W, u8 *out, u32 cap, bool *rle)
+// Literals section + sequences section for a block of n bytes that was parsed into lit[0..nlit) and S (any match finder).
+// Returns the Compressed_Block's size, or 0 when the block should be stored raw (no gain).
+HDN inline u32 zlz_emit_block(u32 n, const u8 *lit, u32 nlit, const ZLzSeqs &S, u32 max_seq, ZLzWork W, u8 *out, u32 cap)
 {
-    *rle = false;
-    if (n == 0) return 0;
-    { u32 i = 1; while (i < n && src[i] == src[0]) i++; if (i == n) { *rle = true; return 0; } }
-    if (n < 16 || n > ZLZ_MAX_BLOCK) return 0;
-    u32 nlit;
-    if (use_lz) nlit = zlz_find(src, n, htab, hstride, lit, S, max_seq);
-    else { S.n = 0; nlit = n; for (u32 i = 0; i < n; i++) lit[i] = src[i]; }
     u32 at = zlz_put_literals(lit, nlit, out, cap);
     if (at + 4 >= n) return 0;
     const u32 nseq = S.n;
@@ -555,6 +547,21 @@ HDN inline u32 zlz_encode_block(const u8 *src, u32 n, bool use_lz, u16 *htab, u3
     if (!bw.ok) return 0;
     at += bw.pos;
     return at < n ? at : 0;
+}
+
+// A complete Compressed_Block for src[0..n) at out (capacity cap >= n).  Returns its size, or 0 when the block should
+// be stored raw (no gain) — the caller emits a Raw_Block (or an RLE_Block when *rle is set).
+HDN inline u32 zlz_encode_block(const u8 *src, u32 n, bool use_lz, u16 *htab, u32 hstride, u8 *lit, ZLzSeqs S, u32 max_seq,
+                                ZLzWork W, u8 *out, u32 cap, bool *rle)
+{
+    *rle = false;
+    if (n == 0) return 0;
+    { u32 i = 1; while (i < n && src[i] == src[0]) i++; if (i == n) { *rle = true; return 0; } }
+    if (n < 16 || n > ZLZ_MAX_BLOCK) return 0;
+    u32 nlit;
+    if (use_lz) nlit = zlz_find(src, n, htab, hstride, lit, S, max_seq);
+    else { S.n = 0; nlit = n; for (u32 i = 0; i < n; i++) lit[i] = src[i]; }
+    return zlz_emit_block(n, lit, nlit, S, max_seq, W, out, cap);
 }
 
 }  // namespace nafz

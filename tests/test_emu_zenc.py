@@ -176,3 +176,27 @@ def test_golden_texts(enc, dec, libzstd, tmp_path):
         streams, _ = oracle.split(text, **kw)
         for s in streams:
             roundtrip(enc, dec, libzstd, tmp_path, s)
+
+
+def test_warp_match_finder_prototype(libzstd, tmp_path):
+    """tests/emu/proto_lzw.cpp: the window-at-a-time match finder planned for the next round (what a warp would run), feeding
+    the shipped literal / sequence coder.  Valid frames, sizes no worse than the serial parse, and about one step per sequence."""
+    exe = _build("proto_lzw", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    rng = np.random.default_rng(5)
+    for data in (ids_stream(20000, 999000), b"".join(b"%d/1\0" % i for i in range(1, 20001)), struct.pack("<I", 150) * 50000,
+                 bytes(rng.integers(0, 4, 70000, dtype=np.uint8)), b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(3000)),
+                 b"", b"x" * 9000, bytes(rng.integers(0, 256, 20000, dtype=np.uint8))):
+        inp, z, zs = str(tmp_path / "i.bin"), str(tmp_path / "w.zst"), str(tmp_path / "s.zst")
+        with open(inp, "wb") as f:
+            f.write(data)
+        p = subprocess.run([exe, inp, z, "8192"], capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr
+        frame = open(z, "rb").read()
+        assert helpers.load_oracle().zstd_decompress(frame) == data
+        if libzstd is not None:
+            assert libzstd_decode(libzstd, frame, len(data)) == data
+        assert subprocess.run([enc, inp, zs, "8192", "1"], capture_output=True).returncode == 0
+        assert len(frame) <= os.path.getsize(zs) * 1.02 + 16
+        stats = dict(kv.split("=") for kv in p.stdout.split())
+        assert int(stats["steps"]) <= int(stats["seqs"]) + int(stats["blocks"]) * 257
