@@ -69,6 +69,10 @@ int nafgpu_create(int device, nafgpu_ctx **out)
         nafz::zstd_build_predef(predef);
         CUDA_TRY(cudaMalloc(&c->d_predef, sizeof predef));
         CUDA_TRY(cudaMemcpy(c->d_predef, predef, sizeof predef, cudaMemcpyHostToDevice));
+        u8 lut[512];
+        build_nuc_lut(NAFGPU_DNA, lut); build_nuc_lut(NAFGPU_RNA, lut + 256);
+        CUDA_TRY(cudaMalloc(&c->d_nuc_lut, sizeof lut));
+        CUDA_TRY(cudaMemcpy(c->d_nuc_lut, lut, sizeof lut, cudaMemcpyHostToDevice));
     } catch (const CudaError &er) {
         g_create_error = std::string("CUDA error during context creation: ") + cudaGetErrorString(er.e) + "\n";
         delete c; return NAFGPU_E_CUDA;
@@ -84,6 +88,7 @@ void nafgpu_destroy(nafgpu_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->arena.release(); c->pinned_out.release(); c->pinned_aux.release(); c->pinned_stage.release();
     if (c->d_predef) cudaFree(c->d_predef);
+    if (c->d_nuc_lut) cudaFree(c->d_nuc_lut);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;

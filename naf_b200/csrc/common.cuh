@@ -221,6 +221,18 @@ template <class In> void exclusive_scan(CudaExec &ex, In in, size_t n, u64 *out)
     ex.prof_end(); ex.launches += 2;
 }
 
+// tables.c:189 nuc_code, with bit 7 = not an expected code for the alphabet (tables.c:72 DNA, :82 RNA)
+inline void build_nuc_lut(int seq_type, u8 lut[256])
+{
+    for (int c = 0; c < 256; c++) {
+        int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
+        const char *order = "-TGKCYSBAWRDMHV"; const char *q = u ? strchr(order, u) : nullptr;
+        lut[c] = u == 'U' ? 1 : (q ? (u8)(q - order) : 15);
+        const char *ok = seq_type == NAFGPU_RNA ? "-ABCDGHKMNRSUVWY" : "-ABCDGHKMNRSTVWY";
+        if (!(u && strchr(ok, u))) lut[c] |= 0x80;
+    }
+}
+
 // ------------------------------------------------------------------ context
 struct Ctx {
     int device = 0;
@@ -229,6 +241,7 @@ struct Ctx {
     PinnedBuf pinned_out, pinned_aux, pinned_stage;
     std::vector<nafz::ZBlockHead> zblock_cache;   // keeps the capacity of the decoder's host block list between calls
     u32 *d_predef = nullptr;                 // predefined FSE tables
+    u8 *d_nuc_lut = nullptr;                 // nuc_code + "unexpected" bit: DNA at 0, RNA at 256
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::string err;
     nafgpu_timing timing{};

@@ -21,6 +21,7 @@
 
 #include "naf_parse.cuh"
 #include "naf_parse_fast.cuh"
+#include "naf_fused.cuh"
 
 namespace nafg {
 
@@ -391,18 +392,7 @@ static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, siz
 
     // ---- sequence stream: 4-bit pack (+ mask) for DNA/RNA, bytes as they are for protein/text
     if (o.seq_type < NAFGPU_PROTEIN) {
-        u8 lut[256];
-        for (int c = 0; c < 256; c++) {                                    // tables.c:189 nuc_code
-            int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
-            const char *order = "-TGKCYSBAWRDMHV"; const char *q = u ? strchr(order, u) : nullptr;
-            lut[c] = u == 'U' ? 1 : (q ? (u8)(q - order) : 15);
-            // bit 7: not an expected code (tables.c:72 DNA, :82 RNA) -- only the canonical-input parser can still meet one here
-            const char *ok = o.seq_type == NAFGPU_RNA ? "-ABCDGHKMNRSUVWY" : "-ABCDGHKMNRSTVWY";
-            if (!(u && strchr(ok, u))) lut[c] |= 0x80;
-        }
-        u8 *d_lut = ex.alloc<u8>(256);
-        ex.upload(d_lut, lut, 256);
-        CUDA_TRY(cudaStreamSynchronize(ex.stream));                        // lut is a stack array
+        const u8 *d_lut = ctx.d_nuc_lut + (o.seq_type == NAFGPU_RNA ? 256 : 0);
         S.n_seq = (n_seq + 1) / 2;
         S.seq = ex.alloc<u8>(S.n_seq + 64);
         u64 nwords = (n_seq + 31) / 32;
@@ -443,6 +433,124 @@ static SplitDev split_streams_impl(Ctx &ctx, CudaExec &ex, const u8 *d_text, siz
     return S;
 }
 
+// confirm_input_format (process.c:547): skip leading white space, the first byte decides.  -> format (0: empty input), *p0 =
+// offset of the first byte after the leading '>' / '@'.  `head` = the first min(n, 64 KB) bytes of the text, on the host.
+static int confirm_format(const u8 *h, size_t head, size_t n, const nafgpu_enc_opts &o, u64 *p0)
+{
+    auto is_space = [](int ch) { return (ch >= 0x09 && ch <= 0x0D) || ch == 0x20; };
+    int fmt = 0; *p0 = 0;
+    u32 last = '\n'; size_t i = 0;
+    while (i < head && is_space(h[i])) { last = h[i]; i++; }
+    if (i == head && head < n) fail(NAFGPU_E_UNSUPPORTED, "more than 64 KB of leading white space\n");
+    if (i < head) {
+        u32 c = h[i];
+        bool at_line_start = last >= 0x0A && last <= 0x0D;
+        if (c == '>' && at_line_start) fmt = NAFGPU_FMT_FASTA;
+        else if (c == '@' && at_line_start) fmt = NAFGPU_FMT_FASTQ;
+        else if (c == '>' || c == '@') die_input(std::string("invalid input - first '") + (char)c + "' is not at the beginning of the line\n");
+        else die_input("input data is in unknown format - first non-space character is neither '>' nor '@'\n");
+        *p0 = i + 1;
+    }
+    if (o.input_format != NAFGPU_FMT_AUTO && fmt && o.input_format != fmt) die_input("input format is different from format specified in the command line\n");
+    return fmt;
+}
+
+// one case bit per base -> flips -> (whole file) mask units / (shard) what the link step needs
+static void mask_from_casebits(CudaExec &ex, SplitDev &S, const u32 *casebits, u64 n_seq, bool shard)
+{
+    const u64 nwords = (n_seq + 31) / 32;
+    u32 prev0 = 0;
+    if (shard) {                                                   // no flip at my position 0: the link step decides about that one
+        u32 cw[2]; ex.download(&cw[0], casebits, 4); ex.download(&cw[1], casebits + (n_seq - 1) / 32, 4);
+        S.first_case = cw[0] & 1; S.last_case = (cw[1] >> ((n_seq - 1) & 31)) & 1;
+        prev0 = S.first_case;
+    }
+    u64 ft = (nwords + 255) / 256;
+    u64 *fcount = ex.alloc<u64>(ft + 1), *fpre = ex.alloc<u64>(ft + 2);
+    KLAUNCH(ex, "k_flip_count", k_flip_count<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fcount, prev0));
+    const u64 *fc = fcount;
+    exclusive_scan(ex, [fc] __device__ (size_t i) { return fc[i]; }, ft, fpre);
+    u64 R; ex.download(&R, fpre + ft, 8);                          // number of flips; runs = R + 1
+    u64 *flip_pos = ex.alloc<u64>(R + 2);
+    if (R) { KLAUNCH(ex, "k_flip_scatter", k_flip_scatter<<<(unsigned)ft, 256, 0, ex.stream>>>(casebits, nwords, fpre, flip_pos, prev0)); }
+    if (shard) {
+        // the spurious flip at n_seq after a masked tail is not a flip of mine
+        if (R) { u64 lastf; ex.download(&lastf, flip_pos + R - 1, 8); if (lastf >= n_seq) R--; }
+        S.flip_pos = flip_pos; S.n_flips = R;
+    } else build_mask_units(ex, flip_pos, R, n_seq, 0, 0, 1, &S.mask, &S.n_mask);
+}
+
+// The single-pass transform (naf_fused.cuh) for canonical input: one kernel reads the text once and writes every stream once.
+// Throws FastFallback when the input is not canonical (or has an error the general parser must word).
+// h_head: the first bytes of the text on the host if the caller has them (host-buffer API), else nullptr.
+static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info, bool shard,
+                                    const u8 *h_head = nullptr)
+{
+    SplitDev S; memset(&S, 0, sizeof S);
+    if (info) memset(info, 0, sizeof *info);
+    S.store_mask = !(o.no_mask || o.seq_type >= NAFGPU_PROTEIN);                                 // ennaf.c:445
+    u64 p0 = 0;
+    const size_t head = n < 65536 ? n : 65536;
+    if (!h_head) {
+        ctx.host_scratch.resize(head + 1);
+        if (head) ex.download(ctx.host_scratch.data(), d_text, head);
+        h_head = ctx.host_scratch.data();
+    }
+    const int fmt = confirm_format(h_head, head, n, o, &p0);
+    S.format = fmt; S.store_qual = fmt == NAFGPU_FMT_FASTQ;
+    if (info) info->format = fmt;
+    if (fmt == 0) {
+        S.len = ex.alloc<u8>(64); S.mask = ex.alloc<u8>(64); S.ids = ex.alloc<u8>(64); S.comm = ex.alloc<u8>(64); S.seq = ex.alloc<u8>(64); S.qual = ex.alloc<u8>(64);
+        return S;
+    }
+    const bool fastq = fmt == NAFGPU_FMT_FASTQ, packed = o.seq_type < NAFGPU_PROTEIN;
+    const u64 ntiles = (n + FT_BYTES - 1) / FT_BYTES;
+    if (ntiles >= (1ull << 31)) throw FastFallback{};
+
+    FusedArgs A; memset(&A, 0, sizeof A);
+    FusedCfg &C = A.C;
+    C.n = n; C.p0 = p0; C.fastq = fastq;
+    C.seq_mode = o.seq_type == NAFGPU_PROTEIN ? FS_PROTEIN : (o.seq_type == NAFGPU_TEXT ? (fastq ? FS_TEXT : FS_TEXT_GT) : FS_PACK4);
+    C.upper = o.seq_type >= NAFGPU_PROTEIN && o.no_mask;
+    C.want_mask = S.store_mask;
+    C.id_check = (o.seq_type == NAFGPU_TEXT && !fastq) ? FC_ID_GT : FC_ID;
+    // destinations at their worst-case sizes (the arena is one slab: untouched bytes cost nothing)
+    C.ids = ex.alloc<u8>(n + 64); C.comm = ex.alloc<u8>(n + 64);
+    C.qual = ex.alloc<u8>(fastq ? n + 64 : 64);
+    C.seq = ex.alloc<u8>((packed ? n / 2 : n) + 64);
+    C.len = ex.alloc<u32>(ntiles * FT_MAXSEG + 16);
+    const u64 cb_words = packed && S.store_mask ? n / 32 + 2 : 1;
+    C.casebits = ex.alloc<u32>(cb_words);
+    if (packed && S.store_mask) ex.zero(C.casebits, cb_words * 4);
+    C.lut = ctx.d_nuc_lut + (o.seq_type == NAFGPU_RNA ? 256 : 0);
+    // look-back records + scalars
+    A.text = d_text; A.ntiles = (u32)ntiles;
+    A.st1 = ex.alloc<u64>(ntiles + 1); A.st2_status = ex.alloc<u32>(ntiles + 1);
+    A.st2_agg = ex.alloc<u64>(ntiles * F2_WORDS + 8); A.st2_inc = ex.alloc<u64>(ntiles * F2_WORDS + 8);
+    ex.zero(A.st1, (ntiles + 1) * 8); ex.zero(A.st2_status, (ntiles + 1) * 4);
+    u64 *scal = ex.alloc<u64>(4 + (sizeof(FusedTotals) + 7) / 8);
+    ex.zero(scal, 32 + sizeof(FusedTotals));
+    A.ticket = (u32 *)scal; A.flag = (u32 *)scal + 1; A.longest = (unsigned long long *)(scal + 1); A.totals = (FusedTotals *)(scal + 4);
+
+    CUDA_TRY(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem::total));
+    KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)ntiles, FUSED_NT, FusedSmem::total, ex.stream>>>(A));
+    KLAUNCH(ex, "k_fused_finish", k_fused_finish<<<1, 1, 0, ex.stream>>>(A));
+    FusedTotals tot; ex.download(&tot, A.totals, sizeof tot);
+    if (tot.flag) throw FastFallback{};
+
+    S.ids = C.ids; S.comm = C.comm; S.qual = C.qual; S.len = (u8 *)C.len;
+    S.n_ids = tot.n_ids; S.n_comm = tot.n_comm; S.n_qual = tot.n_qual; S.n_len = tot.n_rec * 4;
+    S.n_records = tot.n_rec; S.n_bases = tot.n_bases; S.longest = tot.longest;
+    S.seq = C.seq; S.n_seq = packed ? (tot.n_bases + 1) / 2 : tot.n_bases;
+    if (packed) {
+        if (shard && tot.n_bases) { u8 fb; ex.download(&fb, S.seq, 1); S.first_code = fb & 15; }
+        if (S.store_mask && tot.n_bases) mask_from_casebits(ex, S, C.casebits, tot.n_bases, shard);
+    }
+    if (!S.mask) S.mask = ex.alloc<u8>(64);
+    if (info) { info->n_sequences = tot.n_rec; info->longest_line = S.longest; info->n_bases = tot.n_bases; }
+    return S;
+}
+
 // Canonical input goes through the fast parser; anything it does not cover (or any input error, so that the message
 // comes from the exact restatement) is redone by the general one.  --well-formed has its own tables: general only.
 static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)
@@ -450,7 +558,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
     static const bool env_general = getenv("NAFGPU_GENERAL_PARSER") != nullptr;
     if (!o.well_formed && !env_general && !o.general_parser) {
         const Arena::Mark mk = ex.arena->mark();
-        try { return split_streams_impl(ctx, ex, d_text, n, o, info, true); }
+        try { return split_streams_fused(ctx, ex, d_text, n, o, info, false); }
         catch (const FastFallback &) {}
         catch (const NafError &) {}
         CUDA_TRY(cudaStreamSynchronize(ex.stream));
@@ -572,7 +680,7 @@ void shard_begin_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
     static const bool env_general = getenv("NAFGPU_GENERAL_PARSER") != nullptr;
     if (!o.well_formed && !env_general && !o.general_parser) {
         const Arena::Mark mk = ex.arena->mark();
-        try { S = split_streams_impl(ctx, ex, d_text, n, o, info, true, true); done = true; }
+        try { S = split_streams_fused(ctx, ex, d_text, n, o, info, true); done = true; }
         catch (const FastFallback &) {}
         catch (const NafError &) {}
         if (!done) { CUDA_TRY(cudaStreamSynchronize(ex.stream)); ex.arena->rewind(mk); ctx.fast_fallbacks++; }
