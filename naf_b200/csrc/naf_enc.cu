@@ -522,12 +522,11 @@ static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, si
     const u64 cb_words = packed && S.store_mask ? n / 32 + 2 : 1;
     C.casebits = ex.alloc<u32>(cb_words);
     if (packed && S.store_mask) ex.zero(C.casebits, cb_words * 4);
-    C.lut = ctx.d_nuc_lut + (o.seq_type == NAFGPU_RNA ? 256 : 0);
+    A.lut8 = ctx.d_nuc_lut + (o.seq_type == NAFGPU_RNA ? 256 : 0);
     // look-back records + scalars
     A.text = d_text; A.ntiles = (u32)ntiles;
-    A.st1 = ex.alloc<u64>(ntiles + 1); A.st2_status = ex.alloc<u32>(ntiles + 1);
-    A.st2_agg = ex.alloc<u64>(ntiles * F2_WORDS + 8); A.st2_inc = ex.alloc<u64>(ntiles * F2_WORDS + 8);
-    ex.zero(A.st1, (ntiles + 1) * 8); ex.zero(A.st2_status, (ntiles + 1) * 4);
+    A.st1 = ex.alloc<u64>(ntiles + 1); A.st2 = ex.alloc<ulonglong2>(4 * ntiles + 4);
+    ex.zero(A.st1, (ntiles + 1) * 8); ex.zero(A.st2, (4 * ntiles + 4) * 16);
     u64 *scal = ex.alloc<u64>(4 + (sizeof(FusedTotals) + 7) / 8);
     ex.zero(scal, 32 + sizeof(FusedTotals));
     A.ticket = (u32 *)scal; A.flag = (u32 *)scal + 1; A.longest = (unsigned long long *)(scal + 1); A.totals = (FusedTotals *)(scal + 4);

@@ -15,10 +15,10 @@ static const int FUSED_NT = 256, FUSED_CPT = FT_CHUNKS / FUSED_NT, FUSED_SPT = F
 
 struct FusedArgs {
     FusedCfg C;
+    const u8 *lut8;           // nuc_code, bit 7 = unexpected (Ctx::d_nuc_lut)
     const u8 *text;
     u64 *st1;                 // look-back #1: status << 62 | payload, one word per tile
-    u32 *st2_status;          // look-back #2: 0 empty, 1 aggregate, 2 inclusive
-    u64 *st2_agg, *st2_inc;   // [tile][F2_WORDS]
+    ulonglong2 *st2;          // look-back #2: four tagged 16-byte words per tile (aggregate, inclusive x 3)
     u32 *ticket, *flag;
     unsigned long long *longest;
     FusedTotals *totals;
@@ -28,13 +28,53 @@ struct FusedArgs {
 // shared memory carve-up (bytes)
 struct FusedSmem {
     static const u32 o_text = 0, o_stage = o_text + FT_BYTES + 16, o_seg = o_stage + ((FT_STAGE + 15) & ~15u);
-    static const u32 seg_n = FT_MAXSEG + 8;
-    static const u32 o_role = o_seg + 7 * 2 * seg_n, o_lut = (o_role + seg_n + 15) & ~15u, o_sh = o_lut + 256;
+    static const u32 seg_n = FT_MAXSEG + 8, desc_n = FT_MAXDESC + 8;
+    static const u32 o_desc = o_seg + 3 * 2 * seg_n, o_lut = (o_desc + 3 * 2 * desc_n + 15) & ~15u, o_prev = o_lut + 1024, o_sh = o_prev + 64;
     static const u32 o_scan = (o_sh + (u32)sizeof(FusedShared) + 15) & ~15u, o_mbar = o_scan + 34 * 8, total = o_mbar + 16;
 };
 
 __device__ __forceinline__ u64 ld_vol64(const u64 *p) { return *(const volatile u64 *)p; }
-__device__ __forceinline__ u32 ld_vol32(const u32 *p) { return *(const volatile u32 *)p; }
+__device__ __forceinline__ ulonglong2 ld_vol128(const ulonglong2 *p)
+{
+    ulonglong2 v;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_vol128(ulonglong2 *p, u64 x, u64 y)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+
+// Look-back #2 records.  Every 16-byte word carries its own "written" tag and is written once, by one 128-bit store, so a
+// reader needs neither a fence nor a second round trip: it loads all four words of a tile and uses the inclusive state if
+// all three of its words are there, else the aggregate if that is there, else it asks again.
+static const u64 F2_TAG = 1ull << 62;
+__device__ __forceinline__ void f2_put_aggregate(ulonglong2 *rec, const F2 &g)       // fields of ONE tile: 15 / 11 bits each
+{
+    st_vol128(rec, F2_TAG | g.ids | (g.comm << 15) | (g.seq << 30) | (g.qual << 45), g.rec | (g.srec << 11) | (g.qrec << 26) | (g.last << 41));
+}
+__device__ __forceinline__ void f2_put_inclusive(ulonglong2 *rec, const F2 &g)       // sizes < 2^62, records < 2^40, srec / qrec saturated to 32 bits
+{
+    st_vol128(rec + 1, F2_TAG | g.ids, g.comm);
+    st_vol128(rec + 2, F2_TAG | g.seq, g.qual);
+    st_vol128(rec + 3, F2_TAG | g.rec | (g.last << 40), g.srec | (g.qrec << 32));
+}
+// -> 0 nothing yet, 1 aggregate, 2 inclusive
+__device__ __forceinline__ int f2_get(const ulonglong2 *rec, F2 &g)
+{
+    const ulonglong2 a = ld_vol128(rec), i0 = ld_vol128(rec + 1), i1 = ld_vol128(rec + 2), i2 = ld_vol128(rec + 3);
+    if ((i0.x & i1.x & i2.x) & F2_TAG) {
+        g.ids = i0.x & (F2_TAG - 1); g.comm = i0.y; g.seq = i1.x & (F2_TAG - 1); g.qual = i1.y;
+        g.rec = i2.x & ((1ull << 40) - 1); g.last = (i2.x >> 40) & 0x7FF; g.srec = i2.y & 0xFFFFFFFFull; g.qrec = i2.y >> 32;
+        return 2;
+    }
+    if (a.x & F2_TAG) {
+        g.ids = a.x & 0x7FFF; g.comm = (a.x >> 15) & 0x7FFF; g.seq = (a.x >> 30) & 0x7FFF; g.qual = (a.x >> 45) & 0x7FFF;
+        g.rec = a.y & 0x7FF; g.srec = (a.y >> 11) & 0x7FFF; g.qrec = (a.y >> 26) & 0x7FFF; g.last = (a.y >> 41) & 0x7FF;
+        return 1;
+    }
+    return 0;
+}
 
 __device__ __forceinline__ F2 f2_shfl_down(const F2 &v, int d)
 {
@@ -52,18 +92,6 @@ __device__ __forceinline__ F2 f2_bcast0(const F2 &v)
     r.qual = __shfl_sync(0xFFFFFFFFu, v.qual, 0); r.rec = __shfl_sync(0xFFFFFFFFu, v.rec, 0); r.srec = __shfl_sync(0xFFFFFFFFu, v.srec, 0);
     r.qrec = __shfl_sync(0xFFFFFFFFu, v.qrec, 0); r.last = __shfl_sync(0xFFFFFFFFu, v.last, 0);
     return r;
-}
-__device__ __forceinline__ void f2_store(u64 *p, const F2 &v)
-{
-    __stcg(p + 0, v.ids); __stcg(p + 1, v.comm); __stcg(p + 2, v.seq); __stcg(p + 3, v.qual);
-    __stcg(p + 4, v.rec); __stcg(p + 5, v.srec); __stcg(p + 6, v.qrec); __stcg(p + 7, v.last);
-}
-__device__ __forceinline__ F2 f2_load(const u64 *p)
-{
-    F2 v;
-    v.ids = __ldcg(p + 0); v.comm = __ldcg(p + 1); v.seq = __ldcg(p + 2); v.qual = __ldcg(p + 3);
-    v.rec = __ldcg(p + 4); v.srec = __ldcg(p + 5); v.qrec = __ldcg(p + 6); v.last = __ldcg(p + 7);
-    return v;
 }
 
 // look-back #1, by one warp: prefix of f1 elements over the tiles before `tile` (older first), publishing mine
@@ -101,39 +129,38 @@ __device__ F2 fused_lookback2(const FusedArgs &A, u32 tile, const F2 &mine, bool
     const unsigned lane = threadIdx.x & 31;
     const F2 init = f2_initial();
     if (tile == 0) {
-        if (lane == 0) { f2_store(A.st2_inc, f2_compose(init, mine, fastq)); __threadfence(); *(volatile u32 *)A.st2_status = 2; }
+        if (lane == 0) f2_put_inclusive(A.st2, f2_compose(init, mine, fastq));
         return init;
     }
-    if (lane == 0) { f2_store(A.st2_agg + (u64)tile * F2_WORDS, mine); __threadfence(); *(volatile u32 *)(A.st2_status + tile) = 1; }
+    if (lane == 0) f2_put_aggregate(A.st2 + 4ull * tile, mine);
     F2 prefix = init; bool have = false;
     for (long long base = tile;; base -= 32) {
         const long long idx = base - 1 - lane;
-        u32 st;
-        if (idx >= 0) { do { st = ld_vol32(A.st2_status + idx); } while (st == 0); }
-        else st = 3;
-        __threadfence();
-        const unsigned m = __ballot_sync(0xFFFFFFFFu, st >= 2);
+        F2 v = init; int st = 2;
+        if (idx >= 0) { do { st = f2_get(A.st2 + 4ull * idx, v); } while (st == 0); }
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, st == 2);
         const unsigned k = m ? __ffs(m) - 1 : 31;
-        F2 v = init;
-        if (lane <= k && idx >= 0) v = f2_load((st == 2 ? A.st2_inc : A.st2_agg) + (u64)idx * F2_WORDS);
 #pragma unroll
         for (int s = 1; s < 32; s <<= 1) { const F2 o = f2_shfl_down(v, s); if (lane + s <= k) v = f2_compose(o, v, fastq); }
         v = f2_bcast0(v);
         prefix = have ? f2_compose(v, prefix, fastq) : v; have = true;
         if (m) break;
     }
-    if (lane == 0) { f2_store(A.st2_inc + (u64)tile * F2_WORDS, f2_compose(prefix, mine, fastq)); __threadfence(); *(volatile u32 *)(A.st2_status + tile) = 2; }
+    if (lane == 0) f2_put_inclusive(A.st2 + 4ull * tile, f2_compose(prefix, mine, fastq));
     return prefix;
 }
 
-// staging -> global, both congruent mod 16: 16-byte pieces, head and tail bytes by a few threads
-__device__ __forceinline__ void fused_copy_out(u8 *dst, const u8 *stage, u32 len)
+// one staged region -> global: head and tail bytes by a few threads, aligned 16-byte units by all of them
+__device__ __forceinline__ u32 fused_region_out(const FusedTile &T, u32 off, u32 len, u8 *dst, int check, bool upper)
 {
-    const u32 head = min(len, (u32)((16 - ((uintptr_t)dst & 15)) & 15));
+    if (!len) return 0;
+    u32 head = (u32)((16 - ((uintptr_t)dst & 15)) & 15), bad = 0;
+    if (head > len) head = len;
     const u32 nu = (len - head) >> 4, done = head + (nu << 4), tail = len - done;
-    if (threadIdx.x < head) dst[threadIdx.x] = stage[threadIdx.x];
-    else if (threadIdx.x >= 32 && threadIdx.x - 32 < tail) dst[done + threadIdx.x - 32] = stage[done + threadIdx.x - 32];
-    for (u32 u = threadIdx.x; u < nu; u += FUSED_NT) *(uint4 *)(dst + head + 16 * u) = *(const uint4 *)(stage + head + 16 * u);
+    if (threadIdx.x < head) bad |= T.out_byte(off, threadIdx.x, dst, check, upper);
+    else if (threadIdx.x >= 32 && threadIdx.x - 32 < tail) bad |= T.out_byte(off, done + threadIdx.x - 32, dst, check, upper);
+    for (u32 u = threadIdx.x; u < nu; u += FUSED_NT) bad |= T.out_unit(off + head, u, dst + head, check, upper);
+    return bad;
 }
 
 __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
@@ -141,12 +168,11 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
     extern __shared__ __align__(128) u8 smem[];
     FusedTile T;
     T.text = smem + FusedSmem::o_text; T.stage = smem + FusedSmem::o_stage;
-    u16 *seg = (u16 *)(smem + FusedSmem::o_seg);
-    T.nlmask = nullptr;
-    T.seg_end = seg; T.seg_sp = seg + FusedSmem::seg_n; T.seg_off = seg + 2 * FusedSmem::seg_n; T.seg_offb = seg + 3 * FusedSmem::seg_n;
-    T.seg_list = seg + 4 * FusedSmem::seg_n; T.recseq = seg + 5 * FusedSmem::seg_n; T.recqual = seg + 6 * FusedSmem::seg_n;
-    T.seg_role = smem + FusedSmem::o_role;
-    u8 *lut = smem + FusedSmem::o_lut;
+    u16 *seg = (u16 *)(smem + FusedSmem::o_seg), *desc = (u16 *)(smem + FusedSmem::o_desc);
+    T.seg_end = seg; T.recseq = seg + FusedSmem::seg_n; T.recqual = seg + 2 * FusedSmem::seg_n;
+    T.d_src = desc; T.d_len = desc + FusedSmem::desc_n; T.d_dst = desc + 2 * FusedSmem::desc_n;
+    u32 *lut = (u32 *)(smem + FusedSmem::o_lut);
+    u8 *prev = smem + FusedSmem::o_prev;
     FusedShared *sh = (FusedShared *)(smem + FusedSmem::o_sh);
     T.sh = sh;
     u64 *scan = (u64 *)(smem + FusedSmem::o_scan);
@@ -168,25 +194,20 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (C.seq_mode == FS_PACK4) lut[tid] = C.lut[tid];
+    if (C.seq_mode == FS_PACK4) lut[tid] = nuc_lut32(A.lut8[tid]);
     __syncthreads();
     const u32 tile = sh->tile;
     const u64 lo = (u64)tile * FT_BYTES;
     C.lut = lut;
 
-    // ---- the tile -> shared memory
+    // ---- the tile -> shared memory (one bulk asynchronous copy), and the 64 bytes before it
     const bool bulk = lo + FT_BYTES <= C.n && (((uintptr_t)A.text) & 15) == 0;
     if (bulk) {
-        const u32 bar = (u32)__cvta_generic_to_shared(mbar);
         if (tid == 0) {
-            const u32 dst = (u32)__cvta_generic_to_shared(T.text);
+            const u32 bar = (u32)__cvta_generic_to_shared(mbar), dst = (u32)__cvta_generic_to_shared(T.text);
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((u32)FT_BYTES) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(A.text + lo), "r"((u32)FT_BYTES), "r"(bar) : "memory");
-        }
-        u32 done = 0;
-        while (!done) {
-            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
         }
     } else {
         for (u32 c = tid; c < FT_CHUNKS; c += FUSED_NT) {
@@ -201,7 +222,15 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
             *(uint4 *)(T.text + 16 * c) = v;
         }
     }
-    if (tid < 4) ((u32 *)(T.text + FT_BYTES))[tid] = 0;             // the word-wise copies read one word past a segment
+    if (tid >= 64 && tid < 128) { const u32 i = tid - 64; prev[i] = lo + i >= 64 ? A.text[lo + i - 64] : (u8)0; }
+    if (tid < 4) ((u32 *)(T.text + FT_BYTES))[tid] = 0;             // the word-wise copies read one word past a run
+    if (bulk) {
+        const u32 bar = (u32)__cvta_generic_to_shared(mbar);
+        u32 done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(done) : "r"(bar) : "memory");
+        }
+    }
     __syncthreads();
 
     // ---- phase 1: newlines -> line segments
@@ -216,7 +245,14 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
     const bool aborted = nl + 1 > FT_MAXSEG;
     if (!aborted) {
 #pragma unroll
-        for (int k = 0; k < FUSED_CPT; k++) T.put_lines(tid + k * FUSED_NT, m[k], first[k]);
+        for (int k = 0; k < FUSED_CPT; k++) {
+            if (m[k]) {                                              // mostly one newline per chunk at most
+                const u32 b = __ffs(m[k]) - 1;
+                T.seg_end[first[k]] = (u16)(16 * (tid + k * FUSED_NT) + b);
+                const u32 rest = m[k] & (m[k] - 1);
+                if (rest) T.put_lines(tid + k * FUSED_NT, rest, first[k] + 1);
+            }
+        }
     }
     if (tid == 0) { sh->nseg = nl + 1; if (aborted) { sh->abort_ = 1; sh->flag = FU_LINES; } }
     __syncthreads();
@@ -229,11 +265,16 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
         if (lane == 0) {
             sh->entry1 = e1;
             const u64 at = lo + sh->live_lo;
-            const u32 els = fastq ? (u32)(at > C.p0 && A.text[at - 1] == '\n') : (u32)(e1 == FE_LS);
+            const u32 np = at > C.p0 && sh->live_lo == 0 ? (u32)(at - C.p0 < 64 ? at - C.p0 : 64) : 0u;
+            const u8 *pv = prev + 64 - np;
+            const u32 els = fastq ? (u32)(np && pv[np - 1] == '\n') : (u32)(e1 == FE_LS);
             sh->entry_ls = els;
             const u32 role0 = fastq ? (e1 & 3) : (e1 == FE_HDR ? (u32)FR_HDR : (u32)FR_SEQ);
             u32 sp = 0;
-            if (sh->live_lo < sh->live_hi && role0 == FR_HDR && !els) { u32 f = 0; sp = fast_lookback_space(A.text, C.p0, at, f); if (f) sh->flag |= FU_LOOKBACK; }
+            if (sh->live_lo < sh->live_hi && role0 == FR_HDR && !els) {
+                bool resolved; sp = prev_scan(pv, np, resolved);
+                if (!resolved && at - np > C.p0) { u32 f = 0; sp = fast_lookback_space(A.text, C.p0, at - np, f); if (f) sh->flag |= FU_LOOKBACK; }
+            }
             sh->entry_sp = sp;
         }
     }
@@ -241,47 +282,60 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
 
     u32 flag = 0;
     u64 maxlen = 0;
-    F2 agg2 = f2_initial(); agg2.last = 0;
     if (!aborted) {
-        // ---- phase 3: one thread per segment (FUSED_SPT consecutive ones), block scans -> places inside the tile
-        const u32 nseg = nl + 1, j0 = tid * FUSED_SPT;
-        u64 sa[FUSED_SPT], sb[FUSED_SPT], ta = 0, tb = 0;
+        // ---- phase 3: one thread per segment (round r: segment r * FUSED_NT + tid), block scans -> copy descriptors
+        const u32 nseg = nl + 1;
+        u64 sa[FUSED_SPT], sb[FUSED_SPT], pa[FUSED_SPT], pb[FUSED_SPT], tota = 0, totb = 0;
+        u32 rb[FUSED_SPT], sp[FUSED_SPT];
 #pragma unroll
-        for (int k = 0; k < FUSED_SPT; k++) { sa[k] = sb[k] = 0; if (j0 + k < nseg) T.classify(C, j0 + k, sa[k], sb[k], flag); ta += sa[k]; tb += sb[k]; }
-        u64 tota, totb;
-        u64 pa = block_excl_scan(ta, &tota, scan);
-        u64 pb = block_excl_scan(tb, &totb, scan);
+        for (int r = 0; r < FUSED_SPT; r++) {
+            sa[r] = sb[r] = pa[r] = pb[r] = 0; rb[r] = SR_NONE; sp[r] = 0xFFFF;
+            if ((u32)r * FUSED_NT < nseg) {                                  // uniform across the CTA
+                const u32 j = r * FUSED_NT + tid;
+                if (j < nseg) T.classify(C, j, sa[r], sb[r], rb[r], sp[r], flag);
+                u64 ta, tb;
+                pa[r] = tota + block_excl_scan(sa[r], &ta, scan);
+                pb[r] = totb + block_excl_scan(sb[r], &tb, scan);
+                tota += ta; totb += tb;
+            }
+        }
         if (tid == 0) {
             sh->t_ids = (u32)(tota & 0xFFFF); sh->t_comm = (u32)((tota >> 16) & 0xFFFF); sh->t_seq = (u32)((tota >> 32) & 0xFFFF); sh->t_qual = (u32)(tota >> 48);
             sh->t_rec = (u32)(totb & 0xFFFF); sh->n_hdr = (u32)((totb >> 16) & 0xFFFF); sh->n_seq = (u32)((totb >> 32) & 0xFFFF); sh->n_qual = (u32)(totb >> 48);
+            T.layout();
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < FUSED_SPT; k++) { if (j0 + k < nseg) T.place(C, j0 + k, pa, pb); pa += sa[k]; pb += sb[k]; }
+        for (int r = 0; r < FUSED_SPT; r++) { const u32 j = r * FUSED_NT + tid; if (j < nseg) T.place(C, j, pa[r], pb[r], rb[r], sp[r]); }
         __syncthreads();
-        if (warp == 0) agg2 = T.aggregate(C);
     }
-    // ---- look-back #2 (warp 0): global offsets, straddling record / line / byte
+    // ---- phase 4: warp 0 runs look-back #2 (global offsets; the record / line / byte that straddles the tile boundary)
+    //      while the other warps gather the tile's bytes per stream into the staging area
     if (warp == 0) {
+        F2 agg2 = f2_initial(); agg2.last = 0;
+        if (!aborted) agg2 = T.aggregate(C);
         const F2 p2 = fused_lookback2(A, tile, agg2, fastq);
-        if (lane == 0) { sh->pre = p2; if (!aborted) T.layout(C); }
+        if (lane == 0) sh->pre = p2;
+    } else if (!aborted) {
+        const u32 ndesc = sh->n_seq + sh->n_qual + 2 * sh->n_hdr, ngroups = (FUSED_NT - 32) / FT_GROUP;
+        for (u32 k = (tid - 32) / FT_GROUP; k < ndesc; k += ngroups) flag |= T.copy_desc(C, k, tid % FT_GROUP);
     }
     __syncthreads();
 
     if (!aborted) {
-        // ---- phase 5: copies (one 8-lane group per segment), records, lines
-        const u32 nlist = sh->n_seq + sh->n_qual + sh->n_hdr;
-        for (u32 k = tid / FT_GROUP; k < nlist; k += FUSED_NT / FT_GROUP) flag |= T.copy_segment(C, k, tid % FT_GROUP);
+        // ---- phase 5: staging -> global; records, lines
+        const F2 &P = sh->pre;
+        if (fused_region_out(T, sh->s_qual, sh->t_qual, C.qual + P.qual, FC_QUAL, false)) flag |= FU_QUAL;
+        if (C.seq_mode == FS_PACK4) {
+            if (sh->t_seq) {
+                const u32 npieces = ((u32)(P.seq & 31) + sh->t_seq + 31) / 32;
+                for (u32 q = tid; q < npieces; q += FUSED_NT) flag |= T.pack_piece(C, q, [](u32 *p, u32 v) { atomicOr(p, v); });
+            }
+        } else if (fused_region_out(T, sh->s_seq, sh->t_seq, C.seq + P.seq, FC_PROTEIN + (C.seq_mode - FS_PROTEIN), C.upper != 0)) flag |= FU_SEQ;
+        fused_region_out(T, sh->s_ids, sh->t_ids, C.ids + P.ids, FC_NONE, false);
+        fused_region_out(T, sh->s_comm, sh->t_comm, C.comm + P.comm, FC_NONE, false);
         for (u32 k = tid; k < sh->t_rec; k += FUSED_NT) { const u64 L = T.finish_record(C, k, flag); if (L > maxlen) maxlen = L; }
         if (!fastq) for (u32 k = tid; k < sh->n_seq; k += FUSED_NT) { const u64 L = T.line_length(k); if (L > maxlen) maxlen = L; }
-        __syncthreads();
-        // ---- phase 6: staging -> global
-        fused_copy_out(C.ids + sh->pre.ids, T.stage + sh->s_ids, sh->t_ids);
-        fused_copy_out(C.comm + sh->pre.comm, T.stage + sh->s_comm, sh->t_comm);
-        if (C.seq_mode == FS_PACK4 && sh->t_seq) {
-            const u32 npieces = ((u32)(sh->pre.seq & 31) + sh->t_seq + 31) / 32;
-            for (u32 q = tid; q < npieces; q += FUSED_NT) flag |= T.pack_piece(C, q, [](u32 *p, u32 v) { atomicOr(p, v); });
-        }
     }
     if (tid == 0) flag |= sh->flag;
     if (flag) atomicOr(A.flag, flag);
@@ -294,8 +348,11 @@ __global__ void k_fused_finish(const FusedArgs A)
 {
     const bool fastq = A.C.fastq != 0;
     u32 f1 = fastq ? 0u : (u32)FE_HDR; F2 f2 = f2_initial();
-    if (A.ntiles) { f1 = (u32)A.st1[A.ntiles - 1]; f2 = f2_load(A.st2_inc + (u64)(A.ntiles - 1) * F2_WORDS); }
-    fused_finish(A.C, f1, f2, *A.flag, *A.longest, A.text, *A.totals);
+    if (A.ntiles) { f1 = (u32)A.st1[A.ntiles - 1]; f2_get(A.st2 + 4ull * (A.ntiles - 1), f2); }
+    __shared__ u32 lut[256];
+    for (int i = 0; i < 256; i++) lut[i] = nuc_lut32(A.lut8[i]);
+    FusedCfg C = A.C; C.lut = lut;
+    fused_finish(C, f1, f2, *A.flag, *A.longest, A.text, *A.totals);
 }
 
 }  // namespace nafg

@@ -13,13 +13,14 @@
 //   2  look-back #1 (single-pass chained scan over tiles): which kind of line the tile starts in
 //      (FASTQ: lines so far mod 4;  FASTA: header / sequence / line start)
 //   3  one thread per segment: role, first space of a header, bytes per stream; block scan -> offsets inside the tile
-//   4  look-back #2: bytes per stream, records, bases before the tile + what a record / line / byte that straddles
+//   4a look-back #2: bytes per stream, records, bases before the tile + what a record / line / byte that straddles
 //      the tile boundary needs (bases and qualities since the last record end, bases since the last line end, last base)
-//   5  8-lane groups copy segment after segment: quality (and protein / text sequence) straight to global memory as aligned
-//      words, names / comments / bases into a staging area laid out congruent to their destination
-//   6  staging -> global: names and comments as 16-byte pieces; bases as 32-base pieces -> 16 bytes of 4-bit codes + one
-//      word of case bits (the piece is owned by the tile that holds its bytes: a byte shared by two tiles is written by
-//      the later one, which knows the earlier base from look-back #2); per record: length unit, quality-length check
+//   4  look-back #2 runs in one warp WHILE the other warps gather the tile's bytes per stream into a staging area (8-lane
+//      groups, one copy descriptor = one run of bytes of a line, aligned words built from two source words by a funnel shift)
+//   5  staging -> global as aligned 16-byte pieces (the expected-byte checks happen here, on full words): names, comments,
+//      quality (and protein / text sequence); bases as 32-base pieces -> 16 bytes of 4-bit codes + one word of case bits
+//      (a byte shared by two tiles is written by the later one, which knows the earlier base from look-back #2);
+//      per record: length unit, quality-length check
 // All of it is plain C++ over explicit (thread id, thread count) so that tests/emu/emu_fused.cpp runs the same phases
 // on the CPU, thread after thread, against the oracle.
 #pragma once
@@ -57,6 +58,8 @@ HD F2 f2_compose(const F2 &a, const F2 &b, bool fastq)
     r.ids = a.ids + b.ids; r.comm = a.comm + b.comm; r.seq = a.seq + b.seq; r.qual = a.qual + b.qual; r.rec = a.rec + b.rec;
     r.srec = (b.last & F2_R) ? b.srec : a.srec + b.srec;
     r.qrec = (b.last & (fastq ? F2_R : F2_L)) ? b.qrec : a.qrec + b.qrec;
+    if (r.srec > 0xFFFFFFFFull) r.srec = 0xFFFFFFFFull;                 // saturate: 2^32 - 1 or more is FU_BIGREC either way, and the
+    if (r.qrec > 0xFFFFFFFFull) r.qrec = 0xFFFFFFFFull;                 // look-back records keep 32 bits of these two
     r.last = ((b.last & F2_B) ? (b.last & 0x1FF) : (a.last & 0x1FF)) | ((a.last | b.last) & (F2_R | F2_L));
     return r;
 }
@@ -107,32 +110,69 @@ HD u32 funnel_r(u32 lo, u32 hi, u32 shift_bits)       // (hi:lo) >> shift_bits, 
 #endif
 }
 
-// `len` bytes of the tile (shared memory, any alignment) -> dst (shared or global memory, any alignment), by the FT_GROUP
-// lanes of a group: aligned words of dst from two aligned words of the tile, head and tail bytes one lane each.
-// Returns 0x80 flags of bytes that fail the check.
-template <class Byte>                                 // Byte: u8 (plain) or volatile-free global pointer; same code
-HD u32 group_copy(const u8 *tile, u32 src, u32 len, Byte *dst, u32 lane, int check, bool upper)
+// `len` bytes of the tile (shared memory, any alignment) -> staging (shared memory, any alignment), by the FT_GROUP lanes of a
+// group: aligned words of the destination from two aligned words of the tile, head and tail bytes one lane each.
+// Names and comments are checked here (check != FC_NONE), because their terminators share the staged region.
+HD u32 group_copy(const u8 *tile, u32 src, u32 len, u8 *dst, u32 lane, int check)
 {
-    u32 bad = 0;
-    const u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3) < len ? (u32)((4 - ((uintptr_t)dst & 3)) & 3) : len;
+    u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3), bad = 0;
+    if (head > len) head = len;
     const u32 nw = (len - head) >> 2, done = head + (nw << 2), tail = len - done;
     if (lane < head || (lane >= 4 && lane - 4 < tail)) {
-        const u32 i = lane < head ? lane : done + (lane - 4);
-        u32 v = (u32)tile[src + i] * 0x01010101u;
-        bad |= sw_check(check, v);
-        if (upper) v = sw_upper(v);
-        dst[i] = (u8)v;
+        const u32 i = lane < head ? lane : done + lane - 4;
+        const u32 c = tile[src + i];
+        bad |= sw_check(check, c * 0x01010101u);
+        dst[i] = (u8)c;
     }
     const u32 s0 = src + head, sh = (s0 & 3) * 8;
     const u32 *tw = (const u32 *)(tile + (s0 & ~3u));
     u32 *dw = (u32 *)(dst + head);
     for (u32 w = lane; w < nw; w += FT_GROUP) {
-        u32 v = funnel_r(tw[w], tw[w + 1], sh);           // the tile is padded: tw[w + 1] is readable
+        const u32 v = funnel_r(tw[w], tw[w + 1], sh);       // the tile is padded: tw[w + 1] is readable
         bad |= sw_check(check, v);
-        if (upper) v = sw_upper(v);
         dw[w] = v;
     }
     return bad;
+}
+
+// 16 * NQ bytes at any byte offset of a 16-byte aligned shared-memory array: NQ + 1 aligned 16-byte loads (conflict-free when
+// neighbouring lanes read neighbouring pieces), then a window of words picked by the offset's word part -- which is the same
+// for every piece of a region, so the switch is uniform -- and a funnel shift by its byte part.
+template <int NQ> HD void load_unaligned(const u8 *base, u32 off, u32 *out)
+{
+    const uint4 *p = (const uint4 *)(base + (off & ~15u));
+    u32 w[4 * NQ + 4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int k = 0; k <= NQ; k++) { const uint4 q = p[k]; w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w; }
+    const u32 sh = (off & 3) * 8;
+    switch ((off >> 2) & 3) {
+    case 0:
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4 * NQ; k++) out[k] = funnel_r(w[k], w[k + 1], sh);
+        break;
+    case 1:
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4 * NQ; k++) out[k] = funnel_r(w[k + 1], w[k + 2], sh);
+        break;
+    case 2:
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4 * NQ; k++) out[k] = funnel_r(w[k + 2], w[k + 3], sh);
+        break;
+    default:
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4 * NQ; k++) out[k] = funnel_r(w[k + 3], k + 4 < 4 * NQ + 4 ? w[k + 4] : 0u, sh);
+        break;
+    }
 }
 
 // ---- per-tile scalars (shared memory)
@@ -143,7 +183,7 @@ struct FusedShared {
     u32 t_ids, t_comm, t_seq, t_qual, t_rec, n_hdr, n_seq, n_qual;    // totals of the tile
     u32 abort_;                        // tables exceeded: publish, skip the rest
     u32 flag;                          // FU_* raised by this tile
-    u32 s_ids, s_comm, s_seq;          // staging offsets of the three staged regions
+    u32 s_ids, s_comm, s_seq, s_qual;  // staging offsets of the four regions
     F2 pre;                            // look-back #2 prefix
     u64 maxlen;                        // longest line (FASTA) / read (FASTQ) ended in this tile
 };
@@ -151,18 +191,28 @@ struct FusedShared {
 struct FusedCfg {
     u64 n, p0;                         // text size, first byte after the leading '>' / '@'
     int fastq, seq_mode, upper, want_mask, id_check;
-    const u8 *lut;                     // nuc_code with bit 7 = unexpected (4-bit mode)
+    const u32 *lut;                    // nuc_code | "unexpected" << 16 (4-bit mode)
     u8 *ids, *comm, *seq, *qual;       // destinations (seq: packed codes or bytes)
     u32 *len, *casebits;
 };
+HD u32 nuc_lut32(u8 l) { return (u32)(l & 15) | ((u32)(l >> 7) << 16); }      // from the u8 table (bit 7 = unexpected)
 
-// role byte of a segment
-enum : u32 { SR_ROLE = 3, SR_NL = 4, SR_LS = 8, SR_REC = 16, SR_SKIP1 = 32 };      // SR_REC: a record boundary event; SR_SKIP1: first byte is the '@' / '>' marker
+// what classify() hands to place() about one segment
+enum : u32 { SR_ROLE = 3, SR_NL = 4, SR_LS = 8, SR_REC = 16, SR_SKIP1 = 32, SR_SEEN = 64, SR_NONE = 128 };
+static const u32 FT_MAXDESC = 2 * FT_MAXSEG;
+
+// Is there a ' ' after the last '\n' of the `np` bytes before the tile?  (the header the tile starts in has had its first space)
+HD u32 prev_scan(const u8 *prev, u32 np, bool &resolved)
+{
+    resolved = true;
+    for (u32 i = np; i-- > 0;) { const u8 c = prev[i]; if (c == ' ') return 1; if (c == '\n') return 0; }
+    resolved = false;
+    return 0;
+}
 
 struct FusedTile {
     u8 *text, *stage;
-    u16 *nlmask, *seg_end, *seg_sp, *seg_off, *seg_offb, *seg_list, *recseq, *recqual;
-    u8 *seg_role;
+    u16 *seg_end, *d_src, *d_len, *d_dst, *recseq, *recqual;
     FusedShared *sh;
 
     HD u32 seg_start(u32 j) const { return j ? (u32)seg_end[j - 1] + 1 : sh->live_lo; }
@@ -177,8 +227,10 @@ struct FusedTile {
 #endif
         for (int k = 0; k < 4; k++) m |= sw_movemask(sw_eq(w[k], 0x0A0A0A0Au)) << (4 * k);
         const u32 lo = 16 * c, L = sh->live_lo, H = sh->live_hi;
-        if (lo < L) m &= L - lo >= 16 ? 0u : ~0u << (L - lo);
-        if (lo + 16 > H) m &= H <= lo ? 0u : ~(~0u << (H - lo));
+        if (L != 0 || H != FT_BYTES) {
+            if (lo < L) m &= L - lo >= 16 ? 0u : ~0u << (L - lo);
+            if (lo + 16 > H) m &= H <= lo ? 0u : ~(~0u << (H - lo));
+        }
         return m & 0xFFFFu;
     }
     // phase 2: positions of my newlines -> seg_end[first + k]
@@ -206,15 +258,16 @@ struct FusedTile {
 
     // phase 3a: classify segment j; returns its contribution to the two packed scans
     //   A: ids | comm << 16 | seq << 32 | qual << 48        B: rec | n_hdr << 16 | n_seq << 32 | n_qual << 48
-    HD void classify(const FusedCfg &C, u32 j, u64 &A, u64 &B, u32 &flag) const
+    // and what place() needs: role byte (SR_*), position of the header's first space (0xFFFF: none)
+    HD void classify(const FusedCfg &C, u32 j, u64 &A, u64 &B, u32 &rb, u32 &sp, u32 &flag) const
     {
         const u32 nseg = sh->nseg;
         const bool has_nl = j + 1 < nseg;
         const u32 s = seg_start(j), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
         const bool ls = j ? true : sh->entry_ls != 0;
         u32 role, skip1 = 0, rec = 0;
-        A = 0; B = 0;
-        if (!has_nl && s >= e) { seg_role[j] = (u8)(FR_PLUS | (ls ? SR_LS : 0)); seg_sp[j] = 0xFFFF; return; }      // empty tail: nothing
+        A = 0; B = 0; sp = 0xFFFF;
+        if (!has_nl && s >= e) { rb = SR_NONE; return; }                      // empty tail: nothing
         if (C.fastq) {
             role = (sh->entry1 + j) & 3;
             if (ls) {
@@ -229,12 +282,12 @@ struct FusedTile {
                 else role = FR_SEQ;
             } else role = sh->entry1 == FE_HDR ? (u32)FR_HDR : (u32)FR_SEQ;
         }
-        u32 sp = 0xFFFF;
         const u32 b = s + skip1, len = e - b;
+        u32 seen = 0;
         switch (role) {
         case FR_HDR: {
             u32 ids = 0, comm = 0;
-            const bool seen = j == 0 && !ls && sh->entry_sp;
+            seen = j == 0 && !ls && sh->entry_sp;
             if (!seen) {
                 u32 p = b;
                 while (p < e && text[p] != ' ') p++;
@@ -259,29 +312,49 @@ struct FusedTile {
             break;
         }
         B |= rec;
-        seg_sp[j] = (u16)sp;
-        seg_role[j] = (u8)(role | (has_nl ? SR_NL : 0) | (ls ? SR_LS : 0) | (rec ? SR_REC : 0) | (skip1 ? SR_SKIP1 : 0));
+        rb = role | (has_nl ? SR_NL : 0) | (ls ? SR_LS : 0) | (rec ? SR_REC : 0) | (skip1 ? SR_SKIP1 : 0) | (seen ? SR_SEEN : 0);
     }
 
-    // phase 3b: offsets of segment j inside the tile's stream regions, its slot in the per-role list, record marks.
-    // a, b: exclusive prefixes of the packed scans at this segment.
-    HD void place(const FusedCfg &C, u32 j, u64 a, u64 b) const
+    // staging layout (tile-local: known as soon as the tile's totals are)
+    HD void layout() const
     {
-        const u32 r = seg_role[j], role = r & SR_ROLE;
+        sh->s_ids = 0;
+        sh->s_comm = (sh->t_ids + 15) & ~15u;
+        sh->s_seq = ((sh->s_comm + sh->t_comm + 15) & ~15u) + 32;          // the first 32-base piece may start up to 31 bytes before the region
+        sh->s_qual = (sh->s_seq + sh->t_seq + 15) & ~15u;
+    }
+
+    // phase 3b: copy descriptors of segment j (runs of bytes -> staging), terminators, record marks.
+    // a, b: exclusive prefixes of the packed scans at this segment.
+    HD void place(const FusedCfg &C, u32 j, u64 a, u64 b, u32 rb, u32 sp) const
+    {
+        if (rb & SR_NONE) return;
+        const u32 role = rb & SR_ROLE;
         const u32 o_ids = (u32)(a & 0xFFFF), o_comm = (u32)((a >> 16) & 0xFFFF), o_seq = (u32)((a >> 32) & 0xFFFF), o_qual = (u32)(a >> 48);
         const u32 k_rec = (u32)(b & 0xFFFF), k_hdr = (u32)((b >> 16) & 0xFFFF), k_seq = (u32)((b >> 32) & 0xFFFF), k_qual = (u32)(b >> 48);
-        const bool has_nl = r & SR_NL;
-        const u32 s = seg_start(j), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
-        if (!has_nl && s >= e) return;
+        const bool has_nl = rb & SR_NL;
+        const u32 s0 = seg_start(j), s = s0 + ((rb & SR_SKIP1) ? 1 : 0), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
         switch (role) {
-        case FR_HDR:  seg_off[j] = (u16)o_ids; seg_offb[j] = (u16)o_comm; seg_list[sh->n_seq + sh->n_qual + k_hdr] = (u16)j; break;
-        case FR_SEQ:  seg_off[j] = (u16)o_seq; seg_list[k_seq] = (u16)j; break;
-        case FR_QUAL: seg_off[j] = (u16)o_qual; seg_list[sh->n_seq + k_qual] = (u16)j; break;
+        case FR_HDR: {
+            const u32 kn = sh->n_seq + sh->n_qual + k_hdr, kc = kn + sh->n_hdr;
+            u32 nlen = 0, cs = s;
+            if (!(rb & SR_SEEN)) {
+                nlen = (sp != 0xFFFF ? sp : e) - s;
+                if (sp != 0xFFFF || has_nl) stage[sh->s_ids + o_ids + nlen] = 0;
+                cs = sp != 0xFFFF ? sp + 1 : e;
+            }
+            d_src[kn] = (u16)s; d_len[kn] = (u16)nlen; d_dst[kn] = (u16)(sh->s_ids + o_ids);
+            d_src[kc] = (u16)cs; d_len[kc] = (u16)(e - cs); d_dst[kc] = (u16)(sh->s_comm + o_comm);
+            if (has_nl) stage[sh->s_comm + o_comm + (e - cs)] = 0;
+            break;
+        }
+        case FR_SEQ:  d_src[k_seq] = (u16)s; d_len[k_seq] = (u16)(e - s); d_dst[k_seq] = (u16)(sh->s_seq + o_seq); break;
+        case FR_QUAL: { const u32 k = sh->n_seq + k_qual; d_src[k] = (u16)s; d_len[k] = (u16)(e - s); d_dst[k] = (u16)(sh->s_qual + o_qual); break; }
         default: break;
         }
-        if (r & SR_REC) {
+        if (rb & SR_REC) {
             recseq[k_rec] = (u16)o_seq;                                                 // bases of the tile before this boundary
-            if (C.fastq) recqual[k_rec] = (u16)(o_qual + (e - s));                        // quality bytes up to and including this line
+            if (C.fastq) recqual[k_rec] = (u16)(o_qual + (e - s0));                       // quality bytes up to and including this line
         }
     }
 
@@ -296,65 +369,24 @@ struct FusedTile {
         if (nr) g.last |= F2_R;
         if (C.fastq) g.qrec = nr ? sh->t_qual - recqual[nr - 1] : sh->t_qual;
         else {
-            // bases after the last sequence-line end of the tile
+            // bases after the last sequence-line end of the tile (every sequence run but the tile's last segment ends a line)
             g.qrec = sh->t_seq;
             for (u32 k = sh->n_seq; k-- > 0;) {
-                const u32 j = seg_list[k];
-                if (seg_role[j] & SR_NL) {
-                    const u32 s = seg_start(j) + ((seg_role[j] & SR_SKIP1) ? 1 : 0);
-                    g.qrec = sh->t_seq - (seg_off[j] + ((u32)seg_end[j] - s));
-                    g.last |= F2_L;
-                    break;
-                }
+                if ((u32)d_src[k] + d_len[k] < sh->live_hi) { g.qrec = sh->t_seq - ((u32)d_dst[k] - sh->s_seq + d_len[k]); g.last |= F2_L; break; }
             }
         }
-        for (u32 k = sh->n_seq; k-- > 0;) {                                               // last base of the tile
-            const u32 j = seg_list[k];
-            const u32 s = seg_start(j), e = (seg_role[j] & SR_NL) ? (u32)seg_end[j] : sh->live_hi;
-            if (e > s) { g.last |= F2_B | text[e - 1]; break; }
-        }
+        for (u32 k = sh->n_seq; k-- > 0;)                                                 // last base of the tile
+            if (d_len[k]) { g.last |= F2_B | text[(u32)d_src[k] + d_len[k] - 1]; break; }
         return g;
     }
 
-    // staging layout, once the global offsets are known: every staged region congruent (mod 16; bases mod 32) to its destination
-    HD void layout(const FusedCfg &C) const
+    // phase 4: copy descriptor k, by the lanes of one group
+    HD u32 copy_desc(const FusedCfg &C, u32 k, u32 lane) const
     {
-        const F2 &P = sh->pre;
-        const u32 a_ids = (u32)((uintptr_t)(C.ids + P.ids) & 15), a_comm = (u32)((uintptr_t)(C.comm + P.comm) & 15);
-        sh->s_ids = a_ids;
-        sh->s_comm = ((a_ids + sh->t_ids + 15) & ~15u) + a_comm;
-        sh->s_seq = ((sh->s_comm + sh->t_comm + 31) & ~31u) + (u32)(P.seq & 31);
-    }
-
-    // phase 5: the copies of list entry k (a segment), by the lanes of one group
-    HD u32 copy_segment(const FusedCfg &C, u32 k, u32 lane) const
-    {
-        const u32 j = seg_list[k], r = seg_role[j], role = r & SR_ROLE;
-        const bool has_nl = r & SR_NL;
-        const u32 s = seg_start(j) + ((r & SR_SKIP1) ? 1 : 0), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
-        const F2 &P = sh->pre;
-        u32 bad = 0;
-        if (role == FR_SEQ) {
-            if (C.seq_mode == FS_PACK4) bad = group_copy(text, s, e - s, stage + sh->s_seq + seg_off[j], lane, FC_NONE, false);
-            else bad = group_copy(text, s, e - s, C.seq + P.seq + seg_off[j], lane, FC_PROTEIN + (C.seq_mode - FS_PROTEIN), C.upper != 0) ? FU_SEQ : 0;
-        } else if (role == FR_QUAL) {
-            bad = group_copy(text, s, e - s, C.qual + P.qual + seg_off[j], lane, FC_QUAL, false) ? FU_QUAL : 0;
-        } else {                                                             // header: name -> ids, the rest -> comments, terminators
-            const u32 sp = seg_sp[j];
-            const bool seen = j == 0 && !(r & SR_LS) && sh->entry_sp;
-            u8 *di = stage + sh->s_ids + seg_off[j], *dc = stage + sh->s_comm + seg_offb[j];
-            u32 nlen = 0, cs = s;
-            if (!seen) {
-                nlen = (sp != 0xFFFF ? sp : e) - s;
-                bad |= group_copy(text, s, nlen, di, lane, C.id_check, false);
-                if (lane == 7 && (sp != 0xFFFF || has_nl)) di[nlen] = 0;
-                cs = sp != 0xFFFF ? sp + 1 : e;
-            }
-            bad |= group_copy(text, cs, e - cs, dc, lane, FC_COMM, false);
-            if (lane == 6 && has_nl) dc[e - cs] = 0;
-            bad = bad ? FU_BADBYTE : 0;
-        }
-        return bad;
+        const u32 len = d_len[k], nsq = sh->n_seq + sh->n_qual;
+        if (!len) return 0;
+        const int check = k < nsq ? (int)FC_NONE : (k < nsq + sh->n_hdr ? C.id_check : (int)FC_COMM);
+        return group_copy(text, d_src[k], len, stage + d_dst[k], lane, check) ? (u32)FU_BADBYTE : 0u;
     }
 
     // phase 5: record k of the tile ends -> its length unit, the quality-length check, the longest read
@@ -370,20 +402,40 @@ struct FusedTile {
         C.len[P.rec + k] = (u32)sl;
         return C.fastq ? sl : 0;
     }
-    // FASTA: sequence line (list entry k < n_seq) ends -> its length (process.c:389-393)
+    // FASTA: the sequence line of descriptor k < n_seq ends -> its length (process.c:389-393)
     HD u64 line_length(u32 k) const
     {
-        const u32 j = seg_list[k], r = seg_role[j];
-        if (!(r & SR_NL)) return 0;
-        const u32 s = seg_start(j);
-        u64 L = (u64)seg_end[j] - s;
-        // the first line end of the tile closes whatever the earlier tiles left open (every sequence segment but the
-        // tile's last one ends a line, so that is list entry 0)
-        if (k == 0) L = sh->pre.qrec + seg_off[j] + L;
+        if ((u32)d_src[k] + d_len[k] >= sh->live_hi) return 0;                            // no '\n' after it inside the tile
+        u64 L = d_len[k];
+        // the first line end of the tile closes whatever the earlier tiles left open
+        if (k == 0) L += sh->pre.qrec;
         return L;
     }
 
-    // phase 6: piece q of the staged bases (32 bases at a multiple of 32 in the file's base numbering) -> 16 bytes of
+    // phase 5: 16-byte unit u of a staged region -> global (dst + 16 u is 16-byte aligned).  Returns 0x80 flags of bytes
+    // that fail the check.
+    HD u32 out_unit(u32 region_off, u32 u, u8 *dst, int check, bool upper) const
+    {
+        u32 v[4];
+        load_unaligned<1>(stage, region_off + 16 * u, v);
+        u32 bad = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+        for (int k = 0; k < 4; k++) { bad |= sw_check(check, v[k]); if (upper) v[k] = sw_upper(v[k]); }
+        *(uint4 *)(dst + 16 * u) = make_uint4(v[0], v[1], v[2], v[3]);
+        return bad;
+    }
+    HD u32 out_byte(u32 region_off, u32 i, u8 *dst, int check, bool upper) const
+    {
+        u32 v = (u32)stage[region_off + i] * 0x01010101u;
+        const u32 bad = sw_check(check, v);
+        if (upper) v = sw_upper(v);
+        dst[i] = (u8)v;
+        return bad;
+    }
+
+    // phase 5: piece q of the staged bases (32 bases at a multiple of 32 in the file's base numbering) -> 16 bytes of
     // codes + one word of case bits.  Returns FU_SEQ if a base is not an expected code.
     template <class AtomicOr>
     HD u32 pack_piece(const FusedCfg &C, u32 q, AtomicOr atomic_or) const
@@ -393,37 +445,39 @@ struct FusedTile {
         const u32 lo = q == 0 ? (u32)A : 0u;
         const u64 endb = S + sh->t_seq;
         const u32 hi = g0 + 32 <= endb ? 32u : (u32)(endb - g0);
-        const u32 *w = (const u32 *)(stage + (sh->s_seq - (u32)A) + 32 * q);
-        u32 out[4] = {0, 0, 0, 0}, cbits = 0, inv = 0;
+        u32 x[8];
+        load_unaligned<2>(stage, sh->s_seq - (u32)A + 32 * q, x);
+        u32 out[4] = {0, 0, 0, 0}, cbits = 0, inv_any = 0, r[8];
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
         for (int k = 0; k < 8; k++) {
-            const u32 x = w[k];
-            const u32 c0 = C.lut[x & 0xFF], c1 = C.lut[(x >> 8) & 0xFF], c2 = C.lut[(x >> 16) & 0xFF], c3 = C.lut[x >> 24];
-            const u32 codes = (c0 & 15) | ((c1 & 15) << 4) | ((c2 & 15) << 8) | ((c3 & 15) << 12);
-            const u32 invs = ((c0 >> 7) & 1) | ((c1 >> 6) & 2) | ((c2 >> 5) & 4) | ((c3 >> 4) & 8);
-            const u32 ge = ((x & 0xFF) >= 96) | ((((x >> 8) & 0xFF) >= 96) << 1) | ((((x >> 16) & 0xFF) >= 96) << 2) | (((x >> 24) >= 96) << 3);
-            out[k >> 1] |= codes << (16 * (k & 1));
-            cbits |= ge << (4 * k); inv |= invs << (4 * k);
+            const u32 v = x[k];
+            r[k] = C.lut[v & 0xFF] + (C.lut[(v >> 8) & 0xFF] << 4) + (C.lut[(v >> 16) & 0xFF] << 8) + (C.lut[v >> 24] << 12);
+            out[k >> 1] |= (r[k] & 0xFFFF) << (16 * (k & 1));
+            inv_any |= r[k];
+            const u32 t = ((v & (v << 1)) >> 6) & 0x01010101u;            // byte >= 96 (encoders.c:134), exact for bytes < 128
+            cbits |= (((t * 0x01020408u) >> 24) & 15u) << (4 * k);
         }
-        const u32 live = (hi >= 32 ? ~0u : ~(~0u << hi)) & (~0u << lo);
-        cbits &= live; inv &= live;
         u8 *dst = C.seq + (g0 >> 1);
         if (lo == 0 && hi == 32) {
             *(uint4 *)dst = make_uint4(out[0], out[1], out[2], out[3]);
             if (C.want_mask) C.casebits[g0 >> 5] = cbits;
-        } else {
-            // a byte shared with the tile before me is mine (I know its low nibble from look-back #2); a dangling last
-            // low nibble is my successor's (or the finishing step's, at the end of the input)
-            for (u32 b = lo >> 1; 2 * b < hi; b++) {
-                u32 v = (out[b >> 2] >> (8 * (b & 3))) & 0xFF;
-                if (2 * b < lo) v = (v & 0xF0) | (C.lut[P.last & 0xFF] & 15);
-                if (2 * b + 1 >= hi) continue;
-                dst[b] = (u8)v;
-            }
-            if (C.want_mask && cbits) atomic_or(C.casebits + (g0 >> 5), cbits);
+            return (inv_any >> 16) ? (u32)FU_SEQ : 0u;
         }
+        // partial piece (the tile's first / last): only positions [lo, hi) are mine
+        const u32 live = (hi >= 32 ? ~0u : ~(~0u << hi)) & (~0u << lo);
+        u32 inv = 0;
+        for (int k = 0; k < 8; k++) { const u32 f = (r[k] >> 16) & 0x1111u; inv |= (((f * 0x1248u) >> 12) & 15u) << (4 * k); }
+        cbits &= live; inv &= live;
+        // a byte shared with the tile before me is mine (I know its low nibble from look-back #2); a dangling last
+        // low nibble is my successor's (or the finishing step's, at the end of the input)
+        for (u32 b = lo >> 1; 2 * b + 1 < hi; b++) {
+            u32 v = (out[b >> 2] >> (8 * (b & 3))) & 0xFF;
+            if (2 * b < lo) v = (v & 0xF0) | (C.lut[P.last & 0xFF] & 15);
+            dst[b] = (u8)v;
+        }
+        if (C.want_mask && cbits) atomic_or(C.casebits + (g0 >> 5), cbits);
         return inv ? (u32)FU_SEQ : 0u;
     }
 };

@@ -38,7 +38,9 @@ static int run_fused(const std::vector<u8> &text_in, u64 p0, bool fastq, int seq
     C.seq_mode = seq_type == 2 ? FS_PROTEIN : (seq_type == 3 ? (fastq ? FS_TEXT : FS_TEXT_GT) : FS_PACK4);
     C.upper = seq_type >= 2 && no_mask; C.want_mask = seq_type < 2 && !no_mask;
     C.id_check = (seq_type == 3 && !fastq) ? FC_ID_GT : FC_ID;
-    C.lut = lut;
+    u32 lut32[256];
+    for (int c = 0; c < 256; c++) lut32[c] = nuc_lut32(lut[c]);
+    C.lut = lut32;
     C.ids = alloc(n + 2) + 3; C.comm = alloc(n + 2) + 5;                      // odd alignments on purpose
     C.seq = alloc(n + 2); C.qual = alloc(n + 2) + 1;
     C.len = (u32 *)alloc((ntiles * FT_MAXSEG + 2) * 4);
@@ -46,13 +48,10 @@ static int run_fused(const std::vector<u8> &text_in, u64 p0, bool fastq, int seq
 
     // "shared memory"
     u8 *tile = alloc(FT_BYTES + 16), *stage = alloc(FT_STAGE);
-    std::vector<u16> nlmask(FT_CHUNKS), seg_end(FT_MAXSEG + 1), seg_sp(FT_MAXSEG + 1), seg_off(FT_MAXSEG + 1), seg_offb(FT_MAXSEG + 1),
-        seg_list(FT_MAXSEG + 1), recseq(FT_MAXSEG + 1), recqual(FT_MAXSEG + 1);
-    std::vector<u8> seg_role(FT_MAXSEG + 1);
+    std::vector<u16> seg_end(FT_MAXSEG + 8), d_src(FT_MAXDESC + 8), d_len(FT_MAXDESC + 8), d_dst(FT_MAXDESC + 8), recseq(FT_MAXSEG + 8), recqual(FT_MAXSEG + 8);
     FusedShared sh;
-    FusedTile T; T.text = tile; T.stage = stage; T.nlmask = nlmask.data(); T.seg_end = seg_end.data(); T.seg_sp = seg_sp.data();
-    T.seg_off = seg_off.data(); T.seg_offb = seg_offb.data(); T.seg_list = seg_list.data(); T.recseq = recseq.data(); T.recqual = recqual.data();
-    T.seg_role = seg_role.data(); T.sh = &sh;
+    FusedTile T; T.text = tile; T.stage = stage; T.seg_end = seg_end.data(); T.d_src = d_src.data(); T.d_len = d_len.data(); T.d_dst = d_dst.data();
+    T.recseq = recseq.data(); T.recqual = recqual.data(); T.sh = &sh;
 
     u32 run1 = fastq ? 0u : (u32)FE_HDR;           // look-back #1 inclusive state of the tiles so far
     F2 run2 = f2_initial();
@@ -69,51 +68,67 @@ static int run_fused(const std::vector<u8> &text_in, u64 p0, bool fastq, int seq
         sh.live_hi = n >= lo + FT_BYTES ? FT_BYTES : (n > lo ? (u32)(n - lo) : 0);
         if (sh.live_lo > sh.live_hi) sh.live_lo = sh.live_hi;
         // phase 1: newline masks; thread th owns chunks th, th + NT, ...
-        std::vector<u32> cnt(FT_CHUNKS);
-        for (u32 th = 0; th < NT; th++) for (u32 c = th; c < FT_CHUNKS; c += NT) { nlmask[c] = (u16)T.chunk_mask(c); cnt[c] = (u32)__builtin_popcount(nlmask[c]); }
+        std::vector<u32> cnt(FT_CHUNKS), mask(FT_CHUNKS);
+        for (u32 th = 0; th < NT; th++) for (u32 c = th; c < FT_CHUNKS; c += NT) { mask[c] = T.chunk_mask(c); cnt[c] = (u32)__builtin_popcount(mask[c]); }
         u32 Tn = 0; std::vector<u32> first(FT_CHUNKS);
         for (u32 c = 0; c < FT_CHUNKS; c++) { first[c] = Tn; Tn += cnt[c]; }
         sh.nseg = Tn + 1;
         if (sh.nseg > FT_MAXSEG) { sh.abort_ = 1; sh.flag |= FU_LINES; }
         u32 last_nl = 0;
-        if (!sh.abort_) for (u32 th = 0; th < NT; th++) for (u32 c = th; c < FT_CHUNKS; c += NT) T.put_lines(c, nlmask[c], first[c]);
+        if (!sh.abort_) for (u32 th = 0; th < NT; th++) for (u32 c = th; c < FT_CHUNKS; c += NT) T.put_lines(c, mask[c], first[c]);
         if (Tn && !sh.abort_) last_nl = seg_end[Tn - 1];
         // look-back #1
         const u32 agg1 = fastq ? Tn : (sh.abort_ ? (u32)FE_ID : T.fasta_element(Tn, last_nl));
         sh.entry1 = run1;
         run1 = f1_compose(fastq, run1, agg1);
-        if (fastq) sh.entry_ls = lo + sh.live_lo > p0 && gtext[lo + sh.live_lo - 1] == '\n';
-        else sh.entry_ls = sh.entry1 == FE_LS;
-        sh.entry_sp = 0;
         {
+            // the up to 64 bytes before the tile (the kernel prefetches them): line start?  header already past its first space?
+            const u64 at = lo + sh.live_lo;
+            const u32 np = at > p0 ? (u32)(at - p0 < 64 ? at - p0 : 64) : 0;
+            const u8 *prev = gtext.data() + at - np;
+            if (fastq) sh.entry_ls = np && prev[np - 1] == '\n';
+            else sh.entry_ls = sh.entry1 == FE_LS;
+            sh.entry_sp = 0;
             const u32 role0 = fastq ? (sh.entry1 & 3) : (sh.entry1 == FE_HDR ? (u32)FR_HDR : (u32)FR_SEQ);
-            if (sh.live_lo < sh.live_hi && role0 == FR_HDR && !sh.entry_ls) { u32 f = 0; sh.entry_sp = fast_lookback_space(gtext.data(), p0, lo + sh.live_lo, f); if (f) sh.flag |= FU_LOOKBACK; }
+            if (sh.live_lo < sh.live_hi && role0 == FR_HDR && !sh.entry_ls) {
+                bool resolved; sh.entry_sp = prev_scan(prev, np, resolved);
+                if (!resolved && at - np > p0) { u32 f = 0; sh.entry_sp = fast_lookback_space(gtext.data(), p0, at - np, f); if (f) sh.flag |= FU_LOOKBACK; }
+            }
         }
         F2 agg2; memset(&agg2, 0, sizeof agg2);
         if (!sh.abort_) {
-            // phase 3a: thread th owns segments 2 th, 2 th + 1 (the kernel: FT_MAXSEG / threads each, contiguous)
-            const u32 per = (FT_MAXSEG + NT - 1) / NT;
-            std::vector<u64> sa(sh.nseg), sb(sh.nseg);
-            for (u32 th = 0; th < NT; th++) for (u32 j = th * per; j < (th + 1) * per && j < sh.nseg; j++) T.classify(C, j, sa[j], sb[j], sh.flag);
+            // phase 3: thread th owns segments th, th + NT, ...
+            std::vector<u64> sa(sh.nseg), sb(sh.nseg); std::vector<u32> rbv(sh.nseg), spv(sh.nseg);
+            for (u32 th = 0; th < NT; th++) for (u32 j = th; j < sh.nseg; j += NT) T.classify(C, j, sa[j], sb[j], rbv[j], spv[j], sh.flag);
             u64 ra = 0, rb = 0; std::vector<u64> pa(sh.nseg), pb(sh.nseg);
             for (u32 j = 0; j < sh.nseg; j++) { pa[j] = ra; pb[j] = rb; ra += sa[j]; rb += sb[j]; }
             sh.t_ids = ra & 0xFFFF; sh.t_comm = (ra >> 16) & 0xFFFF; sh.t_seq = (ra >> 32) & 0xFFFF; sh.t_qual = (u32)(ra >> 48);
             sh.t_rec = rb & 0xFFFF; sh.n_hdr = (rb >> 16) & 0xFFFF; sh.n_seq = (rb >> 32) & 0xFFFF; sh.n_qual = (u32)(rb >> 48);
-            for (u32 th = 0; th < NT; th++) for (u32 j = th * per; j < (th + 1) * per && j < sh.nseg; j++) T.place(C, j, pa[j], pb[j]);
+            T.layout();
+            for (u32 th = 0; th < NT; th++) for (u32 j = th; j < sh.nseg; j += NT) T.place(C, j, pa[j], pb[j], rbv[j], spv[j]);
             agg2 = T.aggregate(C);
         }
-        // look-back #2
+        // look-back #2 (the kernel: one warp, while the others copy)
         sh.pre = run2;
         run2 = f2_compose(run2, agg2, fastq);
         if (!sh.abort_) {
-            T.layout(C);
-            const u32 nlist = sh.n_seq + sh.n_qual + sh.n_hdr, ngroups = NT / FT_GROUP ? NT / FT_GROUP : 1;
-            for (u32 g = 0; g < ngroups; g++) for (u32 k = g; k < nlist; k += ngroups) for (u32 lane = 0; lane < FT_GROUP; lane++) sh.flag |= T.copy_segment(C, k, lane);
+            const u32 ndesc = sh.n_seq + sh.n_qual + 2 * sh.n_hdr, ngroups = NT / FT_GROUP ? NT / FT_GROUP : 1;
+            for (u32 g = 0; g < ngroups; g++) for (u32 k = g; k < ndesc; k += ngroups) for (u32 lane = 0; lane < FT_GROUP; lane++) sh.flag |= T.copy_desc(C, k, lane);
             for (u32 th = 0; th < NT; th++) for (u32 k = th; k < sh.t_rec; k += NT) { const u64 L = T.finish_record(C, k, sh.flag); if (L > sh.maxlen) sh.maxlen = L; }
             if (!fastq) for (u32 th = 0; th < NT; th++) for (u32 k = th; k < sh.n_seq; k += NT) { const u64 L = T.line_length(k); if (L > sh.maxlen) sh.maxlen = L; }
-            // phase 6: staging -> global
-            for (u32 i = 0; i < sh.t_ids; i++) C.ids[sh.pre.ids + i] = stage[sh.s_ids + i];
-            for (u32 i = 0; i < sh.t_comm; i++) C.comm[sh.pre.comm + i] = stage[sh.s_comm + i];
+            // phase 5: staging -> global, region by region
+            struct Region { u32 off, len; u8 *dst; int check; bool upper; u32 fl; };
+            Region regs[4] = { { sh.s_ids, sh.t_ids, C.ids + sh.pre.ids, FC_NONE, false, FU_BADBYTE },
+                               { sh.s_comm, sh.t_comm, C.comm + sh.pre.comm, FC_NONE, false, FU_BADBYTE },
+                               { sh.s_qual, sh.t_qual, C.qual + sh.pre.qual, FC_QUAL, false, FU_QUAL },
+                               { sh.s_seq, C.seq_mode == FS_PACK4 ? 0u : sh.t_seq, C.seq + sh.pre.seq, FC_PROTEIN + (C.seq_mode - FS_PROTEIN), C.upper != 0, FU_SEQ } };
+            for (auto &R : regs) {
+                u32 head = (u32)((16 - ((uintptr_t)R.dst & 15)) & 15); if (head > R.len) head = R.len;
+                const u32 nu = (R.len - head) >> 4, done = head + (nu << 4);
+                for (u32 i = 0; i < head; i++) if (T.out_byte(R.off, i, R.dst, R.check, R.upper)) sh.flag |= R.fl;
+                for (u32 i = done; i < R.len; i++) if (T.out_byte(R.off, i, R.dst, R.check, R.upper)) sh.flag |= R.fl;
+                for (u32 th = 0; th < NT; th++) for (u32 u = th; u < nu; u += NT) if (T.out_unit(R.off + head, u, R.dst + head, R.check, R.upper)) sh.flag |= R.fl;
+            }
             if (C.seq_mode == FS_PACK4 && sh.t_seq) {
                 const u32 A = (u32)(sh.pre.seq & 31), npieces = (A + sh.t_seq + 31) / 32;
                 for (u32 th = 0; th < NT; th++) for (u32 q = th; q < npieces; q += NT) sh.flag |= T.pack_piece(C, q, atomic_or);
