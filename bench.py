@@ -175,6 +175,8 @@ ALGO_BYTES_PER_BASE = {
     # algorithmic HBM bytes per base of each kernel on the config-2 workload (DESIGN.md "Kernels"):
     # text = 2.185 B/base (2 x 151 + ~25.8 header bytes per 150-base record); streams: 0.5 packed sequence + 1.0 quality
     # + 0.139 ids/comments + 0.027 lengths = 1.67; bases before packing 1.0; .naf 0.83
+    # k_fused (the single-pass encode transform): text read once + every stream written once = SURVEY 8(d)'s "FASTQ split" figure
+    "k_fused": 3.8,
     "k_fast_tiles": 2.185, "k_fast_count": 2.185, "k_fast_scatter": 2.185 + 1.0 + 1.0 + 0.139 + 0.048,   # + per-record arrays
     "k_fsm_reduce": 2.185, "k_fsm_count": 2.185, "k_fsm_scatter": 2.185 + 1.0 + 1.0 + 0.139 + 0.048,
     "k_pack4": 1.0 + 0.5 + 0.031,
@@ -184,6 +186,7 @@ ALGO_BYTES_PER_BASE = {
 # DRAM bytes per base measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch, 1 M reads:
 # profiles/r1k_top_full_1Mreads.summary.txt); bench.py scales them to the launch it timed
 NCU_TRAFFIC_PER_BASE = {
+    "k_fused": 558.5e6 / 150e6,          # profiles/r2c_fused_1Mreads.summary.txt
     "k_fast_tiles": 329.9e6 / 150e6, "k_fast_count": 363.9e6 / 150e6, "k_fast_scatter": 664.9e6 / 150e6, "k_pack4": 213.4e6 / 150e6,
     "k_zenc_hist": 257.5e6 / 150e6, "k_zenc_encode": 351.2e6 / 150e6, "zd_literals": 332.5e6 / 150e6, "k_write_text": 587.9e6 / 150e6,
 }
@@ -271,8 +274,11 @@ def run_ours(args):
         assert tsize == n_text and torch.equal(out, d_text[:n_text]), "device round trip is not bit-exact"
         del out
 
-    sampler = ClockSampler(local)
-    sampler.start()
+    # clocks are sampled by rank 0 only (its own GPU): a forked nvidia-smi every 100 ms on every rank costs host time
+    # inside the timed loop
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     barrier()
     enc_ms, dec_ms, launches_total = 0.0, 0.0, 0
     for _ in range(args.steps):
@@ -306,7 +312,7 @@ def run_ours(args):
         a, b, naf_size2, _, _ = e2e_round()
         e_enc += a; e_dec += b
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler else None
     e2e_ms = (e_enc + e_dec) / args.steps
 
     # ---- live per-kernel times (CUDA events around every launch; separate, un-timed step)
@@ -406,7 +412,7 @@ def run_ours(args):
             roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_base": bpb})
         if name in NCU_TRAFFIC_PER_BASE:
             roofline["traffic"] = NCU_TRAFFIC_PER_BASE[name] * bases
-            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r1k_top_full_1Mreads.summary.txt), scaled per base"
+            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r2c_fused_1Mreads.summary.txt, r1k_top_full_1Mreads.summary.txt), scaled per base"
         line = {
             "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -113,7 +113,12 @@ struct CudaExec {
     void prof_begin(const char *name) { if (prof && prof->on) { Prof::Rec r{name, prof->get(), prof->get()}; cudaEventRecord(r.a, stream); prof->recs.push_back(r); } }
     void prof_end() { if (prof && prof->on) cudaEventRecord(prof->recs.back().b, stream); launches++; }
 
-    template <class T> T *alloc(size_t count) { return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1)); }
+    template <class T> T *alloc(size_t count)
+    {
+        // a count taken from a damaged header must not wrap the byte size into a small allocation
+        if (count > ((size_t)1 << 46) / sizeof(T)) fail(NAFGPU_E_FORMAT, "size field exceeds anything this device could hold\n");
+        return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1));
+    }
     void upload(void *dst, const void *src, size_t n) { if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream)); }
     // upload of a bigger host array that lives in pageable memory: through the context's pinned staging so the DMA is
     // asynchronous and the source may be reused as soon as this returns

@@ -537,18 +537,21 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     u32 *d_id_end = nullptr, *d_cm_end = nullptr;
     auto find_ends = [&](const u8 *s, u64 bytes, const char *name) -> u32 * {
         if (bytes == 0) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - not 0-terminated\n");
+        // terminator offsets are kept as u32: a string stream of 4 GiB or more would wrap them silently
+        if (bytes >= (1ull << 32)) fail(NAFGPU_E_UNSUPPORTED, std::string(name) + " stream of 4 GiB or more is not supported by this build\n");
         u64 ntiles = (bytes + ZT - 1) / ZT;
         u64 *counts = ex.alloc<u64>(ntiles + 1), *prefix = ex.alloc<u64>(ntiles + 2);
-        u32 *end = ex.alloc<u32>(N + 1);
         KLAUNCH(ex, "k_zero_count", k_zero_count<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, counts));
         const u64 *c = counts;
         exclusive_scan(ex, [c] __device__ (size_t i) { return c[i]; }, ntiles, prefix);
-        KLAUNCH(ex, "k_zero_scatter", k_zero_scatter<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, prefix, end, N));
+        // the header's N is not trusted: count the terminators before anything is sized by it
         u64 nzero; u8 last;
         ex.download(&nzero, prefix + ntiles, 8);
         ex.download(&last, s + bytes - 1, 1);
         if (last != 0) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - not 0-terminated\n");
-        if (nzero < N) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - can't read all records\n");
+        if (nzero < N || N > bytes) fail(NAFGPU_E_FORMAT, std::string("corrupted ") + name + " - can't read all records\n");
+        u32 *end = ex.alloc<u32>(N + 1);
+        KLAUNCH(ex, "k_zero_scatter", k_zero_scatter<<<(unsigned)ntiles, 256, 0, ex.stream>>>(s, bytes, prefix, end, N));
         return end;
     };
     if (A.has_ids) d_id_end = find_ends(d_ids, sbytes[SEC_IDS], "ids");
@@ -576,6 +579,9 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         // clamp to the bases actually present (print_dna_buffer_as_fasta never prints past total_seq_length)
         u64 sum; ex.download(&sum, d_seq_start + NR, 8);
         if (sum > total_bases) fail(NAFGPU_E_FORMAT, "corrupted lengths - sum exceeds the sequence size\n");
+        // FASTQ: record i's qualities are quality[seq_start[i] .. +L[i]) -- the stream must hold all of them (the reference never
+        // returns on such a file: refill_quality_buffer_from_file, input.c:409, has nothing left to read)
+        if (view == NAFGPU_OUT_FASTQ && sum > sbytes[SEC_QUAL]) fail(NAFGPU_E_FORMAT, "corrupted quality - shorter than the sum of the sequence lengths\n");
         len_sum = sum;
     }
     A.L = d_L; A.seq_start = d_seq_start;
@@ -635,6 +641,8 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     A.N = NR; A.out_start = d_out_start; A.rec0 = 0;
     u64 total; ex.download(&total, d_out_start + NR, 8);
+    const u64 NR_all = NR;
+    bool range_has_tail = true;                                           // the range ends with the file's last record
     if (ranged) {
         // records [r0, r1) only: their text is the byte range [o0, o1) of the whole output
         const u64 r0 = o.first_record < NR ? o.first_record : NR, r1 = (o.n_records < NR - r0) ? r0 + o.n_records : NR;
@@ -651,6 +659,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         ex.for_each(r1 - r0 + 1, [=] __device__ (size_t i) { local[i] = src[i] - base; }, "range_out_start");
         A.N = NR = r1 - r0; A.out_start = d_out_start = local; A.rec0 = r0;
         total = o01[1] - o01[0];
+        range_has_tail = r1 == NR_all && r1 > r0;
     }
     A.total = total;
     if (total == 0 || NR == 0) return none;
@@ -660,17 +669,17 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     // then in lines of W, with no newline at the end.  Rare and tiny, so it is laid out on the host: the surplus bases are
     // produced by the text kernel as one bare pseudo-record, fetched, wrapped, and put behind the text.
     u64 surplus = 0, surplus_text = 0, line_rem = 0;
-    if (view == NAFGPU_OUT_FASTA && !ranged && len_sum < total_bases) {
+    if (view == NAFGPU_OUT_FASTA && range_has_tail && len_sum < total_bases) {
         surplus = total_bases - len_sum;
         if (surplus > (64u << 20)) fail(NAFGPU_E_UNSUPPORTED, "more than 64 MB of sequence beyond the recorded lengths is not supported by this build\n");
         // length of the last non-empty record: its last line decides the budget (empty records do not touch it)
         u64 last_len = 0;
         for (u64 win = 4096; last_len == 0; win *= 16) {
-            const u64 cnt = win < NR ? win : NR;
+            const u64 cnt = win < NR_all ? win : NR_all;
             std::vector<u64> tail(cnt);
-            ex.download(tail.data(), d_L + (NR - cnt), cnt * 8);
+            ex.download(tail.data(), d_L + (NR_all - cnt), cnt * 8);
             for (u64 i = cnt; i > 0 && last_len == 0; i--) last_len = tail[i - 1];
-            if (cnt == NR) break;
+            if (cnt == NR_all) break;
         }
         if (last_len == 0) surplus = 0;                                  // no record has bases: print_fasta returns before any sequence (output.c:629)
         else if (W == 0) surplus_text = surplus;

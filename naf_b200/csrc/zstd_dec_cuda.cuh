@@ -181,9 +181,8 @@ __global__ void __launch_bounds__(256) k_seq_exec_big_cta(const ZDecArgs a)
 inline void launch_seq_decode(nafg::CudaExec &ex, const ZDecArgs &a)
 {
     if (!a.nblk) return;
-    static bool attr = false;
     const int smem = SD_BLOCKS * FSE_SLOT_ENTRIES * 4;
-    if (!attr) { cudaFuncSetAttribute(k_seq_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    cudaFuncSetAttribute(k_seq_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device: set on every launch (cheap)
     ex.prof_begin("zd_seq_decode");
     k_seq_decode_smem<<<(a.nblk + SD_BLOCKS - 1) / SD_BLOCKS, 32, smem, ex.stream>>>(a);
     ex.prof_end();

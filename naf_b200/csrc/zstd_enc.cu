@@ -260,7 +260,11 @@ __global__ void __launch_bounds__(256) k_zenc_gather(const ZGatherArgs A)
     if (blockIdx.x == fb && threadIdx.x == 0) {
         if (!A.skip_magic) { frame[0] = 0x28; frame[1] = 0xB5; frame[2] = 0x2F; frame[3] = 0xFD; }
         frame[4] = 0x00;                                       // FHD: no content size, no checksum, no dictionary
-        frame[5] = (u8)((ZWINDOW_LOG - 10) << 3);
+        // window descriptor: ennaf --long N declares 2^N for the sequence stream (compressor.c:12-16); never below our own
+        // block span, never above what unnaf accepts (ZSTD_d_windowLogMax 31, input.c:270)
+        int wl = A.wlog[s];
+        wl = wl < ZWINDOW_LOG ? ZWINDOW_LOG : (wl > 31 ? 31 : wl);
+        frame[5] = (u8)((wl - 10) << 3);
     }
     if (threadIdx.x == 0) {
         u32 size_field = B.type == 1 ? B.n : B.csize;          // RLE: regenerated size

@@ -246,10 +246,17 @@ def record_range(n_records: int, rank: int, world: int):
     return first, n_records * (rank + 1) // world - first
 
 
+RANGE_VIEWS = ("default", "fasta", "fastq", "sequences", "ids", "names")   # nafgpu_dec_opts.first_record / n_records apply
+
+
 def decode_shard(ctx, naf, rank: int, world: int, view: str = "default", **kw) -> bytes:
     """This rank's piece of the text of a .naf file: the ranks' pieces, concatenated in rank order, are the full output
     (nafgpu_dec_opts.first_record / n_records; sequence and quality blocks outside the range are not decoded when the
     frames carry no sequences, as ours do).  Every rank needs the whole file (it is the small side: broadcast it)."""
+    if view not in RANGE_VIEWS:
+        # --seq / --4bit / --lengths / --mask / --charcount are not per-record outputs: the library ignores a record range
+        # for them, so one rank (piece) produces the whole output and the others contribute nothing
+        return ctx.decode(naf, view, **kw) if rank == 0 else b""
     n = container.read_header(naf if isinstance(naf, bytes) else bytes(naf)).n_sequences
     first, count = record_range(n, rank, world)
     if count == 0:

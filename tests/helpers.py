@@ -210,3 +210,27 @@ def claim_huge_ids(naf: bytes) -> bytes:
     at = off - len(head)
     assert naf[at:off] == head
     return naf[:at] + container.put_vle((1 << 40) + 1) + container.put_vle(comp) + naf[off:]
+
+
+def replace_section(naf: bytes, k: int, donor: bytes) -> bytes:
+    """the same .naf with section k (0 ids .. 5 quality: VLE sizes + payload) taken from `donor`"""
+    from naf_b200 import container
+    def span(buf):
+        orig, comp, off = container.read_header(buf).sections[k]
+        head = container.put_vle(orig) + container.put_vle(comp)
+        assert buf[off - len(head):off] == head
+        return off - len(head), off + comp
+    a0, a1 = span(naf)
+    d0, d1 = span(donor)
+    return naf[:a0] + donor[d0:d1] + naf[a1:]
+
+
+def claim_records(naf: bytes, n: int) -> bytes:
+    """the same .naf with the header's number of sequences rewritten to n"""
+    from naf_b200 import container
+    h = container.read_header(naf)
+    pos = 4 + (1 if h.version > 1 else 0) + 2
+    ll, p1 = container.get_vle(naf, pos)
+    nn, p2 = container.get_vle(naf, p1)
+    assert nn == h.n_sequences
+    return naf[:p1] + container.put_vle(n) + naf[p2:]

@@ -152,3 +152,23 @@ def test_fasta_surplus_sequence_is_printed_like_the_reference(gpu, oracle, tmp_p
                 if helpers.have_ref():
                     rc, out, err = helpers.ref_run("unnaf", ["--fasta"] + args, naf, timeout=20)
                     assert rc == 0 and out == want, (text, st, kw, err)
+
+
+def test_damaged_headers_that_used_to_read_out_of_bounds(gpu, oracle):
+    """(a) a FASTQ file whose quality stream is shorter than its lengths add up to, (b) a record count far beyond the
+    number of '\\0' terminators in the ids (2^62: the byte size of the offset array wrapped), (c) a ranged decode of (a):
+    all refused as damaged files, and the context keeps working"""
+    import naf_b200
+    long_reads, short_reads = synth.fastq(3000, 150, seed=3), synth.fastq(3000, 100, seed=3)
+    naf, donor = gpu.encode(long_reads), gpu.encode(short_reads)
+    bad_q = helpers.replace_section(naf, 5, donor)
+    for kw in ({}, {"first_record": 2000, "n_records": 1000}):
+        with pytest.raises(naf_b200.NafGpuError) as e:
+            gpu.decode(bad_q, "fastq", **kw)
+        assert e.value.code == -3
+    assert gpu.decode(bad_q, "fasta") == oracle.decode(naf, "fasta")      # FASTA output does not touch the quality
+    for n in (3001, 1 << 40, 1 << 62, (1 << 64) - 1):
+        with pytest.raises(naf_b200.NafGpuError) as e:
+            gpu.decode(helpers.claim_records(naf, n))
+        assert e.value.code == -3, n
+        assert gpu.decode(naf) == long_reads
