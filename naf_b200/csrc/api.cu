@@ -25,16 +25,17 @@ template <class F> static int guarded(nafgpu_ctx *ctx, F f)
         CUDA_TRY(cudaSetDevice(ctx->device));
         if (!ctx->keep_arena) { ctx->arena.reset(); ctx->shard.active = false; }
         ctx->keep_arena = false;
+        ctx->pipe.reset(); ctx->mail.up_used = Mailbox::DOWN;
         f();
         return NAFGPU_OK;
     } catch (const NafError &e) {
-        ctx->err = e.msg; cudaStreamSynchronize(ctx->stream); ctx->timing.parser_fallback = ctx->fast_fallbacks != 0; return e.code;
+        ctx->err = e.msg; ctx->pipe.drain(); cudaStreamSynchronize(ctx->stream); ctx->timing.parser_fallback = ctx->fast_fallbacks != 0; return e.code;
     } catch (const CudaError &e) {
         char buf[512];
         snprintf(buf, sizeof buf, "CUDA error: %s (%s) at %s:%d\n", cudaGetErrorString(e.e), e.what, e.file, e.line);
-        ctx->err = buf; cudaGetLastError(); return NAFGPU_E_CUDA;
+        ctx->err = buf; ctx->pipe.drain(); cudaGetLastError(); return NAFGPU_E_CUDA;
     } catch (const std::exception &e) {
-        ctx->err = std::string("internal error: ") + e.what() + "\n"; return NAFGPU_E_CUDA;
+        ctx->err = std::string("internal error: ") + e.what() + "\n"; ctx->pipe.drain(); return NAFGPU_E_CUDA;
     }
 }
 
@@ -64,6 +65,7 @@ int nafgpu_create(int device, nafgpu_ctx **out)
     try {
         CUDA_TRY(cudaSetDevice(device));
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->pipe.create(); c->mail.create();
         for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
         u32 predef[nafz::FSE_SLOT_ENTRIES];
         nafz::zstd_build_predef(predef);
@@ -86,6 +88,7 @@ void nafgpu_destroy(nafgpu_ctx *c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    c->pipe.drain(); c->pipe.destroy(); c->mail.destroy();
     c->arena.release(); c->pinned_out.release(); c->pinned_aux.release(); c->pinned_stage.release();
     if (c->d_predef) cudaFree(c->d_predef);
     if (c->d_nuc_lut) cudaFree(c->d_nuc_lut);
@@ -106,6 +109,18 @@ void nafgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 }  // extern "C"
 
+// Host-buffer calls on inputs of at least PIPE_MIN bytes overlap their copies with the kernels (HostPipe, common.cuh).
+// NAFGPU_PIPE=0 in the environment turns that off (A/B measurements).
+// NAFGPU_PIPE_MIN / NAFGPU_PIPE_CHUNK (bytes; the chunk is rounded to 64 KB) let the tests run the piped paths on small inputs.
+static u64 env_bytes(const char *name, u64 dflt) { const char *e = getenv(name); return e && *e ? strtoull(e, nullptr, 10) : dflt; }
+static u64 pipe_chunk() { u64 c = env_bytes("NAFGPU_PIPE_CHUNK", 32ull << 20) & ~0xFFFFull; return c ? c : 0x10000; }
+static bool use_pipe(u64 n)
+{
+    const char *env = getenv("NAFGPU_PIPE");
+    if (env && env[0] == '0') return false;
+    return n >= env_bytes("NAFGPU_PIPE_MIN", 64ull << 20);
+}
+
 // host buffer -> device copy with 64 bytes of zero padding after it
 static u8 *to_device(Ctx &c, CudaExec &ex, const u8 *h, size_t n)
 {
@@ -124,6 +139,8 @@ static void finish_timing(Ctx &c, CudaExec &ex)
 {
     CUDA_TRY(cudaEventRecord(c.ev[3], c.stream));
     CUDA_TRY(cudaStreamSynchronize(c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.pipe.in));
+    CUDA_TRY(cudaStreamSynchronize(c.pipe.out));
     CUDA_TRY(cudaGetLastError());
     cudaEventElapsedTime(&c.timing.h2d_ms, c.ev[0], c.ev[1]);
     cudaEventElapsedTime(&c.timing.kernels_ms, c.ev[1], c.ev[2]);
@@ -155,15 +172,29 @@ int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_
     if (!naf || !opts || !text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         nafc::Header h; std::string err;
         if (!nafc::read_header(naf, n, h, false, err)) fail(NAFGPU_E_FORMAT, err);      // fail before any transfer
-        u8 *d_naf = to_device(*c, ex, naf, n);
+        u8 *d_naf;
+        if (use_pipe(n)) {
+            // the file goes up in chunks on its own stream; decode_on_device waits for exactly the bytes each part needs, and
+            // sends finished pieces of the text down on a third stream while the next ones are produced
+            d_naf = ex.alloc<u8>(n + 64);
+            CUDA_TRY(cudaMemsetAsync(d_naf + n, 0, 64, c->stream));
+            ex.pipe = &c->pipe;
+            c->pipe.upload(d_naf, naf, n, pipe_chunk(), c->stream);
+        } else d_naf = to_device(*c, ex, naf, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         DecodeOut r = decode_on_device(*c, ex, d_naf, naf, n, *opts);
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
-        *text = to_pinned(*c, r.d_text, r.size); *text_size = r.size;
+        if (c->pipe.emitting && r.d_text) {
+            // [0, out_done) is already on its way down; whatever was produced outside the piece loop follows
+            u8 *hout = c->pipe.h_out;
+            const u64 done = c->pipe.out_done < r.size ? c->pipe.out_done : r.size;
+            if (r.size > done) CUDA_TRY(cudaMemcpyAsync(hout + done, r.d_text + done, r.size - done, cudaMemcpyDeviceToHost, c->stream));
+            *text = hout; *text_size = r.size;
+        } else { *text = to_pinned(*c, r.d_text, r.size); *text_size = r.size; }
         finish_timing(*c, ex);
     });
 }
@@ -174,7 +205,7 @@ int nafgpu_decode_device(nafgpu_ctx *c, const uint8_t *d_naf, size_t n, const ui
     if (!d_naf || !opts || !d_text || !text_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_text = nullptr; *text_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         const u8 *h = host_copy;
         if (!h) {                                     // no host mirror: fetch the compressed bytes once for the header walk
@@ -197,7 +228,7 @@ int nafgpu_zstd_decompress(nafgpu_ctx *c, const uint8_t *src, size_t n, size_t e
     if (!src || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -229,9 +260,16 @@ int nafgpu_encode(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc
     if ((!text && n) || !opts || !naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
-        u8 *d_text = to_device(*c, ex, text, n);
+        u8 *d_text;
+        if (use_pipe(n)) {
+            // the text goes up in chunks on its own stream; the transform kernel is launched chunk by chunk right behind it
+            d_text = ex.alloc<u8>(n + 64);
+            CUDA_TRY(cudaMemsetAsync(d_text + n, 0, 64, c->stream));
+            ex.pipe = &c->pipe;
+            c->pipe.upload(d_text, text, n, pipe_chunk(), c->stream);
+        } else d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
@@ -246,7 +284,7 @@ int nafgpu_encode_device(nafgpu_ctx *c, const uint8_t *d_text, size_t n, const n
     if ((!d_text && n) || !opts || !d_naf || !naf_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *d_naf = nullptr; *naf_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         EncodeOut r = encode_on_device(*c, ex, d_text, n, *opts, info);
@@ -266,7 +304,7 @@ int nafgpu_zstd_compress_level(nafgpu_ctx *c, const uint8_t *src, size_t n, int 
     if ((!src && n) || !out || !out_size) return NAFGPU_E_ARG;
     return guarded(c, [&] {
         *out = nullptr; *out_size = 0;
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_in = to_device(*c, ex, src, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -282,7 +320,7 @@ int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_
 {
     if ((!text && n) || !opts || !streams || !sizes) return NAFGPU_E_ARG;
     return guarded(c, [&] {
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         u8 *d_text = to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -309,7 +347,7 @@ int nafgpu_shard_begin(nafgpu_ctx *c, const uint8_t *text, size_t n, int text_on
 {
     if ((!text && n) || !opts || !counts) return NAFGPU_E_ARG;
     return guarded(c, [&] {
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         const u8 *d_text = text_on_device ? text : to_device(*c, ex, text, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
@@ -325,7 +363,7 @@ int nafgpu_shard_finish(nafgpu_ctx *c, const nafgpu_shard_link *link, uint64_t r
     if (!c->shard.active) { c->err = "nafgpu_shard_finish without nafgpu_shard_begin\n"; return NAFGPU_E_ARG; }
     c->keep_arena = true;
     return guarded(c, [&] {
-        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
         CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         shard_finish_on_device(*c, ex, *link, raw, body);

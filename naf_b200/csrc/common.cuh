@@ -9,6 +9,11 @@
 #include "../../include/nafgpu.h"
 #include "zstd_hd.cuh"
 
+namespace nafz {
+// what the host walk of one stream's block headers found (zstd_walk_stream, zstd_dec.cuh)
+struct ZWalked { std::vector<ZBlockHead> blocks; std::vector<u32> regen; bool simple = false; u64 consumed = 0; int rc = 0; std::string err; };
+}
+
 namespace nafg {
 
 using nafz::u8; using nafz::u16; using nafz::u32; using nafz::u64; using nafz::i32; using nafz::i64;
@@ -87,6 +92,79 @@ struct PinnedBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+// ------------------------------------------------------------------ host <-> device pipe of the host-buffer calls
+// The reference streams its input through 16 KB / 1 MB windows (ennaf/src/process.c:227-240, compressor.c:120-143) and its
+// output through 128 KB ones (unnaf/src/output.c:640-650).  Here the counterpart is copy / compute overlap: the host
+// buffer goes up in chunks on its own stream, each chunk followed by an event the compute stream waits for right before
+// the first kernel that reads it, and finished pieces of the result go down on a third stream while the kernels for the
+// next piece run.  PCIe is full duplex, so the upload of a call and the download of its result overlap as well.
+struct HostPipe {
+    cudaStream_t in = nullptr, out = nullptr;
+    std::vector<cudaEvent_t> pool; size_t used = 0;
+    // input
+    u64 n_in = 0, chunk = 0; std::vector<cudaEvent_t> in_ev; bool uploading = false; const u8 *h_in = nullptr;
+    // output
+    u8 *h_out = nullptr; u64 out_done = 0; bool emitting = false;
+
+    void create()
+    {
+        CUDA_TRY(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
+    }
+    void destroy()
+    {
+        for (auto e : pool) cudaEventDestroy(e);
+        pool.clear();
+        if (in) cudaStreamDestroy(in);
+        if (out) cudaStreamDestroy(out);
+        in = out = nullptr;
+    }
+    void reset() { used = 0; in_ev.clear(); n_in = 0; uploading = false; h_in = nullptr; h_out = nullptr; out_done = 0; emitting = false; }
+    cudaEvent_t event()
+    {
+        if (used == pool.size()) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pool.push_back(e); }
+        return pool[used++];
+    }
+    // enqueue the whole upload now, in chunks; `after`: an event of the compute stream the copies must not overtake (the
+    // destination may still be in use by what that stream ran before)
+    void upload(u8 *d, const u8 *h, u64 n, u64 chunk_bytes, cudaStream_t compute)
+    {
+        cudaEvent_t e0 = event();
+        CUDA_TRY(cudaEventRecord(e0, compute));
+        CUDA_TRY(cudaStreamWaitEvent(in, e0, 0));
+        n_in = n; chunk = chunk_bytes; uploading = true; h_in = h;
+        for (u64 off = 0; off < n; off += chunk) {
+            const u64 len = n - off < chunk ? n - off : chunk;
+            CUDA_TRY(cudaMemcpyAsync(d + off, h + off, len, cudaMemcpyHostToDevice, in));
+            cudaEvent_t e = event();
+            CUDA_TRY(cudaEventRecord(e, in));
+            in_ev.push_back(e);
+        }
+    }
+    size_t chunks() const { return in_ev.size(); }
+    // the compute stream's next kernels may read input bytes [0, hi)
+    void wait_input(cudaStream_t compute, u64 hi)
+    {
+        if (!uploading || in_ev.empty() || hi == 0) return;
+        size_t c = (size_t)((hi - 1) / chunk);
+        if (c >= in_ev.size()) c = in_ev.size() - 1;
+        CUDA_TRY(cudaStreamWaitEvent(compute, in_ev[c], 0));
+    }
+    void wait_all_input(cudaStream_t compute) { wait_input(compute, n_in); }
+    // result bytes [off, off + len) (device pointer d) are final once the compute stream gets here: send them down
+    void begin_output(u8 *h) { h_out = h; out_done = 0; emitting = true; }
+    void emit(cudaStream_t compute, const u8 *d, u64 off, u64 len)
+    {
+        if (!len) return;
+        cudaEvent_t e = event();
+        CUDA_TRY(cudaEventRecord(e, compute));
+        CUDA_TRY(cudaStreamWaitEvent(out, e, 0));
+        CUDA_TRY(cudaMemcpyAsync(h_out + off, d, len, cudaMemcpyDeviceToHost, out));
+        if (off == out_done) out_done = off + len;
+    }
+    void drain() { if (in) cudaStreamSynchronize(in); if (out) cudaStreamSynchronize(out); }
+};
+
 // ------------------------------------------------------------------ generic kernels for HD bodies
 template <class F> __global__ void k_for_each(size_t n, F f)
 {
@@ -94,6 +172,25 @@ template <class F> __global__ void k_for_each(size_t n, F f)
     if (i < n) f(i);
 }
 template <class F> __global__ void k_for_each_group(F f) { f((size_t)blockIdx.x, threadIdx.x, blockDim.x); }
+
+// Small control transfers (a few counters down, a table of a few KB up) between the kernels of a call must not queue behind
+// the bulk copies a piped host-buffer call keeps in flight on the copy engines -- each would wait for a whole 32-64 MB DMA.
+// They go through a mailbox instead: page-locked host memory the GPU reads / writes directly from a tiny kernel.
+__global__ void k_mail_copy(const u8 *src, u8 *dst, size_t n)
+{
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        const size_t nv = n / 16;
+        for (size_t i = i0; i < nv; i += stride) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
+        for (size_t i = nv * 16 + i0; i < n; i += stride) dst[i] = src[i];
+    } else for (size_t i = i0; i < n; i += stride) dst[i] = src[i];
+}
+struct Mailbox {
+    static const size_t DOWN = 64 << 10, CAP = (64 << 10) + (1 << 20);
+    u8 *p = nullptr; size_t up_used = DOWN;
+    void create() { CUDA_TRY(cudaHostAlloc(&p, CAP, cudaHostAllocMapped | cudaHostAllocPortable)); }
+    void destroy() { if (p) cudaFreeHost(p); p = nullptr; }
+};
 
 // Optional per-launch timing with CUDA events (bench.py's live roofline; off during timed steps).
 struct Prof {
@@ -109,17 +206,31 @@ struct CudaExec {
     Arena *arena;
     Prof *prof = nullptr;
     u32 launches = 0;
+    HostPipe *pipe = nullptr;                // host-buffer calls: chunked copies overlapped with the kernels (else nullptr)
 
     void prof_begin(const char *name) { if (prof && prof->on) { Prof::Rec r{name, prof->get(), prof->get()}; cudaEventRecord(r.a, stream); prof->recs.push_back(r); } }
     void prof_end() { if (prof && prof->on) cudaEventRecord(prof->recs.back().b, stream); launches++; }
 
+    Mailbox *mail = nullptr;
     template <class T> T *alloc(size_t count)
     {
         // a count taken from a damaged header must not wrap the byte size into a small allocation
         if (count > ((size_t)1 << 46) / sizeof(T)) fail(NAFGPU_E_FORMAT, "size field exceeds anything this device could hold\n");
         return (T *)arena->alloc_bytes(sizeof(T) * (count ? count : 1));
     }
-    void upload(void *dst, const void *src, size_t n) { if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream)); }
+    void upload(void *dst, const void *src, size_t n)
+    {
+        if (!n) return;
+        if (mail && n <= (256u << 10)) {                       // through the mailbox: the source may be reused as soon as this returns
+            const size_t need = (n + 15) & ~(size_t)15;
+            if (mail->up_used + need > Mailbox::CAP) { CUDA_TRY(cudaStreamSynchronize(stream)); mail->up_used = Mailbox::DOWN; }
+            u8 *slot = mail->p + mail->up_used; mail->up_used += need;
+            memcpy(slot, src, n);
+            k_mail_copy<<<(unsigned)((n + 4095) / 4096), 256, 0, stream>>>(slot, (u8 *)dst, n);
+            return;
+        }
+        CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream));
+    }
     // upload of a bigger host array that lives in pageable memory: through the context's pinned staging so the DMA is
     // asynchronous and the source may be reused as soon as this returns
     PinnedBuf *staging = nullptr;
@@ -130,10 +241,18 @@ struct CudaExec {
         CUDA_TRY(cudaStreamSynchronize(stream));                 // the staging buffer may still feed an earlier copy
         u8 *p = staging->ensure(n);
         memcpy(p, src, n);
-        CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyHostToDevice, stream));
+        if (pipe && pipe->uploading) k_mail_copy<<<(unsigned)(n / 65536 + 1), 256, 0, stream>>>(p, (u8 *)dst, n);   // not behind the bulk upload
+        else CUDA_TRY(cudaMemcpyAsync(dst, p, n, cudaMemcpyHostToDevice, stream));
     }
     void download(void *dst, const void *src, size_t n)
     {
+        if (mail && n && n <= Mailbox::DOWN) {
+            k_mail_copy<<<1, 256, 0, stream>>>((const u8 *)src, mail->p, n);
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            memcpy(dst, mail->p, n);
+            mail->up_used = Mailbox::DOWN;                       // the stream is idle: every earlier upload slot is free again
+            return;
+        }
         if (n) CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
@@ -244,7 +363,10 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     Arena arena;
     PinnedBuf pinned_out, pinned_aux, pinned_stage;
+    HostPipe pipe;
+    Mailbox mail;
     std::vector<nafz::ZBlockHead> zblock_cache;   // keeps the capacity of the decoder's host block list between calls
+    nafz::ZWalked zwalk[6];                  // per section: the host walk of its block headers (capacity kept between calls)
     u32 *d_predef = nullptr;                 // predefined FSE tables
     u8 *d_nuc_lut = nullptr;                 // nuc_code + "unexpected" bit: DNA at 0, RNA at 256
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};

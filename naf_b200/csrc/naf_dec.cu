@@ -79,6 +79,7 @@ struct TextArgs {
     const u64 *out_start;            // per record: first output byte; [N] = total
     u64 N, total, total_bases;
     u64 rec0;                        // global index of local record 0 (record-range decode): per-record arrays other than out_start are global
+    u64 tile_base;                   // k_write_text: CTA b writes tile tile_base + b (the text is written piece by piece behind an upload)
     u32 lut[4];                      // code_to_nuc as 16 bytes
     u8 *out;
 };
@@ -329,11 +330,12 @@ __global__ void __launch_bounds__(WT_THREADS, 5) k_write_text(const __grid_const
     __shared__ RecS recs[WT_MAXREC];
     __shared__ u32 s_nslow;
     __shared__ u16 slow[WT_THREADS * WT_ITERS];
-    const u64 tile0 = (u64)blockIdx.x * WT_TILE;
+    const u64 tile = A.tile_base + blockIdx.x;
+    const u64 tile0 = tile * WT_TILE;
     const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
     // records first .. last intersect this tile (last = the record holding the first byte of the next tile)
-    const u64 first = tile_first[blockIdx.x];
-    const u32 s_nrec = tile_first[blockIdx.x + 1] - (u32)first + 1;
+    const u64 first = tile_first[tile];
+    const u32 s_nrec = tile_first[tile + 1] - (u32)first + 1;
     if (threadIdx.x == 0) s_nslow = 0;
     if (threadIdx.x < s_nrec && threadIdx.x < WT_MAXREC) rec_fetch(A, first + threadIdx.x, recs[threadIdx.x]);
     __syncthreads();
@@ -460,30 +462,56 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     if (view == NAFGPU_OUT_LENGTHS && !h.has_lengths) return none;
     if (view == NAFGPU_OUT_MASK && !h.has_mask) return none;
 
-    // ---- entropy stage: all needed streams in one batch -- or, when only a range of records is wanted (one rank of a
-    // multi-GPU decode), the small streams first and the sequence / quality streams afterwards, restricted to the bytes
-    // the range needs (frames without sequences, i.e. ours, skip every other block; others are decoded whole)
+    // ---- entropy stage.  The host walks of the block headers (one serial chain per stream) start right away, the long ones
+    // on their own threads; the device work comes in up to three parts:
+    //   (1) the streams the per-record scans need (ids, names, lengths, mask) -- and, unless it is part (3), the sequence
+    //   (2) [the per-record scans below]
+    //   (3) the last big stream (quality for FASTQ, else sequence): after (2) when only a range of records is wanted (one
+    //       rank of a multi-GPU decode: blocks outside the range are skipped), or when the file is still on its way up from
+    //       the host -- then piece by piece behind the upload, each piece's text written and sent down while the next one
+    //       arrives (DecodePieces below).  Otherwise (1) and (3) are one batch.
     const bool ranged = o.n_records != 0 && (view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQUENCES ||
                                             view == NAFGPU_OUT_IDS || view == NAFGPU_OUT_NAMES);
     nafz::ZDecPlan plan;
     plan.blocks.swap(ctx.zblock_cache);                                   // reuse last call's capacity
     struct GiveBack { nafz::ZDecPlan &p; Ctx &c; ~GiveBack() { p.blocks.swap(c.zblock_cache); } } give_back{plan, ctx};
     static const char *what[6] = { "ids", "names", "lengths", "mask", "sequence", "quality" };
-    int sidx[6]; u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
+    u64 sbytes[6]; u64 soff[6]; u64 arena_sz = 0;
     nafz::ZStreamDesc sdesc[6];
     for (int k = 0; k < 6; k++) {
-        sidx[k] = -1; sbytes[k] = 0; soff[k] = 0;
+        sbytes[k] = 0; soff[k] = 0;
         if (!need[k]) continue;
         u64 expect = h.sec[k].orig;
         if (k == SEC_DATA && packed) expect = (h.sec[k].orig + 1) / 2;
         // no zstd frame regenerates more than 128 KB from the 4 bytes of an RLE block: a header that claims more is
         // damaged, and must fail here rather than as a failed multi-terabyte allocation
         if (expect > (h.sec[k].comp + 4) * 32768 + (128u << 10)) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+        if (h.sec[k].comp == 0) fail(NAFGPU_E_FORMAT, std::string("can't decompress: empty zstd stream\n"));
         sbytes[k] = expect; soff[k] = arena_sz;
         nafz::ZStreamDesc sd; sd.src_off = h.sec[k].off; sd.src_len = h.sec[k].comp; sd.out_off = arena_sz; sd.out_size = expect;
         sd.one_frame = (k == SEC_DATA || k == SEC_QUAL) ? 1 : 0; sd.no_magic = 1; sd.need_lo = 0; sd.need_hi = ~0ull;
         sdesc[k] = sd;
         arena_sz += align256(expect + 64);
+    }
+    // host walks
+    struct Walks {
+        nafz::ZWalked *w; std::thread th[6]; bool pending[6] = {false, false, false, false, false, false};
+        void join(int k) { if (pending[k]) { th[k].join(); pending[k] = false; } }
+        ~Walks() { for (int k = 0; k < 6; k++) join(k); }
+    } walks{ctx.zwalk};
+    const int last_big = need[SEC_QUAL] ? SEC_QUAL : (need[SEC_DATA] ? SEC_DATA : -1);
+    bool any_threaded = false;
+    for (int k = 0; k < 6; k++) {
+        if (!need[k]) continue;
+        nafz::ZWalked &w = ctx.zwalk[k];
+        w.blocks.clear(); w.regen.clear(); w.simple = false; w.consumed = 0; w.rc = 0; w.err.clear();
+        const nafz::ZStreamDesc sd = sdesc[k];
+        const bool want_regen = k == last_big;
+        auto body = [&w, sd, h_naf, want_regen]() {
+            w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, want_regen ? &w.regen : nullptr, want_regen ? &w.simple : nullptr);
+        };
+        if (sd.src_len > (8u << 20)) { walks.th[k] = std::thread(body); walks.pending[k] = true; any_threaded = true; }
+        else body();
     }
     u8 *d_streams = ex.alloc<u8>(arena_sz + 256);
     // padding bytes between streams are read by the 16-byte loaders: keep them defined (the streams themselves are
@@ -491,27 +519,42 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     for (int k = 0; k < 6; k++) if (need[k]) ex.zero(d_streams + soff[k] + sbytes[k], align256(sbytes[k] + 64) - sbytes[k]);
     ex.zero(d_streams + arena_sz, 256);
     u64 data_out_size = 0;
-    auto run_batch = [&](bool big_streams) {
-        plan.streams.clear();
-        int in_batch[6], nb = 0;
+    // decode the streams of `mask` (bit k = section k) as one batch
+    auto run_batch = [&](u32 mask) {
+        plan.streams.clear(); plan.blocks.clear();
+        int in_batch[6], nb = 0; u64 in_hi = 0;
         for (int k = 0; k < 6; k++) {
-            const bool big = k == SEC_DATA || k == SEC_QUAL;
-            if (!need[k] || (ranged && big != big_streams)) continue;
-            sidx[k] = (int)plan.streams.size(); plan.streams.push_back(sdesc[k]); in_batch[nb++] = k;
+            if (!need[k] || !((mask >> k) & 1)) continue;
+            walks.join(k);
+            nafz::ZWalked &w = ctx.zwalk[k];
+            if (w.rc) fail(NAFGPU_E_FORMAT, std::string("can't decompress: ") + w.err + "\n");
+            const u32 base = (u32)plan.blocks.size(), si = (u32)plan.streams.size();
+            for (auto &b : w.blocks) { nafz::ZBlockHead hb = b; hb.frame_first_blk += base; hb.stream = (u8)si; plan.blocks.push_back(hb); }
+            plan.streams.push_back(sdesc[k]); in_batch[nb++] = k;
+            if (h.sec[k].off + h.sec[k].comp > in_hi) in_hi = h.sec[k].off + h.sec[k].comp;
         }
         if (!nb) return;
+        plan.results.assign(plan.streams.size(), nafz::ZStreamResult{0, 0, 0});
+        if (ex.pipe) ex.pipe->wait_input(ex.stream, in_hi);
         std::string zerr;
-        int rc = nafz::zstd_decode_batch(ex, d_naf, h_naf, d_streams, plan, ctx.d_predef, zerr);
+        int rc = nafz::zstd_decode_blocks(ex, d_naf, d_streams, plan, ctx.d_predef, zerr);
         if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, std::string("can't decompress: ") + zerr + "\n");
         for (int j = 0; j < nb; j++) {
             const int k = in_batch[j];
-            u64 got = plan.results[sidx[k]].out_size;
+            u64 got = plan.results[j].out_size;
             bool exact = !(k == SEC_DATA || k == SEC_QUAL);
             if (exact ? got != sbytes[k] : got < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
             if (k == SEC_DATA) data_out_size = got;
         }
     };
-    run_batch(false);                       // not ranged: everything
+    const bool rec_text_view = view == NAFGPU_OUT_FASTA || view == NAFGPU_OUT_FASTQ || view == NAFGPU_OUT_SEQUENCES;
+    // piecewise decode of the last big stream behind the upload: decided once its walk says the stream can be cut
+    bool piecewise = false;
+    const u32 all_mask = 0x3F, big_mask = (1u << SEC_DATA) | (1u << SEC_QUAL);
+    u32 later_mask = 0;                                                   // streams decoded after the per-record scans
+    if (ranged) later_mask = big_mask;
+    else if (last_big >= 0 && rec_text_view && (any_threaded || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
+    run_batch(all_mask & ~later_mask);
     const u8 *d_ids = d_streams + soff[SEC_IDS], *d_comm = d_streams + soff[SEC_NAMES], *d_mask = d_streams + soff[SEC_MASK];
     const u8 *d_seq = d_streams + soff[SEC_DATA], *d_qual = d_streams + soff[SEC_QUAL];
     const u32 *d_len = (const u32 *)(d_streams + soff[SEC_LEN]);
@@ -652,7 +695,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
             u64 b01[2]; ex.download(&b01[0], d_seq_start + r0, 8); ex.download(&b01[1], d_seq_start + r1, 8);
             if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
             if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
-            run_batch(true);
+            run_batch(big_mask);
         }
         u64 *local = ex.alloc<u64>(r1 - r0 + 2);
         const u64 *src = d_out_start + r0; const u64 base = o01[0];
@@ -692,13 +735,77 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     u8 *d_text = ex.alloc<u8>(total + surplus_text + 64);
     A.out = d_text;
-    {
-        if (NR >= 0xFFFFFFFFull) fail(NAFGPU_E_UNSUPPORTED, "more than 2^32 - 1 records in one file are not supported by this build\n");
-        u64 ntiles = (total + WT_TILE - 1) / WT_TILE;
-        u32 *tile_first = ex.alloc<u32>(ntiles + 2);
-        KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(d_out_start, NR, ntiles, tile_first));
-        KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)ntiles, WT_THREADS, 0, ex.stream>>>(A, tile_first));
-    }
+    if (NR >= 0xFFFFFFFFull) fail(NAFGPU_E_UNSUPPORTED, "more than 2^32 - 1 records in one file are not supported by this build\n");
+    const u64 ntiles = (total + WT_TILE - 1) / WT_TILE;
+    u32 *tile_first = ex.alloc<u32>(ntiles + 2);
+    KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(d_out_start, NR, ntiles, tile_first));
+    // host-buffer call: finished tiles of the text go down while the next ones are being written
+    const bool sink = ex.pipe && rec_text_view && view != NAFGPU_OUT_CHARCOUNT;
+    if (sink) ex.pipe->begin_output(ctx.pinned_out.ensure(total + surplus_text + 1));
+    auto write_tiles = [&](u64 t0, u64 t1) {
+        const u64 group = sink ? (64ull << 20) / WT_TILE : ntiles;      // tiles per launch when each launch is followed by its copy
+        for (u64 a = t0; a < t1; a += group) {
+            const u64 b = a + group < t1 ? a + group : t1;
+            TextArgs B = A; B.tile_base = a;
+            KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)(b - a), WT_THREADS, 0, ex.stream>>>(B, tile_first));
+            if (sink) { const u64 lo = a * WT_TILE, hi = b * WT_TILE < total ? b * WT_TILE : total; ex.pipe->emit(ex.stream, d_text + lo, lo, hi - lo); }
+        }
+    };
+    if (!ranged && later_mask) {
+        const int k = last_big;
+        const char *env_piece0 = getenv("NAFGPU_PIPE_PIECE");
+        const u64 PIECE_MIN = env_piece0 && *env_piece0 ? strtoull(env_piece0, nullptr, 10) : (48ull << 20);
+        walks.join(k);
+        nafz::ZWalked &w = ctx.zwalk[k];
+        if (w.rc) fail(NAFGPU_E_FORMAT, std::string("can't decompress: ") + w.err + "\n");
+        piecewise = w.simple && ex.pipe && ex.pipe->uploading && surplus == 0 && h.sec[k].comp >= 2 * PIECE_MIN && w.regen.size() == w.blocks.size();
+        if (!piecewise) { run_batch(1u << k); write_tiles(0, ntiles); }
+        else {
+            // pieces of ~PIECE compressed bytes, cut at block boundaries; piece p is decoded as soon as its bytes have arrived,
+            // the records it completes are written and their text sent down while piece p + 1 is still on its way up
+            const u64 PIECE = PIECE_MIN, nblk = w.blocks.size();
+            u64 *d_upto = ex.alloc<u64>(2);
+            u64 i0 = 0, out_off = 0, t_prev = 0;
+            while (i0 < nblk) {
+                u64 i1 = i0, cbytes = 0, regen = 0;
+                while (i1 < nblk && cbytes < PIECE) { cbytes += (u64)w.blocks[i1].csize + 3; regen += w.regen[i1]; i1++; }
+                if (nblk - i1 < 64) while (i1 < nblk) { regen += w.regen[i1]; i1++; }      // no tiny last piece
+                plan.blocks.clear(); plan.streams.clear();
+                for (u64 i = i0; i < i1; i++) {
+                    nafz::ZBlockHead hb = w.blocks[i];
+                    hb.frame_first_blk = 0; hb.stream = 0; hb.out_base = soff[k] + out_off;
+                    hb.first_in_frame = hb.first_in_stream = i == i0;
+                    plan.blocks.push_back(hb);
+                }
+                nafz::ZStreamDesc sd = sdesc[k]; sd.out_off = soff[k] + out_off; sd.out_size = regen;
+                plan.streams.push_back(sd);
+                plan.results.assign(1, nafz::ZStreamResult{0, 0, 0});
+                ex.pipe->wait_input(ex.stream, w.blocks[i1 - 1].src + w.blocks[i1 - 1].csize);
+                std::string zerr;
+                int rc = nafz::zstd_decode_blocks(ex, d_naf, d_streams, plan, ctx.d_predef, zerr);
+                if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, std::string("can't decompress: ") + zerr + "\n");
+                if (plan.results[0].out_size != regen || plan.results[0].nseq != 0) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                out_off += regen;
+                if (out_off > sbytes[k] && !(k == SEC_DATA || k == SEC_QUAL)) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                u64 t_hi = ntiles;
+                if (i1 < nblk) {
+                    const u64 done = (k == SEC_DATA && packed) ? out_off * 2 : out_off;       // bases (qualities) available so far
+                    const u64 *ss = d_seq_start, *os = d_out_start; const u64 nr = NR;
+                    ex.for_each(1, [=] __device__ (size_t) {
+                        u64 lo = 0, hi = nr + 1;                     // largest r in [0, nr] with seq_start[r] <= done: records < r are complete
+                        while (hi - lo > 1) { const u64 mid = (lo + hi) >> 1; if (ss[mid] <= done) lo = mid; else hi = mid; }
+                        d_upto[0] = lo; d_upto[1] = os[lo];
+                    }, "piece_upto");
+                    u64 upto[2]; ex.download(upto, d_upto, 16);
+                    t_hi = upto[1] / WT_TILE;
+                    if (t_hi > ntiles) t_hi = ntiles;
+                } else if (out_off < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                if (t_hi > t_prev) { write_tiles(t_prev, t_hi); t_prev = t_hi; }
+                i0 = i1;
+            }
+            if (k == SEC_DATA) data_out_size = out_off;
+        }
+    } else write_tiles(0, ntiles);
     if (surplus) {
         TextArgs S = A;
         S.prefix = 0; S.with_name = 0; S.name_nl = 0; S.seq_present = 1; S.seq_nl = 0; S.with_qual = 0; S.W = 0; S.rec0 = 0;

@@ -491,6 +491,8 @@ static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, si
     S.store_mask = !(o.no_mask || o.seq_type >= NAFGPU_PROTEIN);                                 // ennaf.c:445
     u64 p0 = 0;
     const size_t head = n < 65536 ? n : 65536;
+    const bool piped = ex.pipe && ex.pipe->uploading;           // host-buffer call: the text is still on its way up, chunk by chunk
+    if (piped) h_head = ex.pipe->h_in;
     if (!h_head) {
         ctx.host_scratch.resize(head + 1);
         if (head) ex.download(ctx.host_scratch.data(), d_text, head);
@@ -532,7 +534,18 @@ static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, si
     A.ticket = (u32 *)scal; A.flag = (u32 *)scal + 1; A.longest = (unsigned long long *)(scal + 1); A.totals = (FusedTotals *)(scal + 4);
 
     CUDA_TRY(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem::total));
-    KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)ntiles, FUSED_NT, FusedSmem::total, ex.stream>>>(A));
+    if (piped) {
+        // one launch per uploaded chunk, each right behind its chunk's copy: tiles are handed out by the global ticket and look
+        // back only (naf_fused.cuh), so a launch needs nothing beyond the bytes that have arrived
+        u64 t0 = 0;
+        for (size_t c = 0; c < ex.pipe->chunks(); c++) {
+            const u64 hi = (c + 1) * ex.pipe->chunk < n ? (c + 1) * ex.pipe->chunk : n;
+            const u64 t1 = c + 1 == ex.pipe->chunks() ? ntiles : hi / FT_BYTES;
+            ex.pipe->wait_input(ex.stream, hi);
+            if (t1 > t0) { KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)(t1 - t0), FUSED_NT, FusedSmem::total, ex.stream>>>(A)); }
+            t0 = t1;
+        }
+    } else { KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)ntiles, FUSED_NT, FusedSmem::total, ex.stream>>>(A)); }
     KLAUNCH(ex, "k_fused_finish", k_fused_finish<<<1, 1, 0, ex.stream>>>(A));
     FusedTotals tot; ex.download(&tot, A.totals, sizeof tot);
     if (tot.flag) throw FastFallback{};
@@ -564,6 +577,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         ex.arena->rewind(mk);
         ctx.fast_fallbacks++;
     }
+    if (ex.pipe) ex.pipe->wait_all_input(ex.stream);           // the general parser's passes each read the whole text
     return split_streams_impl(ctx, ex, d_text, n, o, info, false);
 }
 

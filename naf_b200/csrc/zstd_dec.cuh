@@ -82,6 +82,7 @@ struct ZStreamDesc {
 };
 
 struct ZStreamResult { u64 out_size; u64 nseq; u64 consumed; };
+
 struct ZNeedTab { u64 lo[8], hi[8]; u32 on[8]; };
 
 static const int HUF_SLOT_ENTRIES = 2048;     // u16 each
@@ -90,9 +91,15 @@ static const int FSE_OF_AT = 512, FSE_ML_AT = 768;
 
 // ------------------------------------------------------------------ host: frame / block walk
 // spec "Frame_Header" / "Block_Header"; replaces zstd_decompress.c:819 ZSTD_decompressFrame's header handling.
+// `regen` / `simple` (optional): the regenerated size of every block, as far as the host can tell without decoding, and whether
+// that was possible for all of them -- a SIMPLE stream is one frame whose blocks are all self-contained: raw, RLE, or compressed
+// with their own Huffman table (or raw / RLE literals) and no sequences.  That is what our encoder writes; such a stream can
+// be cut at any block boundary and the pieces decoded on their own, at known output offsets (piecewise decode behind a
+// chunked upload, record-range decode).
 inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, std::vector<ZBlockHead> &blocks,
-                            u64 *consumed, std::string &err)
+                            u64 *consumed, std::string &err, std::vector<u32> *regen = nullptr, bool *simple = nullptr)
 {
+    bool all_simple = true;
     const u8 *p = h + sd.src_off; const u64 n = sd.src_len;
     u64 pos = 0; int frames = 0; bool first_in_stream = true;
     bool skip_magic = sd.no_magic != 0;
@@ -134,6 +141,15 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
             else { b.csize = bsize; b.rsize = type == 0 ? bsize : 0; }
             if (bsize > 128 * 1024 && type != 1) { err = "zstd block larger than 128 KB"; return -1; }
             if (pos + b.csize > n) { err = "zstd block truncated"; return -1; }
+            if (regen) {
+                u32 r = b.rsize;
+                if (type == 2) {
+                    LitHeader lh;
+                    if (all_simple && lit_header_parse(p + pos, b.csize, lh) == Z_OK && lh.type != 3 && (u64)lh.hdr + lh.csize + 1 == b.csize) r = lh.regen;
+                    else all_simple = false;
+                }
+                regen->push_back(r);
+            }
             pos += b.csize;
             // The walk is a chain of dependent reads ~10 KB apart: every header is a cache miss in host memory.  Blocks of
             // one stream have nearly equal sizes, so the headers after the next one are where "same size again" puts
@@ -155,6 +171,7 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
         if (sd.one_frame) break;
     }
     if (sd.one_frame && frames == 0) { err = "no zstd frame"; return -1; }
+    if (simple) *simple = all_simple && frames == 1 && regen != nullptr;
     *consumed = pos;
     return 0;
 }
@@ -708,7 +725,10 @@ struct ZDecPlan {
 };
 
 template <class Exec>
-int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecPlan &plan, const u32 *d_predef, std::string &err)
+int zstd_decode_blocks(Exec &ex, const u8 *d_in, u8 *d_out, ZDecPlan &plan, const u32 *d_predef, std::string &err);
+
+// host walk of every stream of the plan -> plan.blocks
+inline int zstd_walk_plan(const u8 *h_in, ZDecPlan &plan, std::string &err)
 {
     plan.blocks.clear();
     plan.results.assign(plan.streams.size(), ZStreamResult{0, 0, 0});
@@ -732,6 +752,21 @@ int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecP
             plan.results[s].consumed = used[s];
         }
     }
+    return 0;
+}
+
+template <class Exec>
+int zstd_decode_batch(Exec &ex, const u8 *d_in, const u8 *h_in, u8 *d_out, ZDecPlan &plan, const u32 *d_predef, std::string &err)
+{
+    if (int rc = zstd_walk_plan(h_in, plan, err)) return rc;
+    return zstd_decode_blocks(ex, d_in, d_out, plan, d_predef, err);
+}
+
+// device side: plan.blocks (from zstd_walk_plan, or assembled by the caller from walks it ran itself) -> bytes
+template <class Exec>
+int zstd_decode_blocks(Exec &ex, const u8 *d_in, u8 *d_out, ZDecPlan &plan, const u32 *d_predef, std::string &err)
+{
+    if (plan.results.size() != plan.streams.size()) plan.results.assign(plan.streams.size(), ZStreamResult{0, 0, 0});
     const u32 nblk = (u32)plan.blocks.size();
     if (nblk == 0) return 0;
     u32 n_comp = 0;
