@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-records", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--c5-gbp", type=float, default=3.0, help="size of the configs[4] FASTA for the c5_strong sub-record (0 = skip)")
     ap.add_argument("--level", type=int, default=1, help="ennaf -# (1 = the tools' default: LZ77 + FSE sequences on ids/comments/lengths/mask; <= 0 entropy-only)")
     return ap.parse_args()
 
@@ -105,8 +106,9 @@ def split_fastq_pieces(text: bytes, pieces: int):
     return [text[cuts[i]:cuts[i + 1]] for i in range(len(cuts) - 1)]
 
 
-def time_reference(text: bytes, n_bases: int, procs: int, tmp="/dev/shm"):
-    """one round trip with `procs` independent ennaf / unnaf processes; returns (t_enc, t_dec) wall seconds"""
+def time_reference(text: bytes, n_bases: int, procs: int, tmp="/dev/shm", keep_naf=None):
+    """one round trip with `procs` independent ennaf / unnaf processes; returns (t_enc, t_dec) wall seconds.
+    keep_naf: a list that receives the bytes of piece 0's reference-made .naf"""
     work = os.path.join(tmp, f"nafbench_{os.getpid()}")
     os.makedirs(work, exist_ok=True)
     pieces = split_fastq_pieces(text, procs) if procs > 1 else [text]
@@ -125,6 +127,8 @@ def time_reference(text: bytes, n_bases: int, procs: int, tmp="/dev/shm"):
     t2 = time.perf_counter()
     ok = all(open(os.path.join(work, f"out{i}.fq"), "rb").read() == pieces[i] for i in range(len(pieces)))
     naf_bytes = sum(os.path.getsize(os.path.join(work, f"x{i}.naf")) for i in range(len(pieces)))
+    if keep_naf is not None:
+        keep_naf.append(open(os.path.join(work, "x0.naf"), "rb").read())
     for f in os.listdir(work):
         os.remove(os.path.join(work, f))
     os.rmdir(work)
@@ -190,6 +194,63 @@ NCU_TRAFFIC_PER_BASE = {
     "k_fast_tiles": 329.9e6 / 150e6, "k_fast_count": 363.9e6 / 150e6, "k_fast_scatter": 664.9e6 / 150e6, "k_pack4": 213.4e6 / 150e6,
     "k_zenc_hist": 257.5e6 / 150e6, "k_zenc_encode": 351.2e6 / 150e6, "zd_literals": 332.5e6 / 150e6, "k_write_text": 587.9e6 / 150e6,
 }
+
+
+def make_c5_device(torch, n_bases, n_records=24, width=60, seed=4242):
+    """BASELINE configs[4] on the device (the host generator needs minutes for 3 Gbp): one human-like FASTA, `n_records`
+    equal chromosomes, lines of `width`, ~50 % soft-masked in runs U[100,5000], twenty 50 kbp N gaps, a planted 8 kbp repeat.
+    Deterministic for a given torch build and GPU type, so every rank can make its own identical copy.  -> uint8 tensor"""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    acgt = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device="cuda")
+    seq = acgt[torch.randint(0, 4, (n_bases,), generator=g, device="cuda", dtype=torch.uint8).long()] if n_bases < (1 << 28) else None
+    if seq is None:                                            # in slices: the index tensor of torch's gather is int64
+        seq = torch.empty(n_bases, dtype=torch.uint8, device="cuda")
+        step = 1 << 28
+        for a in range(0, n_bases, step):
+            b = min(n_bases, a + step)
+            seq[a:b] = acgt[torch.randint(0, 4, (b - a,), generator=g, device="cuda", dtype=torch.uint8).long()]
+    if n_bases > 40000:
+        unit = seq[1000:9000].clone()
+        for at in torch.randint(10000, n_bases - 9000, (6,), generator=g, device="cuda").tolist():
+            seq[at:at + 8000] = unit
+    gap = min(50000, n_bases // 20)
+    for at in torch.randint(0, max(1, n_bases - gap), (20,), generator=g, device="cuda").tolist():
+        seq[at:at + gap] = ord("N")
+    # soft mask: alternating gap / run lengths -> +1 / -1 deltas -> running sum > 0
+    est = int(n_bases / 5100 * 1.3) + 8
+    gaps = torch.randint(100, 5001, (est,), generator=g, device="cuda")
+    runs = torch.randint(100, 5001, (est,), generator=g, device="cuda")
+    starts = torch.cumsum(gaps + torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), runs[:-1]]), 0)
+    ends = torch.clamp(starts + runs, max=n_bases)
+    keep = starts < n_bases
+    step = 1 << 28
+    for a in range(0, n_bases, step):                           # per slice: delta array in int8 is enough (runs do not nest)
+        b = min(n_bases, a + step)
+        delta = torch.zeros(b - a + 1, dtype=torch.int8, device="cuda")
+        st = starts[keep & (starts >= a) & (starts < b)] - a
+        en = ends[keep & (ends > a) & (ends <= b)] - a          # an end at b lands in the spare slot and is dropped
+        delta[st] += 1
+        delta[en] -= 1
+        inside = int(((starts < a) & (ends > a) & keep).any().item())        # a run that began before this slice
+        m = (torch.cumsum(delta[:-1].to(torch.int32), 0) + inside) > 0
+        seq[a:b] |= m.to(torch.uint8) * 0x20
+        del delta, m
+    cuts = [n_bases * r // n_records for r in range(n_records + 1)]
+    heads = [b">chr%d synthetic soft-masked\n" % (r + 1) for r in range(n_records)]
+    sizes = [len(heads[r]) + (cuts[r + 1] - cuts[r]) + ((cuts[r + 1] - cuts[r]) + width - 1) // width for r in range(n_records)]
+    out = torch.full((sum(sizes) + 64,), 10, dtype=torch.uint8, device="cuda")
+    at = 0
+    for r in range(n_records):
+        out[at:at + len(heads[r])] = torch.tensor(list(heads[r]), dtype=torch.uint8, device="cuda")
+        at += len(heads[r])
+        L = cuts[r + 1] - cuts[r]
+        pos = torch.arange(L, device="cuda", dtype=torch.int64)
+        out[at + pos + pos // width] = seq[cuts[r]:cuts[r + 1]]
+        at += L + (L + width - 1) // width
+        del pos
+    out[at:] = 0
+    return out, at, n_records
 
 
 def run_ours(args):
@@ -386,6 +447,73 @@ def run_ours(args):
         except Exception as e:                # the headline numbers above do not depend on this path
             single = {"error": repr(e)[:300]}
 
+    # ---- BASELINE configs[4]: ONE 3 Gbp soft-masked FASTA (24 records) decoded by all ranks -- strong scaling.  Every rank makes
+    # the same text on its device (untimed), rank 0 encodes it, the .naf (a quarter of the text) is broadcast and kept in HBM
+    # with a host mirror as after reading the file; timed: every rank decodes its share of the records, max over ranks.
+    c5 = None
+    if args.c5_gbp > 0:
+        try:
+            from naf_b200 import sharded
+            n5 = int(args.c5_gbp * 1e9)
+            d_c5, n5_text, n5_rec = make_c5_device(torch, n5)
+            fopts = api.make_enc_opts(level=args.level)
+            meta = torch.zeros(1, dtype=torch.int64, device="cuda")
+            d_file = None
+            if rank == 0:
+                enc_t = []
+                for rep in range(3):
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    addr5, size5, info5 = ctx.encode_device(d_c5.data_ptr(), n5_text, fopts)
+                    torch.cuda.synchronize(); enc_t.append(time.perf_counter() - t0)
+                d_file = torch.empty(size5, dtype=torch.uint8, device="cuda")
+                ctx_copy_d2d(d_file, addr5, size5)
+                meta[0] = size5
+            if world > 1:
+                dist.broadcast(meta, src=0)
+                if rank != 0:
+                    d_file = torch.empty(int(meta.item()), dtype=torch.uint8, device="cuda")
+                dist.broadcast(d_file, src=0)
+            h_file = d_file.cpu().pin_memory()
+            first, count = sharded.record_range(n5_rec, rank, world)
+            ropts = api.make_dec_opts(first_record=first, n_records=count) if world > 1 else api.make_dec_opts()
+            dts, tsz, tad = [], 0, 0
+            for rep in range(4):
+                barrier(); t0 = time.perf_counter()
+                if count:
+                    tad, tsz = ctx.decode_device(d_file.data_ptr(), d_file.numel(), (h_file.data_ptr(), h_file.numel()), ropts)
+                torch.cuda.synchronize()
+                dts.append(time.perf_counter() - t0)
+            # my piece must be exactly my byte range of the text
+            sz = torch.tensor([tsz], dtype=torch.int64, device="cuda")
+            allsz = [torch.zeros_like(sz) for _ in range(world)]
+            if world > 1:
+                dist.all_gather(allsz, sz)
+            else:
+                allsz = [sz]
+            off = sum(int(x.item()) for x in allsz[:rank])
+            ok5 = torch.tensor([1], dtype=torch.int64, device="cuda")
+            if not args.no_verify:
+                got = torch.empty(tsz, dtype=torch.uint8, device="cuda")
+                if tsz:
+                    ctx_copy_d2d(got, tad, tsz)
+                ok5[0] = int(bool(torch.equal(got, d_c5[off:off + tsz])) and sum(int(x.item()) for x in allsz) == n5_text)
+                del got
+            td5 = torch.tensor([min(dts[1:])], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(td5, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ok5, op=dist.ReduceOp.MIN)
+            c5 = {"workload": f"{args.c5_gbp} Gbp soft-masked FASTA, {n5_rec} records, line width 60, ONE .naf (BASELINE configs[4])",
+                  "scaling": "strong", "n_gpus": world, "text_bytes": n5_text, "naf_bytes": int(d_file.numel()),
+                  "decode_ms": float(td5.item()) * 1e3, "decode_gbases_s": n5 / float(td5.item()) / 1e9,
+                  "timing": "wall clock around nafgpu_decode_device + synchronize, device-resident .naf with host mirror, best of 3, max over ranks",
+                  "verified_all_ranks": bool(ok5.item())}
+            if rank == 0:
+                c5["encode_ms_1gpu"] = min(enc_t[1:]) * 1e3
+                c5["encode_gbases_s_1gpu"] = n5 / min(enc_t[1:]) / 1e9
+            del d_c5, d_file, h_file
+        except Exception as e:
+            c5 = {"error": repr(e)[:300]}
+
     # ---- reduce over ranks: max time
     t = torch.tensor([dev_ms, e2e_ms, enc_ms / args.steps, dec_ms / args.steps, e_enc / args.steps, e_dec / args.steps], device="cuda", dtype=torch.float64)
     if world > 1:
@@ -427,13 +555,33 @@ def run_ours(args):
                     "decode_gbases_s": total_bases / (e_dec1 * 1e-3) / 1e9, "ms_per_step": e2e_ms},
             "gpu_launches": launches_total,
             "single_file": single,
+            "c5_strong": c5,
             "clocks": clocks,
             "roofline": roofline,
         }
         if not args.no_cpu_baseline and ref_bin("ennaf") and ref_bin("unnaf"):
             srec = min(records, args.cpu_sample_records)
             sample = synth.fastq(srec, READ_LEN, seed=42)
-            te, td, _ = time_reference(sample, srec * READ_LEN, 1)
+            ref_naf = []
+            te, td, _ = time_reference(sample, srec * READ_LEN, 1, keep_naf=ref_naf)
+            # the drop-in case for existing archives: the file the unmodified `ennaf -1` just made (128 KB blocks, inherited
+            # tables, FSE-coded sequences, matches across blocks), decoded on the device and compared with the sample
+            try:
+                hn = torch.frombuffer(bytearray(ref_naf[0]), dtype=torch.uint8).pin_memory()
+                dn = hn.cuda()
+                rts = []
+                for rep in range(4):
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    ra, rs = ctx.decode_device(dn.data_ptr(), dn.numel(), (hn.data_ptr(), hn.numel()), dopts)
+                    torch.cuda.synchronize(); rts.append(time.perf_counter() - t0)
+                got = torch.empty(rs, dtype=torch.uint8, device="cuda")
+                ctx_copy_d2d(got, ra, rs)
+                okr = rs == len(sample) and bool(torch.equal(got.cpu(), torch.frombuffer(bytearray(sample), dtype=torch.uint8)))
+                line["ref_made"] = {"workload": f"first {srec} reads of the workload encoded by the unmodified ennaf -1", "naf_bytes": len(ref_naf[0]),
+                                    "decode_ms": min(rts[1:]) * 1e3, "decode_gbases_s": srec * READ_LEN / min(rts[1:]) / 1e9, "verified": okr}
+                del got, dn, hn
+            except Exception as e:
+                line["ref_made"] = {"error": repr(e)[:300]}
             line["cpu_baseline"] = {"value": srec * READ_LEN / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
                                     "encode_gbases_s": srec * READ_LEN / te / 1e9, "decode_gbases_s": srec * READ_LEN / td / 1e9,
                                     "sample": f"first {srec} reads of the same workload, oracle/_ref ennaf -1 + unnaf (single-threaded tools), /dev/shm"}
