@@ -84,7 +84,10 @@ typedef struct {
     const char *title;          /* ennaf --title, NULL = none */
     int32_t  general_parser;    /* 1: skip the canonical-input fast parser and use the general (process.c-exact FSM) one;
                                    results are identical either way -- for tests and profiling */
-    int32_t  reserved;
+    int32_t  no_block_index;    /* 1: do not append the block index -- a zstd skippable frame behind the lengths frame that lists the
+                                   compressed size of every block of the sequence / quality frames.  The reference reads sections with
+                                   ZSTD_decompress (unnaf/src/input.c:211), which skips it; our decoder uses it to find all blocks
+                                   without walking the chain of block headers (multi-GPU decode starts everywhere at once). */
 } nafgpu_enc_opts;
 
 typedef struct {

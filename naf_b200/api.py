@@ -28,7 +28,7 @@ class EncOpts(C.Structure):
     _fields_ = [("seq_type", C.c_int32), ("input_format", C.c_int32), ("no_mask", C.c_int32), ("strict", C.c_int32),
                 ("well_formed", C.c_int32), ("have_line_length", C.c_int32), ("line_length", C.c_uint64),
                 ("level", C.c_int32), ("window_log", C.c_int32), ("title", C.c_char_p), ("general_parser", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("no_block_index", C.c_int32)]
 
 
 class DecOpts(C.Structure):
@@ -142,7 +142,7 @@ def _as_ptr(buf):
 
 
 def make_enc_opts(seq_type="dna", fmt=0, no_mask=False, strict=False, well_formed=False, line_length=None, level=1,
-                  window_log=0, title: Optional[str] = None, general_parser=False) -> EncOpts:
+                  window_log=0, title: Optional[str] = None, general_parser=False, block_index=True) -> EncOpts:
     o = EncOpts()
     o.seq_type = _SEQ_TYPES.get(seq_type, seq_type) if isinstance(seq_type, str) else int(seq_type)
     o.input_format = {"fasta": 1, "fastq": 2}.get(fmt, fmt) if isinstance(fmt, str) else int(fmt)
@@ -152,6 +152,7 @@ def make_enc_opts(seq_type="dna", fmt=0, no_mask=False, strict=False, well_forme
     o.level, o.window_log = int(level), int(window_log)
     o.title = title.encode() if title is not None else None
     o.general_parser = int(general_parser)
+    o.no_block_index = int(not block_index)
     return o
 
 

@@ -5,13 +5,14 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/nafgpu.h"
 #include "zstd_hd.cuh"
 
 namespace nafz {
 // what the host walk of one stream's block headers found (zstd_walk_stream, zstd_dec.cuh)
-struct ZWalked { std::vector<ZBlockHead> blocks; std::vector<u32> regen; bool simple = false; u64 consumed = 0; int rc = 0; std::string err; };
+struct ZWalked { std::vector<ZBlockHead> blocks; std::vector<u32> regen; std::vector<std::pair<u64, u64>> skips; bool simple = false; u64 consumed = 0; int rc = 0; std::string err; };
 }
 
 namespace nafg {

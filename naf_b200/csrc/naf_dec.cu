@@ -13,6 +13,7 @@
 // all streams are entropy-decoded together (zstd_dec.cuh), prefix sums give every record its place in
 // the output text, and ONE kernel (k_write_text) then materialises the text: each thread produces 16
 // consecutive output bytes, wherever they fall — header, wrapped sequence line, '+' line or quality.
+#include <chrono>
 #include "common.cuh"
 #include "container.hpp"
 #include "zstd_dec.cuh"
@@ -501,14 +502,60 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     } walks{ctx.zwalk};
     const int last_big = need[SEC_QUAL] ? SEC_QUAL : (need[SEC_DATA] ? SEC_DATA : -1);
     bool any_threaded = false;
+    static const bool trace = getenv("NAFGPU_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what_) {
+        if (!trace) return;
+        cudaStreamSynchronize(ex.stream);
+        fprintf(stderr, "nafgpu trace: %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what_);
+    };
+    // block index (zstd_walk_indexed): a skippable frame behind the lengths frame of files we wrote.  The lengths section is
+    // small -- walk it first (even if this view does not print lengths) and look.
+    nafz::ZIndexEntry index[6]; bool indexed[6] = {false, false, false, false, false, false};
+    static const bool use_index = !(getenv("NAFGPU_INDEX") && getenv("NAFGPU_INDEX")[0] == '0');
+    if (use_index && h.sec[SEC_LEN].present && h.sec[SEC_LEN].comp >= 2 && (need[SEC_DATA] || need[SEC_QUAL])) {
+        nafz::ZWalked &w = ctx.zwalk[SEC_LEN];
+        w.blocks.clear(); w.regen.clear(); w.skips.clear(); w.simple = false; w.consumed = 0; w.rc = 0; w.err.clear();
+        nafz::ZStreamDesc sd = sdesc[SEC_LEN];
+        if (!need[SEC_LEN]) { sd.src_off = h.sec[SEC_LEN].off; sd.src_len = h.sec[SEC_LEN].comp; sd.out_off = 0; sd.out_size = 0; sd.one_frame = 0; sd.no_magic = 1; }
+        w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, nullptr, nullptr, &w.skips);
+        for (auto &sk : w.skips) {
+            const u8 *q = h_naf + sk.first; const u64 sz = sk.second;
+            if (sz < 12 || memcmp(q, "NAFGIDX1", 8) != 0) continue;
+            const u32 ns = q[8] | (q[9] << 8) | (q[10] << 16) | ((u32)q[11] << 24);
+            if (ns > 2 || sz < 12 + (u64)ns * 24) continue;
+            u64 arr = 12 + (u64)ns * 24;
+            for (u32 j = 0; j < ns; j++) {
+                const u8 *e = q + 12 + 24 * j;
+                auto rd32 = [&](int o) { return (u32)e[o] | ((u32)e[o + 1] << 8) | ((u32)e[o + 2] << 16) | ((u32)e[o + 3] << 24); };
+                nafz::ZIndexEntry ie; ie.section = rd32(0); ie.nblk = rd32(4); ie.regen = rd32(8); ie.reserved = rd32(12);
+                ie.total = (u64)rd32(16) | ((u64)rd32(20) << 32); ie.csize = q + arr;
+                if (arr + 2ull * ie.nblk > sz) break;
+                arr += 2ull * ie.nblk;
+                if ((ie.section == SEC_DATA || ie.section == SEC_QUAL) && need[ie.section] && ie.total == sbytes[ie.section]) { index[ie.section] = ie; indexed[ie.section] = true; }
+            }
+        }
+    }
     for (int k = 0; k < 6; k++) {
         if (!need[k]) continue;
         nafz::ZWalked &w = ctx.zwalk[k];
-        w.blocks.clear(); w.regen.clear(); w.simple = false; w.consumed = 0; w.rc = 0; w.err.clear();
+        if (k == SEC_LEN && use_index && (need[SEC_DATA] || need[SEC_QUAL])) continue;          // walked above
+        w.blocks.clear(); w.regen.clear(); w.skips.clear(); w.simple = false; w.consumed = 0; w.rc = 0; w.err.clear();
         const nafz::ZStreamDesc sd = sdesc[k];
-        const bool want_regen = k == last_big;
-        auto body = [&w, sd, h_naf, want_regen]() {
+        if (indexed[k]) {
+            const auto t0 = std::chrono::steady_clock::now();
+            const bool ok = nafz::zstd_walk_indexed(h_naf, sd, index[k], w.blocks, w.regen, &w.consumed);
+            if (trace) fprintf(stderr, "nafgpu trace: block index of section %d: %zu blocks, %s, %.3f ms\n", k, w.blocks.size(), ok ? "used" : "REJECTED",
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            if (ok) { w.simple = true; continue; }
+            w.blocks.clear(); w.regen.clear();
+        }
+        const bool want_regen = k == last_big || (ranged && (k == SEC_DATA || k == SEC_QUAL));
+        auto body = [&w, sd, h_naf, want_regen, k]() {
+            const auto t0 = std::chrono::steady_clock::now();
             w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, want_regen ? &w.regen : nullptr, want_regen ? &w.simple : nullptr);
+            if (trace) fprintf(stderr, "nafgpu trace: host walk of section %d: %zu blocks, %.3f ms\n", k, w.blocks.size(),
+                               std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         };
         if (sd.src_len > (8u << 20)) { walks.th[k] = std::thread(body); walks.pending[k] = true; any_threaded = true; }
         else body();
@@ -522,16 +569,40 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     // decode the streams of `mask` (bit k = section k) as one batch
     auto run_batch = [&](u32 mask) {
         plan.streams.clear(); plan.blocks.clear();
-        int in_batch[6], nb = 0; u64 in_hi = 0;
+        int in_batch[6], nb = 0; u64 in_hi = 0; u64 slice_regen[6];
         for (int k = 0; k < 6; k++) {
             if (!need[k] || !((mask >> k) & 1)) continue;
             walks.join(k);
             nafz::ZWalked &w = ctx.zwalk[k];
             if (w.rc) fail(NAFGPU_E_FORMAT, std::string("can't decompress: ") + w.err + "\n");
             const u32 base = (u32)plan.blocks.size(), si = (u32)plan.streams.size();
-            for (auto &b : w.blocks) { nafz::ZBlockHead hb = b; hb.frame_first_blk += base; hb.stream = (u8)si; plan.blocks.push_back(hb); }
-            plan.streams.push_back(sdesc[k]); in_batch[nb++] = k;
-            if (h.sec[k].off + h.sec[k].comp > in_hi) in_hi = h.sec[k].off + h.sec[k].comp;
+            nafz::ZStreamDesc sd = sdesc[k];
+            slice_regen[nb] = ~0ull;
+            if (w.simple && w.regen.size() == w.blocks.size() && (sd.need_lo > 0 || sd.need_hi < sbytes[k])) {
+                // a stream of self-contained blocks and only bytes [need_lo, need_hi) wanted: the blocks outside never reach the device
+                u64 off = 0, off0 = 0, sum = 0; size_t i0 = w.blocks.size(), i1 = 0;
+                for (size_t i = 0; i < w.blocks.size(); i++) {
+                    const u64 lo = off, hi = off + w.regen[i];
+                    if (hi > sd.need_lo && lo < sd.need_hi) { if (i0 == w.blocks.size()) { i0 = i; off0 = lo; } i1 = i + 1; sum += w.regen[i]; }
+                    off = hi;
+                }
+                if (off < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                if (k == SEC_DATA) data_out_size = off;
+                if (i1 <= i0) continue;                                  // nothing of this stream is wanted
+                for (size_t i = i0; i < i1; i++) {
+                    nafz::ZBlockHead hb = w.blocks[i];
+                    hb.frame_first_blk = base; hb.stream = (u8)si; hb.out_base = sd.out_off + off0;
+                    hb.first_in_frame = hb.first_in_stream = i == i0;
+                    plan.blocks.push_back(hb);
+                    const u64 end = hb.src + hb.csize; if (end > in_hi) in_hi = end;
+                }
+                sd.out_off += off0; sd.out_size = sum; sd.need_lo = 0; sd.need_hi = ~0ull;
+                slice_regen[nb] = sum;
+            } else {
+                for (auto &b : w.blocks) { nafz::ZBlockHead hb = b; hb.frame_first_blk += base; hb.stream = (u8)si; plan.blocks.push_back(hb); }
+                if (h.sec[k].off + h.sec[k].comp > in_hi) in_hi = h.sec[k].off + h.sec[k].comp;
+            }
+            plan.streams.push_back(sd); in_batch[nb++] = k;
         }
         if (!nb) return;
         plan.results.assign(plan.streams.size(), nafz::ZStreamResult{0, 0, 0});
@@ -542,6 +613,10 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         for (int j = 0; j < nb; j++) {
             const int k = in_batch[j];
             u64 got = plan.results[j].out_size;
+            if (slice_regen[j] != ~0ull) {                                // a slice of a simple stream: exactly what the walk promised, no sequences
+                if (got != slice_regen[j] || plan.results[j].nseq != 0) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                continue;
+            }
             bool exact = !(k == SEC_DATA || k == SEC_QUAL);
             if (exact ? got != sbytes[k] : got < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
             if (k == SEC_DATA) data_out_size = got;
@@ -554,7 +629,9 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     u32 later_mask = 0;                                                   // streams decoded after the per-record scans
     if (ranged) later_mask = big_mask;
     else if (last_big >= 0 && rec_text_view && (any_threaded || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
+    mark("walks started / index read");
     run_batch(all_mask & ~later_mask);
+    mark("first batch decoded");
     const u8 *d_ids = d_streams + soff[SEC_IDS], *d_comm = d_streams + soff[SEC_NAMES], *d_mask = d_streams + soff[SEC_MASK];
     const u8 *d_seq = d_streams + soff[SEC_DATA], *d_qual = d_streams + soff[SEC_QUAL];
     const u32 *d_len = (const u32 *)(d_streams + soff[SEC_LEN]);
@@ -629,25 +706,6 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     A.L = d_L; A.seq_start = d_seq_start;
 
-    // ---- mask: run-length units -> one bit per base (output.c:295 semantics, two-scan formulation)
-    if (need[SEC_MASK] && packed && nM > 0 && view != NAFGPU_OUT_FASTQ) {
-        u64 words = (total_bases + 31) / 32 + 2;
-        u32 *bits = ex.alloc<u32>(words);
-        ex.zero(bits, words * 4);
-        u64 *ustart = ex.alloc<u64>(nM + 1), *utog = ex.alloc<u64>(nM + 1);
-        const u8 *m = d_mask;
-        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)m[k]; }, nM, ustart);
-        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)(m[k] != 255); }, nM, utog);
-        const u64 tb = total_bases;
-        ex.for_each(nM, [=] __device__ (size_t k) {
-            if (!(utog[k] & 1)) return;
-            u64 lo = ustart[k], hi = lo + m[k];
-            if (hi > tb) hi = tb;
-            if (lo < hi) nafz::set_bits(bits, lo, hi);
-        });
-        A.maskbits = bits;
-    }
-
     // ---- record layout per view
     switch (view) {
     case NAFGPU_OUT_FASTA:     A.prefix = '>'; A.with_name = 1; A.name_nl = 1; A.seq_present = 1; A.seq_nl = 1; break;
@@ -684,8 +742,10 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     A.N = NR; A.out_start = d_out_start; A.rec0 = 0;
     u64 total; ex.download(&total, d_out_start + NR, 8);
+    mark("per-record scans done");
     const u64 NR_all = NR;
     bool range_has_tail = true;                                           // the range ends with the file's last record
+    u64 range_b0 = 0, range_b1 = total_bases;                             // bases of the records of this call
     if (ranged) {
         // records [r0, r1) only: their text is the byte range [o0, o1) of the whole output
         const u64 r0 = o.first_record < NR ? o.first_record : NR, r1 = (o.n_records < NR - r0) ? r0 + o.n_records : NR;
@@ -693,6 +753,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         ex.download(&o01[0], d_out_start + r0, 8); ex.download(&o01[1], d_out_start + r1, 8);
         if (need[SEC_DATA] || need[SEC_QUAL]) {
             u64 b01[2]; ex.download(&b01[0], d_seq_start + r0, 8); ex.download(&b01[1], d_seq_start + r1, 8);
+            range_b0 = b01[0]; range_b1 = b01[1];
             if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
             if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
             run_batch(big_mask);
@@ -706,6 +767,29 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     }
     A.total = total;
     if (total == 0 || NR == 0) return none;
+    mark("range streams decoded");
+    // ---- mask: run-length units -> one bit per base (output.c:295 semantics, two-scan formulation); only over the bases this
+    // call prints
+    if (need[SEC_MASK] && packed && nM > 0 && view != NAFGPU_OUT_FASTQ) {
+        u64 words = (total_bases + 31) / 32 + 2;
+        u32 *bits = ex.alloc<u32>(words);
+        const u64 b0 = range_b0, b1 = range_has_tail ? total_bases : range_b1;
+        const u64 w0 = b0 / 32, w1 = (b1 + 31) / 32 + 2 < words ? (b1 + 31) / 32 + 2 : words;
+        if (w1 > w0) ex.zero(bits + w0, (w1 - w0) * 4);
+        u64 *ustart = ex.alloc<u64>(nM + 1), *utog = ex.alloc<u64>(nM + 1);
+        const u8 *m = d_mask;
+        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)m[k]; }, nM, ustart);
+        exclusive_scan(ex, [m] __device__ (size_t k) { return (u64)(m[k] != 255); }, nM, utog);
+        const u64 tb = total_bases < b1 ? total_bases : b1;
+        ex.for_each(nM, [=] __device__ (size_t k) {
+            if (!(utog[k] & 1)) return;
+            u64 lo = ustart[k], hi = lo + m[k];
+            if (lo < b0) lo = b0;
+            if (hi > tb) hi = tb;
+            if (lo < hi) nafz::set_bits(bits, lo, hi);
+        });
+        A.maskbits = bits;
+    }
     // ---- FASTA: sequence data beyond what the length units add up to.  ennaf's id-byte bug (an unexpected byte in an id puts
     // its '?' into the SEQUENCE buffer, process.c:366,485) writes such files, and print_dna_buffer_as_fasta
     // (output.c:420-427) prints the surplus after the last record: first into whatever is left of that record's last line,
@@ -733,6 +817,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
             surplus_text += sz;
         }
     }
+    mark("mask bits built");
     u8 *d_text = ex.alloc<u8>(total + surplus_text + 64);
     A.out = d_text;
     if (NR >= 0xFFFFFFFFull) fail(NAFGPU_E_UNSUPPORTED, "more than 2^32 - 1 records in one file are not supported by this build\n");
@@ -806,6 +891,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
             if (k == SEC_DATA) data_out_size = out_off;
         }
     } else write_tiles(0, ntiles);
+    mark("text written");
     if (surplus) {
         TextArgs S = A;
         S.prefix = 0; S.with_name = 0; S.name_nl = 0; S.seq_present = 1; S.seq_nl = 0; S.with_qual = 0; S.W = 0; S.rec0 = 0;

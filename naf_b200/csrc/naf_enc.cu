@@ -625,6 +625,32 @@ EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
     for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(sp[k], ss[k], k == 4 ? o.window_log : 0, lz && k < 4); }
     zstd_compress_batch(ctx, ex, batch);                       // sizes known on the host afterwards
 
+    // ---- block index: the compressed size of every block of the sequence / quality frames, as a skippable frame behind the
+    // lengths frame (a section is read with ZSTD_decompress, unnaf/src/input.c:211, which skips such frames:
+    // zstd/lib/decompress/zstd_decompress.c ZSTD_decompressMultiFrame).  Our decoder then finds every block without walking
+    // the chain of headers (zstd_dec.cuh: zstd_walk_indexed) -- which is what lets N GPUs start on their parts at once.
+    struct IdxStream { u32 section, nblk, regen, first_block; u64 total; };
+    std::vector<IdxStream> idx;
+    static const bool env_index = !(getenv("NAFGPU_INDEX") && getenv("NAFGPU_INDEX")[0] == '0');
+    if (env_index && !o.no_block_index)
+        for (int j = 0; j < ns; j++) {
+            const int k = which[j];
+            const u32 nblk = batch.first_block[j + 1] - batch.first_block[j];
+            if ((k == 4 || k == 5) && !batch.lz[j] && nblk >= 64) idx.push_back(IdxStream{(u32)k, nblk, ZBS, batch.first_block[j], ss[k]});
+        }
+    std::vector<u8> idx_head;
+    u64 idx_bytes = 0;
+    if (!idx.empty()) {
+        u64 payload = 12 + 24 * idx.size();
+        for (auto &e : idx) payload += 2ull * e.nblk;
+        auto put32 = [&](u32 v) { for (int b = 0; b < 4; b++) idx_head.push_back((u8)(v >> (8 * b))); };
+        put32(0x184D2A5Eu); put32((u32)payload);
+        for (const char *t = "NAFGIDX1"; *t; t++) idx_head.push_back((u8)*t);
+        put32((u32)idx.size());
+        for (auto &e : idx) { put32(e.section); put32(e.nblk); put32(e.regen); put32(0); put32((u32)e.total); put32((u32)(e.total >> 32)); }
+        idx_bytes = 8 + payload;
+    }
+
     std::vector<u8> hdr;
     hdr.push_back(0x01); hdr.push_back(0xF9); hdr.push_back(0xEC);
     if (o.seq_type == NAFGPU_DNA) hdr.push_back(1); else { hdr.push_back(2); hdr.push_back((u8)o.seq_type); }
@@ -636,21 +662,31 @@ EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
     if (has_title) { size_t tl = strlen(o.title); nafc::put_vle(hdr, tl); hdr.insert(hdr.end(), o.title, o.title + tl); }
     // layout: [hdr][vle vle payload]...
     std::vector<std::vector<u8>> sec_hdr(ns);
-    u64 total = hdr.size();
+    u64 total = hdr.size(), idx_at = 0;
     std::vector<u64> payload_at(ns);
     for (int j = 0; j < ns; j++) {
         int k = which[j];
         u64 csz = batch.frame_size[j] - 4;                     // magic stripped (compressor.c:158)
+        if (k == 2 && idx_bytes) csz += idx_bytes;
         nafc::put_vle(sec_hdr[j], orig[k]); nafc::put_vle(sec_hdr[j], csz);
         total += sec_hdr[j].size();
         payload_at[j] = total; total += csz;
+        if (k == 2 && idx_bytes) idx_at = payload_at[j] + batch.frame_size[j] - 4;
         info->stream_comp[k] = csz; info->stream_raw[k] = ss[k];
     }
     u8 *d_naf = ex.alloc<u8>(total + 64);
-    std::vector<u8> small(hdr);
     // upload the header and the tiny per-section headers; gather the frames next to them
     ex.upload(d_naf, hdr.data(), hdr.size());
     for (int j = 0; j < ns; j++) ex.upload(d_naf + payload_at[j] - sec_hdr[j].size(), sec_hdr[j].data(), sec_hdr[j].size());
+    if (idx_bytes) {
+        ex.upload(d_naf + idx_at, idx_head.data(), idx_head.size());
+        u64 at = idx_at + idx_head.size();
+        for (auto &e : idx) {
+            const ZEncBlock *blk = batch.d_blocks + e.first_block; u8 *dst = d_naf + at;
+            ex.for_each(e.nblk, [=] __device__ (size_t i) { const u32 c = blk[i].csize; dst[2 * i] = (u8)c; dst[2 * i + 1] = (u8)(c >> 8); }, "zenc_block_index");
+            at += 2ull * e.nblk;
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(ex.stream));                // the small host vectors above must outlive the copies
     for (int j = 0; j < ns; j++) batch.dest[j] = d_naf + payload_at[j] - 4;   // frame byte i lands at dest + i; bytes 0..3 (magic) are skipped
     zstd_gather_frames(ctx, ex, batch, true);
