@@ -504,7 +504,7 @@ HD void k_stream_totals(const ZDecArgs &a, u32 i, ZStreamResult *res)
 
 // K5 — one Huffman stream (thread t = 4*block + k)
 // `staged`: the block's decode table already copied next to the thread (shared memory on the GPU), or nullptr
-HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr)
+HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr, u32 ring_slot0 = 0, u32 ring_stride = 0)
 {
     u32 i = t >> 2, k = t & 3;
     const ZBlock &b = a.blk[i];
@@ -520,6 +520,9 @@ HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr)
     u32 n = b.lit_csize - tree;
     u8 *dst = b.nseq == 0 ? a.out + b.out_off : a.lit_scratch + b.lit_off;
     if (b.lit_streams == 1) {
+#ifdef __CUDA_ARCH__
+        if (ring_stride) { if (!huf_decode_stream_ring(table, hb.huf_bits, p, n, dst, b.lit_regen, ring_slot0, ring_stride)) zerr(a, Z_ERR_HUF_STREAM, i); return; }
+#endif
         if (!huf_decode_stream(table, hb.huf_bits, p, n, dst, b.lit_regen)) zerr(a, Z_ERR_HUF_STREAM, i);
         return;
     }
@@ -532,6 +535,9 @@ HD void k_literals(const ZDecArgs &a, u32 t, const u16 *staged = nullptr)
     if (k >= 1) { off += s1; len = s2; }
     if (k >= 2) { off += s2; len = s3; }
     if (k == 3) { off += s3; len = n - 6 - s1 - s2 - s3; cnt = b.lit_regen - 3 * seg; }
+#ifdef __CUDA_ARCH__
+    if (ring_stride) { if (!huf_decode_stream_ring(table, hb.huf_bits, p + off, len, dst + (size_t)k * seg, cnt, ring_slot0, ring_stride)) zerr(a, Z_ERR_HUF_STREAM, i); return; }
+#endif
     if (!huf_decode_stream(table, hb.huf_bits, p + off, len, dst + (size_t)k * seg, cnt)) zerr(a, Z_ERR_HUF_STREAM, i);
 }
 

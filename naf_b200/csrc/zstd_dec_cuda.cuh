@@ -17,6 +17,7 @@ static const int LIT_TAB_ENTRIES = 16384;                        // u16 entries 
 __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs a)
 {
     __shared__ __align__(16) u16 tabs[LIT_TAB_ENTRIES];
+    __shared__ __align__(16) uint4 ring[HUF_RING * LIT_WARPS * 32];   // slot s of thread t: ring[s * 128 + t] (zstd_hd.cuh: BackBitsR)
     __shared__ u32 tab_off[LIT_BLOCKS], tab_words[LIT_BLOCKS];
     __shared__ const u32 *tab_src[LIT_BLOCKS];
     const u32 tid = threadIdx.x, lane = tid & 31;
@@ -56,7 +57,10 @@ __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs
     }
     __syncthreads();
     const u32 i = first + tid / 4;
-    if (i < a.nblk) { const u32 off = tab_off[tid / 4]; k_literals(a, i * 4 + (tid & 3), off == 0xFFFFFFFFu ? nullptr : tabs + off); }
+    if (i < a.nblk) {
+        const u32 off = tab_off[tid / 4];
+        k_literals(a, i * 4 + (tid & 3), off == 0xFFFFFFFFu ? nullptr : tabs + off, (u32)__cvta_generic_to_shared(ring + tid), (u32)(LIT_WARPS * 32 * sizeof(uint4)));
+    }
 }
 
 inline void launch_literals(nafg::CudaExec &ex, const ZDecArgs &a)

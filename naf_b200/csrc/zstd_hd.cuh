@@ -313,6 +313,13 @@ struct BackBitsQ {
     u32 n0, n1, n2, n3;          // the chunk below the queue, requested one queue ahead: its load latency is covered by
                                  // the decoding of the four queued words instead of stalling the warp
     u32 hi, sh;                  // aligned word holding the cursor, cursor misalignment in bits
+#ifdef __CUDA_ARCH__
+    // On the GPU a stream is decoded by one thread and what bounds it is the chain of dependent instructions from one
+    // symbol to the next (ncu: ~23 dependent instructions per symbol with the 64-bit buffer, warps mostly waiting on their own
+    // previous instruction).  So the buffer is two 32-bit registers moved by funnel shifts: peek = one shift of `bh`,
+    // skip = one funnel shift, and the bit accounting (`left`) is derived at the end from the number of words taken.
+    u32 bh, bl; int npop, loaded0;
+#endif
 
     HD void request()
     {
@@ -336,6 +343,9 @@ struct BackBitsQ {
         const int pad = 8 - hibit(last);          // zero padding bits + the end-mark bit
         const u8 *p = s + n - 8;                  // the top 8 bytes (may start below s for tiny streams: don't-care bits)
         bb = BackBits::load64(p) << pad; nb = 64 - pad; left = (i64)n * 8 - pad;
+#ifdef __CUDA_ARCH__
+        bh = (u32)(bb >> 32); bl = (u32)bb; npop = 0; loaded0 = 64 - pad;
+#endif
         const u32 a = (u32)((uintptr_t)p & 3);
         sh = a * 8;
         const u8 *wa = p - a;                     // aligned word holding the cursor
@@ -348,6 +358,22 @@ struct BackBitsQ {
         qn = (int)j + 1;
         return true;
     }
+#ifdef __CUDA_ARCH__
+    HD void refill()
+    {
+        if (nb <= 32) {                                         // then bl == 0: every valid bit is in bh
+            const u32 lw = pop();
+            const u32 v = __funnelshift_r(lw, hi, sh);          // low word of (hi : lw) >> sh; sh is 0, 8, 16 or 24
+            hi = lw;
+            bh |= __funnelshift_rc(v, 0u, (u32)nb);             // v >> nb (0 when nb == 32)
+            bl = __funnelshift_lc(0u, v, (u32)(32 - nb));       // v << (32 - nb) (0 when nb == 0)
+            nb += 32; npop++;
+        }
+    }
+    HD u32 peek(int n) const { return bh >> (32 - n); }         // 1 <= n <= 32
+    HD void skip(int n) { bh = __funnelshift_l(bl, bh, (u32)n); bl <<= n; nb -= n; }      // n <= 11 (Huffman code lengths)
+    HD bool exact() const { return (i64)loaded0 + 32ll * npop - nb == left; }
+#else
     HD void refill()
     {
         if (nb <= 32) {
@@ -360,6 +386,7 @@ struct BackBitsQ {
     HD u32 peek(int n) const { return (u32)(bb >> (64 - n)); }      // 1 <= n <= 32
     HD void skip(int n) { bb <<= n; nb -= n; left -= n; }
     HD bool exact() const { return left == 0; }
+#endif
 };
 
 // One Huffman-coded stream -> nout symbols.  Replaces decompress/huf_decompress.c:350
@@ -406,6 +433,126 @@ HD bool huf_decode_stream(const u16 *table, int max_bits, const u8 *src, size_t 
     }
     return b.exact();
 }
+
+static const int HUF_RING = 4;                                 // slots per lane of the shared-memory ring below
+#ifdef __CUDA_ARCH__
+// The same stream decoded on the GPU with its compressed bytes staged through shared memory.
+//
+// Why: a warp's 32 lanes decode 32 different streams and run out of queued words at different moments.  With the
+// register-only reader above every such moment is a 16-byte global load into the SAME architectural registers for whichever
+// lane needs it, and a register's scoreboard belongs to the warp, not to a lane: the lane that refills next waits for the
+// load another lane issued a few cycles ago (ncu: a quarter of all stall samples sit on the moves out of those registers).
+// Here the global -> on-chip step is cp.async into a per-lane ring of four 16-byte slots, topped up at a point all lanes reach
+// together (once per 16 symbols) and awaited one iteration later; a lane that runs dry only does a shared-memory load.
+struct BackBitsR {
+    u32 bh, bl; int nb, npop, loaded0; i64 left;
+    u32 w0, w1, w2, w3; int qn; u32 n0, n1, n2, n3;
+    u32 hw, sh;
+    const uint4 *gp; const u8 *src;
+    u32 sbase, stride, issued, taken;                          // shared-memory address of slot 0, bytes between my slots
+
+    __device__ __forceinline__ void top_up()
+    {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            if (issued - taken < (u32)HUF_RING) {
+                const u32 slot = sbase + (issued & (HUF_RING - 1)) * stride;
+                if ((uintptr_t)(gp + 1) > (uintptr_t)src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gp) : "memory");
+                else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot), "r"(0u) : "memory");
+                gp--; issued++;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    __device__ __forceinline__ void take()
+    {
+        const u32 slot = sbase + (taken & (HUF_RING - 1)) * stride;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3) : "r"(slot) : "memory");
+        taken++;
+    }
+    __device__ __forceinline__ void fetch() { w0 = n0; w1 = n1; w2 = n2; w3 = n3; qn = 4; take(); }
+    __device__ __forceinline__ u32 pop() { if (qn == 0) fetch(); const u32 x = w3; w3 = w2; w2 = w1; w1 = w0; qn--; return x; }
+    __device__ __forceinline__ bool init(const u8 *s, size_t n, u32 ring_slot0, u32 ring_stride)
+    {
+        src = s; sbase = ring_slot0; stride = ring_stride; issued = taken = 0; npop = 0; qn = 0; hw = 0;
+        w0 = w1 = w2 = w3 = n0 = n1 = n2 = n3 = 0;
+        if (n == 0) return false;
+        const u8 last = s[n - 1];
+        if (last == 0) return false;
+        const int pad = 8 - hibit(last);
+        const u8 *p = s + n - 8;
+        const u64 bb = BackBits::load64(p) << pad;
+        bh = (u32)(bb >> 32); bl = (u32)bb; nb = 64 - pad; loaded0 = nb; left = (i64)n * 8 - pad;
+        const u32 a = (u32)((uintptr_t)p & 3);
+        sh = a * 8;
+        const u8 *wa = p - a;
+        if (a) hw = *(const u32 *)wa;
+        const u8 *na = wa - 4;
+        const u32 j = (u32)(((uintptr_t)na >> 2) & 3);
+        gp = (const uint4 *)((uintptr_t)na & ~(uintptr_t)15);
+        top_up(); top_up();                                    // four chunks: the one holding `na` and the three below it
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        take(); fetch();                                       // w = chunk holding `na`, n = the next one
+        for (u32 k = j; k < 3; k++) { w3 = w2; w2 = w1; w1 = w0; }
+        qn = (int)j + 1;
+        top_up();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return true;
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (nb <= 32) {
+            const u32 lw = pop();
+            const u32 v = __funnelshift_r(lw, hw, sh);
+            hw = lw;
+            bh |= __funnelshift_rc(v, 0u, (u32)nb);
+            bl = __funnelshift_lc(0u, v, (u32)(32 - nb));
+            nb += 32; npop++;
+        }
+    }
+    __device__ __forceinline__ u32 peek(int n) const { return bh >> (32 - n); }
+    __device__ __forceinline__ void skip(int n) { bh = __funnelshift_l(bl, bh, (u32)n); bl <<= n; nb -= n; }
+    __device__ __forceinline__ bool exact() const { return (i64)loaded0 + 32ll * npop - nb == left; }
+};
+
+// ring_slot0: shared-memory address (cvta'd) of this thread's first 16-byte slot; ring_stride: bytes to its next slot
+__device__ __forceinline__ bool huf_decode_stream_ring(const u16 *table, int max_bits, const u8 *src, size_t n, u8 *dst, size_t nout,
+                                                       u32 ring_slot0, u32 ring_stride)
+{
+    BackBitsR b;
+    if (!b.init(src, n, ring_slot0, ring_stride)) return false;
+    size_t i = 0;
+    while (i < nout && (((uintptr_t)(dst + i)) & 15)) {       // <= 15 symbols: at most two slots
+        b.refill();
+        const u32 e = table[b.peek(max_bits)];
+        dst[i++] = (u8)e; b.skip((int)(e >> 8));
+    }
+    for (; i + 16 <= nout; i += 16) {
+        b.top_up();                                            // what the last iteration took out goes back in ...
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // ... and what was requested an iteration ago has arrived
+        u32 w[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            u32 v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (!(j & 1)) b.refill();
+                const u32 e = table[b.peek(max_bits)];
+                v |= (e & 0xFF) << (8 * j); b.skip((int)(e >> 8));
+            }
+            w[k] = v;
+        }
+        *(uint4 *)(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    for (; i < nout; i++) {
+        b.refill();
+        const u32 e = table[b.peek(max_bits)];
+        dst[i] = (u8)e; b.skip((int)(e >> 8));
+    }
+    return b.exact();
+}
+#endif
 
 // ------------------------------------------------------------------ literals section header
 // spec "Literals_Section_Header"; replaces decompress/zstd_decompress_block.c:79 ZSTD_decodeLiteralsBlock's parsing.
