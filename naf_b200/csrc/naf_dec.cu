@@ -426,7 +426,25 @@ __global__ void k_charcount(const u8 *text, u64 n, unsigned long long *counts)
 static inline u64 align256(u64 v) { return (v + 255) & ~255ull; }
 
 // d_naf: the whole file on the device; h_naf: the same bytes on the host (header + block walk)
+static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o, bool allow_index, bool *used_index);
+
+// A file whose streams are fine but whose block index is damaged must still decode (the reference never looks at the index):
+// if a call that relied on the index fails, it is repeated once with the header walk.
 DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o)
+{
+    bool used_index = false;
+    const Arena::Mark mk = ex.arena->mark();
+    try { return decode_impl(ctx, ex, d_naf, h_naf, n, o, true, &used_index); }
+    catch (const NafError &e) {
+        if (!used_index || e.code != NAFGPU_E_FORMAT || (ex.pipe && ex.pipe->emitting && ex.pipe->out_done)) throw;
+    }
+    CUDA_TRY(cudaStreamSynchronize(ex.stream));
+    ex.arena->rewind(mk);
+    if (ex.pipe) { ex.pipe->wait_all_input(ex.stream); ex.pipe->emitting = false; }
+    return decode_impl(ctx, ex, d_naf, h_naf, n, o, false, &used_index);
+}
+
+static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_naf, size_t n, const nafgpu_dec_opts &o, bool allow_index, bool *used_index)
 {
     using namespace nafc;
     Header h; std::string err;
@@ -512,13 +530,14 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     // block index (zstd_walk_indexed): a skippable frame behind the lengths frame of files we wrote.  The lengths section is
     // small -- walk it first (even if this view does not print lengths) and look.
     nafz::ZIndexEntry index[6]; bool indexed[6] = {false, false, false, false, false, false};
-    static const bool use_index = !(getenv("NAFGPU_INDEX") && getenv("NAFGPU_INDEX")[0] == '0');
+    static const bool env_index = !(getenv("NAFGPU_INDEX") && getenv("NAFGPU_INDEX")[0] == '0');
+    const bool use_index = env_index && allow_index;
     if (use_index && h.sec[SEC_LEN].present && h.sec[SEC_LEN].comp >= 2 && (need[SEC_DATA] || need[SEC_QUAL])) {
         nafz::ZWalked &w = ctx.zwalk[SEC_LEN];
         w.blocks.clear(); w.regen.clear(); w.skips.clear(); w.simple = false; w.consumed = 0; w.rc = 0; w.err.clear();
         nafz::ZStreamDesc sd = sdesc[SEC_LEN];
         if (!need[SEC_LEN]) { sd.src_off = h.sec[SEC_LEN].off; sd.src_len = h.sec[SEC_LEN].comp; sd.out_off = 0; sd.out_size = 0; sd.one_frame = 0; sd.no_magic = 1; }
-        w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, nullptr, nullptr, &w.skips);
+        w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, &w.regen, &w.simple, &w.skips);
         for (auto &sk : w.skips) {
             const u8 *q = h_naf + sk.first; const u64 sz = sk.second;
             if (sz < 12 || memcmp(q, "NAFGIDX1", 8) != 0) continue;
@@ -544,13 +563,13 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
         const nafz::ZStreamDesc sd = sdesc[k];
         if (indexed[k]) {
             const auto t0 = std::chrono::steady_clock::now();
-            const bool ok = nafz::zstd_walk_indexed(h_naf, sd, index[k], w.blocks, w.regen, &w.consumed);
+            const bool ok = nafz::zstd_walk_indexed(h_naf, sd, index[k], w.blocks, w.regen, &w.consumed, false);
             if (trace) fprintf(stderr, "nafgpu trace: block index of section %d: %zu blocks, %s, %.3f ms\n", k, w.blocks.size(), ok ? "used" : "REJECTED",
                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-            if (ok) { w.simple = true; continue; }
+            if (ok) { w.simple = true; *used_index = true; continue; }
             w.blocks.clear(); w.regen.clear();
         }
-        const bool want_regen = k == last_big || (ranged && (k == SEC_DATA || k == SEC_QUAL));
+        const bool want_regen = true;        // cheap (the literals header sits next to the block header) and it decides the fast path
         auto body = [&w, sd, h_naf, want_regen, k]() {
             const auto t0 = std::chrono::steady_clock::now();
             w.rc = nafz::zstd_walk_stream(h_naf, sd, 0, w.blocks, &w.consumed, w.err, want_regen ? &w.regen : nullptr, want_regen ? &w.simple : nullptr);
@@ -570,29 +589,53 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
     auto run_batch = [&](u32 mask) {
         plan.streams.clear(); plan.blocks.clear();
         int in_batch[6], nb = 0; u64 in_hi = 0; u64 slice_regen[6];
+        bool all_simple = true;
         for (int k = 0; k < 6; k++) {
             if (!need[k] || !((mask >> k) & 1)) continue;
             walks.join(k);
             nafz::ZWalked &w = ctx.zwalk[k];
             if (w.rc) fail(NAFGPU_E_FORMAT, std::string("can't decompress: ") + w.err + "\n");
+            if (!(w.simple && w.regen.size() == w.blocks.size())) all_simple = false;
+        }
+        plan.simple = all_simple;
+        for (int k = 0; k < 6; k++) {
+            if (!need[k] || !((mask >> k) & 1)) continue;
+            nafz::ZWalked &w = ctx.zwalk[k];
+            if (!all_simple && indexed[k] && !w.blocks.empty() && w.blocks[0].type == 0xFF) {
+                // the batch takes the general path (another stream of it has dependent blocks): that one wants the block types
+                // from the host, so read the headers after all -- or walk the stream if they disagree with the index
+                if (!nafz::zstd_walk_indexed(h_naf, sdesc[k], index[k], w.blocks, w.regen, &w.consumed, true)) {
+                    w.blocks.clear(); w.regen.clear();
+                    w.rc = nafz::zstd_walk_stream(h_naf, sdesc[k], 0, w.blocks, &w.consumed, w.err, &w.regen, &w.simple);
+                    if (w.rc) fail(NAFGPU_E_FORMAT, std::string("can't decompress: ") + w.err + "\n");
+                }
+            }
             const u32 base = (u32)plan.blocks.size(), si = (u32)plan.streams.size();
             nafz::ZStreamDesc sd = sdesc[k];
             slice_regen[nb] = ~0ull;
-            if (w.simple && w.regen.size() == w.blocks.size() && (sd.need_lo > 0 || sd.need_hi < sbytes[k])) {
-                // a stream of self-contained blocks and only bytes [need_lo, need_hi) wanted: the blocks outside never reach the device
+            const bool simple_stream = w.simple && w.regen.size() == w.blocks.size();
+            const bool sliced = simple_stream && (sd.need_lo > 0 || sd.need_hi < sbytes[k]);
+            if (simple_stream && (sliced || all_simple)) {
+                // a stream of self-contained blocks: only the blocks that hold bytes [need_lo, need_hi) reach the device, and
+                // (when the whole batch is like that) each block is told where its output goes
                 u64 off = 0, off0 = 0, sum = 0; size_t i0 = w.blocks.size(), i1 = 0;
                 for (size_t i = 0; i < w.blocks.size(); i++) {
                     const u64 lo = off, hi = off + w.regen[i];
-                    if (hi > sd.need_lo && lo < sd.need_hi) { if (i0 == w.blocks.size()) { i0 = i; off0 = lo; } i1 = i + 1; sum += w.regen[i]; }
+                    if ((hi > sd.need_lo && lo < sd.need_hi) || (!sliced && w.regen[i] == 0)) { if (i0 == w.blocks.size()) { i0 = i; off0 = lo; } i1 = i + 1; sum += w.regen[i]; }
                     off = hi;
                 }
-                if (off < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
+                const bool exact = !(k == SEC_DATA || k == SEC_QUAL);
+                if (exact ? off != sbytes[k] : off < sbytes[k]) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[k] + "\n");
                 if (k == SEC_DATA) data_out_size = off;
                 if (i1 <= i0) continue;                                  // nothing of this stream is wanted
+                u64 at = off0;
                 for (size_t i = i0; i < i1; i++) {
                     nafz::ZBlockHead hb = w.blocks[i];
-                    hb.frame_first_blk = base; hb.stream = (u8)si; hb.out_base = sd.out_off + off0;
+                    hb.frame_first_blk = base; hb.stream = (u8)si;
                     hb.first_in_frame = hb.first_in_stream = i == i0;
+                    if (all_simple) { hb.out_base = sd.out_off + at; hb.rsize = w.regen[i]; }
+                    else hb.out_base = sd.out_off + off0;
+                    at += w.regen[i];
                     plan.blocks.push_back(hb);
                     const u64 end = hb.src + hb.csize; if (end > in_hi) in_hi = end;
                 }
@@ -856,12 +899,15 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
                 while (i1 < nblk && cbytes < PIECE) { cbytes += (u64)w.blocks[i1].csize + 3; regen += w.regen[i1]; i1++; }
                 if (nblk - i1 < 64) while (i1 < nblk) { regen += w.regen[i1]; i1++; }      // no tiny last piece
                 plan.blocks.clear(); plan.streams.clear();
+                u64 pre = 0;
                 for (u64 i = i0; i < i1; i++) {
                     nafz::ZBlockHead hb = w.blocks[i];
-                    hb.frame_first_blk = 0; hb.stream = 0; hb.out_base = soff[k] + out_off;
+                    hb.frame_first_blk = 0; hb.stream = 0; hb.out_base = soff[k] + out_off + pre; hb.rsize = w.regen[i];
                     hb.first_in_frame = hb.first_in_stream = i == i0;
+                    pre += w.regen[i];
                     plan.blocks.push_back(hb);
                 }
+                plan.simple = true;
                 nafz::ZStreamDesc sd = sdesc[k]; sd.out_off = soff[k] + out_off; sd.out_size = regen;
                 plan.streams.push_back(sd);
                 plan.results.assign(1, nafz::ZStreamResult{0, 0, 0});

@@ -187,8 +187,10 @@ inline int zstd_walk_stream(const u8 *h, const ZStreamDesc &sd, int stream_idx, 
 // against the index; any disagreement -> false, and the caller walks the stream the usual way.
 struct ZIndexEntry { u32 section, nblk, regen, reserved; u64 total; const u8 *csize; };    // csize: nblk little-endian u16
 
+// read_headers = false: the file is not touched at all -- the blocks get type 0xFF ("see the header"), and the device, which
+// reads every block anyway, checks the header against the index (zstd_decode_blocks, simple plans only).
 inline bool zstd_walk_indexed(const u8 *h, const ZStreamDesc &sd, const ZIndexEntry &e, std::vector<ZBlockHead> &blocks, std::vector<u32> &regen,
-                              u64 *consumed)
+                              u64 *consumed, bool read_headers = true)
 {
     blocks.clear(); regen.clear();
     if (!sd.no_magic || sd.src_len < 2 || e.nblk == 0 || e.regen == 0 || e.regen > 128 * 1024) return false;
@@ -202,6 +204,17 @@ inline bool zstd_walk_indexed(const u8 *h, const ZStreamDesc &sd, const ZIndexEn
     at[e.nblk] = pos;
     if (pos != n) return false;
     blocks.reserve(e.nblk); regen.reserve(e.nblk);
+    if (!read_headers) {
+        for (u32 i = 0; i < e.nblk; i++) {
+            const u32 want = i + 1 < e.nblk ? e.regen : (u32)(e.total - (u64)(e.nblk - 1) * e.regen);
+            ZBlockHead b;
+            b.src = sd.src_off + at[i] + 3; b.type = 0xFF; b.stream = 0; b.first_in_frame = b.first_in_stream = i == 0; b.frame_first_blk = 0;
+            b.out_base = sd.out_off; b.csize = (u32)(at[i + 1] - at[i] - 3); b.rsize = want;
+            blocks.push_back(b); regen.push_back(want);
+        }
+        *consumed = n;
+        return true;
+    }
     for (u32 i = 0; i < e.nblk; i++) {
         if (i + 24 < e.nblk) __builtin_prefetch(p + at[i + 24], 0, 0);
         const u64 q = at[i];
@@ -776,6 +789,11 @@ template <class Exec> void launch_literals(Exec &ex, const ZDecArgs &a)
 //   void for_each(n, F(index))                 grid of n threads
 //   void for_each_group(ngroups, threads, F(group, tid, nthreads))
 struct ZDecPlan {
+    // simple = every block is self-contained (raw, RLE, or compressed with its own Huffman table and no sequences) AND the
+    // caller knows where each one's output goes: blocks[i].out_base is block i's own arena offset and, for a compressed block,
+    // blocks[i].rsize the bytes it must regenerate.  Then nothing depends on another block and the two block scans (table
+    // provenance, output offsets, repeat-offset history) are skipped.
+    bool simple = false;
     std::vector<ZBlockHead> blocks;
     std::vector<ZStreamDesc> streams;
     std::vector<ZStreamResult> results;
@@ -827,14 +845,16 @@ int zstd_decode_blocks(Exec &ex, const u8 *d_in, u8 *d_out, ZDecPlan &plan, cons
     const u32 nblk = (u32)plan.blocks.size();
     if (nblk == 0) return 0;
     u32 n_comp = 0;
-    for (auto &b : plan.blocks) n_comp += b.type == 2;
+    for (auto &b : plan.blocks) n_comp += b.type == 2 || b.type == 0xFF;
 
     ZDecArgs a; memset(&a, 0, sizeof a);
     a.in = d_in; a.out = d_out; a.nblk = nblk; a.predef = d_predef;
     a.blk = ex.template alloc<ZBlock>(nblk);
     a.status = ex.template alloc<u32>(4);
+    const ZBlockHead *plan_heads = nullptr;
     {
         ZBlockHead *heads = ex.template alloc<ZBlockHead>(nblk);
+        plan_heads = heads;
         ex.upload_staged(heads, plan.blocks.data(), sizeof(ZBlockHead) * nblk);
         ZBlock *blk = a.blk;
         ex.for_each(nblk, [=] HDN (size_t i) {
@@ -847,6 +867,41 @@ int zstd_decode_blocks(Exec &ex, const u8 *d_in, u8 *d_out, ZDecPlan &plan, cons
         }, "zd_block_headers");
     }
     ex.zero(a.status, 16);
+    if (plan.simple) {
+        a.huf_pool = ex.template alloc<u16>((size_t)(n_comp ? nblk : 1) * HUF_SLOT_ENTRIES);
+        a.fse_pool = nullptr; a.lit_scratch = nullptr; a.seq = nullptr;
+        const ZBlockHead *heads = plan_heads;
+        ex.for_each(nblk, [=] HDN (size_t i) {
+            ZBlock &b = a.blk[i];
+            if (b.type == 0xFF) {                                 // from a block index: the header decides, and must agree with it
+                const u8 *hp = a.in + b.src - 3;
+                const u32 bh = hp[0] | (hp[1] << 8) | ((u32)hp[2] << 16), type = (bh >> 1) & 3, bsize = bh >> 3, want = heads[i].rsize;
+                bool ok = type != 3;
+                if (type == 1) { ok = ok && b.csize == 1 && bsize == want; b.rsize = bsize; }
+                else if (type == 0) { ok = ok && bsize == b.csize && bsize == want; b.rsize = bsize; }
+                else { ok = ok && bsize == b.csize; b.rsize = 0; }
+                if (!ok) { zerr(a, Z_ERR_SIZE, (u32)i); b.type = 0; b.rsize = 0; b.csize = 0; return; }
+                b.type = (u8)type;
+            }
+            k_block_headers(a, (u32)i);
+            b.out_off = heads[i].out_base; b.frame_out = b.out_off; b.seq_cum = 0;
+            if (b.type == 2) {
+                if (b.nseq != 0 || b.lit_type == 3 || b.lit_regen != heads[i].rsize) { zerr(a, Z_ERR_SIZE, (u32)i); b.type = 0; b.rsize = 0; b.csize = 0; return; }
+                b.huf_src = b.lit_type == 2 ? (i32)i : -1; b.huf_slot = (u32)i;
+            }
+        }, "zd_block_headers");
+        if (n_comp) ex.for_each(nblk, [=] HDN (size_t i) { k_huf_table(a, (u32)i); }, "zd_huf_table", 64);
+        if (n_comp) launch_literals(ex, a);
+        ex.for_each_group(nblk, 256, [=] HDN (size_t i, unsigned tid, unsigned nt) { k_copy_block(a, (u32)i, tid, nt); }, "zd_copy_block");
+        u32 st[4];
+        ex.download(st, a.status, 16);
+        if (st[0]) { err = "corrupt zstd data (code " + std::to_string(st[0]) + ", block " + std::to_string(st[1]) + ")"; return -1; }
+        // every compressed block regenerated exactly what the caller expected of it (checked above), raw / RLE sizes were read
+        // by the host: the streams' sizes are the sums of those
+        for (auto &r : plan.results) { r.out_size = 0; r.nseq = 0; }
+        for (auto &b : plan.blocks) plan.results[b.stream].out_size += b.rsize;
+        return 0;
+    }
     // Two block scans in three phases: per-chunk serial (~1.1 us per block, measured on B200), ONE thread over the chunk
     // aggregates (~0.66 us per chunk), per-chunk serial again.  2 * 1.1 * nblk / c + 0.66 * c is least at c = sqrt(3.3 nblk).
     {

@@ -172,3 +172,24 @@ def test_damaged_headers_that_used_to_read_out_of_bounds(gpu, oracle):
             gpu.decode(helpers.claim_records(naf, n))
         assert e.value.code == -3, n
         assert gpu.decode(naf) == long_reads
+
+
+def test_damaged_block_index_falls_back_to_the_header_walk(gpu, oracle):
+    """our files carry a block index (a zstd skippable frame behind the lengths frame, which the reference skips); a file
+    whose index is damaged but whose streams are fine must still decode -- by the walk -- and a file without one as well"""
+    from naf_b200 import container
+    text = synth.fastq(40_000, 150, seed=41)
+    naf = gpu.encode(text)
+    plain = gpu.encode(text, block_index=False)
+    assert len(naf) > len(plain) and gpu.decode(plain) == text
+    at = naf.find(b"NAFGIDX1")
+    assert at > 0 and plain.find(b"NAFGIDX1") < 0
+    h = container.read_header(naf)
+    orig, comp, off = h.sections[2]
+    assert off < at < off + comp                                    # inside the lengths section
+    for delta in (40, 41, 60, 200):                                 # bytes of the entry table / of the size arrays
+        bad = bytearray(naf)
+        bad[at + delta] ^= 0x15
+        assert gpu.decode(bytes(bad)) == text, delta
+        assert oracle.decode(bytes(bad)) == text
+    assert oracle.decode(naf) == text

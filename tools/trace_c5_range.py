@@ -15,8 +15,10 @@ dn = torch.zeros(size + 64, dtype=torch.uint8, device="cuda"); cudart.cudaMemcpy
 for part in (0, parts - 1):
     first = nrec * part // parts; cnt = nrec * (part + 1) // parts - first
     o = api.make_dec_opts(first_record=first, n_records=cnt)
-    for rep in range(3):
-        os.environ.pop("NAFGPU_TRACE_ON", None)
+    for rep in range(4):
+        ctx.profile(rep == 3)
         torch.cuda.synchronize(); t = time.perf_counter()
         ctx.decode_device(dn.data_ptr(), size, (hn.data_ptr(), size), o)
         torch.cuda.synchronize(); print(f"part {part}/{parts} rep {rep}: {(time.perf_counter() - t) * 1e3:.3f} ms", file=sys.stderr)
+    for name, cnt, ms in ctx.profile_report():
+        print(f"    {name:22s} x{cnt:3d} {ms:8.3f} ms", file=sys.stderr)
