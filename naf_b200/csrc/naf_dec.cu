@@ -671,7 +671,38 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
     const u32 all_mask = 0x3F, big_mask = (1u << SEC_DATA) | (1u << SEC_QUAL);
     u32 later_mask = 0;                                                   // streams decoded after the per-record scans
     if (ranged) later_mask = big_mask;
-    else if (last_big >= 0 && rec_text_view && (any_threaded || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
+    // A record range of a file with few records (a genome: one length per chromosome): when the lengths frame is a handful of
+    // raw / RLE blocks the host reads it where it lies, knows which bases the range covers before any device work, and the
+    // sequence / quality blocks of the range join the first batch -- one pass through the decoder's latency instead of two.
+    if (ranged && need[SEC_LEN] && (need[SEC_DATA] || need[SEC_QUAL]) && sbytes[SEC_LEN] <= (1u << 20) && sbytes[SEC_LEN] % 4 == 0) {
+        const nafz::ZWalked &w = ctx.zwalk[SEC_LEN];
+        bool plain = w.rc == 0 && !w.blocks.empty();
+        u64 regen = 0;
+        for (auto &b : w.blocks) { plain = plain && b.type < 2; regen += b.rsize; }
+        if (plain && regen == sbytes[SEC_LEN]) {
+            std::vector<u8> hl; hl.reserve(regen);
+            for (auto &b : w.blocks) { if (b.type == 0) hl.insert(hl.end(), h_naf + b.src, h_naf + b.src + b.rsize); else hl.insert(hl.end(), b.rsize, h_naf[b.src]); }
+            // lengths -> bases before record r (continuation units merged: output.c:390-393)
+            const u64 nunits = regen / 4, r0 = o.first_record, r1 = o.first_record + o.n_records < o.first_record ? ~0ull : o.first_record + o.n_records;
+            u64 rec = 0, bases = 0, b0 = 0, b1 = 0; bool have0 = false, have1 = false;
+            for (u64 k = 0; k < nunits; k++) {
+                if (rec == r0 && !have0) { b0 = bases; have0 = true; }
+                if (rec == r1 && !have1) { b1 = bases; have1 = true; }
+                const u32 v = (u32)hl[4 * k] | ((u32)hl[4 * k + 1] << 8) | ((u32)hl[4 * k + 2] << 16) | ((u32)hl[4 * k + 3] << 24);
+                bases += v;
+                if (v != 0xFFFFFFFFu) rec++;
+            }
+            if (!have0) b0 = bases;
+            if (!have1) b1 = bases;
+            if (bases <= h.sec[SEC_DATA].orig && b0 <= b1) {
+                if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b0 / 2 : b0; sdesc[SEC_DATA].need_hi = packed ? (b1 + 1) / 2 : b1; }
+                if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b0; sdesc[SEC_QUAL].need_hi = b1; }
+                later_mask = 0;
+            }
+        }
+    }
+    else if (last_big >= 0 && rec_text_view && (walks.pending[last_big] || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
+    (void)any_threaded;
     mark("walks started / index read");
     run_batch(all_mask & ~later_mask);
     mark("first batch decoded");
@@ -797,9 +828,11 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         if (need[SEC_DATA] || need[SEC_QUAL]) {
             u64 b01[2]; ex.download(&b01[0], d_seq_start + r0, 8); ex.download(&b01[1], d_seq_start + r1, 8);
             range_b0 = b01[0]; range_b1 = b01[1];
-            if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
-            if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
-            run_batch(big_mask);
+            if (later_mask) {
+                if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
+                if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
+                run_batch(big_mask);
+            }
         }
         u64 *local = ex.alloc<u64>(r1 - r0 + 2);
         const u64 *src = d_out_start + r0; const u64 base = o01[0];

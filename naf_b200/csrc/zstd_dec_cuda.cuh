@@ -11,11 +11,16 @@
 
 namespace nafz {
 
-static const int LIT_WARPS = 4, LIT_BLOCKS = LIT_WARPS * 8;     // 128 threads = 32 blocks x 4 streams per CTA
+// LIT_WARPS = 4: 128 threads = 32 blocks x 4 streams per CTA, the shape for files with tens of thousands of blocks (their tables
+// are 1 KB or less -- our encoder limits code lengths by alphabet size -- so all 32 fit the 32 KB of staging).
+// LIT_WARPS = 1: 8 blocks per CTA, for small batches (a range of a multi-GPU decode, the small streams of a file): those are
+// bound by the latency of ONE stream, so occupancy is irrelevant, and 8 tables fit even at the format's 11-bit maximum (4 KB
+// each) -- the mask stream's run lengths are near-uniform bytes and do get long codes.
 static const int LIT_TAB_ENTRIES = 16384;                        // u16 entries of decode tables staged per CTA (32 KB)
 
-__global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs a)
+template <int LIT_WARPS> __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs a)
 {
+    constexpr int LIT_BLOCKS = LIT_WARPS * 8;
     __shared__ __align__(16) u16 tabs[LIT_TAB_ENTRIES];
     __shared__ __align__(16) uint4 ring[HUF_RING * LIT_WARPS * 32];   // slot s of thread t: ring[s * 128 + t] (zstd_hd.cuh: BackBitsR)
     __shared__ u32 tab_off[LIT_BLOCKS], tab_words[LIT_BLOCKS];
@@ -27,7 +32,7 @@ __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs
     if (tid < 32) {
         const u32 i = first + lane;
         i32 src = -1; u32 need = 0;
-        if (i < a.nblk) {
+        if (i < a.nblk && lane < (u32)LIT_BLOCKS) {
             const ZBlock &b = a.blk[i];
             if (b.type == 2 && b.lit_type >= 2 && !b.skip && b.huf_src >= 0 && a.blk[b.huf_src].huf_bits) { src = b.huf_src; need = 1u << a.blk[b.huf_src].huf_bits; }
         }
@@ -43,9 +48,11 @@ __global__ void __launch_bounds__(LIT_WARPS * 32) k_literals_smem(const ZDecArgs
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, lead_lane, d); if (lane >= (u32)d && t > lead_lane) lead_lane = t; }
         const u32 lead_off = __shfl_sync(0xFFFFFFFFu, staged ? off : 0xFFFFFFFFu, lead_lane < 0 ? 0 : lead_lane);
-        tab_off[lane] = need && lead_lane >= 0 ? lead_off : 0xFFFFFFFFu;
-        tab_words[lane] = staged ? (need + 1) / 2 : 0;
-        tab_src[lane] = src >= 0 ? (const u32 *)(a.huf_pool + (size_t)a.blk[src].huf_slot * HUF_SLOT_ENTRIES) : nullptr;
+        if (lane < (u32)LIT_BLOCKS) {
+            tab_off[lane] = need && lead_lane >= 0 ? lead_off : 0xFFFFFFFFu;
+            tab_words[lane] = staged ? (need + 1) / 2 : 0;
+            tab_src[lane] = src >= 0 ? (const u32 *)(a.huf_pool + (size_t)a.blk[src].huf_slot * HUF_SLOT_ENTRIES) : nullptr;
+        }
     }
     __syncthreads();
     for (int j = 0; j < LIT_BLOCKS; j++) {
@@ -67,7 +74,8 @@ inline void launch_literals(nafg::CudaExec &ex, const ZDecArgs &a)
 {
     if (!a.nblk) return;
     ex.prof_begin("zd_literals");
-    k_literals_smem<<<(a.nblk + LIT_BLOCKS - 1) / LIT_BLOCKS, LIT_WARPS * 32, 0, ex.stream>>>(a);
+    if (a.nblk <= 8192) k_literals_smem<1><<<(a.nblk + 7) / 8, 32, 0, ex.stream>>>(a);
+    else k_literals_smem<4><<<(a.nblk + 31) / 32, 128, 0, ex.stream>>>(a);
     ex.prof_end();
 }
 

@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(256) k_zenc_encode(const ZEncArgs A, const ZEn
     u8 *slot = A.slots + B.slot_off;
     const u32 tid = threadIdx.x;
 
-    if (n == 0 || M.mode == 0) { if (tid == 0) { B.type = 0; B.csize = n; } return; }
+    // (blocks of at most 512 bytes stay raw: nothing to gain, and a decoder can read a tiny stream -- the lengths of a genome's
+    // two dozen records -- on the host without entropy decoding, naf_dec.cu)
+    if (n == 0 || M.mode == 0 || (n <= 512 && M.mode != 1)) { if (tid == 0) { B.type = 0; B.csize = n; } return; }
     if (M.mode == 1) { if (tid == 0) { slot[0] = M.rle_sym; B.type = 1; B.csize = 1; } return; }
     { const u32 e = M.ctab[tid]; ctab[tid] = (e & 0xFFF) | ((e >> 12) << 16); }
     if (tid == 0) s_mode = 2;

@@ -177,8 +177,9 @@ template <class H> HDN inline void zenc_huf_build(const H *hist, ZEncMeta &M)
         for (u32 i = 0; i < nsym; i++) { u32 d = idp[lp[i]] + 1u; if (d > 39) d = 39; num[d]++; }
         // Length limit: the format allows 11 bits; our decoder stages one 2^maxbits-entry table per block in shared memory, and 32
         // blocks share 32 KB (zstd_dec_cuda.cuh), so 9-bit codes are what keeps every lookup of a CTA on chip.  With at most 64
-        // distinct symbols (4-bit sequence, qualities, ids) the limit costs well under 0.1 % of the block.
-        const u32 MAXB = nsym <= 64 ? 9 : (nsym <= 128 ? 10 : 11);
+        // distinct symbols (4-bit sequence, qualities, ids) the limit costs well under 0.1 % of the block; beyond that 10 bits (half
+        // the tables staged).
+        const u32 MAXB = nsym <= 64 ? 9 : 10;
         for (u32 i = MAXB + 1; i < 40; i++) { num[MAXB] += num[i]; num[i] = 0; }
         u32 total = 0;
         for (u32 i = 1; i <= MAXB; i++) total += num[i] << (MAXB - i);
