@@ -190,13 +190,136 @@ __global__ void __launch_bounds__(256) k_seq_exec_big_cta(const ZDecArgs a)
     for (u32 k = tid; k + lit_used < b.lit_regen; k += 256) o[k] = lit[k];
 }
 
+// ---- K4 as ONE WARP per block (replaces zstd_decompress_block.c:937 ZSTD_decodeSequence's loop).
+// The FSE state chain is serial, so a block's sequences are decoded by one lane -- what the other 31 do is keep everything that
+// lane touches on chip: the three decode tables (expanded so that an entry also carries the extra-bit count and base value
+// of its symbol), the bitstream (a 1 KB shared-memory window that the warp refills 512 bytes at a time, coalesced, at points
+// all lanes reach together), and the decoded sequences (staged eight at a time and stored by the whole warp).  One sequence
+// is then a table lookup and a window read -- both from shared memory, both issued at once, since the window's position is
+// known before the symbols are -- and a few shifts: ~80 cycles instead of the ~1,000 of the thread-per-block version, whose
+// bit reader fetched from global memory (ncu, profiles/r2h: 10 ms for the ids / comments of 2 M reads written by ennaf).
+static const int SDW_WARPS = 4;
+struct SdwWindow { u32 v2, v1, v0; };      // 96 bits, the most significant bit of v2 is the stream's next bit
+
+__device__ __forceinline__ SdwWindow sdw_window(const u32 *ring, uintptr_t bits_addr, int P)
+{
+    const int bitpos = P - 96;
+    const int q = bitpos >> 3;                                   // floor, also when negative
+    const u32 s = (u32)(bitpos - 8 * q);
+    const uintptr_t A = bits_addr + (intptr_t)q;
+    const u32 sh = (u32)(A & 3) * 8 + s;
+    const u32 i0 = (u32)(A >> 2);
+    const u32 w0 = ring[i0 & 255], w1 = ring[(i0 + 1) & 255], w2 = ring[(i0 + 2) & 255], w3 = ring[(i0 + 3) & 255];
+    SdwWindow w;
+    w.v0 = __funnelshift_r(w0, w1, sh); w.v1 = __funnelshift_r(w1, w2, sh); w.v2 = __funnelshift_r(w2, w3, sh);
+    return w;
+}
+// the n bits (0 <= n <= 32) that start `skip` bits (0 <= skip <= 64) below the top of the window
+__device__ __forceinline__ u32 sdw_field(const SdwWindow &w, u32 skip, u32 n)
+{
+    if (n == 0) return 0;
+    u32 hi, lo;
+    if (skip < 32) { hi = w.v2; lo = w.v1; } else if (skip < 64) { hi = w.v1; lo = w.v0; skip -= 32; } else { hi = w.v0; lo = 0; skip -= 64; }
+    const u32 top = __funnelshift_l(lo, hi, skip);               // skip < 32
+    return top >> (32 - n);
+}
+
+__global__ void __launch_bounds__(SDW_WARPS * 32) k_seq_decode_warp(const ZDecArgs a)
+{
+    __shared__ uint2 tabs[SDW_WARPS][FSE_SLOT_ENTRIES];          // .x = FSE entry, .y = extra bits | value base << 8 | bad symbol << 31
+    __shared__ u32 rings[SDW_WARPS][256];                        // bitstream window: word (addr >> 2) & 255 holds global bytes addr .. addr + 3
+    __shared__ u32 stage[SDW_WARPS][48];                         // 8 sequences x 6 words
+    const u32 lane = threadIdx.x & 31, w = threadIdx.x >> 5, i = blockIdx.x * SDW_WARPS + w;
+    if (i >= a.nblk) return;
+    ZBlock &b = a.blk[i];
+    if (lane == 0) { b.repfn = repfn_identity(); b.match_total = 0; }
+    if (b.type != 2 || b.nseq == 0) return;
+    if (b.ll_src < 0 || b.of_src < 0 || b.ml_src < 0) { if (lane == 0) b.nseq = 0; return; }
+    int ll_log, of_log, ml_log;
+    const u32 *tl = fse_table_for(a, b.ll_src, 0, &ll_log), *to = fse_table_for(a, b.of_src, 1, &of_log), *tm = fse_table_for(a, b.ml_src, 2, &ml_log);
+    uint2 *T = tabs[w]; u32 *ring = rings[w];
+    for (u32 k = lane; k < (1u << ll_log); k += 32) { const u32 e = tl[k], c = fse_sym(e); T[k] = make_uint2(e, c > 35 ? 0x80000000u : (ll_bits_of(c) | (ll_base_of(c) << 8))); }
+    for (u32 k = lane; k < (1u << of_log); k += 32) { const u32 e = to[k], c = fse_sym(e); T[FSE_OF_AT + k] = make_uint2(e, c > 31 ? 0x80000000u : c); }
+    for (u32 k = lane; k < (1u << ml_log); k += 32) { const u32 e = tm[k], c = fse_sym(e); T[FSE_ML_AT + k] = make_uint2(e, c > 52 ? 0x80000000u : (ml_bits_of(c) | (ml_base_of(c) << 8))); }
+    const u8 *bits = a.in + b.src + b.bits_off; const u32 n = b.csize - b.bits_off;
+    const u8 last = n ? bits[n - 1] : 0;
+    if (n == 0 || last == 0) { if (lane == 0) { zerr(a, Z_ERR_SEQ_STREAM, i); b.nseq = 0; } return; }
+    const uintptr_t bits_addr = (uintptr_t)bits, end_addr = bits_addr + n, base_addr = (uintptr_t)a.in;
+    uintptr_t glo = ((end_addr - 1) & ~(uintptr_t)511) - 512;    // window = [glo, glo + 1024), the stream's last byte in its upper half
+    auto load_words = [&](uintptr_t from, u32 nwords) {          // aligned words; nothing is read below the input buffer or past the stream's last word
+        for (u32 k = lane; k < nwords; k += 32) {
+            const uintptr_t ad = from + 4 * (uintptr_t)k;
+            u32 v = 0;
+            if (ad >= base_addr && ad < ((end_addr + 3) & ~(uintptr_t)3)) v = *(const u32 *)ad;
+            ring[(ad >> 2) & 255] = v;
+        }
+    };
+    load_words(glo, 256);
+    __syncwarp();
+    int P = (int)(n * 8) - (8 - hibit(last));                   // payload bits not yet read
+    u32 sl = 0, so = 0, sm = 0, bad = 0;
+    u64 lit_total = 0, match_total = 0;
+    RepFn rf = repfn_identity();
+    if (lane == 0) {
+        const SdwWindow win = sdw_window(ring, bits_addr, P);
+        sl = sdw_field(win, 0, (u32)ll_log); so = sdw_field(win, (u32)ll_log, (u32)of_log); sm = sdw_field(win, (u32)(ll_log + of_log), (u32)ml_log);
+        P -= ll_log + of_log + ml_log;
+    }
+    ZSeq *seq = a.seq + b.seq_base;
+    const u32 nseq = b.nseq;
+    for (u32 k0 = 0; k0 < nseq; k0 += 8) {
+        const u32 m = nseq - k0 < 8 ? nseq - k0 : 8;
+        if (lane == 0) {
+            for (u32 j = 0; j < m; j++) {
+                const SdwWindow win = sdw_window(ring, bits_addr, P);
+                const uint2 el = T[sl], eo = T[FSE_OF_AT + so], em = T[FSE_ML_AT + sm];
+                bad |= (el.y | eo.y | em.y) & 0x80000000u;
+                const u32 oc = eo.y & 31, mlb = em.y & 0xFF, llb = el.y & 0xFF;
+                const u32 c1 = oc, c2 = c1 + mlb, c3 = c2 + llb;
+                const u32 ofv = (1u << oc) + sdw_field(win, 0, oc);
+                const u32 ml = ((em.y >> 8) & 0x7FFFFF) + sdw_field(win, c1, mlb);
+                const u32 ll = ((el.y >> 8) & 0x7FFFFF) + sdw_field(win, c2, llb);
+                u32 used = c3;
+                if (k0 + j + 1 < nseq) {
+                    const u32 nl = fse_nb(el.x), nm = fse_nb(em.x), no = fse_nb(eo.x);
+                    sl = fse_base(el.x) + sdw_field(win, c3, nl);
+                    sm = fse_base(em.x) + sdw_field(win, c3 + nl, nm);
+                    so = fse_base(eo.x) + sdw_field(win, c3 + nl + nm, no);
+                    used += nl + nm + no;
+                    sl &= 511; sm &= 511; so &= 255;                 // (a damaged table cannot send a state outside its table)
+                }
+                P -= (int)used;
+                u32 *st = stage[w] + 6 * j;
+                st[0] = ll; st[1] = ml; st[2] = ofv; st[3] = (u32)lit_total; st[4] = (u32)(lit_total + match_total); st[5] = i;
+                repfn_step(rf, ofv, ll);
+                lit_total += ll; match_total += ml;
+            }
+        }
+        __syncwarp();
+        P = __shfl_sync(0xFFFFFFFFu, P, 0);
+        {   // eight sequences = 48 words, stored by the warp
+            u32 *dst = (u32 *)(seq + k0);
+            if (lane < 6 * m) dst[lane] = stage[w][lane];
+            if (lane + 32 < 6 * m) dst[lane + 32] = stage[w][lane + 32];
+        }
+        if (P < 0) break;                                        // ran past the start of the stream: reported below
+        // refill: once the cursor is in the lower half, the upper half takes the 512 bytes below the window
+        const uintptr_t cur = bits_addr + (uintptr_t)((P > 0 ? P - 1 : 0) >> 3);
+        if (cur < glo + 512 && glo + 16 > bits_addr) { load_words(glo - 512, 128); glo -= 512; }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (bad || P != 0) { zerr(a, Z_ERR_SEQ_STREAM, i); b.nseq = 0; return; }
+        if (lit_total > b.lit_regen || lit_total + match_total > 128 * 1024 + 0u) { zerr(a, Z_ERR_SIZE, i); b.nseq = 0; return; }
+        b.match_total = (u32)match_total; b.repfn = rf;
+    }
+}
+
 inline void launch_seq_decode(nafg::CudaExec &ex, const ZDecArgs &a)
 {
     if (!a.nblk) return;
-    const int smem = SD_BLOCKS * FSE_SLOT_ENTRIES * 4;
-    cudaFuncSetAttribute(k_seq_decode_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device: set on every launch (cheap)
     ex.prof_begin("zd_seq_decode");
-    k_seq_decode_smem<<<(a.nblk + SD_BLOCKS - 1) / SD_BLOCKS, 32, smem, ex.stream>>>(a);
+    k_seq_decode_warp<<<(a.nblk + SDW_WARPS - 1) / SDW_WARPS, SDW_WARPS * 32, 0, ex.stream>>>(a);
     ex.prof_end();
 }
 inline void launch_seq_resolve(nafg::CudaExec &ex, const ZDecArgs &a)
