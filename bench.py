@@ -136,6 +136,34 @@ def time_reference(text: bytes, n_bases: int, procs: int, tmp="/dev/shm", keep_n
     return t1 - t0, t2 - t1, naf_bytes
 
 
+def time_cli(text: bytes, tmp="/dev/shm"):
+    """wall clock of OUR command-line tools on one file (process start, CUDA context, file read and write included)"""
+    work = os.path.join(tmp, f"nafcli_{os.getpid()}")
+    os.makedirs(work, exist_ok=True)
+    fin, fnaf, fout = (os.path.join(work, x) for x in ("in.fq", "x.naf", "out.fq"))
+    with open(fin, "wb") as f:
+        f.write(text)
+    env = dict(os.environ, TMPDIR=work)
+    ours = lambda t: os.path.join(ROOT, "bin", t)
+    best = [1e9, 1e9]
+    for rep in range(2):
+        t0 = time.perf_counter()
+        subprocess.run([ours("ennaf"), fin, "-o", fnaf], check=True, env=env)
+        t1 = time.perf_counter()
+        subprocess.run([ours("unnaf"), fnaf, "-o", fout], check=True, env=env)
+        t2 = time.perf_counter()
+        best = [min(best[0], t1 - t0), min(best[1], t2 - t1)]
+    ok = open(fout, "rb").read() == text
+    # and the reference's unnaf on the file our ennaf wrote
+    subprocess.run([ref_bin("unnaf"), fnaf, "-o", fout], check=True, env=env)
+    ok = ok and open(fout, "rb").read() == text
+    naf_bytes = os.path.getsize(fnaf)
+    for f in os.listdir(work):
+        os.remove(os.path.join(work, f))
+    os.rmdir(work)
+    return best[0], best[1], naf_bytes, ok
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -582,6 +610,22 @@ def run_ours(args):
                 del got, dn, hn
             except Exception as e:
                 line["ref_made"] = {"error": repr(e)[:300]}
+            # wall clock of the drop-in tools on the same file (SURVEY 8d / BASELINE.md 3.5): bin/ennaf, bin/unnaf vs the reference's
+            try:
+                if os.access(os.path.join(ROOT, "bin", "ennaf"), os.X_OK):
+                    # the whole workload of this rank as one file: the tools' fixed costs (process start, CUDA context ~0.5 s)
+                    # weigh less than on the 2 M-read sample; the reference needs ~11 s for it, once
+                    full = h_text[:n_text].numpy().tobytes()
+                    ce, cd, cn, cok = time_cli(full)
+                    rte, rtd, _ = time_reference(full, bases, 1)
+                    ce0, cd0, _, _ = time_cli(synth.fastq(1000, READ_LEN, seed=7))
+                    line["cli_wall_clock"] = {"workload": f"{records} reads ({n_text} bytes of text) as one file on /dev/shm; process start, CUDA context and file I/O included",
+                                              "ours_ennaf_s": ce, "ours_unnaf_s": cd, "reference_ennaf_s": rte, "reference_unnaf_s": rtd,
+                                              "speedup_ennaf": rte / ce, "speedup_unnaf": rtd / cd, "naf_bytes": cn, "verified_incl_reference_unnaf": cok,
+                                              "ours_fixed_cost_s": {"ennaf_1000_reads": ce0, "unnaf_1000_reads": cd0}}
+                    del full
+            except Exception as e:
+                line["cli_wall_clock"] = {"error": repr(e)[:300]}
             line["cpu_baseline"] = {"value": srec * READ_LEN / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
                                     "encode_gbases_s": srec * READ_LEN / te / 1e9, "decode_gbases_s": srec * READ_LEN / td / 1e9,
                                     "sample": f"first {srec} reads of the same workload, oracle/_ref ennaf -1 + unnaf (single-threaded tools), /dev/shm"}

@@ -144,7 +144,12 @@ int main(int argc, char **argv)
         while (ext > in_path && ext[-1] != '/' && ext[-1] != '\\' && ext[-1] != '.') ext--;
         if (ext > in_path && ext[-1] == '.') fmt_ext = parse_fmt(ext);
     }
-    Input in; load_input(in_path, in);
+    // The input is read in pieces straight into page-locked buffers the library rotates: piece k is on its way to the device
+    // while piece k + 1 is being read (a file or a pipe alike; the reference reads through a 16 KB buffer, process.c:227).
+    Input in;
+    int in_fd = in_path ? open(in_path, O_RDONLY) : 0;
+    if (in_fd < 0) die("can't open input file\n");
+    if (fstat(in_fd, &in.st) == 0) in.have_stat = in_path != nullptr;
 
     static std::string auto_path;
     if (!force_stdout && !g_out_path && isatty(fileno(stdout))) {
@@ -158,7 +163,22 @@ int main(int argc, char **argv)
     o.have_line_length = have_line_length; o.line_length = line_length; o.level = level; o.window_log = window_log; o.title = title;
     nafgpu_ctx *ctx = make_ctx();
     const uint8_t *naf = nullptr; size_t naf_size = 0; nafgpu_enc_info info;
-    int rc = nafgpu_encode(ctx, in.data, in.size, &o, &naf, &naf_size, &info);
+    const size_t hint = in.have_stat && S_ISREG(in.st.st_mode) ? (size_t)in.st.st_size : 0;
+    if (nafgpu_encode_begin(ctx, &o, hint) != 0) die("%s", nafgpu_last_error(ctx));
+    for (;;) {
+        void *buf = nullptr; size_t cap = 0, got = 0;
+        if (nafgpu_encode_buffer(ctx, &buf, &cap) != 0) die("%s", nafgpu_last_error(ctx));
+        while (got < cap) {
+            ssize_t k = read(in_fd, (char *)buf + got, cap - got);
+            if (k < 0) { if (errno == EINTR) continue; die("can't read input\n"); }
+            if (k == 0) break;
+            got += (size_t)k;
+        }
+        if (got && nafgpu_encode_feed(ctx, got) != 0) die("%s", nafgpu_last_error(ctx));
+        if (got < cap) break;
+    }
+    if (in_path) close(in_fd);
+    int rc = nafgpu_encode_end(ctx, &naf, &naf_size, &info);
     if (rc != 0) die("%s", nafgpu_last_error(ctx));
     if (fmt_ext != NAFGPU_FMT_AUTO && info.format && fmt_ext != info.format) warn("input file extension does not match its actual format\n");
     if (fmt_ext != NAFGPU_FMT_AUTO && fmt_cli != NAFGPU_FMT_AUTO && fmt_ext != fmt_cli) warn("input file extension does not match format specified in the command line\n");

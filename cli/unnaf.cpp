@@ -1,6 +1,7 @@
 // unnaf — drop-in command line of the reference's decompressor (unnaf/src/unnaf.c:282-447), host side only:
 // argument parsing, output naming, stat transfer, and the text formatting of the views whose payload is a
-// header field or a tiny stream (output.c:7-260).  Sequence-sized views are one call to nafgpu_decode().
+// header field or a tiny stream (output.c:7-260).  Sequence-sized views are one call to nafgpu_decode_to(), which delivers
+// the text in pieces as it comes down from the device.
 #include "cli_common.hpp"
 
 enum View { UNDECIDED, FORMAT_NAME, PART_LIST, PART_SIZES, NUMBER, TITLE, IDS, NAMES, LENGTHS, TOTAL_LENGTH, MASK, TOTAL_MASK_LENGTH,
@@ -172,6 +173,16 @@ int main(int argc, char **argv)
         if (!ctx) ctx = make_ctx();
         if (nafgpu_decode(ctx, in.data, in.size, &o, p, n) != 0) die("%s", nafgpu_last_error(ctx));
     };
+    // the text-sized views are written as they come down: nafgpu_decode_to hands over pieces of a few tens of MB in order, each
+    // written to the file while the next is on its way from the device (the reference writes through 128 KB buffers, output.c:640)
+    auto gpu_stream = [&](int type, bool mask_on) {
+        nafgpu_dec_opts o; memset(&o, 0, sizeof o);
+        o.out_type = type; o.no_mask = !mask_on; o.have_line_length = have_line_length; o.line_length = line_length;
+        nafgpu_ctx *ctx = make_ctx();
+        size_t total = 0;
+        auto sink = [](void *user, const uint8_t *piece, size_t k) -> int { write_all((FILE *)user, piece, k); return 0; };
+        if (nafgpu_decode_to(ctx, in.data, in.size, &o, sink, out, &total) != 0) die("%s", nafgpu_last_error(ctx));
+    };
     const uint8_t *p = nullptr; size_t n = 0;
 
     if (view == FORMAT_NAME) fprintf(out, "%s sequences%s in NAF format version %d\n", type_name[h.seq_type], h.quality ? " with qualities" : "", h.version);
@@ -193,8 +204,8 @@ int main(int argc, char **argv)
         else if (view == TITLE) { if (h.title) fwrite(in.data + h.title_off, 1, h.title_len, out); fputc('\n', out); }
         else if (h.N != 0) {
             switch (view) {
-            case IDS: gpu_view(NAFGPU_OUT_IDS, true, &p, &n); write_all(out, p, n); break;
-            case NAMES: gpu_view(NAFGPU_OUT_NAMES, true, &p, &n); write_all(out, p, n); break;
+            case IDS: gpu_stream(NAFGPU_OUT_IDS, true); break;
+            case NAMES: gpu_stream(NAFGPU_OUT_NAMES, true); break;
             case LENGTHS: {                                                                  // output.c:180
                 if (!h.lengths) break;
                 gpu_view(NAFGPU_OUT_LENGTHS, true, &p, &n);
@@ -223,10 +234,10 @@ int main(int argc, char **argv)
                 if (view == TOTAL_MASK_LENGTH) fprintf(out, "%llu\n", total);
                 break;
             }
-            case FOUR_BIT: gpu_view(NAFGPU_OUT_4BIT, true, &p, &n); write_all(out, p, n); break;
-            case DNA: case SEQ: case MASKED_DNA: gpu_view(NAFGPU_OUT_SEQ, use_mask, &p, &n); write_all(out, p, n); break;
-            case UNMASKED_DNA: gpu_view(NAFGPU_OUT_SEQ, false, &p, &n); write_all(out, p, n); break;
-            case SEQUENCES: gpu_view(NAFGPU_OUT_SEQUENCES, use_mask, &p, &n); write_all(out, p, n); break;
+            case FOUR_BIT: gpu_stream(NAFGPU_OUT_4BIT, true); break;
+            case DNA: case SEQ: case MASKED_DNA: gpu_stream(NAFGPU_OUT_SEQ, use_mask); break;
+            case UNMASKED_DNA: gpu_stream(NAFGPU_OUT_SEQ, false); break;
+            case SEQUENCES: gpu_stream(NAFGPU_OUT_SEQUENCES, use_mask); break;
             case CHARCOUNT: {                                                                // output.c:596-598
                 if (!h.data) break;
                 gpu_view(NAFGPU_OUT_CHARCOUNT, use_mask, &p, &n);
@@ -237,11 +248,11 @@ int main(int argc, char **argv)
                 for (unsigned i = 127; i < 256; i++) if (c[i]) fprintf(out, "\\x%02X\t%llu\n", i, c[i]);
                 break;
             }
-            case FASTA: case MASKED_FASTA: gpu_view(NAFGPU_OUT_FASTA, use_mask, &p, &n); write_all(out, p, n); break;
-            case UNMASKED_FASTA: gpu_view(NAFGPU_OUT_FASTA, false, &p, &n); write_all(out, p, n); break;
+            case FASTA: case MASKED_FASTA: gpu_stream(NAFGPU_OUT_FASTA, use_mask); break;
+            case UNMASKED_FASTA: gpu_stream(NAFGPU_OUT_FASTA, false); break;
             case FASTQ:
                 if (!h.quality) die("FASTQ output requested, but input has no qualities\n");
-                gpu_view(NAFGPU_OUT_FASTQ, false, &p, &n); write_all(out, p, n); break;
+                gpu_stream(NAFGPU_OUT_FASTQ, false); break;
             default: die("unknown output requested\n");
             }
         }

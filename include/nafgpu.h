@@ -150,6 +150,28 @@ int nafgpu_encode(nafgpu_ctx *ctx, const uint8_t *text, size_t n, const nafgpu_e
 int nafgpu_decode(nafgpu_ctx *ctx, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts,
                   const uint8_t **text, size_t *text_size);
 
+/* ---- the hot path, streamed (what the command-line tools call: pipes, files read and written in pieces) ----
+ * The reference reads its input through a 16 KB buffer (ennaf/src/process.c:227-240) and writes its output through 128 KB
+ * ones (unnaf/src/output.c:640-650); it never holds a file in memory.  These calls keep that shape at the boundary -- the
+ * caller hands over / receives the text in pieces of a few tens of MB, in page-locked buffers the library rotates, so that
+ * reading the next piece (or writing the previous one) overlaps the PCIe copy of the current one -- while the device works on
+ * the whole text at once.
+ *
+ *   nafgpu_encode_begin    start a text; size_hint = its size if known (a regular file), else 0
+ *   nafgpu_encode_buffer   a page-locked buffer to put the next piece of text into (*cap bytes at most)
+ *   nafgpu_encode_feed     the buffer now holds n bytes: they go up while the caller fills the other buffer
+ *   nafgpu_encode_end      no more text: transform + compress, result as from nafgpu_encode
+ *
+ *   nafgpu_decode_to       nafgpu_decode whose text is delivered in order, piece by piece, to `write` (which returns 0 to go
+ *                          on; anything else stops the call with NAFGPU_E_ARG); *text_size = total bytes delivered */
+int nafgpu_encode_begin(nafgpu_ctx *ctx, const nafgpu_enc_opts *opts, size_t size_hint);
+int nafgpu_encode_buffer(nafgpu_ctx *ctx, void **buf, size_t *cap);
+int nafgpu_encode_feed(nafgpu_ctx *ctx, size_t n);
+int nafgpu_encode_end(nafgpu_ctx *ctx, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info);
+typedef int (*nafgpu_write_fn)(void *user, const uint8_t *piece, size_t n);
+int nafgpu_decode_to(nafgpu_ctx *ctx, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts,
+                     nafgpu_write_fn write, void *user, size_t *text_size);
+
 /* ---- the hot path, device-resident (bench `value`, pipelines that keep data in HBM) ----
  * d_text / d_naf are device pointers on ctx's device; outputs are device pointers into ctx's arena.
  * `host_copy` (may be NULL) is a host mirror of the compressed input used only to walk zstd block

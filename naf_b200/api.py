@@ -58,12 +58,15 @@ class ShardLink(C.Structure):
                 ("next_first_code", C.c_uint8), ("is_last", C.c_uint8), ("store_qual", C.c_uint8), ("pad", C.c_uint8 * 4)]
 
 
+WRITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t)
+
 # every symbol include/nafgpu.h declares (tests check the .so exports exactly these)
 EXPORTS = [
     "nafgpu_create", "nafgpu_destroy", "nafgpu_last_error", "nafgpu_version", "nafgpu_get_timing", "nafgpu_stream",
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
     "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_zstd_compress_level", "nafgpu_split", "nafgpu_profile",
     "nafgpu_profile_report", "nafgpu_shard_begin", "nafgpu_shard_finish", "nafgpu_shard_fetch",
+    "nafgpu_encode_begin", "nafgpu_encode_buffer", "nafgpu_encode_feed", "nafgpu_encode_end", "nafgpu_decode_to",
 ]
 
 _lib = None
@@ -110,6 +113,11 @@ def load_library():
     lib.nafgpu_shard_begin.argtypes = [vp, vp, sz, C.c_int, C.POINTER(EncOpts), C.POINTER(ShardCounts), C.POINTER(EncInfo)]
     lib.nafgpu_shard_finish.argtypes = [vp, C.POINTER(ShardLink), C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64 * 6)]
     lib.nafgpu_shard_fetch.argtypes = [vp, C.c_int, vp]
+    lib.nafgpu_encode_begin.argtypes = [vp, C.POINTER(EncOpts), sz]
+    lib.nafgpu_encode_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    lib.nafgpu_encode_feed.argtypes = [vp, sz]
+    lib.nafgpu_encode_end.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(EncInfo)]
+    lib.nafgpu_decode_to.argtypes = [vp, vp, sz, C.POINTER(DecOpts), WRITE_FN, vp, C.POINTER(sz)]
     _lib = lib
     return lib
 
@@ -256,6 +264,41 @@ class NafGpu:
         if view == "charcount":
             return container.format_charcount(raw) if raw else b""
         return raw
+
+    # ---- hot path, streamed (what the command-line tools use)
+    def encode_pieces(self, pieces, size_hint: int = 0, **kw) -> bytes:
+        """text as an iterable of byte pieces (any sizes) -> .naf; each piece is on its way to the device while the next is read"""
+        opts = make_enc_opts(**kw)
+        self._check(self.lib.nafgpu_encode_begin(self.h, C.byref(opts), size_hint))
+        buf, cap, fill = C.c_void_p(), C.c_size_t(), 0
+        self._check(self.lib.nafgpu_encode_buffer(self.h, C.byref(buf), C.byref(cap)))
+        for piece in pieces:
+            mv, at = memoryview(piece), 0
+            while at < len(mv):
+                k = min(cap.value - fill, len(mv) - at)
+                C.memmove(buf.value + fill, (C.c_char * k).from_buffer_copy(mv[at:at + k]), k)
+                fill += k; at += k
+                if fill == cap.value:
+                    self._check(self.lib.nafgpu_encode_feed(self.h, fill))
+                    self._check(self.lib.nafgpu_encode_buffer(self.h, C.byref(buf), C.byref(cap)))
+                    fill = 0
+        if fill:
+            self._check(self.lib.nafgpu_encode_feed(self.h, fill))
+        out, size, info = C.c_void_p(), C.c_size_t(), EncInfo()
+        self._check(self.lib.nafgpu_encode_end(self.h, C.byref(out), C.byref(size), C.byref(info)))
+        return _bytes_at(out.value or 0, size.value)
+
+    def decode_to(self, naf, write, view="default", no_mask=False, line_length=None) -> int:
+        """unnaf with the text handed to write(bytes) piece by piece, in order; returns the number of bytes delivered"""
+        p, n, keep = _as_ptr(naf)
+        opts = make_dec_opts(view, no_mask, line_length)
+
+        def cb(user, ptr, k):
+            write(C.string_at(ptr, k))
+            return 0
+        fn, total = WRITE_FN(cb), C.c_size_t()
+        self._check(self.lib.nafgpu_decode_to(self.h, p, n, C.byref(opts), fn, None, C.byref(total)))
+        return total.value
 
     # ---- hot path, device-resident
     def encode_device(self, d_ptr: int, n: int, opts: EncOpts):

@@ -89,6 +89,8 @@ void nafgpu_destroy(nafgpu_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->pipe.drain(); c->pipe.destroy(); c->mail.destroy();
+    for (int b = 0; b < 2; b++) { if (c->ingest.rot[b]) cudaFreeHost(c->ingest.rot[b]); if (c->ingest.ev[b]) cudaEventDestroy(c->ingest.ev[b]); }
+    if (c->ingest.d_text) cudaFree(c->ingest.d_text);
     c->arena.release(); c->pinned_out.release(); c->pinned_aux.release(); c->pinned_stage.release();
     if (c->d_predef) cudaFree(c->d_predef);
     if (c->d_nuc_lut) cudaFree(c->d_nuc_lut);
@@ -195,6 +197,118 @@ int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_
             if (r.size > done) CUDA_TRY(cudaMemcpyAsync(hout + done, r.d_text + done, r.size - done, cudaMemcpyDeviceToHost, c->stream));
             *text = hout; *text_size = r.size;
         } else { *text = to_pinned(*c, r.d_text, r.size); *text_size = r.size; }
+        finish_timing(*c, ex);
+    });
+}
+
+int nafgpu_decode_to(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts, nafgpu_write_fn write, void *user, size_t *text_size)
+{
+    if (!naf || !opts || !write) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        if (text_size) *text_size = 0;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        nafc::Header h; std::string err;
+        if (!nafc::read_header(naf, n, h, false, err)) fail(NAFGPU_E_FORMAT, err);
+        // the file goes up in chunks (pageable memory is fine: it is the small side), the text comes down through two rotating
+        // page-locked buffers and is handed to `write` piece by piece while the next piece is on its way
+        u8 *d_naf = ex.alloc<u8>(n + 64);
+        CUDA_TRY(cudaMemsetAsync(d_naf + n, 0, 64, c->stream));
+        ex.pipe = &c->pipe;
+        c->pipe.rot_create();
+        c->pipe.sink = write; c->pipe.sink_user = user;
+        c->pipe.upload(d_naf, naf, n, pipe_chunk(), c->stream);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        DecodeOut r = decode_on_device(*c, ex, d_naf, naf, n, *opts);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        if (r.d_text && r.size) {
+            const u64 done = c->pipe.emitting ? (c->pipe.out_done < r.size ? c->pipe.out_done : r.size) : 0;
+            if (!c->pipe.emitting) c->pipe.begin_output(nullptr);
+            if (r.size > done) c->pipe.emit(c->stream, r.d_text + done, done, r.size - done);
+        }
+        c->pipe.rot_flush_all();
+        if (text_size) *text_size = r.size;
+        const bool failed = c->pipe.sink_failed;
+        finish_timing(*c, ex);
+        if (failed) fail(NAFGPU_E_ARG, "the output callback reported an error\n");
+    });
+}
+
+/* ---- text arriving in pieces ---- */
+static const size_t INGEST_ROT = 32u << 20;
+
+int nafgpu_encode_begin(nafgpu_ctx *c, const nafgpu_enc_opts *opts, size_t size_hint)
+{
+    if (!c || !opts) return NAFGPU_E_ARG;
+    try {
+        c->err.clear();
+        CUDA_TRY(cudaSetDevice(c->device));
+        Ctx::Ingest &g = c->ingest;
+        CUDA_TRY(cudaStreamSynchronize(c->pipe.in));
+        g.active = true; g.opts = *opts; g.n = 0; g.cur = 0; g.busy[0] = g.busy[1] = false;
+        g.has_title = opts->title != nullptr; g.title = opts->title ? opts->title : ""; g.opts.title = nullptr;
+        for (int b = 0; b < 2; b++) if (!g.rot[b]) {
+            CUDA_TRY(cudaHostAlloc(&g.rot[b], INGEST_ROT, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&g.ev[b], cudaEventDisableTiming));
+        }
+        const size_t want = (size_hint ? size_hint : (size_t)(256u << 20)) + 64;
+        if (g.cap < want) { if (g.d_text) cudaFree(g.d_text); g.d_text = nullptr; g.cap = 0; CUDA_TRY(cudaMalloc(&g.d_text, want)); g.cap = want; }
+        return NAFGPU_OK;
+    } catch (const CudaError &e) {
+        c->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + "\n"; cudaGetLastError(); c->ingest.active = false; return NAFGPU_E_CUDA;
+    }
+}
+
+int nafgpu_encode_buffer(nafgpu_ctx *c, void **buf, size_t *cap)
+{
+    if (!c || !buf || !cap || !c->ingest.active) return NAFGPU_E_ARG;
+    Ctx::Ingest &g = c->ingest;
+    if (g.busy[g.cur]) { if (cudaEventSynchronize(g.ev[g.cur]) != cudaSuccess) { c->err = "CUDA error while uploading the text\n"; return NAFGPU_E_CUDA; } g.busy[g.cur] = false; }
+    *buf = g.rot[g.cur]; *cap = INGEST_ROT;
+    return NAFGPU_OK;
+}
+
+int nafgpu_encode_feed(nafgpu_ctx *c, size_t n)
+{
+    if (!c || !c->ingest.active || n > INGEST_ROT) return NAFGPU_E_ARG;
+    if (!n) return NAFGPU_OK;
+    Ctx::Ingest &g = c->ingest;
+    try {
+        CUDA_TRY(cudaSetDevice(c->device));
+        if (g.n + n + 64 > g.cap) {                               // size unknown in advance (a pipe): grow geometrically, copy on the device
+            const size_t ncap = (g.cap > (g.n + n + 64) / 2 ? g.cap * 2 : g.n + n + 64) + (64u << 20);
+            u8 *nd = nullptr;
+            CUDA_TRY(cudaMalloc(&nd, ncap));
+            CUDA_TRY(cudaMemcpyAsync(nd, g.d_text, g.n, cudaMemcpyDeviceToDevice, c->pipe.in));
+            CUDA_TRY(cudaStreamSynchronize(c->pipe.in));
+            cudaFree(g.d_text); g.d_text = nd; g.cap = ncap;
+        }
+        CUDA_TRY(cudaMemcpyAsync(g.d_text + g.n, g.rot[g.cur], n, cudaMemcpyHostToDevice, c->pipe.in));
+        CUDA_TRY(cudaEventRecord(g.ev[g.cur], c->pipe.in));
+        g.busy[g.cur] = true; g.cur ^= 1; g.n += n;
+        return NAFGPU_OK;
+    } catch (const CudaError &e) {
+        c->err = std::string("CUDA error: ") + cudaGetErrorString(e.e) + "\n"; cudaGetLastError(); return NAFGPU_E_CUDA;
+    }
+}
+
+int nafgpu_encode_end(nafgpu_ctx *c, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info)
+{
+    if (!c || !naf || !naf_size || !c->ingest.active) return NAFGPU_E_ARG;
+    c->ingest.active = false;
+    return guarded(c, [&] {
+        *naf = nullptr; *naf_size = 0;
+        Ctx::Ingest &g = c->ingest;
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->pipe.in));              // every piece has arrived
+        g.busy[0] = g.busy[1] = false;
+        CUDA_TRY(cudaMemsetAsync(g.d_text + g.n, 0, 64, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        nafgpu_enc_opts o = g.opts; o.title = g.has_title ? g.title.c_str() : nullptr;
+        EncodeOut r = encode_on_device(*c, ex, g.d_text, g.n, o, info);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        *naf = to_pinned(*c, r.d_naf, r.size); *naf_size = r.size;
         finish_timing(*c, ex);
     });
 }

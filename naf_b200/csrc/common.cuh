@@ -106,21 +106,46 @@ struct HostPipe {
     u64 n_in = 0, chunk = 0; std::vector<cudaEvent_t> in_ev; bool uploading = false; const u8 *h_in = nullptr;
     // output
     u8 *h_out = nullptr; u64 out_done = 0; bool emitting = false;
+    // output delivered to a callback instead of one big host buffer: two page-locked buffers take turns, the callback gets
+    // piece k while piece k + 1 comes down
+    int (*sink)(void *, const u8 *, size_t) = nullptr; void *sink_user = nullptr; bool sink_failed = false;
+    static const u64 ROT = 32ull << 20;
+    u8 *rot[2] = {nullptr, nullptr}; cudaEvent_t rot_ev[2] = {nullptr, nullptr}; u64 rot_len[2] = {0, 0}; bool rot_busy[2] = {false, false}; int rot_next = 0;
 
     void create()
     {
         CUDA_TRY(cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking));
     }
+    void rot_create()
+    {
+        for (int b = 0; b < 2; b++) if (!rot[b]) {
+            CUDA_TRY(cudaHostAlloc(&rot[b], ROT, cudaHostAllocDefault));
+            CUDA_TRY(cudaEventCreateWithFlags(&rot_ev[b], cudaEventDisableTiming));
+        }
+    }
+    void rot_flush(int b)
+    {
+        if (!rot_busy[b]) return;
+        CUDA_TRY(cudaEventSynchronize(rot_ev[b]));
+        rot_busy[b] = false;
+        if (sink && !sink_failed && sink(sink_user, rot[b], rot_len[b]) != 0) sink_failed = true;
+    }
+    void rot_flush_all() { rot_flush(rot_next); rot_flush(rot_next ^ 1); }
     void destroy()
     {
+        for (int b = 0; b < 2; b++) { if (rot[b]) cudaFreeHost(rot[b]); if (rot_ev[b]) cudaEventDestroy(rot_ev[b]); rot[b] = nullptr; rot_ev[b] = nullptr; }
         for (auto e : pool) cudaEventDestroy(e);
         pool.clear();
         if (in) cudaStreamDestroy(in);
         if (out) cudaStreamDestroy(out);
         in = out = nullptr;
     }
-    void reset() { used = 0; in_ev.clear(); n_in = 0; uploading = false; h_in = nullptr; h_out = nullptr; out_done = 0; emitting = false; }
+    void reset()
+    {
+        used = 0; in_ev.clear(); n_in = 0; uploading = false; h_in = nullptr; h_out = nullptr; out_done = 0; emitting = false;
+        sink = nullptr; sink_user = nullptr; sink_failed = false; rot_busy[0] = rot_busy[1] = false; rot_next = 0;
+    }
     cudaEvent_t event()
     {
         if (used == pool.size()) { cudaEvent_t e; CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); pool.push_back(e); }
@@ -160,6 +185,18 @@ struct HostPipe {
         cudaEvent_t e = event();
         CUDA_TRY(cudaEventRecord(e, compute));
         CUDA_TRY(cudaStreamWaitEvent(out, e, 0));
+        if (sink) {                                              // in order, through the two rotating buffers
+            for (u64 at = 0; at < len; at += ROT) {
+                const u64 m = len - at < ROT ? len - at : ROT;
+                const int b = rot_next;
+                rot_flush(b);                                    // the piece this buffer still holds goes to the callback first
+                CUDA_TRY(cudaMemcpyAsync(rot[b], d + at, m, cudaMemcpyDeviceToHost, out));
+                CUDA_TRY(cudaEventRecord(rot_ev[b], out));
+                rot_busy[b] = true; rot_len[b] = m; rot_next ^= 1;
+            }
+            if (off == out_done) out_done = off + len;
+            return;
+        }
         CUDA_TRY(cudaMemcpyAsync(h_out + off, d, len, cudaMemcpyDeviceToHost, out));
         if (off == out_done) out_done = off + len;
     }
@@ -366,6 +403,12 @@ struct Ctx {
     PinnedBuf pinned_out, pinned_aux, pinned_stage;
     HostPipe pipe;
     Mailbox mail;
+    // text arriving in pieces (nafgpu_encode_begin .. _end): its device buffer lives outside the per-call arena
+    struct Ingest {
+        bool active = false; nafgpu_enc_opts opts{}; std::string title; bool has_title = false;
+        u8 *d_text = nullptr; size_t cap = 0, n = 0;
+        u8 *rot[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool busy[2] = {false, false}; int cur = 0;
+    } ingest;
     std::vector<nafz::ZBlockHead> zblock_cache;   // keeps the capacity of the decoder's host block list between calls
     nafz::ZWalked zwalk[6];                  // per section: the host walk of its block headers (capacity kept between calls)
     u32 *d_predef = nullptr;                 // predefined FSE tables

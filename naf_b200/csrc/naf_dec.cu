@@ -902,7 +902,7 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
     KLAUNCH(ex, "k_tile_first", k_tile_first<<<(unsigned)((ntiles + 1 + 255) / 256), 256, 0, ex.stream>>>(d_out_start, NR, ntiles, tile_first));
     // host-buffer call: finished tiles of the text go down while the next ones are being written
     const bool sink = ex.pipe && rec_text_view && view != NAFGPU_OUT_CHARCOUNT;
-    if (sink) ex.pipe->begin_output(ctx.pinned_out.ensure(total + surplus_text + 1));
+    if (sink) ex.pipe->begin_output(ex.pipe->sink ? nullptr : ctx.pinned_out.ensure(total + surplus_text + 1));   // (a callback sink brings its own two buffers)
     auto write_tiles = [&](u64 t0, u64 t1) {
         const u64 group = sink ? (64ull << 20) / WT_TILE : ntiles;      // tiles per launch when each launch is followed by its copy
         for (u64 a = t0; a < t1; a += group) {

@@ -101,3 +101,23 @@ def test_piped_errors_leave_the_context_usable(gpu):
         with pytest.raises(naf_b200.NafGpuError):
             gpu.decode(naf[:len(naf) - 1000])
         assert gpu.decode(naf) == text
+
+
+def test_streamed_calls_equal_the_one_shot_calls(gpu, oracle):
+    """nafgpu_encode_begin / _buffer / _feed / _end and nafgpu_decode_to (what bin/ennaf and bin/unnaf call): text handed over and
+    received in pieces, same bytes as the one-shot calls; also when the total size was not announced (a pipe)"""
+    for name, text, kw in texts():
+        naf = gpu.encode(text, **kw)
+        for hint in (len(text), 0):
+            pieces = [text[i:i + 5_000_011] for i in range(0, len(text), 5_000_011)]
+            assert gpu.encode_pieces(pieces, size_hint=hint, **kw) == naf, (name, hint)
+        for view in ("default", "fasta", "seq", "ids"):
+            got = []
+            total = gpu.decode_to(naf, got.append, view)
+            want = gpu.decode(naf, view)
+            assert b"".join(got) == want and total == len(want), (name, view)
+        with env(**SMALL):
+            got = []
+            gpu.decode_to(naf, got.append)
+            assert b"".join(got) == text, name
+    assert gpu.encode_pieces([]) == gpu.encode(b"")
