@@ -178,14 +178,23 @@ int main(int argc, char **argv)
         if (got < cap) break;
     }
     if (in_path) close(in_fd);
-    int rc = nafgpu_encode_end(ctx, &naf, &naf_size, &info);
+    // the file is written as it comes down (nothing file-sized is allocated on the host); an input the library refuses leaves
+    // no output file behind: the callback creates it on its first piece
+    struct Sink { FILE *f; bool force_stdout; } sink{nullptr, force_stdout};
+    auto write_piece = [](void *user, const uint8_t *piece, size_t k) -> int {
+        Sink *s = (Sink *)user;
+        if (!s->f) s->f = open_output(g_out_path, s->force_stdout);
+        write_all(s->f, piece, k);
+        return 0;
+    };
+    int rc = nafgpu_encode_end_to(ctx, write_piece, &sink, &naf_size, &info);
     if (rc != 0) die("%s", nafgpu_last_error(ctx));
+    (void)naf;
     if (fmt_ext != NAFGPU_FMT_AUTO && info.format && fmt_ext != info.format) warn("input file extension does not match its actual format\n");
     if (fmt_ext != NAFGPU_FMT_AUTO && fmt_cli != NAFGPU_FMT_AUTO && fmt_ext != fmt_cli) warn("input file extension does not match format specified in the command line\n");
 
-    FILE *out = open_output(g_out_path, force_stdout);
+    FILE *out = sink.f ? sink.f : open_output(g_out_path, force_stdout);
     if (verbose) msg("Output line length: %llu\n", have_line_length ? line_length : (unsigned long long)info.longest_line);
-    write_all(out, naf, naf_size);
     close_output(out, in, in_path && g_out_path && !force_stdout);
     if (!well_formed) {
         static const char *tn[4] = { "DNA", "RNA", "protein", "text" };

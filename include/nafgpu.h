@@ -161,6 +161,7 @@ int nafgpu_decode(nafgpu_ctx *ctx, const uint8_t *naf, size_t n, const nafgpu_de
  *   nafgpu_encode_buffer   a page-locked buffer to put the next piece of text into (*cap bytes at most)
  *   nafgpu_encode_feed     the buffer now holds n bytes: they go up while the caller fills the other buffer
  *   nafgpu_encode_end      no more text: transform + compress, result as from nafgpu_encode
+ *   nafgpu_encode_end_to   the same, with the .naf delivered in order, piece by piece, to `write` (no file-sized host buffer)
  *
  *   nafgpu_decode_to       nafgpu_decode whose text is delivered in order, piece by piece, to `write` (which returns 0 to go
  *                          on; anything else stops the call with NAFGPU_E_ARG); *text_size = total bytes delivered */
@@ -169,6 +170,7 @@ int nafgpu_encode_buffer(nafgpu_ctx *ctx, void **buf, size_t *cap);
 int nafgpu_encode_feed(nafgpu_ctx *ctx, size_t n);
 int nafgpu_encode_end(nafgpu_ctx *ctx, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info);
 typedef int (*nafgpu_write_fn)(void *user, const uint8_t *piece, size_t n);
+int nafgpu_encode_end_to(nafgpu_ctx *ctx, nafgpu_write_fn write, void *user, size_t *naf_size, nafgpu_enc_info *info);
 int nafgpu_decode_to(nafgpu_ctx *ctx, const uint8_t *naf, size_t n, const nafgpu_dec_opts *opts,
                      nafgpu_write_fn write, void *user, size_t *text_size);
 

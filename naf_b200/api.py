@@ -66,7 +66,7 @@ EXPORTS = [
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
     "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_zstd_compress_level", "nafgpu_split", "nafgpu_profile",
     "nafgpu_profile_report", "nafgpu_shard_begin", "nafgpu_shard_finish", "nafgpu_shard_fetch",
-    "nafgpu_encode_begin", "nafgpu_encode_buffer", "nafgpu_encode_feed", "nafgpu_encode_end", "nafgpu_decode_to",
+    "nafgpu_encode_begin", "nafgpu_encode_buffer", "nafgpu_encode_feed", "nafgpu_encode_end", "nafgpu_encode_end_to", "nafgpu_decode_to",
 ]
 
 _lib = None
@@ -117,6 +117,7 @@ def load_library():
     lib.nafgpu_encode_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_encode_feed.argtypes = [vp, sz]
     lib.nafgpu_encode_end.argtypes = [vp, C.POINTER(vp), C.POINTER(sz), C.POINTER(EncInfo)]
+    lib.nafgpu_encode_end_to.argtypes = [vp, WRITE_FN, vp, C.POINTER(sz), C.POINTER(EncInfo)]
     lib.nafgpu_decode_to.argtypes = [vp, vp, sz, C.POINTER(DecOpts), WRITE_FN, vp, C.POINTER(sz)]
     _lib = lib
     return lib
@@ -266,7 +267,7 @@ class NafGpu:
         return raw
 
     # ---- hot path, streamed (what the command-line tools use)
-    def encode_pieces(self, pieces, size_hint: int = 0, **kw) -> bytes:
+    def encode_pieces(self, pieces, size_hint: int = 0, write=None, **kw) -> bytes:
         """text as an iterable of byte pieces (any sizes) -> .naf; each piece is on its way to the device while the next is read"""
         opts = make_enc_opts(**kw)
         self._check(self.lib.nafgpu_encode_begin(self.h, C.byref(opts), size_hint))
@@ -285,6 +286,13 @@ class NafGpu:
         if fill:
             self._check(self.lib.nafgpu_encode_feed(self.h, fill))
         out, size, info = C.c_void_p(), C.c_size_t(), EncInfo()
+        if write is not None:                  # the .naf delivered piece by piece as well
+            def cb(user, ptr, k):
+                write(C.string_at(ptr, k))
+                return 0
+            fn = WRITE_FN(cb)
+            self._check(self.lib.nafgpu_encode_end_to(self.h, fn, None, C.byref(size), C.byref(info)))
+            return b""
         self._check(self.lib.nafgpu_encode_end(self.h, C.byref(out), C.byref(size), C.byref(info)))
         return _bytes_at(out.value or 0, size.value)
 

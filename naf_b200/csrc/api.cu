@@ -292,9 +292,24 @@ int nafgpu_encode_feed(nafgpu_ctx *c, size_t n)
     }
 }
 
+static int encode_end_impl(nafgpu_ctx *c, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info, nafgpu_write_fn write, void *user);
+
 int nafgpu_encode_end(nafgpu_ctx *c, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info)
 {
     if (!c || !naf || !naf_size || !c->ingest.active) return NAFGPU_E_ARG;
+    return encode_end_impl(c, naf, naf_size, info, nullptr, nullptr);
+}
+int nafgpu_encode_end_to(nafgpu_ctx *c, nafgpu_write_fn write, void *user, size_t *naf_size, nafgpu_enc_info *info)
+{
+    if (!c || !write || !c->ingest.active) return NAFGPU_E_ARG;
+    const uint8_t *unused = nullptr; size_t sz = 0;
+    const int rc = encode_end_impl(c, &unused, &sz, info, write, user);
+    if (naf_size) *naf_size = sz;
+    return rc;
+}
+
+static int encode_end_impl(nafgpu_ctx *c, const uint8_t **naf, size_t *naf_size, nafgpu_enc_info *info, nafgpu_write_fn write, void *user)
+{
     c->ingest.active = false;
     return guarded(c, [&] {
         *naf = nullptr; *naf_size = 0;
@@ -308,6 +323,18 @@ int nafgpu_encode_end(nafgpu_ctx *c, const uint8_t **naf, size_t *naf_size, nafg
         nafgpu_enc_opts o = g.opts; o.title = g.has_title ? g.title.c_str() : nullptr;
         EncodeOut r = encode_on_device(*c, ex, g.d_text, g.n, o, info);
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        if (write) {                                              // the file comes down through the two rotating buffers, piece by piece
+            c->pipe.rot_create();
+            c->pipe.sink = write; c->pipe.sink_user = user;
+            c->pipe.begin_output(nullptr);
+            c->pipe.emit(c->stream, r.d_naf, 0, r.size);
+            c->pipe.rot_flush_all();
+            *naf_size = r.size;
+            const bool failed = c->pipe.sink_failed;
+            finish_timing(*c, ex);
+            if (failed) fail(NAFGPU_E_ARG, "the output callback reported an error\n");
+            return;
+        }
         *naf = to_pinned(*c, r.d_naf, r.size); *naf_size = r.size;
         finish_timing(*c, ex);
     });

@@ -111,6 +111,9 @@ def test_streamed_calls_equal_the_one_shot_calls(gpu, oracle):
         for hint in (len(text), 0):
             pieces = [text[i:i + 5_000_011] for i in range(0, len(text), 5_000_011)]
             assert gpu.encode_pieces(pieces, size_hint=hint, **kw) == naf, (name, hint)
+            got = []
+            gpu.encode_pieces(pieces, size_hint=hint, write=got.append, **kw)
+            assert b"".join(got) == naf, (name, hint)
         for view in ("default", "fasta", "seq", "ids"):
             got = []
             total = gpu.decode_to(naf, got.append, view)
