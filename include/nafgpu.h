@@ -237,6 +237,12 @@ typedef struct {
     uint8_t  pad[4];
 } nafgpu_shard_link;
 
+/* Where to cut a text into `pieces` record-aligned shards: cuts[0] = 0, cuts[pieces] = n, cuts[k] = offset of the first record
+ * start at or after k * n / pieces (FASTA: a '>' at a line start; FASTQ: after every 4th line counted from the top of the
+ * text -- exact, a quality line may begin with '@').  Found on the GPU: newline ordinals by a prefix sum over per-tile counts
+ * (the record-boundary scan of process.c:358,477 restated data-parallel).  text: host pointer, or device pointer if text_on_device. */
+int nafgpu_record_cuts(nafgpu_ctx *ctx, const uint8_t *text, size_t n, int text_on_device, int pieces, uint64_t *cuts /* pieces + 1 */);
+
 int nafgpu_shard_begin(nafgpu_ctx *ctx, const uint8_t *text, size_t n, int text_on_device, const nafgpu_enc_opts *opts,
                        nafgpu_shard_counts *counts, nafgpu_enc_info *info);
 int nafgpu_shard_finish(nafgpu_ctx *ctx, const nafgpu_shard_link *link, uint64_t raw[6], uint64_t body[6]);

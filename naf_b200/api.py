@@ -66,7 +66,7 @@ EXPORTS = [
     "nafgpu_host_alloc", "nafgpu_host_free", "nafgpu_encode", "nafgpu_decode", "nafgpu_encode_device",
     "nafgpu_decode_device", "nafgpu_zstd_decompress", "nafgpu_zstd_compress", "nafgpu_zstd_compress_level", "nafgpu_split", "nafgpu_profile",
     "nafgpu_profile_report", "nafgpu_shard_begin", "nafgpu_shard_finish", "nafgpu_shard_fetch",
-    "nafgpu_encode_begin", "nafgpu_encode_buffer", "nafgpu_encode_feed", "nafgpu_encode_end", "nafgpu_encode_end_to", "nafgpu_decode_to",
+    "nafgpu_record_cuts", "nafgpu_encode_begin", "nafgpu_encode_buffer", "nafgpu_encode_feed", "nafgpu_encode_end", "nafgpu_encode_end_to", "nafgpu_decode_to",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load_library():
     lib.nafgpu_shard_begin.argtypes = [vp, vp, sz, C.c_int, C.POINTER(EncOpts), C.POINTER(ShardCounts), C.POINTER(EncInfo)]
     lib.nafgpu_shard_finish.argtypes = [vp, C.POINTER(ShardLink), C.POINTER(C.c_uint64 * 6), C.POINTER(C.c_uint64 * 6)]
     lib.nafgpu_shard_fetch.argtypes = [vp, C.c_int, vp]
+    lib.nafgpu_record_cuts.argtypes = [vp, vp, sz, C.c_int, C.c_int, C.POINTER(C.c_uint64)]
     lib.nafgpu_encode_begin.argtypes = [vp, C.POINTER(EncOpts), sz]
     lib.nafgpu_encode_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     lib.nafgpu_encode_feed.argtypes = [vp, sz]
@@ -336,6 +337,13 @@ class NafGpu:
 
     def shard_fetch(self, stream: int, dst_address: int):
         self._check(self.lib.nafgpu_shard_fetch(self.h, stream, dst_address))
+
+    def record_cuts(self, text, pieces: int, on_device: bool = False):
+        """record-aligned cut points of a text, found on the GPU: [0, c1, ..., n] (pieces + 1 offsets)"""
+        p, n, keep = _as_ptr(text)
+        cuts = (C.c_uint64 * (pieces + 1))()
+        self._check(self.lib.nafgpu_record_cuts(self.h, p, n, int(on_device), pieces, cuts))
+        return list(cuts)
 
     # ---- stages
     def zstd_decompress(self, frame, expected_size: int = 0, one_frame: bool = False) -> bytes:

@@ -9,6 +9,7 @@ DecodeOut decode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *h_
 EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
 SplitOut split_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info);
 EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_t n, int window_log, int level);
+void record_cuts_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, int pieces, uint64_t *cuts);
 void shard_begin_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_shard_counts *counts, nafgpu_enc_info *info);
 void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &link, uint64_t raw[6], uint64_t body[6]);
 }
@@ -482,6 +483,20 @@ int nafgpu_split(nafgpu_ctx *c, const uint8_t *text, size_t n, const nafgpu_enc_
 
 
 /* ---- one file from several shards (multi-GPU encode; naf_b200/sharded.py drives the exchange) ---- */
+
+int nafgpu_record_cuts(nafgpu_ctx *c, const uint8_t *text, size_t n, int text_on_device, int pieces, uint64_t *cuts)
+{
+    if ((!text && n) || !cuts || pieces < 1) return NAFGPU_E_ARG;
+    return guarded(c, [&] {
+        CudaExec ex{c->stream, &c->arena, &c->prof}; ex.staging = &c->pinned_stage; ex.mail = &c->mail;
+        CUDA_TRY(cudaEventRecord(c->ev[0], c->stream));
+        const u8 *d_text = text_on_device ? text : to_device(*c, ex, text, n);
+        CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
+        record_cuts_on_device(*c, ex, d_text, n, pieces, cuts);
+        CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));
+        finish_timing(*c, ex);
+    });
+}
 
 int nafgpu_shard_begin(nafgpu_ctx *c, const uint8_t *text, size_t n, int text_on_device, const nafgpu_enc_opts *opts,
                        nafgpu_shard_counts *counts, nafgpu_enc_info *info)

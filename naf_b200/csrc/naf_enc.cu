@@ -707,6 +707,111 @@ EncodeOut zstd_compress_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_src, size_
 }
 
 
+// ------------------------------------------------------------------ record-aligned cut points (shards of one text)
+// Where may a text be cut so that every piece starts a record?  FASTA: before a '>' at a line start.  FASTQ: after every 4th
+// line counted from the top of the text (a quality line may begin with '@', so only counting is exact) -- 4-line records
+// without blank lines, what the canonical-input transform accepts.  The newline ordinals come from a prefix sum over
+// per-tile counts; each cut is then found by one CTA: the k-th newline of the text, or the first "\n>" at or after the target.
+static const u32 CUT_TILE = 16384, CUT_NT = 256;
+__global__ void __launch_bounds__(CUT_NT) k_cut_tiles(const u8 *text, u64 n, u64 *nl_count, u32 *first_gt)
+{
+    __shared__ u64 sm[33];
+    __shared__ u32 s_first;
+    const u64 lo = (u64)blockIdx.x * CUT_TILE;
+    if (threadIdx.x == 0) s_first = 0xFFFFFFFFu;
+    __syncthreads();
+    u32 c = 0, first = 0xFFFFFFFFu;
+    const u64 b0 = lo + (u64)threadIdx.x * 64;
+    for (u32 i = 0; i < 64; i++) {
+        const u64 p = b0 + i;
+        if (p >= n) break;
+        const u8 ch = text[p];
+        if (ch == '\n') { c++; if (p + 1 < n && text[p + 1] == '>' && first == 0xFFFFFFFFu) first = (u32)(p - lo); }   // position of the '\n'
+    }
+    u64 tot; block_excl_scan(c, &tot, sm);
+    if (first != 0xFFFFFFFFu) atomicMin(&s_first, first);
+    __syncthreads();
+    if (threadIdx.x == 0) { nl_count[blockIdx.x] = tot; first_gt[blockIdx.x] = s_first; }
+}
+// one CTA per cut k = 1 .. pieces - 1
+__global__ void __launch_bounds__(CUT_NT) k_cut_find(const u8 *text, u64 n, int fastq, u32 pieces, u64 ntiles, const u64 *nl_pre, const u32 *first_gt, u64 *cuts)
+{
+    __shared__ u64 sm[33];
+    __shared__ u64 s_val;
+    const u32 k = blockIdx.x + 1, tid = threadIdx.x;
+    const u64 t = (u64)((unsigned __int128)n * k / pieces);
+    const u64 T = t / CUT_TILE;
+    if (tid == 0) s_val = ~0ull;
+    __syncthreads();
+    if (!fastq) {
+        // first "\n>" whose '\n' is at or after t: inside tile T by position, then the first later tile that has one
+        const u64 lo = T * CUT_TILE;
+        for (u32 i = 0; i < 64; i++) {
+            const u64 p = lo + (u64)tid * 64 + i;
+            if (p >= t && p + 1 < n && text[p] == '\n' && text[p + 1] == '>') { atomicMin((unsigned long long *)&s_val, (unsigned long long)p); break; }
+        }
+        __syncthreads();
+        if (s_val == ~0ull) {
+            for (u64 base = T + 1; base < ntiles; base += CUT_NT) {
+                const u64 tile = base + tid;
+                if (tile < ntiles && first_gt[tile] != 0xFFFFFFFFu) atomicMin((unsigned long long *)&s_val, (unsigned long long)(tile * CUT_TILE + first_gt[tile]));
+                __syncthreads();
+                if (s_val != ~0ull) break;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) cuts[k] = s_val == ~0ull ? n : s_val + 1;
+        return;
+    }
+    // FASTQ: newlines strictly before t -> ordinal of the first newline at or after t; the record end at or after it
+    u32 c = 0;
+    {
+        const u64 lo = T * CUT_TILE + (u64)tid * 64;
+        for (u32 i = 0; i < 64; i++) { const u64 p = lo + i; if (p < t && p < n && text[p] == '\n') c++; }
+    }
+    u64 tot; block_excl_scan(c, &tot, sm);
+    const u64 before = nl_pre[T] + tot, total = nl_pre[ntiles];
+    const u64 J = before + ((3 - (before & 3)) & 3);                       // smallest ordinal >= before with J % 4 == 3
+    if (J >= total) { if (tid == 0) cuts[k] = n; return; }
+    // tile holding newline J: nl_pre[tile] <= J < nl_pre[tile + 1]
+    u64 a = T, b = ntiles;
+    while (b - a > 1) { const u64 mid = (a + b) >> 1; if (nl_pre[mid] <= J) a = mid; else b = mid; }
+    const u64 want = J - nl_pre[a];                                        // ordinal inside tile a
+    u32 mine = 0;
+    const u64 lo = a * CUT_TILE + (u64)tid * 64;
+    for (u32 i = 0; i < 64; i++) { const u64 p = lo + i; if (p < n && text[p] == '\n') mine++; }
+    u64 tot2; const u64 pre = block_excl_scan(mine, &tot2, sm);
+    if (want >= pre && want < pre + mine) {
+        u64 seen = pre;
+        for (u32 i = 0; i < 64; i++) { const u64 p = lo + i; if (p < n && text[p] == '\n') { if (seen == want) { s_val = p; break; } seen++; } }
+    }
+    __syncthreads();
+    if (tid == 0) cuts[k] = s_val == ~0ull ? n : s_val + 1;
+}
+
+void record_cuts_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, int pieces, uint64_t *cuts)
+{
+    cuts[0] = 0; cuts[pieces] = n;
+    if (pieces <= 1 || n == 0) { for (int k = 1; k < pieces; k++) cuts[k] = n; return; }
+    const size_t head = n < 65536 ? n : 65536;
+    ctx.host_scratch.resize(head + 1);
+    ex.download(ctx.host_scratch.data(), d_text, head);
+    nafgpu_enc_opts o; memset(&o, 0, sizeof o);
+    u64 p0 = 0;
+    const int fmt = confirm_format(ctx.host_scratch.data(), head, n, o, &p0);
+    if (fmt == 0) { for (int k = 1; k < pieces; k++) cuts[k] = n; return; }
+    const u64 ntiles = (n + CUT_TILE - 1) / CUT_TILE;
+    u64 *cnt = ex.alloc<u64>(ntiles + 1), *pre = ex.alloc<u64>(ntiles + 2), *d_cuts = ex.alloc<u64>(pieces + 1);
+    u32 *fgt = ex.alloc<u32>(ntiles + 1);
+    KLAUNCH(ex, "k_cut_tiles", k_cut_tiles<<<(unsigned)ntiles, CUT_NT, 0, ex.stream>>>(d_text, n, cnt, fgt));
+    const u64 *c = cnt;
+    exclusive_scan(ex, [c] __device__ (size_t i) { return c[i]; }, ntiles, pre);
+    KLAUNCH(ex, "k_cut_find", k_cut_find<<<(unsigned)(pieces - 1), CUT_NT, 0, ex.stream>>>(d_text, n, fmt == NAFGPU_FMT_FASTQ, (u32)pieces, ntiles, pre, fgt, d_cuts));
+    std::vector<u64> h(pieces + 1);
+    ex.download(h.data() + 1, d_cuts + 1, (size_t)(pieces - 1) * 8);
+    for (int k = 1; k < pieces; k++) cuts[k] = h[k] > cuts[k - 1] ? (h[k] < n ? h[k] : n) : cuts[k - 1];     // monotone
+}
+
 // ------------------------------------------------------------------ shards of one file (multi-GPU encode)
 
 // packed stream of bases[1:] from the packed stream of bases[0:]: out[j] = in[j] >> 4 | in[j+1] << 4

@@ -240,6 +240,12 @@ def split_records(text: bytes, pieces: int) -> List[bytes]:
     return [text[cuts[i]:cuts[i + 1]] for i in range(pieces)]
 
 
+def split_records_gpu(ctx, text, pieces: int, on_device: bool = False):
+    """The same cut points found on the GPU (nafgpu_record_cuts: newline ordinals by a prefix sum over tiles) -- what the
+    multi-GPU tools use; `text` may be a (device address, nbytes) pair.  Returns the list of pieces + 1 offsets."""
+    return ctx.record_cuts(text, pieces, on_device=on_device)
+
+
 def record_range(n_records: int, rank: int, world: int):
     """records [first, first + count) of rank `rank` when `n_records` are dealt out evenly"""
     first = n_records * rank // world

@@ -351,3 +351,25 @@ def test_stream_gpu(oracle):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.gpu
+def test_record_cuts_on_the_gpu_equal_the_host_splitter(gpu):
+    """nafgpu_record_cuts (newline ordinals by a prefix sum over tiles, one CTA per cut) against sharded.split_records: FASTQ
+    whose quality lines begin with '@', FASTA with records far longer than a tile, leading white space, more pieces than records"""
+    rng = np.random.default_rng(6)
+    recs = []
+    for i in range(2500):
+        L = int(rng.integers(20, 300))
+        seq = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)])
+        qual = b"@" + bytes(rng.choice(np.frombuffer(b"@+IJ#>", dtype=np.uint8), L - 1))
+        recs.append(b"@r%d x\n" % i + seq + b"\n+\n" + qual + b"\n")
+    texts = [b"".join(recs), synth.fastq(5000, 150, seed=3), synth.fasta_softmasked(3_000_000, 60, seed=4, n_records=5),
+             synth.ont_fasta(40, 10000, 50000, seed=5), b"\n \n" + synth.fasta_reads(50, 100, seed=6), b">only\nACGT\n", b""]
+    for text in texts:
+        for pieces in (1, 2, 3, 8, 64):
+            want = [0]
+            for p in sharded.split_records(text, pieces):
+                want.append(want[-1] + len(p))
+            want += [len(text)] * (pieces + 1 - len(want))
+            assert sharded.split_records_gpu(gpu, text, pieces) == want, (len(text), pieces)

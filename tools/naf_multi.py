@@ -48,9 +48,8 @@ def main():
 
     if a.mode == "encode":
         cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
-        if rank == 0:
-            pieces = sharded.split_records(data.tobytes(), world)
-            cuts[1:] = torch.tensor(np.cumsum([len(p) for p in pieces]), dtype=torch.int64)
+        if rank == 0:                                       # record boundaries from the GPU scan (nafgpu_record_cuts)
+            cuts[:] = torch.tensor(sharded.split_records_gpu(ctx, data, world), dtype=torch.int64)
         dist.broadcast(cuts, src=0)
         lo, hi = int(cuts[rank]), int(cuts[rank + 1])
         mine = data[lo:hi].tobytes()
