@@ -409,6 +409,207 @@ __global__ void __launch_bounds__(WT_THREADS, 5) k_write_text(const __grid_const
         wt_chunk_generic(A, recs, first, nrec, nrec_total, tile0 + (u64)slow[k] * 16, tile1);
 }
 
+// ------------------------------------------------------------------ the text writer, second formulation: compose in shared memory
+// k_write_text above decides per 16-byte chunk of OUTPUT what it holds; a third of the chunks straddle a boundary (header,
+// "+", line ends) and go through a long generic composer at a few lanes per warp (ncu, profiles/r2l: 1.47 warp instructions
+// per byte of text, 16 of 32 lanes active).  Here the unit of work is a PIECE of the record layout instead -- at most 64
+// bytes of a header, of one sequence line, of a quality string -- and one LANE owns a piece: it finds its record once, then
+// copies 16 bytes at a time into a shared-memory image of the tile (aligned words of the image; bases through the 4-bit
+// table, 16 per step; a few edge bytes one by one).  Pieces are enumerated kind by kind, so the lanes of a warp mostly do
+// the same thing to different pieces.  The image then goes to HBM as aligned 16-byte stores.
+// Layout rules as in rec_text_size / rec_bounds (output.c:369-406, output-fastq.c:100).
+static const u32 CT_P = 64;                 // bytes per piece
+struct CtRec { u64 s_lo; u32 n_h, h_lo, n_s, q_lo, n_q, ppl; };   // a record's pieces that intersect the tile: header, sequence, quality area
+
+// image bytes [lo, hi) (tile-relative) <- src[0 .. hi - lo), src a global pointer of any alignment; one lane
+__device__ __forceinline__ void ct_lane_bytes(u8 *img, u32 lo, u32 hi, const u8 *src, bool upper)
+{
+    while (lo < hi && (lo & 3)) { u8 c = __ldg(src++); if (upper && c >= 'a' && c <= 'z') c -= 32; img[lo++] = c; }
+    u32 *dw = (u32 *)(img + lo);
+    u32 nw = (hi - lo) >> 2;
+    while (nw >= 4) {
+        uint4 v = load_bytes16(src);
+        if (upper) { v.x = upper4(v.x); v.y = upper4(v.y); v.z = upper4(v.z); v.w = upper4(v.w); }
+        dw[0] = v.x; dw[1] = v.y; dw[2] = v.z; dw[3] = v.w;
+        dw += 4; src += 16; lo += 16; nw -= 4;
+    }
+    while (lo < hi) { u8 c = __ldg(src++); if (upper && c >= 'a' && c <= 'z') c -= 32; img[lo++] = c; }
+}
+// image bytes [lo, hi) <- bases b0 .. b0 + (hi - lo); one lane
+__device__ __forceinline__ void ct_lane_bases(const TextArgs &A, u8 *img, u32 lo, u32 hi, u64 b0)
+{
+    if (!A.packed) { ct_lane_bytes(img, lo, hi, A.seq + b0, A.upper != 0); return; }
+    while (lo < hi && (lo & 3)) img[lo++] = base_at(A, b0++);
+    u32 *dw = (u32 *)(img + lo);
+    u32 nw = (hi - lo) >> 2;
+    while (nw >= 4) {
+        const u64 nib = load_nibbles16(A.seq, b0);
+        u32 w0 = nib4_to_ascii((u32)nib & 0xFFFF, A.lut), w1 = nib4_to_ascii((u32)(nib >> 16) & 0xFFFF, A.lut);
+        u32 w2 = nib4_to_ascii((u32)(nib >> 32) & 0xFFFF, A.lut), w3 = nib4_to_ascii((u32)(nib >> 48) & 0xFFFF, A.lut);
+        if (A.maskbits) {
+            const u32 mb = load_maskbits16(A.maskbits, b0);
+            w0 += bits4_to_case(mb & 15); w1 += bits4_to_case((mb >> 4) & 15); w2 += bits4_to_case((mb >> 8) & 15); w3 += bits4_to_case((mb >> 12) & 15);
+        }
+        dw[0] = w0; dw[1] = w1; dw[2] = w2; dw[3] = w3;
+        dw += 4; b0 += 16; lo += 16; nw -= 4;
+    }
+    while (lo < hi) img[lo++] = base_at(A, b0++);
+}
+// one byte of a record's header area [0, c): prefix, id, separator, comment, newline
+__device__ __forceinline__ u8 ct_header_byte(const TextArgs &A, const RecInfo &R, u32 r)
+{
+    if (r < R.a) return A.prefix;
+    if (r >= R.b) return '\n';
+    const u32 k = r - (u32)R.a;
+    if (A.has_ids && k < R.id_len) return __ldg(A.ids + R.id_s + k);
+    if (A.has_ids && A.has_names) { if (k == R.id_len) return A.sep; return __ldg(A.comm + R.cm_s + (k - R.id_len - 1)); }
+    return __ldg(A.comm + R.cm_s + k);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_constant__ TextArgs A, const u32 *tile_first)
+{
+    __shared__ __align__(16) u8 img[WT_TILE + 16];
+    __shared__ RecS recs[WT_MAXREC];
+    __shared__ CtRec cr[WT_MAXREC];
+    __shared__ u32 pre_h[WT_MAXREC + 1], pre_s[WT_MAXREC + 1], pre_q[WT_MAXREC + 1];
+    __shared__ u64 sm[33];
+    const u32 tid = threadIdx.x;
+    const u64 tile = A.tile_base + blockIdx.x;
+    const u64 tile0 = tile * WT_TILE;
+    const u64 tile1 = tile0 + WT_TILE < A.total ? tile0 + WT_TILE : A.total;
+    const u64 first = tile_first[tile];
+    const u32 nrec_total = tile_first[tile + 1] - (u32)first + 1;
+    if (nrec_total > (u32)WT_MAXREC) {
+        // more records in 16 KB than the tables hold (records of a few dozen bytes): chunk by chunk through the generic composer
+        if (tid < WT_MAXREC) rec_fetch(A, first + tid, recs[tid]);
+        __syncthreads();
+        for (u64 q0 = tile0 + 16ull * tid; q0 < tile1; q0 += 16ull * WT_THREADS) wt_chunk_generic(A, recs, first, WT_MAXREC, nrec_total, q0, tile1);
+        return;
+    }
+    const u32 nrec = nrec_total;
+    const bool wrapped = A.W > 0 && A.seq_nl == 1;
+    u32 ch = 0, cs = 0, cq = 0;
+    if (tid < nrec) {
+        rec_fetch(A, first + tid, recs[tid]);
+        RecInfo R; rec_bounds(A, recs[tid], R);
+        const u64 o = recs[tid].out0;
+        CtRec c; c.s_lo = 0; c.n_h = c.h_lo = c.n_s = c.q_lo = c.n_q = 0; c.ppl = 1;
+        // header area [0, c): pieces of CT_P bytes
+        if (R.c > 0 && o < tile1 && o + R.c > tile0) {
+            const u64 lo = tile0 > o ? (tile0 - o) / CT_P : 0;
+            u64 hi = (R.c + CT_P - 1) / CT_P;
+            if (o + R.c > tile1) hi = (tile1 - o + CT_P - 1) / CT_P;
+            c.h_lo = (u32)lo; c.n_h = (u32)(hi - lo);
+        }
+        // sequence area [c, d).  wrapped: lines of W bases, each followed by '\n' (stride W + 1), a line cut into ppl pieces;
+        // else ONE line of L bases, the area's single trailing '\n' (if any) written by its last piece
+        if (A.seq_present && R.d > R.c) {
+            const u64 a0 = o + R.c, a1 = o + R.d;
+            if (a0 < tile1 && a1 > tile0) {
+                if (wrapped) {
+                    const u64 stride = A.W + 1, nline = (R.L + A.W - 1) / A.W, ppl = (A.W + CT_P - 1) / CT_P;
+                    u64 lo = tile0 > a0 ? (tile0 - a0) / stride : 0, hi = (tile1 - a0 + stride - 1) / stride;
+                    if (hi > nline) hi = nline;
+                    if (lo >= nline) lo = nline - 1;
+                    if (ppl > 0xFFFFu || (hi - lo) * ppl > 0x7FFFFFFFull) { c.ppl = 0; }      // absurd widths: generic composer (below)
+                    else { c.ppl = (u32)ppl; c.s_lo = lo * ppl; c.n_s = (u32)((hi > lo ? hi - lo : 1) * ppl); }
+                } else {
+                    const u64 np = R.L ? (R.L + CT_P - 1) / CT_P : 1;     // L == 0 with a newline: one piece that is only the '\n'
+                    u64 lo = tile0 > a0 ? (tile0 - a0) / CT_P : 0, hi = (tile1 - a0 + CT_P - 1) / CT_P;
+                    if (hi > np) hi = np;
+                    if (lo >= np) lo = np - 1;
+                    c.s_lo = lo; c.n_s = (u32)(hi > lo ? hi - lo : 1);
+                }
+            }
+        }
+        // quality area [d, e): "+\n" (piece 0), then pieces of CT_P qualities, the last one followed by '\n'
+        if (A.with_qual) {
+            const u64 a0 = o + R.d, a1 = o + R.e;
+            if (a0 < tile1 && a1 > tile0) {
+                const u64 np = 1 + (R.L ? (R.L + CT_P - 1) / CT_P : 1);
+                u64 lo = 0, hi = np;
+                if (tile0 > a0 + 2) lo = 1 + (tile0 - a0 - 2) / CT_P;
+                if (tile1 < a1) { hi = tile1 <= a0 + 2 ? 1 : 1 + (tile1 - a0 - 2 + CT_P - 1) / CT_P; if (hi > np) hi = np; }
+                if (lo >= np) lo = np - 1;
+                c.q_lo = (u32)lo; c.n_q = (u32)(hi > lo ? hi - lo : 1);
+            }
+        }
+        cr[tid] = c;
+        ch = c.n_h; cs = c.n_s; cq = c.n_q;
+    }
+    // three scans packed into one: header pieces (bits 0-20), sequence pieces (21-41), quality pieces (42-62) -- a tile holds
+    // at most a few hundred of each (a record's pieces are clipped to the tile; absurdly narrow lines fall back below)
+    const bool fits = ch < (1u << 13) && cs < (1u << 13) && cq < (1u << 13);
+    const u32 bad = __syncthreads_or(!fits || (tid < nrec && cr[tid].ppl == 0));
+    if (bad) {
+        for (u64 q0 = tile0 + 16ull * tid; q0 < tile1; q0 += 16ull * WT_THREADS) wt_chunk_generic(A, recs, first, nrec, nrec_total, q0, tile1);
+        return;
+    }
+    u64 total; const u64 pre = block_excl_scan((u64)ch | ((u64)cs << 21) | ((u64)cq << 42), &total, sm);
+    if (tid < nrec) { pre_h[tid] = (u32)(pre & 0x1FFFFF); pre_s[tid] = (u32)((pre >> 21) & 0x1FFFFF); pre_q[tid] = (u32)(pre >> 42); }
+    if (tid == 0) { pre_h[nrec] = (u32)(total & 0x1FFFFF); pre_s[nrec] = (u32)((total >> 21) & 0x1FFFFF); pre_q[nrec] = (u32)(total >> 42); }
+    __syncthreads();
+    const u32 nh = pre_h[nrec], ns = pre_s[nrec], nq = pre_q[nrec];
+    auto find = [&](const u32 *p, u32 x) { u32 lo = 0, hi = nrec; while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (p[mid] <= x) lo = mid; else hi = mid; } return lo; };
+    // ---- sequence pieces (the bulk; first, so that the short kinds fill the lanes they leave idle)
+    for (u32 g = tid; g < ns; g += WT_THREADS) {
+        const u32 r = find(pre_s, g);
+        const RecS &rs = recs[r]; const CtRec c = cr[r];
+        RecInfo R; rec_bounds(A, rs, R);
+        const u64 idx = c.s_lo + (g - pre_s[r]);
+        u64 x0, b0, nb; bool nl;
+        if (wrapped) {
+            const u64 line = idx / c.ppl, sub = idx - line * c.ppl;
+            const u64 lb = line * A.W, ll = R.L - lb < A.W ? R.L - lb : A.W;             // the line's bases
+            const u64 s0 = sub * CT_P;
+            nb = ll > s0 ? (ll - s0 < CT_P ? ll - s0 : CT_P) : 0;
+            b0 = lb + s0; x0 = rs.out0 + R.c + line * (A.W + 1) + s0;
+            nl = nb > 0 && s0 + nb == ll;                        // the piece that holds the line's last base writes its '\n' (every line has a base)
+        } else {
+            b0 = idx * CT_P; nb = R.L > b0 ? (R.L - b0 < CT_P ? R.L - b0 : CT_P) : 0;
+            x0 = rs.out0 + R.c + b0;
+            nl = b0 + nb >= R.L && R.d - R.c > R.L;
+        }
+        const u64 x1 = x0 + nb;
+        const u64 y0 = x0 > tile0 ? x0 : tile0, y1 = x1 < tile1 ? x1 : tile1;
+        if (y1 > y0) ct_lane_bases(A, img, (u32)(y0 - tile0), (u32)(y1 - tile0), rs.sbase + b0 + (y0 - x0));
+        if (nl && x1 >= tile0 && x1 < tile1) img[x1 - tile0] = '\n';
+    }
+    // ---- quality-area pieces
+    for (u32 g = tid; g < nq; g += WT_THREADS) {
+        const u32 r = find(pre_q, g);
+        const RecS &rs = recs[r]; const CtRec c = cr[r];
+        RecInfo R; rec_bounds(A, rs, R);
+        const u64 a0 = rs.out0 + R.d, idx = c.q_lo + (g - pre_q[r]);
+        if (idx == 0) {
+            if (a0 >= tile0 && a0 < tile1) img[a0 - tile0] = '+';
+            if (a0 + 1 >= tile0 && a0 + 1 < tile1) img[a0 + 1 - tile0] = '\n';
+            continue;
+        }
+        const u64 b0 = (idx - 1) * CT_P, nb = R.L > b0 ? (R.L - b0 < CT_P ? R.L - b0 : CT_P) : 0;
+        const u64 x0 = a0 + 2 + b0, x1 = x0 + nb;
+        const u64 y0 = x0 > tile0 ? x0 : tile0, y1 = x1 < tile1 ? x1 : tile1;
+        if (y1 > y0) ct_lane_bytes(img, (u32)(y0 - tile0), (u32)(y1 - tile0), A.qual + rs.sbase + b0 + (y0 - x0), false);
+        if (b0 + nb >= R.L && x1 >= tile0 && x1 < tile1) img[x1 - tile0] = '\n';
+    }
+    // ---- header pieces
+    for (u32 g = tid; g < nh; g += WT_THREADS) {
+        const u32 r = find(pre_h, g);
+        const RecS &rs = recs[r]; const CtRec c = cr[r];
+        RecInfo R; rec_bounds(A, rs, R);
+        const u64 idx = c.h_lo + (g - pre_h[r]);
+        const u64 x0 = rs.out0 + idx * CT_P, x1 = x0 + CT_P < rs.out0 + R.c ? x0 + CT_P : rs.out0 + R.c;
+        const u64 y0 = x0 > tile0 ? x0 : tile0, y1 = x1 < tile1 ? x1 : tile1;
+        for (u64 q = y0; q < y1; q++) img[q - tile0] = ct_header_byte(A, R, (u32)(q - rs.out0));
+    }
+    __syncthreads();
+    // the image -> HBM (A.out + tile0 is 16-byte aligned: tiles are 16 KB and the arena hands out 256-byte aligned memory)
+    const u32 T = (u32)(tile1 - tile0);
+    const uint4 *iv = (const uint4 *)img; uint4 *ov = (uint4 *)(A.out + tile0);
+    for (u32 k = tid; k < T / 16; k += WT_THREADS) ov[k] = iv[k];
+    for (u32 k = (T & ~15u) + tid; k < T; k += WT_THREADS) A.out[tile0 + k] = img[k];
+}
+
 // histogram of the produced text (unnaf --charcount, output.c:544)
 __global__ void k_charcount(const u8 *text, u64 n, unsigned long long *counts)
 {
@@ -908,7 +1109,9 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         for (u64 a = t0; a < t1; a += group) {
             const u64 b = a + group < t1 ? a + group : t1;
             TextArgs B = A; B.tile_base = a;
-            KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)(b - a), WT_THREADS, 0, ex.stream>>>(B, tile_first));
+            static const bool old_writer = getenv("NAFGPU_OLD_WRITER") != nullptr;      // A/B: the per-chunk formulation
+            if (old_writer) { KLAUNCH(ex, "k_write_text", k_write_text<<<(unsigned)(b - a), WT_THREADS, 0, ex.stream>>>(B, tile_first)); }
+            else { KLAUNCH(ex, "k_compose_text", k_compose_text<<<(unsigned)(b - a), WT_THREADS, 0, ex.stream>>>(B, tile_first)); }
             if (sink) { const u64 lo = a * WT_TILE, hi = b * WT_TILE < total ? b * WT_TILE : total; ex.pipe->emit(ex.stream, d_text + lo, lo, hi - lo); }
         }
     };
