@@ -73,7 +73,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnafgpu.so")
+    """NAFGPU_LIB names another build of the same library (A/B measurements of kernel variants); there is still no fallback."""
+    return os.environ.get("NAFGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libnafgpu.so")
 
 
 def load_library():

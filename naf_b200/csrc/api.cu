@@ -68,6 +68,13 @@ int nafgpu_create(int device, nafgpu_ctx **out)
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->pipe.create(); c->mail.create();
         for (auto &ev : c->ev) CUDA_TRY(cudaEventCreate(&ev));
+        {
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->side_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->side_join, cudaEventDisableTiming));
+        }
         u32 predef[nafz::FSE_SLOT_ENTRIES];
         nafz::zstd_build_predef(predef);
         CUDA_TRY(cudaMalloc(&c->d_predef, sizeof predef));
@@ -96,6 +103,9 @@ void nafgpu_destroy(nafgpu_ctx *c)
     if (c->d_predef) cudaFree(c->d_predef);
     if (c->d_nuc_lut) cudaFree(c->d_nuc_lut);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->side_fork) cudaEventDestroy(c->side_fork);
+    if (c->side_join) cudaEventDestroy(c->side_join);
+    if (c->side) cudaStreamDestroy(c->side);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }

@@ -414,6 +414,9 @@ struct Ctx {
     u32 *d_predef = nullptr;                 // predefined FSE tables
     u8 *d_nuc_lut = nullptr;                 // nuc_code + "unexpected" bit: DNA at 0, RNA at 256
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // side stream (higher priority) for the latency-bound thread-per-block kernels of the text-like streams: they run next to
+    // the throughput kernels of the two big streams instead of in front of them
+    cudaStream_t side = nullptr; cudaEvent_t side_fork = nullptr, side_join = nullptr;
     std::string err;
     nafgpu_timing timing{};
     std::vector<u8> host_scratch;

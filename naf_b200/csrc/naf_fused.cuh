@@ -223,7 +223,8 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
         }
     }
     if (tid >= 64 && tid < 128) { const u32 i = tid - 64; prev[i] = lo + i >= 64 ? A.text[lo + i - 64] : (u8)0; }
-    if (tid < 4) ((u32 *)(T.text + FT_BYTES))[tid] = 0;             // the word-wise copies read one word past a run
+    // the word-wise copies read one word past a run; its first byte is the text's next one (a CR LF pair may straddle the tiles)
+    if (tid < 4) ((u32 *)(T.text + FT_BYTES))[tid] = tid == 0 && lo + FT_BYTES < C.n ? (u32)A.text[lo + FT_BYTES] : 0u;
     if (bulk) {
         const u32 bar = (u32)__cvta_generic_to_shared(mbar);
         u32 done = 0;

@@ -113,7 +113,7 @@ HD u32 funnel_r(u32 lo, u32 hi, u32 shift_bits)       // (hi:lo) >> shift_bits, 
 // `len` bytes of the tile (shared memory, any alignment) -> staging (shared memory, any alignment), by the FT_GROUP lanes of a
 // group: aligned words of the destination from two aligned words of the tile, head and tail bytes one lane each.
 // Names and comments are checked here (check != FC_NONE), because their terminators share the staged region.
-HD u32 group_copy(const u8 *tile, u32 src, u32 len, u8 *dst, u32 lane, int check)
+template <bool CHECK> HD u32 group_copy(const u8 *tile, u32 src, u32 len, u8 *dst, u32 lane, int check)
 {
     u32 head = (u32)((4 - ((uintptr_t)dst & 3)) & 3), bad = 0;
     if (head > len) head = len;
@@ -121,7 +121,7 @@ HD u32 group_copy(const u8 *tile, u32 src, u32 len, u8 *dst, u32 lane, int check
     if (lane < head || (lane >= 4 && lane - 4 < tail)) {
         const u32 i = lane < head ? lane : done + lane - 4;
         const u32 c = tile[src + i];
-        bad |= sw_check(check, c * 0x01010101u);
+        if (CHECK) bad |= sw_check(check, c * 0x01010101u);
         dst[i] = (u8)c;
     }
     const u32 s0 = src + head, sh = (s0 & 3) * 8;
@@ -129,7 +129,7 @@ HD u32 group_copy(const u8 *tile, u32 src, u32 len, u8 *dst, u32 lane, int check
     u32 *dw = (u32 *)(dst + head);
     for (u32 w = lane; w < nw; w += FT_GROUP) {
         const u32 v = funnel_r(tw[w], tw[w + 1], sh);       // the tile is padded: tw[w + 1] is readable
-        bad |= sw_check(check, v);
+        if (CHECK) bad |= sw_check(check, v);
         dw[w] = v;
     }
     return bad;
@@ -216,6 +216,17 @@ struct FusedTile {
     FusedShared *sh;
 
     HD u32 seg_start(u32 j) const { return j ? (u32)seg_end[j - 1] + 1 : sh->live_lo; }
+    // Where the content of segment j (starting at s) ends: at its '\n', or at the end of the live range.  FASTA: a '\r' right
+    // before the '\n' is part of the line end -- '\r' is an end-of-line byte to process.c (tables.c:28 is_eol_arr) and runs of
+    // them collapse (process.c:383-399), so CR LF files split exactly like LF files.  The '\n' may be the first byte of the
+    // next tile (text[FT_BYTES] is readable and holds it).  Any other '\r' stays content and fails the checks of what consumes
+    // it.  (FASTQ: the reference dies on CR LF input; the '\r' stays content here too and the general parser reports it.)
+    HD u32 seg_content_end(bool fastq, u32 j, u32 s, bool has_nl) const
+    {
+        const u32 e = has_nl ? (u32)seg_end[j] : sh->live_hi;
+        if (!fastq && e > s && text[e - 1] == '\r' && (has_nl || (e == FT_BYTES && text[FT_BYTES] == '\n'))) return e - 1;
+        return e;
+    }
 
     // phase 1: newline mask of chunk c (16 bytes), restricted to the live range
     HD u32 chunk_mask(u32 c) const
@@ -263,7 +274,7 @@ struct FusedTile {
     {
         const u32 nseg = sh->nseg;
         const bool has_nl = j + 1 < nseg;
-        const u32 s = seg_start(j), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
+        const u32 s = seg_start(j), e = seg_content_end(C.fastq != 0, j, s, has_nl);
         const bool ls = j ? true : sh->entry_ls != 0;
         u32 role, skip1 = 0, rec = 0;
         A = 0; B = 0; sp = 0xFFFF;
@@ -333,7 +344,7 @@ struct FusedTile {
         const u32 o_ids = (u32)(a & 0xFFFF), o_comm = (u32)((a >> 16) & 0xFFFF), o_seq = (u32)((a >> 32) & 0xFFFF), o_qual = (u32)(a >> 48);
         const u32 k_rec = (u32)(b & 0xFFFF), k_hdr = (u32)((b >> 16) & 0xFFFF), k_seq = (u32)((b >> 32) & 0xFFFF), k_qual = (u32)(b >> 48);
         const bool has_nl = rb & SR_NL;
-        const u32 s0 = seg_start(j), s = s0 + ((rb & SR_SKIP1) ? 1 : 0), e = has_nl ? (u32)seg_end[j] : sh->live_hi;
+        const u32 s0 = seg_start(j), s = s0 + ((rb & SR_SKIP1) ? 1 : 0), e = seg_content_end(C.fastq != 0, j, s0, has_nl);
         switch (role) {
         case FR_HDR: {
             const u32 kn = sh->n_seq + sh->n_qual + k_hdr, kc = kn + sh->n_hdr;
@@ -385,8 +396,9 @@ struct FusedTile {
     {
         const u32 len = d_len[k], nsq = sh->n_seq + sh->n_qual;
         if (!len) return 0;
-        const int check = k < nsq ? (int)FC_NONE : (k < nsq + sh->n_hdr ? C.id_check : (int)FC_COMM);
-        return group_copy(text, d_src[k], len, stage + d_dst[k], lane, check) ? (u32)FU_BADBYTE : 0u;
+        if (k < nsq) { group_copy<false>(text, d_src[k], len, stage + d_dst[k], lane, FC_NONE); return 0; }   // sequence / quality: checked on their way out
+        const int check = k < nsq + sh->n_hdr ? C.id_check : (int)FC_COMM;
+        return group_copy<true>(text, d_src[k], len, stage + d_dst[k], lane, check) ? (u32)FU_BADBYTE : 0u;
     }
 
     // phase 5: record k of the tile ends -> its length unit, the quality-length check, the longest read

@@ -32,9 +32,12 @@ using nafz::ZEncMeta; using nafz::BitW;
 
 static const u32 ZBS = 32 * 1024;            // uncompressed bytes per block (Huffman-only streams)
 static const u32 ZSLOT = ZBS + 512;          // bytes reserved per block for its compressed content
-static const u32 ZLB = 8 * 1024;             // uncompressed bytes per block of an LZ stream (one thread encodes a block)
-static const u32 ZLSLOT = ZLB + 512;
-static const u32 ZLZ_MAXSEQ = ZLB / 4;
+static const u32 ZLB_MAX = 8 * 1024;         // uncompressed bytes per block of an LZ stream (one thread encodes a block)
+static u32 zlb_bytes()                       // NAFGPU_ZLB=1024..8192 (A/B measurements); a thread's latency is proportional to it
+{
+    static const u32 v = [] { const char *e = getenv("NAFGPU_ZLB"); const u32 x = e ? (u32)atoi(e) : 0u; return x >= 256 && x <= ZLB_MAX ? x : ZLB_MAX; }();
+    return v;
+}
 static const int ZWINDOW_LOG = 17;
 
 struct ZEncBlock {
@@ -54,7 +57,7 @@ struct ZEncBatch {
     void add(const u8 *p, u64 bytes, int window_log, bool with_lz = false) { src.push_back(p); n.push_back(bytes); wlog.push_back(window_log); lz.push_back(with_lz ? 1 : 0); }
 };
 
-struct ZEncArgs { ZEncBlock *blk; u8 *slots; };
+struct ZEncArgs { ZEncBlock *blk; u8 *slots; };      // blk: the first block the three Huffman kernels look at (LZ streams lie before it)
 struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u64 slot_base[8]; u32 first[9]; u32 bs[8]; u32 lz[8]; u32 ns; };
 struct ZEncFirstBlocks { u32 v[9]; };
 
@@ -286,11 +289,10 @@ __global__ void __launch_bounds__(256) k_zenc_gather(const ZGatherArgs A)
 // ---- LZ streams: one thread per 8 KB block runs nafz::zlz_encode_block (match finder, literal Huffman, FSE-coded sequences).
 // The 32 hash tables of a CTA live in shared memory, interleaved so that entry e of lane l sits in bank l; the rest of a
 // block's scratch (literals, sequence arrays, symbol codes, FSE state tables) is a private slice of one HBM workspace.
-static const u32 ZLZ_WORK_LIT = ZLB + 64, ZLZ_WORK_SEQ = ZLZ_MAXSEQ * 2, ZLZ_WORK_SPOS = 1280 * 2, ZLZ_WORK_TSYM = 512,
-                 ZLZ_WORK_CODES = 3 * ZLZ_MAXSEQ;
-static const u32 ZLZ_WORK = ZLZ_WORK_LIT + 3 * ZLZ_WORK_SEQ + ZLZ_WORK_SPOS + ZLZ_WORK_TSYM + ZLZ_WORK_CODES;
+static const u32 ZLZ_WORK_SPOS = 1280 * 2, ZLZ_WORK_TSYM = 512;
 static const u32 ZLZ_SMEM = 32 * (1u << nafz::ZLZ_HLOG) * 2;
-struct ZLzArgs { ZEncBlock *blk; u8 *slots; u8 *work; u32 first[9]; u32 lzfirst[9]; u32 ns; u32 nlz; };
+struct ZLzArgs { ZEncBlock *blk; u8 *slots; u8 *work; u32 first[9]; u32 lzfirst[9]; u32 ns; u32 nlz; u32 zlb; };
+HD u32 zlz_work_bytes(u32 zlb) { return ((zlb + 64) + 3 * (zlb / 4) * 2 + ZLZ_WORK_SPOS + ZLZ_WORK_TSYM + 3 * (zlb / 4) + 15) & ~15u; }
 
 __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
 {
@@ -300,13 +302,14 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
     u32 s = 0;
     while (s + 1 < A.ns && j >= A.lzfirst[s + 1]) s++;
     ZEncBlock &B = A.blk[A.first[s] + (j - A.lzfirst[s])];
-    u8 *w = A.work + (size_t)j * ZLZ_WORK;
-    u8 *lit = w; w += ZLZ_WORK_LIT;
-    nafz::ZLzSeqs S; S.ll = (u16 *)w; w += ZLZ_WORK_SEQ; S.ml = (u16 *)w; w += ZLZ_WORK_SEQ; S.ov = (u16 *)w; w += ZLZ_WORK_SEQ; S.n = 0;
+    const u32 zlb = A.zlb, maxseq = zlb / 4;
+    u8 *w = A.work + (size_t)j * zlz_work_bytes(zlb);
+    u8 *lit = w; w += zlb + 64;
+    nafz::ZLzSeqs S; S.ll = (u16 *)w; w += maxseq * 2; S.ml = (u16 *)w; w += maxseq * 2; S.ov = (u16 *)w; w += maxseq * 2; S.n = 0;
     nafz::ZLzWork W; W.spos = (u16 *)w; w += ZLZ_WORK_SPOS; W.tsym = w; w += ZLZ_WORK_TSYM; W.codes = w;
     u8 *slot = A.slots + B.slot_off;
     bool rle = false;
-    const u32 cs = nafz::zlz_encode_block(B.src, B.n, true, htabs + threadIdx.x, 32, lit, S, ZLZ_MAXSEQ, W, slot, ZLSLOT, &rle);
+    const u32 cs = nafz::zlz_encode_block(B.src, B.n, true, htabs + threadIdx.x, 32, lit, S, maxseq, W, slot, zlb + 512, &rle);
     if (cs) { B.type = 2; B.csize = cs; }
     else if (rle) { slot[0] = B.src[0]; B.type = 1; B.csize = 1; }
     else { B.type = 0; B.csize = B.n; }
@@ -320,7 +323,9 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     ZEncStreamTab tab; memset(&tab, 0, sizeof tab);
     ZLzArgs L; memset(&L, 0, sizeof L);
     b.first_block.assign(ns + 1, 0);
-    u64 slot_total = 0; u32 nlz = 0;
+    u64 slot_total = 0; u32 nlz = 0; bool side = false;
+    const u32 ZLB = zlb_bytes(), ZLSLOT = ZLB + 512;
+    L.zlb = ZLB;
     for (size_t s = 0; s < ns; s++) {
         const u32 bs = b.lz[s] ? ZLB : ZBS, slot = b.lz[s] ? ZLSLOT : ZSLOT;
         const u32 nb = (u32)(b.n[s] ? (b.n[s] + bs - 1) / bs : 1);
@@ -348,18 +353,34 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
         }, "zenc_init_blocks");
     }
     if (nlz) {
-        L.blk = b.d_blocks; L.slots = b.d_slots; L.work = ex.alloc<u8>((size_t)nlz * ZLZ_WORK);
+        L.blk = b.d_blocks; L.slots = b.d_slots; L.work = ex.alloc<u8>((size_t)nlz * zlz_work_bytes(ZLB));
         CUDA_TRY(cudaFuncSetAttribute(k_zenc_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZLZ_SMEM));
-        KLAUNCH(ex, "k_zenc_lz", k_zenc_lz<<<(nlz + 31) / 32, 32, ZLZ_SMEM, ex.stream>>>(L));
+        // next to the Huffman kernels of the big streams, not in front of them (when profiling: in line, so that its time is its own)
+        static const bool env_side = !(getenv("NAFGPU_SIDE") && getenv("NAFGPU_SIDE")[0] == '0');
+        side = env_side && ctx.side && !(ex.prof && ex.prof->on);
+        if (side) {
+            CUDA_TRY(cudaEventRecord(ctx.side_fork, ex.stream));
+            CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.side_fork, 0));
+            k_zenc_lz<<<(nlz + 31) / 32, 32, ZLZ_SMEM, ctx.side>>>(L);
+            CUDA_TRY(cudaEventRecord(ctx.side_join, ctx.side));
+            ex.launches++;
+        } else KLAUNCH(ex, "k_zenc_lz", k_zenc_lz<<<(nlz + 31) / 32, 32, ZLZ_SMEM, ex.stream>>>(L));
     }
-    ZEncArgs A{b.d_blocks, b.d_slots};
-    u16 *d_hists = ex.alloc<u16>((size_t)b.nblocks * 256);
-    ZEncMeta *d_metas = ex.alloc<ZEncMeta>(b.nblocks);
+    // the Huffman kernels skip LZ blocks; when the LZ streams come first (they do in a .naf) they are not even launched for them
+    u32 base = 0;
+    { size_t s = 0; while (s < ns && b.lz[s]) s++; bool tail_plain = true; for (size_t t = s; t < ns; t++) if (b.lz[t]) tail_plain = false; if (tail_plain) base = b.first_block[s]; }
+    const u32 nhuf = b.nblocks - base;
+    ZEncArgs A{b.d_blocks + base, b.d_slots};
+    u16 *d_hists = ex.alloc<u16>((size_t)nhuf * 256);
+    ZEncMeta *d_metas = ex.alloc<ZEncMeta>(nhuf);
     CUDA_TRY(cudaFuncSetAttribute(k_zenc_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZHIST_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(k_zenc_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZENC_SMEM));
-    KLAUNCH(ex, "k_zenc_hist", k_zenc_hist<<<b.nblocks, 256, ZHIST_SMEM, ex.stream>>>(A, d_hists));
-    KLAUNCH(ex, "k_zenc_tables", k_zenc_tables<<<(b.nblocks + 63) / 64, 64, 0, ex.stream>>>(A, b.nblocks, d_hists, d_metas));
-    KLAUNCH(ex, "k_zenc_encode", k_zenc_encode<<<b.nblocks, 256, ZENC_SMEM, ex.stream>>>(A, d_metas));
+    if (nhuf) {
+        KLAUNCH(ex, "k_zenc_hist", k_zenc_hist<<<nhuf, 256, ZHIST_SMEM, ex.stream>>>(A, d_hists));
+        KLAUNCH(ex, "k_zenc_tables", k_zenc_tables<<<(nhuf + 63) / 64, 64, 0, ex.stream>>>(A, nhuf, d_hists, d_metas));
+        KLAUNCH(ex, "k_zenc_encode", k_zenc_encode<<<nhuf, 256, ZENC_SMEM, ex.stream>>>(A, d_metas));
+    }
+    if (side) CUDA_TRY(cudaStreamWaitEvent(ex.stream, ctx.side_join, 0));
     b.d_off = ex.alloc<u64>(b.nblocks + 2);
     const ZEncBlock *db = b.d_blocks;
     exclusive_scan(ex, [db] __device__ (size_t i) { return (u64)db[i].csize + 3; }, b.nblocks, b.d_off);
@@ -375,7 +396,6 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     ex.download(h_fs, d_fs, ns * 8);
     b.frame_size.assign(ns, 0); b.dest.assign(ns, nullptr);
     for (size_t s = 0; s < ns; s++) b.frame_size[s] = h_fs[s];
-    (void)ctx;
 }
 
 static void zstd_gather_frames(Ctx &ctx, CudaExec &ex, ZEncBatch &b, bool skip_magic)

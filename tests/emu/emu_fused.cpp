@@ -63,6 +63,7 @@ static int run_fused(const std::vector<u8> &text_in, u64 p0, bool fastq, int seq
         memset(&sh, 0, sizeof sh);
         memset(stage, 0xDD, FT_STAGE);
         memcpy(tile, gtext.data() + lo, FT_BYTES); memset(tile + FT_BYTES, 0, 16);
+        if (lo + FT_BYTES < n) tile[FT_BYTES] = gtext[lo + FT_BYTES];
         sh.tile = (u32)t;
         sh.live_lo = p0 > lo ? (p0 - lo >= FT_BYTES ? FT_BYTES : (u32)(p0 - lo)) : 0;
         sh.live_hi = n >= lo + FT_BYTES ? FT_BYTES : (n > lo ? (u32)(n - lo) : 0);

@@ -159,6 +159,25 @@ def test_split_canonical_uses_fast_parser(gpu, oracle):
         check_split(gpu, oracle, text[:at] + byte + text[at + 1:], expect_fast=False)
 
 
+def test_crlf_fasta_uses_fast_parser(gpu, oracle):
+    """CR LF FASTA (process.c: '\\r' is an end-of-line byte, runs of them collapse) splits like LF FASTA in the single-pass
+    transform -- no fallback -- and equals the oracle; line widths that put CR | LF across 16 KB tile boundaries; a stray CR
+    still goes to the general parser"""
+    rng = np.random.default_rng(23)
+    fa = synth.fasta_softmasked(2_000_000, width=60, seed=42, n_records=5, repeats=True, n_gaps=2).replace(b"\n", b"\r\n")
+    cases = [(fa, {}), (fa[:-1], {}), (fa[:-2], {}), (synth.ont_fasta(20, 1000, 50000, seed=43).replace(b"\n", b"\r\n"), {}),
+             (synth.protein_fasta(5000, 300, seed=44).replace(b"\n", b"\r\n"), {"seq_type": "protein"}),
+             (synth.protein_fasta(2000, 300, seed=45).replace(b"\n", b"\r\n"), {"seq_type": "text", "no_mask": True})]
+    for w in (61, 62, 63, 126, 127, 254, 1022, 16382, 16383):
+        s = bytes(np.frombuffer(b"ACGTacgtN-", dtype=np.uint8)[rng.integers(0, 10, 40 * w + 7)])
+        cases.append((b"".join(b">r%d some comment here\r\n" % i + b"\r\n".join(s[k:k + w] for k in range(0, len(s), w)) + b"\r\n" for i in range(4)), {}))
+    for text, kw in cases:
+        check_split(gpu, oracle, text, expect_fast=not text.endswith(b"\r"), **kw)
+    check_split(gpu, oracle, fa[:1_000_000] + b"\r" + fa[1_000_000:], expect_fast=False)
+    naf = gpu.encode(fa)
+    assert gpu.decode(naf) == fa.replace(b"\r\n", b"\n")
+
+
 def test_zstd_compress_roundtrip(gpu, oracle):
     """our frames are valid zstd: the oracle decoder (pinned to libzstd) regenerates the input"""
     rng = np.random.default_rng(3)

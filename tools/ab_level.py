@@ -1,6 +1,6 @@
 """A/B of the encoder's parse levels on one GPU, device-resident (CUDA events on the library's stream):
     python tools/ab_level.py RECORDS [OUT.json]
-level -1 = entropy-only parse of every stream; level 1 = LZ77 + FSE-coded sequences on ids / comments / lengths / mask.
+level 1 = entropy-only parse of every stream; level 2 = LZ77 + FSE-coded sequences on ids / comments / lengths / mask.
 Each level: 2 warm-up + 3 timed round trips (bit-exact check on the device), then one profiled step (per-kernel ms)."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +16,7 @@ stream = torch.cuda.ExternalStream(ctx.lib.nafgpu_stream(ctx.h))
 cudart = C.CDLL("libcudart.so"); cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
 res = {"records": n, "text_bytes": n_text, "levels": {}}
 d_naf = torch.zeros(n_text // 2 + 4096, dtype=torch.uint8, device="cuda")
-for level in (-1, 1):
+for level in (1, 2):
     eo, do = api.make_enc_opts(level=level), api.make_dec_opts()
     enc, dec = [], []
     for it in range(5):
