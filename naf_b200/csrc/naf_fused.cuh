@@ -1,6 +1,6 @@
 // naf_fused.cuh — the single-pass encode transform as one sm_100a kernel (logic: naf_fused_hd.cuh).
 //
-// k_fused: one CTA per 16 KB tile of text.  Tiles are handed out by an atomic ticket, so a tile's predecessors are always
+// k_fused: one CTA (512 threads) per 32 KB tile of text.  Tiles are handed out by an atomic ticket, so a tile's predecessors are always
 // resident or finished and the two chained look-backs (decoupled look-back: every tile publishes its own aggregate at once
 // and its inclusive state as soon as it knows its prefix) cannot deadlock.  The tile reaches shared memory by one bulk
 // asynchronous copy (cp.async.bulk + mbarrier; UBLKCP in SASS); everything after that works out of shared memory and every
@@ -11,7 +11,7 @@
 
 namespace nafg {
 
-static const int FUSED_NT = 256, FUSED_CPT = FT_CHUNKS / FUSED_NT, FUSED_SPT = FT_MAXSEG / FUSED_NT;
+static const int FUSED_NT = FT_BYTES / 64, FUSED_CPT = FT_CHUNKS / FUSED_NT, FUSED_SPT = FT_MAXSEG / FUSED_NT;      // 64 bytes of text per thread
 
 struct FusedArgs {
     FusedCfg C;
@@ -49,9 +49,9 @@ __device__ __forceinline__ void st_vol128(ulonglong2 *p, u64 x, u64 y)
 // reader needs neither a fence nor a second round trip: it loads all four words of a tile and uses the inclusive state if
 // all three of its words are there, else the aggregate if that is there, else it asks again.
 static const u64 F2_TAG = 1ull << 62;
-__device__ __forceinline__ void f2_put_aggregate(ulonglong2 *rec, const F2 &g)       // fields of ONE tile: 15 / 11 bits each
+__device__ __forceinline__ void f2_put_aggregate(ulonglong2 *rec, const F2 &g)       // fields of ONE tile: byte counts <= FT_BYTES <= 2^16 - 1, records <= 2^12 - 1
 {
-    st_vol128(rec, F2_TAG | g.ids | (g.comm << 15) | (g.seq << 30) | (g.qual << 45), g.rec | (g.srec << 11) | (g.qrec << 26) | (g.last << 41));
+    st_vol128(rec, F2_TAG | g.ids | (g.comm << 16) | (g.seq << 32) | (g.last << 48), g.qual | (g.rec << 16) | (g.srec << 28) | (g.qrec << 44));
 }
 __device__ __forceinline__ void f2_put_inclusive(ulonglong2 *rec, const F2 &g)       // sizes < 2^62, records < 2^40, srec / qrec saturated to 32 bits
 {
@@ -69,8 +69,8 @@ __device__ __forceinline__ int f2_get(const ulonglong2 *rec, F2 &g)
         return 2;
     }
     if (a.x & F2_TAG) {
-        g.ids = a.x & 0x7FFF; g.comm = (a.x >> 15) & 0x7FFF; g.seq = (a.x >> 30) & 0x7FFF; g.qual = (a.x >> 45) & 0x7FFF;
-        g.rec = a.y & 0x7FF; g.srec = (a.y >> 11) & 0x7FFF; g.qrec = (a.y >> 26) & 0x7FFF; g.last = (a.y >> 41) & 0x7FF;
+        g.ids = a.x & 0xFFFF; g.comm = (a.x >> 16) & 0xFFFF; g.seq = (a.x >> 32) & 0xFFFF; g.last = (a.x >> 48) & 0x7FF;
+        g.qual = a.y & 0xFFFF; g.rec = (a.y >> 16) & 0xFFF; g.srec = (a.y >> 28) & 0xFFFF; g.qrec = (a.y >> 44) & 0xFFFF;
         return 1;
     }
     return 0;
@@ -163,7 +163,7 @@ __device__ __forceinline__ u32 fused_region_out(const FusedTile &T, u32 off, u32
     return bad;
 }
 
-__global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
+__global__ void __launch_bounds__(FUSED_NT, 1024 / FUSED_NT) k_fused(const FusedArgs A)
 {
     extern __shared__ __align__(128) u8 smem[];
     FusedTile T;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(FUSED_NT, 4) k_fused(const FusedArgs A)
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (C.seq_mode == FS_PACK4) lut[tid] = nuc_lut32(A.lut8[tid]);
+    if (C.seq_mode == FS_PACK4 && tid < 256) lut[tid] = nuc_lut32(A.lut8[tid]);
     __syncthreads();
     const u32 tile = sh->tile;
     const u64 lo = (u64)tile * FT_BYTES;

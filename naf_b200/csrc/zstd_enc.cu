@@ -90,7 +90,8 @@ template <class F> __device__ __forceinline__ void zenc_each(bool full, const u8
         }
     } else for (u32 i = t0; i < t1; i++) f((u32)src[i]);
 }
-template <class F> __device__ __forceinline__ void zenc_each_rev(bool full, const u8 *src, u32 t0, u32 t1, F f)
+// backwards, two symbols per call (the bit assembly checks for a full word once per pair); an odd one goes to f1
+template <class F2, class F1> __device__ __forceinline__ void zenc_each_rev2(bool full, const u8 *src, u32 t0, u32 t1, F2 f2, F1 f1)
 {
     if (full) {
         const uint4 *v = (const uint4 *)(src + t0);
@@ -99,9 +100,13 @@ template <class F> __device__ __forceinline__ void zenc_each_rev(bool full, cons
             const uint4 x = __ldg(v + i);
             const u32 w[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
-            for (int k = 3; k >= 0; k--) { f(w[k] >> 24); f((w[k] >> 16) & 0xFF); f((w[k] >> 8) & 0xFF); f(w[k] & 0xFF); }
+            for (int k = 3; k >= 0; k--) { f2(w[k] >> 24, (w[k] >> 16) & 0xFF); f2((w[k] >> 8) & 0xFF, w[k] & 0xFF); }
         }
-    } else for (u32 i = t1; i > t0; i--) f((u32)src[i - 1]);
+    } else {
+        u32 i = t1;
+        for (; i >= t0 + 2; i -= 2) f2((u32)src[i - 1], (u32)src[i - 2]);
+        if (i > t0) f1((u32)src[i - 1]);
+    }
 }
 
 __global__ void __launch_bounds__(256, 3) k_zenc_hist(const ZEncArgs A, u16 *hists)
@@ -220,30 +225,29 @@ __global__ void __launch_bounds__(256) k_zenc_encode(const ZEncArgs A, const ZEn
         u32 byte_base = lit_hdr + tree_len + (nstreams == 4 ? 6 : 0);
         for (u32 j = 0; j < k; j++) byte_base += s_stream_bytes[j];
         // symbols later in the stream sit at lower bit positions: my first bit = bits of all threads after me in my stream
-        u64 ab = (u64)byte_base * 8 + (pre_bits[(k + 1) * tps] - (pre_bits[tid] + bits));     // absolute bit position of my next bit
-        u64 acc = 0; u32 fill = 0;
-        bool aligned = (ab & 31) == 0;
-        auto flush32 = [&]() {                                // acc holds >= 32 bits
-            if (aligned) { outw[ab >> 5] = (u32)acc; acc >>= 32; fill -= 32; ab += 32; }
-            else {                                            // first partial word: top it up, then run aligned
-                const u32 sh = (u32)(ab & 31), take = 32 - sh;
-                atomicOr(&outw[ab >> 5], (u32)acc << sh);
-                acc >>= take; fill -= take; ab += take; aligned = true;
-            }
+        const u64 ab = (u64)byte_base * 8 + (pre_bits[(k + 1) * tps] - (pre_bits[tid] + bits));     // absolute bit position of my first bit
+        // The accumulator is kept word-aligned: it starts with ab % 32 zero bits below my first code, so every flush is one
+        // whole word -- an atomicOr for my first word (its low bits belong to the thread after me), plain stores after that.
+        // A full word is looked for once per two symbols (codes are at most 11 bits: 31 + 22 < 64), at a point all lanes reach
+        // together, instead of after every symbol at whichever symbol a lane happens to fill up.
+        u32 wi = (u32)(ab >> 5), fill = (u32)(ab & 31);
+        u64 acc = 0;
+        bool first = true;
+        auto flush32 = [&]() {
+            if (first) { atomicOr(&outw[wi], (u32)acc); first = false; } else outw[wi] = (u32)acc;
+            acc >>= 32; fill -= 32; wi++;
         };
-        zenc_each_rev(full, src, t0, t1, [&](u32 c) {
-            const u32 e = ctab[c];
-            acc |= (u64)(e & 0xFFFF) << fill; fill += e >> 16;
-            if (fill >= 32) flush32();
-        });
+        zenc_each_rev2(full, src, t0, t1,
+            [&](u32 c1, u32 c0) {
+                const u32 e1 = ctab[c1], e0 = ctab[c0];
+                acc |= (u64)(e1 & 0xFFFF) << fill; fill += e1 >> 16;
+                acc |= (u64)(e0 & 0xFFFF) << fill; fill += e0 >> 16;
+                if (fill >= 32) flush32();
+            },
+            [&](u32 c) { const u32 e = ctab[c]; acc |= (u64)(e & 0xFFFF) << fill; fill += e >> 16; if (fill >= 32) flush32(); });
         if (q == 0) { acc |= 1ull << fill; fill++; }          // end mark right above the first symbol's code
         while (fill >= 32) flush32();
-        if (fill) {                                           // remainder (< 32 bits): may still straddle a word when not aligned yet
-            const u32 sh = (u32)(ab & 31);
-            const u32 v = (u32)acc & ((1u << fill) - 1);
-            atomicOr(&outw[ab >> 5], v << sh);
-            if (sh && sh + fill > 32) atomicOr(&outw[(ab >> 5) + 1], v >> (32 - sh));
-        }
+        if (fill) atomicOr(&outw[wi], (u32)acc);              // my last, partial word: its high bits belong to the thread before me
     }
     __syncthreads();
     {
