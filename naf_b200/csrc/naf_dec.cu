@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(WT_THREADS, 5) k_write_text(const __grid_const
 // the same thing to different pieces.  The image then goes to HBM as aligned 16-byte stores.
 // Layout rules as in rec_text_size / rec_bounds (output.c:369-406, output-fastq.c:100).
 static const u32 CT_P = 64;                 // bytes per piece
+static const u32 CT_PH = 16;                // bytes per piece of a header area (composed byte by byte: kept short, they set the time of the slowest lane)
 struct CtRec { u64 s_lo; u32 n_h, h_lo, n_s, q_lo, n_q, ppl; };   // a record's pieces that intersect the tile: header, sequence, quality area
 
 // image bytes [lo, hi) (tile-relative) <- src[0 .. hi - lo), src a global pointer of any alignment; one lane
@@ -466,7 +467,7 @@ __device__ __forceinline__ u8 ct_header_byte(const TextArgs &A, const RecInfo &R
     return __ldg(A.comm + R.cm_s + k);
 }
 
-__global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_constant__ TextArgs A, const u32 *tile_first)
+__global__ void __launch_bounds__(WT_THREADS, 5) k_compose_text(const __grid_constant__ TextArgs A, const u32 *tile_first)
 {
     __shared__ __align__(16) u8 img[WT_TILE + 16];
     __shared__ RecS recs[WT_MAXREC];
@@ -494,11 +495,11 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_con
         RecInfo R; rec_bounds(A, recs[tid], R);
         const u64 o = recs[tid].out0;
         CtRec c; c.s_lo = 0; c.n_h = c.h_lo = c.n_s = c.q_lo = c.n_q = 0; c.ppl = 1;
-        // header area [0, c): pieces of CT_P bytes
+        // header area [0, c): pieces of CT_PH bytes
         if (R.c > 0 && o < tile1 && o + R.c > tile0) {
-            const u64 lo = tile0 > o ? (tile0 - o) / CT_P : 0;
-            u64 hi = (R.c + CT_P - 1) / CT_P;
-            if (o + R.c > tile1) hi = (tile1 - o + CT_P - 1) / CT_P;
+            const u64 lo = tile0 > o ? (tile0 - o) / CT_PH : 0;
+            u64 hi = (R.c + CT_PH - 1) / CT_PH;
+            if (o + R.c > tile1) hi = (tile1 - o + CT_PH - 1) / CT_PH;
             c.h_lo = (u32)lo; c.n_h = (u32)(hi - lo);
         }
         // sequence area [c, d).  wrapped: lines of W bases, each followed by '\n' (stride W + 1), a line cut into ppl pieces;
@@ -551,7 +552,11 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_con
     __syncthreads();
     const u32 nh = pre_h[nrec], ns = pre_s[nrec], nq = pre_q[nrec];
     auto find = [&](const u32 *p, u32 x) { u32 lo = 0, hi = nrec; while (hi - lo > 1) { const u32 mid = (lo + hi) >> 1; if (p[mid] <= x) lo = mid; else hi = mid; } return lo; };
-    // ---- sequence pieces (the bulk; first, so that the short kinds fill the lanes they leave idle)
+    // The three kinds are enumerated one after the other and dealt out round-robin ACROSS the kinds: the first quality piece goes
+    // to the thread after the one that took the last sequence piece, and so on -- every loop starting at thread 0 left the upper
+    // warps of a CTA idle behind a barrier (a tile has about 120 + 140 + 60 pieces for 256 threads; ncu: a third of all stall
+    // samples sat on that barrier).
+    // ---- sequence pieces (the bulk)
     for (u32 g = tid; g < ns; g += WT_THREADS) {
         const u32 r = find(pre_s, g);
         const RecS &rs = recs[r]; const CtRec c = cr[r];
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_con
         if (nl && x1 >= tile0 && x1 < tile1) img[x1 - tile0] = '\n';
     }
     // ---- quality-area pieces
-    for (u32 g = tid; g < nq; g += WT_THREADS) {
+    for (u32 g = (tid + WT_THREADS - ns % WT_THREADS) % WT_THREADS; g < nq; g += WT_THREADS) {
         const u32 r = find(pre_q, g);
         const RecS &rs = recs[r]; const CtRec c = cr[r];
         RecInfo R; rec_bounds(A, rs, R);
@@ -593,12 +598,12 @@ __global__ void __launch_bounds__(WT_THREADS, 4) k_compose_text(const __grid_con
         if (b0 + nb >= R.L && x1 >= tile0 && x1 < tile1) img[x1 - tile0] = '\n';
     }
     // ---- header pieces
-    for (u32 g = tid; g < nh; g += WT_THREADS) {
+    for (u32 g = (tid + WT_THREADS - (ns + nq) % WT_THREADS) % WT_THREADS; g < nh; g += WT_THREADS) {
         const u32 r = find(pre_h, g);
         const RecS &rs = recs[r]; const CtRec c = cr[r];
         RecInfo R; rec_bounds(A, rs, R);
         const u64 idx = c.h_lo + (g - pre_h[r]);
-        const u64 x0 = rs.out0 + idx * CT_P, x1 = x0 + CT_P < rs.out0 + R.c ? x0 + CT_P : rs.out0 + R.c;
+        const u64 x0 = rs.out0 + idx * CT_PH, x1 = x0 + CT_PH < rs.out0 + R.c ? x0 + CT_PH : rs.out0 + R.c;
         const u64 y0 = x0 > tile0 ? x0 : tile0, y1 = x1 < tile1 ? x1 : tile1;
         for (u64 q = y0; q < y1; q++) img[q - tile0] = ct_header_byte(A, R, (u32)(q - rs.out0));
     }
