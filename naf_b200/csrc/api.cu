@@ -24,6 +24,8 @@ template <class F> static int guarded(nafgpu_ctx *ctx, F f)
     try {
         ctx->err.clear(); ctx->fast_fallbacks = 0;
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (ctx->side) cudaStreamSynchronize(ctx->side);        // nothing of an earlier (failed) call may still be using the arena
+        ctx->early = Ctx::EarlyZ();
         if (!ctx->keep_arena) { ctx->arena.reset(); ctx->shard.active = false; }
         ctx->keep_arena = false;
         ctx->pipe.reset(); ctx->mail.up_used = Mailbox::DOWN;

@@ -417,6 +417,16 @@ struct Ctx {
     // side stream (higher priority) for the latency-bound thread-per-block kernels of the text-like streams: they run next to
     // the throughput kernels of the two big streams instead of in front of them
     cudaStream_t side = nullptr; cudaEvent_t side_fork = nullptr, side_join = nullptr;
+    // Host-buffer encode: the two big streams (sequence, quality) are compressed WHILE the text is still arriving -- every few
+    // uploaded chunks the blocks that have become complete go through the Huffman kernels on the side stream (zstd_enc.cu
+    // zenc_early_*), so that only the last blocks and the small streams are left when the upload ends.
+    struct EarlyZ {
+        bool on = false;
+        const u8 *src[2] = {nullptr, nullptr};   // sequence, quality stream
+        void *blk[2] = {nullptr, nullptr};       // ZEncBlock[max blocks]
+        u8 *slots[2] = {nullptr, nullptr};
+        u64 max_blocks[2] = {0, 0}, done[2] = {0, 0};
+    } early;
     std::string err;
     nafgpu_timing timing{};
     std::vector<u8> host_scratch;

@@ -480,6 +480,17 @@ static void mask_from_casebits(CudaExec &ex, SplitDev &S, const u32 *casebits, u
     } else build_mask_units(ex, flip_pos, R, n_seq, 0, 0, 1, &S.mask, &S.n_mask);
 }
 
+// zstd_enc.cu (same translation unit, below): compression of the big streams behind the upload
+static void zenc_early_begin(Ctx &ctx, CudaExec &ex, const u8 *seq, u64 seq_max_bytes, const u8 *qual, u64 qual_max_bytes);
+static void zenc_early_step(Ctx &ctx, u64 seq_bytes, u64 qual_bytes);
+static void zenc_early_abort(Ctx &ctx);
+struct EarlyTotals { u64 seq, qual; };
+__global__ void k_early_totals(const ulonglong2 *rec, EarlyTotals *out)      // the inclusive look-back #2 record of a chunk's last tile
+{
+    F2 g; f2_get(rec, g);
+    out->seq = g.seq; out->qual = g.qual;
+}
+
 // The single-pass transform (naf_fused.cuh) for canonical input: one kernel reads the text once and writes every stream once.
 // Throws FastFallback when the input is not canonical (or has an error the general parser must word).
 // h_head: the first bytes of the text on the host if the caller has them (host-buffer API), else nullptr.
@@ -536,14 +547,33 @@ static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, si
     CUDA_TRY(cudaFuncSetAttribute(k_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FusedSmem::total));
     if (piped) {
         // one launch per uploaded chunk, each right behind its chunk's copy: tiles are handed out by the global ticket and look
-        // back only (naf_fused.cuh), so a launch needs nothing beyond the bytes that have arrived
+        // back only (naf_fused.cuh), so a launch needs nothing beyond the bytes that have arrived.  Every EARLY_GROUP chunks the
+        // stream sizes so far go to the host (mailbox + event), which then has the blocks that became complete compressed on the
+        // side stream while the next chunks are still on their way up.
+        static const bool env_early = !(getenv("NAFGPU_EARLY") && getenv("NAFGPU_EARLY")[0] == '0');
+        const size_t EARLY_GROUP = 8, nchunks = ex.pipe->chunks();
+        const bool early = env_early && !shard && ctx.side && ex.mail && !(ex.prof && ex.prof->on) && nchunks >= 2 * EARLY_GROUP && nchunks / EARLY_GROUP <= 240;
+        std::vector<cudaEvent_t> gev;
+        EarlyTotals *slots = early ? (EarlyTotals *)(ex.mail->p + (48u << 10)) : nullptr;
+        if (early) zenc_early_begin(ctx, ex, C.seq, (packed ? n / 2 : n) + 64, C.qual, fastq ? n + 64 : 0);
         u64 t0 = 0;
-        for (size_t c = 0; c < ex.pipe->chunks(); c++) {
+        for (size_t c = 0; c < nchunks; c++) {
             const u64 hi = (c + 1) * ex.pipe->chunk < n ? (c + 1) * ex.pipe->chunk : n;
-            const u64 t1 = c + 1 == ex.pipe->chunks() ? ntiles : hi / FT_BYTES;
+            const u64 t1 = c + 1 == nchunks ? ntiles : hi / FT_BYTES;
             ex.pipe->wait_input(ex.stream, hi);
             if (t1 > t0) { KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)(t1 - t0), FUSED_NT, FusedSmem::total, ex.stream>>>(A)); }
             t0 = t1;
+            if (early && (c + 1) % EARLY_GROUP == 0 && c + 1 < nchunks && t1 > 0) {
+                k_early_totals<<<1, 1, 0, ex.stream>>>(A.st2 + 4ull * (t1 - 1), slots + gev.size());
+                cudaEvent_t e = ex.pipe->event();
+                CUDA_TRY(cudaEventRecord(e, ex.stream));
+                gev.push_back(e);
+            }
+        }
+        for (size_t g = 0; g < gev.size(); g++) {
+            CUDA_TRY(cudaEventSynchronize(gev[g]));
+            const EarlyTotals t = slots[g];
+            zenc_early_step(ctx, packed ? t.seq / 2 : t.seq, t.qual);      // (a byte of codes still waiting for its second base is not final)
         }
     } else { KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)ntiles, FUSED_NT, FusedSmem::total, ex.stream>>>(A)); }
     KLAUNCH(ex, "k_fused_finish", k_fused_finish<<<1, 1, 0, ex.stream>>>(A));
@@ -573,6 +603,7 @@ static SplitDev split_streams(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n
         try { return split_streams_fused(ctx, ex, d_text, n, o, info, false); }
         catch (const FastFallback &) {}
         catch (const NafError &) {}
+        zenc_early_abort(ctx);
         CUDA_TRY(cudaStreamSynchronize(ex.stream));
         ex.arena->rewind(mk);
         ctx.fast_fallbacks++;

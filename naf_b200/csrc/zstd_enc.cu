@@ -44,7 +44,7 @@ struct ZEncBlock {
     const u8 *src; u32 n; u32 stream; u32 last;
     u32 type;      // 0 raw (content = src bytes), 1 RLE, 2 compressed (content in slot)
     u32 csize;     // content bytes
-    u32 lz;        // block of an LZ stream: k_zenc_lz does everything, the three Huffman kernels pass
+    u32 lz;        // 1: block of an LZ stream (k_zenc_lz does everything), 2: compressed earlier, behind the upload; the three Huffman kernels pass
     u64 slot_off;  // where my slot starts in the slot pool
 };
 
@@ -58,7 +58,8 @@ struct ZEncBatch {
 };
 
 struct ZEncArgs { ZEncBlock *blk; u8 *slots; };      // blk: the first block the three Huffman kernels look at (LZ streams lie before it)
-struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u64 slot_base[8]; u32 first[9]; u32 bs[8]; u32 lz[8]; u32 ns; };
+struct ZEncStreamTab { const u8 *src[8]; u64 n[8]; u64 slot_base[8]; u32 first[9]; u32 bs[8]; u32 lz[8]; u32 ns;
+                       const ZEncBlock *early[8]; const u8 *early_slots[8]; u32 early_done[8]; };
 struct ZEncFirstBlocks { u32 v[9]; };
 
 // Three kernels per batch of 32 KB blocks.  Shared-memory atomics cost 32-64 cycles per warp instruction on this
@@ -319,6 +320,65 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
     else { B.type = 0; B.csize = B.n; }
 }
 
+// ---- host-buffer encode: the big streams compressed behind the upload (Ctx::EarlyZ; called from split_streams_fused)
+static void zenc_early_begin(Ctx &ctx, CudaExec &ex, const u8 *seq, u64 seq_max_bytes, const u8 *qual, u64 qual_max_bytes)
+{
+    Ctx::EarlyZ &E = ctx.early;
+    E = Ctx::EarlyZ();
+    const u8 *src[2] = {seq, qual}; const u64 mx[2] = {seq_max_bytes, qual_max_bytes};
+    for (int k = 0; k < 2; k++) {
+        E.src[k] = src[k]; E.max_blocks[k] = mx[k] / ZBS;
+        if (!E.max_blocks[k]) continue;
+        E.blk[k] = ex.alloc<ZEncBlock>(E.max_blocks[k]);
+        E.slots[k] = ex.alloc<u8>(E.max_blocks[k] * ZSLOT + 64);
+    }
+    static bool attr_done[64] = {};
+    int dev = 0; cudaGetDevice(&dev);
+    if (dev < 64 && !attr_done[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(k_zenc_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZHIST_SMEM));
+        CUDA_TRY(cudaFuncSetAttribute(k_zenc_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZENC_SMEM));
+        attr_done[dev] = true;
+    }
+    E.on = true;
+    // the side stream must not start before what the compute stream did to the arena so far (memsets of the look-back records)
+    CUDA_TRY(cudaEventRecord(ctx.side_fork, ex.stream));
+    CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.side_fork, 0));
+}
+// the first seq_bytes / qual_bytes of the two streams are final: compress the blocks that have become complete.  The caller has
+// synchronised with the kernels that wrote them (event), so these launches need no further ordering.
+static void zenc_early_step(Ctx &ctx, u64 seq_bytes, u64 qual_bytes)
+{
+    Ctx::EarlyZ &E = ctx.early;
+    if (!E.on) return;
+    const u64 avail[2] = {seq_bytes, qual_bytes};
+    for (int k = 0; k < 2; k++) {
+        u64 upto = avail[k] / ZBS; if (upto > E.max_blocks[k]) upto = E.max_blocks[k];
+        if (upto <= E.done[k]) continue;
+        const u64 d0 = E.done[k], cnt = upto - d0;
+        ZEncBlock *blk = (ZEncBlock *)E.blk[k] + d0;
+        const u8 *src = E.src[k] + d0 * ZBS;
+        k_for_each<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx.side>>>((size_t)cnt, [=] __device__ (size_t i) {
+            ZEncBlock e; e.src = src + i * ZBS; e.n = ZBS; e.stream = 0; e.last = 0; e.type = 0; e.csize = 0; e.lz = 0; e.slot_off = (d0 + i) * ZSLOT;
+            blk[i] = e;
+        });
+        // scratch (histograms, codes) lives until the side stream has run these three kernels: taken from the arena, which is
+        // only reset by the next call (after the side stream has drained)
+        u16 *hists = (u16 *)ctx.arena.alloc_bytes((size_t)cnt * 512);
+        ZEncMeta *metas = (ZEncMeta *)ctx.arena.alloc_bytes((size_t)cnt * sizeof(ZEncMeta));
+        ZEncArgs A{blk, E.slots[k]};
+        k_zenc_hist<<<(unsigned)cnt, 256, ZHIST_SMEM, ctx.side>>>(A, hists);
+        k_zenc_tables<<<(unsigned)((cnt + 63) / 64), 64, 0, ctx.side>>>(A, (u32)cnt, hists, metas);
+        k_zenc_encode<<<(unsigned)cnt, 256, ZENC_SMEM, ctx.side>>>(A, metas);
+        CUDA_TRY(cudaGetLastError());
+        E.done[k] = upto;
+    }
+}
+static void zenc_early_abort(Ctx &ctx)
+{
+    if (ctx.early.on && ctx.side) cudaStreamSynchronize(ctx.side);
+    ctx.early = Ctx::EarlyZ();
+}
+
 static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
 {
     const size_t ns = b.src.size();
@@ -327,7 +387,7 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     ZEncStreamTab tab; memset(&tab, 0, sizeof tab);
     ZLzArgs L; memset(&L, 0, sizeof L);
     b.first_block.assign(ns + 1, 0);
-    u64 slot_total = 0; u32 nlz = 0; bool side = false;
+    u64 slot_total = 0; u32 nlz = 0; bool side = false, any_early = false;
     const u32 ZLB = zlb_bytes(), ZLSLOT = ZLB + 512;
     L.zlb = ZLB;
     for (size_t s = 0; s < ns; s++) {
@@ -336,6 +396,11 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
         b.first_block[s + 1] = b.first_block[s] + nb;
         tab.src[s] = b.src[s]; tab.n[s] = b.n[s]; tab.first[s] = b.first_block[s]; tab.bs[s] = bs; tab.lz[s] = (u32)b.lz[s];
         tab.slot_base[s] = slot_total; slot_total += (u64)nb * slot;
+        for (int k = 0; k < 2; k++)
+            if (ctx.early.on && !b.lz[s] && ctx.early.done[k] && b.src[s] == ctx.early.src[k]) {
+                tab.early[s] = (const ZEncBlock *)ctx.early.blk[k]; tab.early_slots[s] = ctx.early.slots[k];
+                tab.early_done[s] = (u32)(ctx.early.done[k] < nb ? ctx.early.done[k] : nb); any_early = true;
+            }
         L.first[s] = b.first_block[s]; L.lzfirst[s] = nlz; if (b.lz[s]) nlz += nb;
     }
     b.nblocks = b.first_block[ns];
@@ -343,9 +408,14 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
     L.first[ns] = b.nblocks; L.lzfirst[ns] = nlz; L.ns = (u32)ns; L.nlz = nlz;
     b.d_blocks = ex.alloc<ZEncBlock>(b.nblocks);
     b.d_slots = ex.alloc<u8>(slot_total + 64);
+    if (any_early) {                                           // what the side stream compressed behind the upload is part of this batch
+        CUDA_TRY(cudaEventRecord(ctx.side_join, ctx.side));
+        CUDA_TRY(cudaStreamWaitEvent(ex.stream, ctx.side_join, 0));
+    }
     {
         ZEncBlock *blk = b.d_blocks;
         const u32 fin = b.final_shard ? 1u : 0u;
+        const u8 *slots0 = b.d_slots;
         ex.for_each(b.nblocks, [=] __device__ (size_t i) {
             u32 s = 0;
             while (s + 1 < tab.ns && (u32)i >= tab.first[s + 1]) s++;
@@ -353,6 +423,10 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
             const u64 k = i - tab.first[s], off = k * bs, left = tab.n[s] - (tab.n[s] < off ? tab.n[s] : off);
             ZEncBlock e; e.src = tab.src[s] + off; e.n = (u32)(left < bs ? left : bs); e.stream = s; e.last = ((u32)i + 1 == tab.first[s + 1]) & fin;
             e.type = 0; e.csize = 0; e.lz = tab.lz[s]; e.slot_off = tab.slot_base[s] + k * (tab.lz[s] ? ZLSLOT : ZSLOT);
+            if (k < tab.early_done[s]) {                          // done already: take its result, its slot is in the early pool
+                const ZEncBlock d = tab.early[s][k];
+                e.type = d.type; e.csize = d.csize; e.lz = 2; e.slot_off = (u64)((tab.early_slots[s] + d.slot_off) - slots0);
+            }
             blk[i] = e;
         }, "zenc_init_blocks");
     }
