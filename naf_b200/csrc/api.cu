@@ -198,7 +198,7 @@ int nafgpu_decode(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_dec_
             d_naf = ex.alloc<u8>(n + 64);
             CUDA_TRY(cudaMemsetAsync(d_naf + n, 0, 64, c->stream));
             ex.pipe = &c->pipe;
-            c->pipe.upload(d_naf, naf, n, pipe_chunk(), c->stream);
+            c->pipe.defer_upload(d_naf, naf, n, pipe_chunk(), c->stream);      // decode_on_device starts it, in the order it wants the bytes
         } else d_naf = to_device(*c, ex, naf, n);
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         DecodeOut r = decode_on_device(*c, ex, d_naf, naf, n, *opts);
@@ -230,7 +230,7 @@ int nafgpu_decode_to(nafgpu_ctx *c, const uint8_t *naf, size_t n, const nafgpu_d
         ex.pipe = &c->pipe;
         c->pipe.rot_create();
         c->pipe.sink = write; c->pipe.sink_user = user;
-        c->pipe.upload(d_naf, naf, n, pipe_chunk(), c->stream);
+        c->pipe.defer_upload(d_naf, naf, n, pipe_chunk(), c->stream);      // decode_on_device starts it, in the order it wants the bytes
         CUDA_TRY(cudaEventRecord(c->ev[1], c->stream));
         DecodeOut r = decode_on_device(*c, ex, d_naf, naf, n, *opts);
         CUDA_TRY(cudaEventRecord(c->ev[2], c->stream));

@@ -144,6 +144,7 @@ struct HostPipe {
     void reset()
     {
         used = 0; in_ev.clear(); n_in = 0; uploading = false; h_in = nullptr; h_out = nullptr; out_done = 0; emitting = false;
+        deferred = ordered = false; def_d = nullptr; def_compute = nullptr; ord_lo.clear(); ord_hi.clear(); ord_ev.clear();
         sink = nullptr; sink_user = nullptr; sink_failed = false; rot_busy[0] = rot_busy[1] = false; rot_next = 0;
     }
     cudaEvent_t event()
@@ -168,9 +169,47 @@ struct HostPipe {
         }
     }
     size_t chunks() const { return in_ev.size(); }
+    // An upload whose ORDER is decided later: a decoder that has read the headers may want the two big streams of a FASTQ file
+    // piece by piece in turns (sequence piece 0, quality piece 0, sequence piece 1 ...), so that the first records can be
+    // written -- and their text sent down -- while most of the file is still on the host.  start_upload(nullptr) = front to back.
+    bool deferred = false, ordered = false; u8 *def_d = nullptr; cudaStream_t def_compute = nullptr;
+    std::vector<u64> ord_lo, ord_hi; std::vector<cudaEvent_t> ord_ev;           // in the order the copies were queued
+    void defer_upload(u8 *d, const u8 *h, u64 n, u64 chunk_bytes, cudaStream_t compute)
+    {
+        def_d = d; h_in = h; n_in = n; chunk = chunk_bytes; def_compute = compute; deferred = true; uploading = true;
+    }
+    void start_upload(const std::vector<std::pair<u64, u64>> *order)
+    {
+        if (!deferred) return;
+        deferred = false;
+        if (!order) { upload(def_d, h_in, n_in, chunk, def_compute); return; }
+        cudaEvent_t e0 = event();
+        CUDA_TRY(cudaEventRecord(e0, def_compute));
+        CUDA_TRY(cudaStreamWaitEvent(in, e0, 0));
+        ordered = true;
+        for (auto &r : *order)
+            for (u64 off = r.first; off < r.second; off += chunk) {
+                const u64 len = r.second - off < chunk ? r.second - off : chunk;
+                CUDA_TRY(cudaMemcpyAsync(def_d + off, h_in + off, len, cudaMemcpyHostToDevice, in));
+                cudaEvent_t e = event();
+                CUDA_TRY(cudaEventRecord(e, in));
+                ord_lo.push_back(off); ord_hi.push_back(off + len); ord_ev.push_back(e);
+            }
+    }
+    // the compute stream's next kernels may read input bytes [lo, hi)
+    void wait_range(cudaStream_t compute, u64 lo, u64 hi)
+    {
+        if (deferred) start_upload(nullptr);
+        if (!uploading || hi <= lo) return;
+        if (!ordered) { wait_input(compute, hi); return; }
+        for (size_t i = ord_ev.size(); i-- > 0;)                                  // the last copy queued that touches the range: the earlier ones are done by then
+            if (ord_lo[i] < hi && ord_hi[i] > lo) { CUDA_TRY(cudaStreamWaitEvent(compute, ord_ev[i], 0)); return; }
+    }
     // the compute stream's next kernels may read input bytes [0, hi)
     void wait_input(cudaStream_t compute, u64 hi)
     {
+        if (deferred) start_upload(nullptr);
+        if (ordered) { wait_range(compute, 0, hi); return; }
         if (!uploading || in_ev.empty() || hi == 0) return;
         size_t c = (size_t)((hi - 1) / chunk);
         if (c >= in_ev.size()) c = in_ev.size() - 1;

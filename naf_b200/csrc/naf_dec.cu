@@ -909,6 +909,42 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
     }
     else if (last_big >= 0 && rec_text_view && (walks.pending[last_big] || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
     (void)any_threaded;
+    // FASTQ from a host buffer whose two big streams can both be cut at block boundaries (files we wrote: the block index says
+    // so before a byte has gone up): the file is uploaded small streams first, then sequence piece 0, quality piece 0, sequence
+    // piece 1 ... and each pair of pieces is decoded, its records written and their text sent down while the rest is still on
+    // the host.  Front to back, nothing can be written before the whole sequence stream AND the first quality piece are up.
+    struct DuoPiece { size_t s0, s1, q0, q1; };
+    std::vector<DuoPiece> duo;
+    static const bool env_duo = !(getenv("NAFGPU_DUO") && getenv("NAFGPU_DUO")[0] == '0');
+    if (env_duo && ex.pipe && ex.pipe->deferred && !ranged && view == NAFGPU_OUT_FASTQ && need[SEC_DATA] && need[SEC_QUAL] &&
+        !walks.pending[SEC_DATA] && !walks.pending[SEC_QUAL] && h.sec[SEC_DATA].off < h.sec[SEC_QUAL].off) {
+        const nafz::ZWalked &ws = ctx.zwalk[SEC_DATA], &wq = ctx.zwalk[SEC_QUAL];
+        const char *env_piece0 = getenv("NAFGPU_PIPE_PIECE");
+        const u64 PIECE = env_piece0 && *env_piece0 ? strtoull(env_piece0, nullptr, 10) : (48ull << 20);
+        const bool cuttable = ws.rc == 0 && wq.rc == 0 && ws.simple && wq.simple && ws.regen.size() == ws.blocks.size() && wq.regen.size() == wq.blocks.size() &&
+                              !ws.blocks.empty() && !wq.blocks.empty() && h.sec[SEC_QUAL].comp >= 2 * PIECE && ws.blocks[0].src >= 3 && wq.blocks[0].src >= 3;
+        if (cuttable) {
+            size_t si = 0, qi = 0; u64 sreg = 0, qreg = 0;
+            while (qi < wq.blocks.size()) {
+                DuoPiece pc; pc.s0 = si; pc.q0 = qi;
+                u64 cbytes = 0;
+                while (qi < wq.blocks.size() && cbytes < PIECE) { cbytes += (u64)wq.blocks[qi].csize + 3; qreg += wq.regen[qi]; qi++; }
+                if (wq.blocks.size() - qi < 64) while (qi < wq.blocks.size()) { qreg += wq.regen[qi]; qi++; }          // no tiny last piece
+                if (qi == wq.blocks.size()) while (si < ws.blocks.size()) { sreg += ws.regen[si]; si++; }              // the last piece takes what is left
+                else while (si < ws.blocks.size() && (packed ? sreg * 2 : sreg) < qreg) { sreg += ws.regen[si]; si++; } // the bases of these qualities
+                pc.s1 = si; pc.q1 = qi;
+                duo.push_back(pc);
+            }
+            std::vector<std::pair<u64, u64>> order;
+            auto sstart = [&](size_t i) { return i < ws.blocks.size() ? ws.blocks[i].src - 3 : wq.blocks[0].src - 3; };
+            auto qstart = [&](size_t i) { return i < wq.blocks.size() ? wq.blocks[i].src - 3 : (u64)n; };
+            order.push_back({0, sstart(0)});
+            for (auto &pc : duo) { order.push_back({sstart(pc.s0), sstart(pc.s1)}); order.push_back({qstart(pc.q0), qstart(pc.q1)}); }
+            ex.pipe->start_upload(&order);
+            later_mask = big_mask;
+        }
+    }
+    if (ex.pipe) ex.pipe->start_upload(nullptr);                          // (unless it has just been started in that order)
     mark("walks started / index read");
     run_batch(all_mask & ~later_mask);
     mark("first batch decoded");
@@ -1120,7 +1156,64 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
             if (sink) { const u64 lo = a * WT_TILE, hi = b * WT_TILE < total ? b * WT_TILE : total; ex.pipe->emit(ex.stream, d_text + lo, lo, hi - lo); }
         }
     };
-    if (!ranged && later_mask) {
+    if (!duo.empty() && surplus != 0) { run_batch(big_mask); write_tiles(0, ntiles); }       // (a file with bases beyond its lengths: whole, as before)
+    else if (!duo.empty()) {
+        const nafz::ZWalked *wk[2] = { &ctx.zwalk[SEC_DATA], &ctx.zwalk[SEC_QUAL] };
+        const int sec[2] = { SEC_DATA, SEC_QUAL };
+        u64 *d_upto = ex.alloc<u64>(2);
+        u64 out_off[2] = {0, 0}, t_prev = 0;
+        for (size_t p = 0; p < duo.size(); p++) {
+            const size_t i0[2] = { duo[p].s0, duo[p].q0 }, i1[2] = { duo[p].s1, duo[p].q1 };
+            plan.blocks.clear(); plan.streams.clear();
+            u64 regen[2] = {0, 0}; int slot[2] = {-1, -1};
+            for (int s = 0; s < 2; s++) {
+                if (i1[s] <= i0[s]) continue;
+                const int k = sec[s]; const nafz::ZWalked &w = *wk[s];
+                const u32 base = (u32)plan.blocks.size();
+                u64 pre = 0;
+                for (size_t i = i0[s]; i < i1[s]; i++) {
+                    nafz::ZBlockHead hb = w.blocks[i];
+                    hb.frame_first_blk = base; hb.stream = (u8)plan.streams.size(); hb.out_base = soff[k] + out_off[s] + pre; hb.rsize = w.regen[i];
+                    hb.first_in_frame = hb.first_in_stream = i == i0[s];
+                    pre += w.regen[i];
+                    plan.blocks.push_back(hb);
+                }
+                nafz::ZStreamDesc sd = sdesc[k]; sd.out_off = soff[k] + out_off[s]; sd.out_size = pre;
+                slot[s] = (int)plan.streams.size();
+                plan.streams.push_back(sd);
+                regen[s] = pre;
+                ex.pipe->wait_range(ex.stream, w.blocks[i0[s]].src - 3, w.blocks[i1[s] - 1].src + w.blocks[i1[s] - 1].csize);
+            }
+            plan.simple = true;
+            plan.results.assign(plan.streams.size(), nafz::ZStreamResult{0, 0, 0});
+            std::string zerr;
+            int rc = nafz::zstd_decode_blocks(ex, d_naf, d_streams, plan, ctx.d_predef, zerr);
+            if (rc) fail(rc == -2 ? NAFGPU_E_UNSUPPORTED : NAFGPU_E_FORMAT, std::string("can't decompress: ") + zerr + "\n");
+            for (int s = 0; s < 2; s++) {
+                if (slot[s] < 0) continue;
+                if (plan.results[slot[s]].out_size != regen[s] || plan.results[slot[s]].nseq != 0) fail(NAFGPU_E_FORMAT, std::string("can't decompress ") + what[sec[s]] + "\n");
+                out_off[s] += regen[s];
+            }
+            u64 t_hi = ntiles;
+            if (p + 1 < duo.size()) {
+                const u64 bases_up = packed ? out_off[0] * 2 : out_off[0];
+                const u64 done = bases_up < out_off[1] ? bases_up : out_off[1];      // bases AND qualities available so far
+                const u64 *ss = d_seq_start, *os = d_out_start; const u64 nr = NR;
+                ex.for_each(1, [=] __device__ (size_t) {
+                    u64 lo = 0, hi = nr + 1;                         // largest r in [0, nr] with seq_start[r] <= done: records < r are complete
+                    while (hi - lo > 1) { const u64 mid = (lo + hi) >> 1; if (ss[mid] <= done) lo = mid; else hi = mid; }
+                    d_upto[0] = lo; d_upto[1] = os[lo];
+                }, "piece_upto");
+                u64 upto[2]; ex.download(upto, d_upto, 16);
+                t_hi = upto[1] / WT_TILE;
+                if (t_hi > ntiles) t_hi = ntiles;
+            } else if (out_off[0] < sbytes[SEC_DATA] || out_off[1] < sbytes[SEC_QUAL]) fail(NAFGPU_E_FORMAT, "can't decompress sequence\n");
+            if (t_hi > t_prev) { write_tiles(t_prev, t_hi); t_prev = t_hi; }
+        }
+        data_out_size = out_off[0];
+        piecewise = true;
+    }
+    else if (!ranged && later_mask) {
         const int k = last_big;
         const char *env_piece0 = getenv("NAFGPU_PIPE_PIECE");
         const u64 PIECE_MIN = env_piece0 && *env_piece0 ? strtoull(env_piece0, nullptr, 10) : (48ull << 20);
