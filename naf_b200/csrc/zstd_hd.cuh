@@ -446,16 +446,20 @@ static const int HUF_RING = 4;                                 // slots per lane
 // together (once per 16 symbols) and awaited one iteration later; a lane that runs dry only does a shared-memory load.
 struct BackBitsR {
     u32 bh, bl; int nb, npop, loaded0; i64 left;
-    u32 w0, w1, w2, w3; int qn; u32 n0, n1, n2, n3;
     u32 hw, sh;
     const uint4 *gp; const u8 *src;
-    u32 sbase, stride, issued, taken;                          // shared-memory address of slot 0, bytes between my slots
+    u32 sbase, stride, issued;                                 // shared-memory address of slot 0, bytes between my slots
+    u32 c;                                                     // words taken out of the ring so far (+ the words of the first chunk above my first one)
 
+    // Words are read straight out of the ring, one 32-bit shared-memory load per refill, addressed by a counter: chunk c / 4
+    // sits in slot (c / 4) % HUF_RING, and inside a chunk the words are used from the highest address down.  (The first
+    // version of this reader moved whole chunks into a four-word register queue -- a nested branch inside the refill branch, at
+    // a different symbol for every lane: ncu showed 21 of 32 lanes active over the whole kernel.)
     __device__ __forceinline__ void top_up()
     {
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            if (issued - taken < (u32)HUF_RING) {
+            if (issued - (c >> 2) < (u32)HUF_RING) {
                 const u32 slot = sbase + (issued & (HUF_RING - 1)) * stride;
                 if ((uintptr_t)(gp + 1) > (uintptr_t)src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot), "l"(gp) : "memory");
                 else asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(slot), "r"(0u) : "memory");
@@ -464,18 +468,17 @@ struct BackBitsR {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    __device__ __forceinline__ void take()
+    __device__ __forceinline__ u32 pop()
     {
-        const u32 slot = sbase + (taken & (HUF_RING - 1)) * stride;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(n0), "=r"(n1), "=r"(n2), "=r"(n3) : "r"(slot) : "memory");
-        taken++;
+        const u32 at = sbase + ((c >> 2) & (HUF_RING - 1)) * stride + ((3u - (c & 3u)) << 2);
+        u32 x;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(at) : "memory");
+        c++;
+        return x;
     }
-    __device__ __forceinline__ void fetch() { w0 = n0; w1 = n1; w2 = n2; w3 = n3; qn = 4; take(); }
-    __device__ __forceinline__ u32 pop() { if (qn == 0) fetch(); const u32 x = w3; w3 = w2; w2 = w1; w1 = w0; qn--; return x; }
     __device__ __forceinline__ bool init(const u8 *s, size_t n, u32 ring_slot0, u32 ring_stride)
     {
-        src = s; sbase = ring_slot0; stride = ring_stride; issued = taken = 0; npop = 0; qn = 0; hw = 0;
-        w0 = w1 = w2 = w3 = n0 = n1 = n2 = n3 = 0;
+        src = s; sbase = ring_slot0; stride = ring_stride; issued = 0; c = 0; npop = 0; hw = 0;
         if (n == 0) return false;
         const u8 last = s[n - 1];
         if (last == 0) return false;
@@ -492,11 +495,7 @@ struct BackBitsR {
         gp = (const uint4 *)((uintptr_t)na & ~(uintptr_t)15);
         top_up(); top_up();                                    // four chunks: the one holding `na` and the three below it
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-        take(); fetch();                                       // w = chunk holding `na`, n = the next one
-        for (u32 k = j; k < 3; k++) { w3 = w2; w2 = w1; w1 = w0; }
-        qn = (int)j + 1;
-        top_up();
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        c = 3 - j;                                             // the first word I use is word j of the first chunk
         return true;
     }
     __device__ __forceinline__ void refill()
