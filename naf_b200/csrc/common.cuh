@@ -411,8 +411,26 @@ template <class In> __global__ void k_scan_apply(In in, size_t n, const u64 *til
     if (base <= n && n < base + SCAN_ITEMS) out[n] = p - 0;      // thread owning position n writes the total
 }
 
+// a few thousand items (the records of a genome, the blocks of a range): one CTA, one launch instead of three
+template <class In> __global__ void __launch_bounds__(1024) k_scan_small(In in, size_t n, u64 *out)
+{
+    __shared__ u64 sm[33];
+    const size_t per = (n + 1023) / 1024, lo = (size_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    u64 s = 0;
+    for (size_t i = lo; i < hi; i++) s += in(i);
+    u64 total; u64 p = block_excl_scan(s, &total, sm);
+    for (size_t i = lo; i < hi; i++) { out[i] = p; p += in(i); }
+    if (threadIdx.x == 0) out[n] = total;
+}
+
 template <class In> void exclusive_scan(CudaExec &ex, In in, size_t n, u64 *out)
 {
+    if (n <= 16384) {
+        ex.prof_begin("scan");
+        k_scan_small<<<1, 1024, 0, ex.stream>>>(in, n, out);
+        ex.prof_end();
+        return;
+    }
     size_t ntiles = (n + SCAN_TILE) / SCAN_TILE;          // >= 1, and covers index n
     u64 *tiles = ex.alloc<u64>(ntiles + 1);
     ex.prof_begin("scan");

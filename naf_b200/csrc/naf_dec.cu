@@ -1066,10 +1066,17 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         // records [r0, r1) only: their text is the byte range [o0, o1) of the whole output
         const u64 r0 = o.first_record < NR ? o.first_record : NR, r1 = (o.n_records < NR - r0) ? r0 + o.n_records : NR;
         u64 o01[2] = { total, total };
-        ex.download(&o01[0], d_out_start + r0, 8); ex.download(&o01[1], d_out_start + r1, 8);
-        if (need[SEC_DATA] || need[SEC_QUAL]) {
-            u64 b01[2]; ex.download(&b01[0], d_seq_start + r0, 8); ex.download(&b01[1], d_seq_start + r1, 8);
-            range_b0 = b01[0]; range_b1 = b01[1];
+        const bool want_b = need[SEC_DATA] || need[SEC_QUAL];
+        {   // the four range bounds in one read-back (each download is a synchronisation)
+            u64 *d4 = ex.alloc<u64>(4);
+            const u64 *os = d_out_start, *ss = d_seq_start;
+            ex.for_each(1, [=] __device__ (size_t) { d4[0] = os[r0]; d4[1] = os[r1]; d4[2] = want_b ? ss[r0] : 0; d4[3] = want_b ? ss[r1] : 0; }, "range_bounds");
+            u64 h4[4]; ex.download(h4, d4, 32);
+            o01[0] = h4[0]; o01[1] = h4[1];
+            if (want_b) { range_b0 = h4[2]; range_b1 = h4[3]; }
+        }
+        if (want_b) {
+            const u64 b01[2] = { range_b0, range_b1 };
             if (later_mask) {
                 if (need[SEC_DATA]) { sdesc[SEC_DATA].need_lo = packed ? b01[0] / 2 : b01[0]; sdesc[SEC_DATA].need_hi = packed ? (b01[1] + 1) / 2 : b01[1]; }
                 if (need[SEC_QUAL]) { sdesc[SEC_QUAL].need_lo = b01[0]; sdesc[SEC_QUAL].need_hi = b01[1]; }
