@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--c5-gbp", type=float, default=3.0, help="size of the configs[4] FASTA for the c5_strong sub-record (0 = skip)")
-    ap.add_argument("--level", type=int, default=1, help="ennaf -# (1 = the tools' default: LZ77 + FSE sequences on ids/comments/lengths/mask; <= 0 entropy-only)")
+    ap.add_argument("--level", type=int, default=1, help="ennaf -# (1 = the tools' default: every stream entropy-coded; >= 2: + LZ77 / FSE-coded sequences on ids, comments, lengths, mask)")
     return ap.parse_args()
 
 
@@ -213,14 +213,15 @@ ALGO_BYTES_PER_BASE = {
     "k_fsm_reduce": 2.185, "k_fsm_count": 2.185, "k_fsm_scatter": 2.185 + 1.0 + 1.0 + 0.139 + 0.048,
     "k_pack4": 1.0 + 0.5 + 0.031,
     "k_zenc_hist": 1.67, "k_zenc_encode": 1.67 + 0.83, "k_zenc_gather": 2 * 0.83,
-    "zd_literals": 0.83 + 1.67, "k_write_text": 1.67 + 0.19 + 2.185,
+    "zd_literals": 0.83 + 1.67, "k_write_text": 1.67 + 0.19 + 2.185, "k_compose_text": 1.67 + 0.19 + 2.185,
 }
 # DRAM bytes per base measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum of one launch, 1 M reads:
 # profiles/r1k_top_full_1Mreads.summary.txt); bench.py scales them to the launch it timed
 NCU_TRAFFIC_PER_BASE = {
-    "k_fused": 558.5e6 / 150e6,          # profiles/r2c_fused_1Mreads.summary.txt
+    "k_fused": (985.9e6 + 775.0e6) / 450e6,   # profiles/r3h_fused_3Mreads.summary.txt (32 KB tiles)
     "k_fast_tiles": 329.9e6 / 150e6, "k_fast_count": 363.9e6 / 150e6, "k_fast_scatter": 664.9e6 / 150e6, "k_pack4": 213.4e6 / 150e6,
     "k_zenc_hist": 257.5e6 / 150e6, "k_zenc_encode": 351.2e6 / 150e6, "zd_literals": 332.5e6 / 150e6, "k_write_text": 587.9e6 / 150e6,
+    "k_compose_text": (558.1e6 + 607.7e6) / 300e6,   # profiles/r2x_compose_text_2Mreads.summary.txt
 }
 
 
@@ -568,7 +569,7 @@ def run_ours(args):
             roofline.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_base": bpb})
         if name in NCU_TRAFFIC_PER_BASE:
             roofline["traffic"] = NCU_TRAFFIC_PER_BASE[name] * bases
-            roofline["traffic_source"] = "ncu --set full at 1 M reads (profiles/r2c_fused_1Mreads.summary.txt, r1k_top_full_1Mreads.summary.txt), scaled per base"
+            roofline["traffic_source"] = "ncu --set full at 3 M reads (profiles/r3h_fused_3Mreads.summary.txt; other kernels: r2x_compose_text_2Mreads, r1k_top_full_1Mreads), scaled per base"
         line = {
             "metric": METRIC, "value": total_bases / (dev_ms * 1e-3) / 1e9, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

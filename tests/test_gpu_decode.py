@@ -131,6 +131,24 @@ def test_absurd_sizes_fail_cleanly_and_leave_the_context_usable(gpu, oracle):
         assert gpu.encode(text) == naf
 
 
+def test_stated_limits_are_refused_not_wrapped(gpu):
+    """An ids stream of 4 GiB (terminator offsets are 32-bit) is refused with NAFGPU_E_UNSUPPORTED and a message that says so --
+    not decoded with wrapped offsets.  The file is 130 KB: a frame of 32,768 RLE blocks of 128 KB of zeros."""
+    import naf_b200
+    from naf_b200.container import put_vle
+    nblk = 32768
+    frame = bytes([0x00, (17 - 10) << 3])
+    for i in range(nblk):
+        bh = (1 if i == nblk - 1 else 0) | (1 << 1) | (131072 << 3)
+        frame += bytes([bh & 0xFF, (bh >> 8) & 0xFF, (bh >> 16) & 0xFF, 0])
+    naf = bytes([0x01, 0xF9, 0xEC, 1, 1 << 5, ord(" ")]) + put_vle(0) + put_vle(1 << 32) + put_vle(1 << 32) + put_vle(len(frame)) + frame
+    with pytest.raises(naf_b200.NafGpuError) as e:
+        gpu.decode(naf, "ids")
+    assert e.value.code == -4 and "4 GiB" in e.value.message, (e.value.code, e.value.message)
+    text = synth.fastq(500, 150, seed=6)
+    assert gpu.decode(gpu.encode(text)) == text
+
+
 def test_fasta_surplus_sequence_is_printed_like_the_reference(gpu, oracle, tmp_path):
     """ennaf's id-byte bug (an unexpected byte in an id puts its replacement into the SEQUENCE) makes files whose
     sequence is longer than their lengths add up to; unnaf prints the surplus after the last record, into what is left of its
