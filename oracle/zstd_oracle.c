@@ -7,7 +7,7 @@
  * ZSTD_decompress (zstd/lib/decompress/zstd_decompress.c:1030) and the ZSTD_decompressStream
  * loop (…:1867) yield for the streams inside a .naf file.  Pinned against the reference's
  * libzstd (oracle/_ref/libzstd.so) on frames from levels -5..22, --long, and decodecorpus
- * (tests/test_oracle_zstd.py).
+ * (tests/test_oracle.py::test_oracle_zstd_vs_golden_frames over tests/golden/zstd, made by tools/make_golden.py).
  */
 #include "oracle.h"
 
