@@ -165,10 +165,13 @@ int main(int argc, char **argv)
     const uint8_t *naf = nullptr; size_t naf_size = 0; nafgpu_enc_info info;
     const size_t hint = in.have_stat && S_ISREG(in.st.st_mode) ? (size_t)in.st.st_size : 0;
     if (nafgpu_encode_begin(ctx, &o, hint) != 0) die("%s", nafgpu_last_error(ctx));
+    const bool in_regular = in_path && fd_is_regular(in_fd);           // then the pieces are read by a few threads at once
+    off_t in_off = 0;
     for (;;) {
         void *buf = nullptr; size_t cap = 0, got = 0;
         if (nafgpu_encode_buffer(ctx, &buf, &cap) != 0) die("%s", nafgpu_last_error(ctx));
-        while (got < cap) {
+        if (in_regular) { got = par_pread(in_fd, (uint8_t *)buf, cap, in_off); in_off += (off_t)got; }
+        else while (got < cap) {
             ssize_t k = read(in_fd, (char *)buf + got, cap - got);
             if (k < 0) { if (errno == EINTR) continue; die("can't read input\n"); }
             if (k == 0) break;
@@ -180,15 +183,16 @@ int main(int argc, char **argv)
     if (in_path) close(in_fd);
     // the file is written as it comes down (nothing file-sized is allocated on the host); an input the library refuses leaves
     // no output file behind: the callback creates it on its first piece
-    struct Sink { FILE *f; bool force_stdout; } sink{nullptr, force_stdout};
+    struct Sink { FILE *f; bool force_stdout; PieceWriter w; } sink{nullptr, force_stdout, {}};
     auto write_piece = [](void *user, const uint8_t *piece, size_t k) -> int {
         Sink *s = (Sink *)user;
-        if (!s->f) s->f = open_output(g_out_path, s->force_stdout);
-        write_all(s->f, piece, k);
+        if (!s->f) { s->f = open_output(g_out_path, s->force_stdout); s->w.attach(s->f); }
+        s->w.put(piece, k);
         return 0;
     };
     int rc = nafgpu_encode_end_to(ctx, write_piece, &sink, &naf_size, &info);
     if (rc != 0) die("%s", nafgpu_last_error(ctx));
+    if (sink.f) sink.w.finish();
     (void)naf;
     if (fmt_ext != NAFGPU_FMT_AUTO && info.format && fmt_ext != info.format) warn("input file extension does not match its actual format\n");
     if (fmt_ext != NAFGPU_FMT_AUTO && fmt_cli != NAFGPU_FMT_AUTO && fmt_ext != fmt_cli) warn("input file extension does not match format specified in the command line\n");

@@ -180,8 +180,10 @@ int main(int argc, char **argv)
         o.out_type = type; o.no_mask = !mask_on; o.have_line_length = have_line_length; o.line_length = line_length;
         nafgpu_ctx *ctx = make_ctx();
         size_t total = 0;
-        auto sink = [](void *user, const uint8_t *piece, size_t k) -> int { write_all((FILE *)user, piece, k); return 0; };
-        if (nafgpu_decode_to(ctx, in.data, in.size, &o, sink, out, &total) != 0) die("%s", nafgpu_last_error(ctx));
+        PieceWriter w; w.attach(out);
+        auto sink = [](void *user, const uint8_t *piece, size_t k) -> int { ((PieceWriter *)user)->put(piece, k); return 0; };
+        if (nafgpu_decode_to(ctx, in.data, in.size, &o, sink, &w, &total) != 0) die("%s", nafgpu_last_error(ctx));
+        w.finish();
     };
     const uint8_t *p = nullptr; size_t n = 0;
 
