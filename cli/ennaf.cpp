@@ -208,7 +208,5 @@ int main(int argc, char **argv)
         report((const unsigned long long *)info.unexpected[3], "quality");
     }
     if (verbose) msg("Processed %llu sequences\n", (unsigned long long)info.n_sequences);
-    g_success = true;
-    nafgpu_destroy(ctx);
-    return 0;
+    exit_done();
 }

@@ -260,6 +260,5 @@ int main(int argc, char **argv)
         }
     }
     close_output(out, in, in_path && g_out_path && !force_stdout);
-    g_success = true;
-    return 0;
+    exit_done();
 }
