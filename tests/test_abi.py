@@ -47,3 +47,16 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 assert "liboracle" not in src and "oracle/" not in src and "import oracle" not in src, os.path.join(dp, f)
+
+
+def test_cli_threaded_file_io(tmp_path):
+    """cli/cli_common.hpp: pieces written with pwrite by four threads behind a stdio prefix, read back with pread in pieces of
+    several sizes (short read at the end of the file), and the stdio path for pipes (tests/emu/cli_io_check.cpp)"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_build", "cli_io_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(ROOT, "tests", "emu", "cli_io_check.cpp"), "-L", os.path.join(ROOT, "naf_b200"), "-lnafgpu",
+                    "-Wl,-rpath," + os.path.join(ROOT, "naf_b200"), "-pthread"], check=True)
+    p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", (p.returncode, p.stdout, p.stderr)
