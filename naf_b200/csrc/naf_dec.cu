@@ -18,6 +18,7 @@
 #include "container.hpp"
 #include "zstd_dec.cuh"
 #include "zstd_dec_cuda.cuh"
+#include "duo_plan.hpp"
 
 namespace nafg {
 
@@ -913,8 +914,7 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
     // so before a byte has gone up): the file is uploaded small streams first, then sequence piece 0, quality piece 0, sequence
     // piece 1 ... and each pair of pieces is decoded, its records written and their text sent down while the rest is still on
     // the host.  Front to back, nothing can be written before the whole sequence stream AND the first quality piece are up.
-    struct DuoPiece { size_t s0, s1, q0, q1; };
-    std::vector<DuoPiece> duo;
+    std::vector<DuoPiece> duo;                                            // (duo_plan.hpp)
     static const bool env_duo = !(getenv("NAFGPU_DUO") && getenv("NAFGPU_DUO")[0] == '0');
     if (env_duo && ex.pipe && ex.pipe->deferred && !ranged && view == NAFGPU_OUT_FASTQ && need[SEC_DATA] && need[SEC_QUAL] &&
         !walks.pending[SEC_DATA] && !walks.pending[SEC_QUAL] && h.sec[SEC_DATA].off < h.sec[SEC_QUAL].off) {
@@ -922,26 +922,13 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         const char *env_piece0 = getenv("NAFGPU_PIPE_PIECE");
         const u64 PIECE = env_piece0 && *env_piece0 ? strtoull(env_piece0, nullptr, 10) : (48ull << 20);
         const bool cuttable = ws.rc == 0 && wq.rc == 0 && ws.simple && wq.simple && ws.regen.size() == ws.blocks.size() && wq.regen.size() == wq.blocks.size() &&
-                              !ws.blocks.empty() && !wq.blocks.empty() && h.sec[SEC_QUAL].comp >= 2 * PIECE && ws.blocks[0].src >= 3 && wq.blocks[0].src >= 3;
+                              h.sec[SEC_QUAL].comp >= 2 * PIECE;
         if (cuttable) {
-            size_t si = 0, qi = 0; u64 sreg = 0, qreg = 0;
-            while (qi < wq.blocks.size()) {
-                DuoPiece pc; pc.s0 = si; pc.q0 = qi;
-                u64 cbytes = 0;
-                while (qi < wq.blocks.size() && cbytes < PIECE) { cbytes += (u64)wq.blocks[qi].csize + 3; qreg += wq.regen[qi]; qi++; }
-                if (wq.blocks.size() - qi < 64) while (qi < wq.blocks.size()) { qreg += wq.regen[qi]; qi++; }          // no tiny last piece
-                if (qi == wq.blocks.size()) while (si < ws.blocks.size()) { sreg += ws.regen[si]; si++; }              // the last piece takes what is left
-                else while (si < ws.blocks.size() && (packed ? sreg * 2 : sreg) < qreg) { sreg += ws.regen[si]; si++; } // the bases of these qualities
-                pc.s1 = si; pc.q1 = qi;
-                duo.push_back(pc);
-            }
+            std::vector<DuoBlock> sb(ws.blocks.size()), qb(wq.blocks.size());
+            for (size_t i = 0; i < sb.size(); i++) sb[i] = DuoBlock{ws.blocks[i].src, ws.blocks[i].csize, (u32)ws.regen[i]};
+            for (size_t i = 0; i < qb.size(); i++) qb[i] = DuoBlock{wq.blocks[i].src, wq.blocks[i].csize, (u32)wq.regen[i]};
             std::vector<std::pair<u64, u64>> order;
-            auto sstart = [&](size_t i) { return i < ws.blocks.size() ? ws.blocks[i].src - 3 : wq.blocks[0].src - 3; };
-            auto qstart = [&](size_t i) { return i < wq.blocks.size() ? wq.blocks[i].src - 3 : (u64)n; };
-            order.push_back({0, sstart(0)});
-            for (auto &pc : duo) { order.push_back({sstart(pc.s0), sstart(pc.s1)}); order.push_back({qstart(pc.q0), qstart(pc.q1)}); }
-            ex.pipe->start_upload(&order);
-            later_mask = big_mask;
+            if (duo_plan(sb, qb, packed, PIECE, n, duo, order)) { ex.pipe->start_upload(&order); later_mask = big_mask; }
         }
     }
     if (ex.pipe) ex.pipe->start_upload(nullptr);                          // (unless it has just been started in that order)

@@ -60,3 +60,14 @@ def test_cli_threaded_file_io(tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "naf_b200"), "-pthread"], check=True)
     p = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert p.returncode == 0 and p.stdout.strip() == "ok", (p.returncode, p.stdout, p.stderr)
+
+
+def test_interleaved_upload_plan_invariants():
+    """naf_b200/csrc/duo_plan.hpp (the order in which a FASTQ .naf goes up for the interleaved decode): every byte exactly once,
+    whole blocks per piece, bases before their qualities -- 3,000 random block lists (tests/emu/duo_plan_check.cpp)"""
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "_build", "duo_plan_check")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(ROOT, "tests", "emu", "duo_plan_check.cpp")], check=True)
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.strip() == "ok", (p.returncode, p.stdout, p.stderr)
