@@ -588,7 +588,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
         }
-        if not args.no_cpu_baseline and ref_bin("ennaf") and ref_bin("unnaf"):
+        # the CPU legs (cpu_baseline, ref_made, cli_wall_clock) run at N = 1 only: at N > 1 the other ranks would sit in the barrier
+        if world == 1 and not args.no_cpu_baseline and ref_bin("ennaf") and ref_bin("unnaf"):
             srec = min(records, args.cpu_sample_records)
             sample = synth.fastq(srec, READ_LEN, seed=42)
             ref_naf = []
