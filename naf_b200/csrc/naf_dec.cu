@@ -726,7 +726,6 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         ~Walks() { for (int k = 0; k < 6; k++) join(k); }
     } walks{ctx.zwalk};
     const int last_big = need[SEC_QUAL] ? SEC_QUAL : (need[SEC_DATA] ? SEC_DATA : -1);
-    bool any_threaded = false;
     static const bool trace = getenv("NAFGPU_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto mark = [&](const char *what_) {
@@ -783,7 +782,7 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
             if (trace) fprintf(stderr, "nafgpu trace: host walk of section %d: %zu blocks, %.3f ms\n", k, w.blocks.size(),
                                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         };
-        if (sd.src_len > (8u << 20)) { walks.th[k] = std::thread(body); walks.pending[k] = true; any_threaded = true; }
+        if (sd.src_len > (8u << 20)) { walks.th[k] = std::thread(body); walks.pending[k] = true; }
         else body();
     }
     u8 *d_streams = ex.alloc<u8>(arena_sz + 256);
@@ -909,7 +908,6 @@ static DecodeOut decode_impl(Ctx &ctx, CudaExec &ex, const u8 *d_naf, const u8 *
         }
     }
     else if (last_big >= 0 && rec_text_view && (walks.pending[last_big] || (ex.pipe && ex.pipe->uploading))) later_mask = 1u << last_big;
-    (void)any_threaded;
     // FASTQ from a host buffer whose two big streams can both be cut at block boundaries (files we wrote: the block index says
     // so before a byte has gone up): the file is uploaded small streams first, then sequence piece 0, quality piece 0, sequence
     // piece 1 ... and each pair of pieces is decoded, its records written and their text sent down while the rest is still on
