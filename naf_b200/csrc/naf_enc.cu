@@ -559,7 +559,9 @@ static SplitDev split_streams_fused(Ctx &ctx, CudaExec &ex, const u8 *d_text, si
         u64 t0 = 0;
         for (size_t c = 0; c < nchunks; c++) {
             const u64 hi = (c + 1) * ex.pipe->chunk < n ? (c + 1) * ex.pipe->chunk : n;
-            const u64 t1 = c + 1 == nchunks ? ntiles : hi / FT_BYTES;
+            // a tile also reads the byte behind it (a CR LF pair may straddle two tiles): the last tile of a chunk waits for the
+            // next chunk
+            const u64 t1 = c + 1 == nchunks ? ntiles : (hi - 1) / FT_BYTES;
             ex.pipe->wait_input(ex.stream, hi);
             if (t1 > t0) { KLAUNCH(ex, "k_fused", k_fused<<<(unsigned)(t1 - t0), FUSED_NT, FusedSmem::total, ex.stream>>>(A)); }
             t0 = t1;
