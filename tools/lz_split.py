@@ -1,5 +1,6 @@
+"""Per-kernel times of a level-2 encode of 10 M reads (NAFGPU_ZLB / NAFGPU_LIB select block size and build): where k_zenc_lz's time goes."""
 import sys, os
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, naf_b200
 from naf_b200 import api, synth
 n = 10_000_000

@@ -1,5 +1,6 @@
+"""A small piped encode + decode of every input shape at both levels, for compute-sanitizer (memcheck / racecheck)."""
 import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import naf_b200
 from naf_b200 import synth
 ctx = naf_b200.NafGpu(0)
