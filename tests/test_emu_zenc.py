@@ -200,3 +200,30 @@ def test_warp_match_finder_prototype(libzstd, tmp_path):
         assert len(frame) <= os.path.getsize(zs) * 1.02 + 16
         stats = dict(kv.split("=") for kv in p.stdout.split())
         assert int(stats["steps"]) <= int(stats["seqs"]) + int(stats["blocks"]) * 257
+
+
+def test_column_match_finder_prototype(libzstd, tmp_path):
+    """tests/emu/proto_lzcol.cpp: a match finder made of maps and scans only (candidate offset = the same column of the previous
+    '\\0'-terminated record, else the previous 4-byte unit; runs of matching bytes are the matches), feeding the shipped literal /
+    sequence coder.  Valid frames on anything; on the streams it is for, within 15 % of the serial hash parse."""
+    exe = _build("proto_lzcol", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    rng = np.random.default_rng(6)
+    text_like = (ids_stream(20000, 999000), b"".join(b"%d/1\0" % i for i in range(1, 20001)), struct.pack("<I", 150) * 50000)
+    other = (b"".join(struct.pack("<I", 100 + (i * 7) % 3) for i in range(30000)),       # period of three units: not a candidate it has
+             bytes(rng.integers(0, 4, 70000, dtype=np.uint8)), b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(3000)),
+             b"", b"x" * 9000, bytes(rng.integers(0, 256, 20000, dtype=np.uint8)), b"\0" * 5000 + b"ab\0" * 3000, b"no terminator at all " * 700)
+    for data in text_like + other:
+        for bs in ("8192", "1000"):
+            inp, z, zs = str(tmp_path / "i.bin"), str(tmp_path / "c.zst"), str(tmp_path / "s.zst")
+            with open(inp, "wb") as f:
+                f.write(data)
+            p = subprocess.run([exe, inp, z, bs], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            frame = open(z, "rb").read()
+            assert helpers.load_oracle().zstd_decompress(frame) == data
+            if libzstd is not None:
+                assert libzstd_decode(libzstd, frame, len(data)) == data
+            if data in text_like and bs == "8192":
+                assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
+                assert len(frame) <= os.path.getsize(zs) * 1.15 + 64, (len(frame), os.path.getsize(zs))
