@@ -227,3 +227,33 @@ def test_column_match_finder_prototype(libzstd, tmp_path):
             if data in text_like and bs == "8192":
                 assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
                 assert len(frame) <= os.path.getsize(zs) * 1.15 + 64, (len(frame), os.path.getsize(zs))
+
+
+def test_shared_table_block_coder_prototype(libzstd, tmp_path):
+    """tests/emu/proto_shared.cpp: one Huffman code and one set of FSE tables per STREAM (from a sample of its blocks); the first
+    block carries them, every later block is Treeless_Literals + Repeat_Mode -- what a block then costs is serial coding against
+    read-only tables.  libzstd and the oracle must decode the frames (they track the tables across blocks, raw and RLE blocks in
+    between included); sizes stay within 1.4 x of per-block tables on the text-like streams."""
+    exe = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    rng = np.random.default_rng(8)
+    text_like = (ids_stream(60000, 1), b"".join(b"%d/1\0" % i for i in range(1, 60001)), struct.pack("<I", 150) * 50000)
+    other = (b"x" * 9000 + ids_stream(3000, 5) + b"y" * 20000 + ids_stream(3000, 77777),          # RLE blocks before and between
+             bytes(rng.integers(0, 256, 9000, dtype=np.uint8)) + ids_stream(4000, 123),           # a raw block first
+             ids_stream(3000, 1) + bytes(rng.integers(0, 256, 20000, dtype=np.uint8)) + ids_stream(3000, 9),   # bytes the sample never saw
+             bytes(rng.integers(0, 4, 70000, dtype=np.uint8)), b"", b"q" * 30000, bytes(rng.integers(0, 256, 20000, dtype=np.uint8)),
+             b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(3000)))
+    for data in text_like + other:
+        for bs in ("8192", "2048", "1000"):
+            inp, z, zs = str(tmp_path / "i.bin"), str(tmp_path / "c.zst"), str(tmp_path / "s.zst")
+            with open(inp, "wb") as f:
+                f.write(data)
+            p = subprocess.run([exe, inp, z, bs], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            frame = open(z, "rb").read()
+            assert helpers.load_oracle().zstd_decompress(frame) == data, (len(data), bs)
+            if libzstd is not None:
+                assert libzstd_decode(libzstd, frame, len(data)) == data, (len(data), bs)
+            if data in text_like and bs == "8192":
+                assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
+                assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs))
