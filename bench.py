@@ -15,6 +15,10 @@ naturally; no data-path collective) and `value` is all ranks' bases / max-over-r
   cpu_baseline  the UNMODIFIED reference (oracle/_ref ennaf + unnaf, 1 thread: that is all it has) on a
           bounded sample of the same workload, timed on this box's host cores
 
+  c5_strong  BASELINE configs[4]: ONE 3 Gbp soft-masked FASTA decoded by all ranks, each its share of the records ("strong");
+          every piece compared with the text
+  ref_made, ref_made_full, cli_wall_clock  (N = 1 only) the .naf the unmodified ennaf -1 makes of the 2 M-read sample / of the
+          whole workload, decoded on the device and compared; wall clock of bin/ennaf, bin/unnaf against the reference's tools
   single_file  (N > 1 only, extra to the contract) ONE .naf from all ranks' shards -- count all-gather, link, gather of zstd
           blocks over NCCL (naf_b200/sharded.py) -- and every rank decoding its record range of that one file; verified
 
