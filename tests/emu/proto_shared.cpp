@@ -9,8 +9,9 @@
 // produce has a probability (count * 16 + 1); a block with a literal byte the sample never saw stores its literals raw.
 // Neither fallback changes the decoder's entropy state.
 // Blocks stay self-contained in what they reference (matches inside the block, repeat offsets the block pushed itself).
-//   proto_shared IN OUT.zst BLOCK_SIZE      (prints sizes; frames are checked by libzstd and the oracle in the test)
-#include "../../naf_b200/csrc/zstd_enc_hd.cuh"
+//   proto_shared IN OUT.zst BLOCK_SIZE [col]     (col: sequences from the column match finder of proto_lzcol.cpp instead of the
+//   serial hash parse -- the two prototypes together; prints sizes; frames are checked by libzstd and the oracle in the test)
+#include "lzcol.hpp"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -161,6 +162,7 @@ int main(int argc, char **argv)
     fclose(f);
     const u32 bs = (u32)atoi(argv[3]);
     if (bs < 64 || bs > ZLZ_MAX_BLOCK) return 2;
+    const bool use_col = argc > 4 && !strcmp(argv[4], "col");
     const u32 max_seq = bs / 4;
     std::vector<u8> out = { 0x28, 0xB5, 0x2F, 0xFD, 0x00, (u8)((17 - 10) << 3) };
     std::vector<u16> htab(1u << ZLZ_HLOG), sll(max_seq), sml(max_seq), sov(max_seq), spos(1280);
@@ -177,7 +179,7 @@ int main(int argc, char **argv)
         if (len) { u32 i = 1; while (i < len && src[i] == src[0]) i++; P[b].rle = i == len; }
         if (P[b].rle || len < 16) continue;
         ZLzSeqs S{sll.data(), sml.data(), sov.data(), 0};
-        const u32 nlit = zlz_find(src, len, htab.data(), 1, lit.data(), S, max_seq);
+        const u32 nlit = use_col ? find_columns(src, len, lit.data(), S, max_seq) : zlz_find(src, len, htab.data(), 1, lit.data(), S, max_seq);
         P[b].lit.assign(lit.begin(), lit.begin() + nlit);
         P[b].ll.assign(sll.begin(), sll.begin() + S.n); P[b].ml.assign(sml.begin(), sml.begin() + S.n); P[b].ov.assign(sov.begin(), sov.begin() + S.n);
         P[b].parsed = true;

@@ -23,7 +23,7 @@ CSRC = os.path.join(ROOT, "naf_b200", "csrc")
 def _build(name, deps):
     os.makedirs(BUILD, exist_ok=True)
     exe, src = os.path.join(BUILD, name), os.path.join(ROOT, "tests", "emu", name + ".cpp")
-    deps = [src] + [os.path.join(CSRC, d) for d in deps]
+    deps = [src, os.path.join(ROOT, "tests", "emu", "lzcol.hpp")] + [os.path.join(CSRC, d) for d in deps]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
         subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unused-function", "-o", exe, src], check=True)
     return exe
@@ -234,7 +234,7 @@ def test_shared_table_block_coder_prototype(libzstd, tmp_path):
     block carries them, every later block is Treeless_Literals + Repeat_Mode -- what a block then costs is serial coding against
     read-only tables.  libzstd and the oracle must decode the frames (they track the tables across blocks, raw and RLE blocks in
     between included); sizes stay within 1.4 x of per-block tables on the text-like streams."""
-    exe = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    exe = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])      # (also includes tests/emu/lzcol.hpp)
     enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
     rng = np.random.default_rng(8)
     text_like = (ids_stream(60000, 1), b"".join(b"%d/1\0" % i for i in range(1, 60001)), struct.pack("<I", 150) * 50000)
@@ -248,12 +248,13 @@ def test_shared_table_block_coder_prototype(libzstd, tmp_path):
             inp, z, zs = str(tmp_path / "i.bin"), str(tmp_path / "c.zst"), str(tmp_path / "s.zst")
             with open(inp, "wb") as f:
                 f.write(data)
-            p = subprocess.run([exe, inp, z, bs], capture_output=True, text=True)
-            assert p.returncode == 0, p.stderr
-            frame = open(z, "rb").read()
-            assert helpers.load_oracle().zstd_decompress(frame) == data, (len(data), bs)
-            if libzstd is not None:
-                assert libzstd_decode(libzstd, frame, len(data)) == data, (len(data), bs)
-            if data in text_like and bs == "8192":
-                assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
-                assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs))
+            for finder in ([], ["col"]):                      # sequences from the serial hash parse / from proto_lzcol's column finder
+                p = subprocess.run([exe, inp, z, bs] + finder, capture_output=True, text=True)
+                assert p.returncode == 0, p.stderr
+                frame = open(z, "rb").read()
+                assert helpers.load_oracle().zstd_decompress(frame) == data, (len(data), bs, finder)
+                if libzstd is not None:
+                    assert libzstd_decode(libzstd, frame, len(data)) == data, (len(data), bs, finder)
+                if data in text_like and bs == "8192":
+                    assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
+                    assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs), finder)
