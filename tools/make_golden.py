@@ -118,6 +118,11 @@ def extra_cases():
     cases["long31"] = (synth.fasta_softmasked(50_000, width=60, seed=8, n_records=2), ["-22", "--long", "31"], {})
     cases["title_linelen"] = (fasta([(b"x", dna(100))], 30), ["--title", "My title", "--line-length", "17"], {})
     cases["ont_iupac"] = (synth.ont_fasta(12, 2000, 9000, seed=9), [], {})
+    # CR LF line ends ('\r' is an end-of-line byte to process.c, runs of them collapse): headers with and without comments, an
+    # empty record, a blank line, soft-masked runs across line ends, last line without a line end.  (CRs that are NOT line ends: the differential fuzz in tests/test_oracle.py)
+    crlf = fasta([(b"c1 comment here", soft(dna(333), [(50, 130)])), (b"c2", b""), (b"c3", dna(61)), (b"c4 x", dna(120))], 60)
+    cases["crlf_fasta"] = (crlf.replace(b"\n", b"\r\n")[:-2].replace(b">c3\r\n", b">c3\r\n\r\n"), [], {})
+    cases["crlf_protein"] = (synth.protein_fasta(40, 130, seed=11).replace(b"\n", b"\r\n"), ["--protein"], {})
 
     manifest = []
     for name, (text, eargs, _) in cases.items():
