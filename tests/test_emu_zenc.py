@@ -258,3 +258,72 @@ def test_shared_table_block_coder_prototype(libzstd, tmp_path):
                 if data in text_like and bs == "8192":
                     assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
                     assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs), finder)
+
+
+def _zlzc_cases():
+    rng = np.random.default_rng(9)
+    rnd = random.Random(9)
+    text_like = [ids_stream(60000, 1), b"".join(b"%d/1\0" % i for i in range(1, 60001)), struct.pack("<I", 150) * 50000,
+                 b"".join(b"A00123:45:HXXXX:1:%d:%d:%d\0" % (1101 + i // 500, 1000 + (i * 37) % 9000, 2000 + (i * 91) % 30000) for i in range(8000))]
+    other = [b"x" * 9000 + ids_stream(3000, 5) + b"y" * 20000 + ids_stream(3000, 77777),          # RLE blocks before and between
+             bytes(rng.integers(0, 256, 9000, dtype=np.uint8)) + ids_stream(4000, 123),           # a raw block first
+             ids_stream(3000, 1) + bytes(rng.integers(0, 256, 20000, dtype=np.uint8)) + ids_stream(3000, 9),   # bytes the sample never saw
+             bytes(rng.integers(0, 4, 70000, dtype=np.uint8)), b"", b"a", b"q" * 30000, bytes(rng.integers(0, 256, 20000, dtype=np.uint8)),
+             b"".join(bytes([65 + (i * i) % 23]) * (1 + i % 40) for i in range(3000)),            # runs: candidate 4 against the column
+             b"".join(struct.pack("<I", int(v)) for v in rng.integers(10000, 50000, 9000)),      # ONT-like length units: no sequences at all
+             bytes([255]) * 30000 + bytes(rng.integers(0, 255, 5000, dtype=np.uint8)),           # mask units
+             b"\0" * 5000 + b"ab\0" * 3000 + b"\0\0abcdefgh\0" * 500, b"no terminator at all " * 700,
+             b"".join(b"r%d\0" % (i % 7) * (1 + i % 3) for i in range(9000)),                     # records of changing length, runs across records
+             ids_stream(700, 1)[:8192] + b"z" * 8192 + ids_stream(5000, 4)]                       # exactly one full block, then RLE, then more
+    for _ in range(12):                                                                           # mixtures of copies, runs, noise and terminators
+        n, out, alpha = rnd.choice([17, 200, 5000, 8192, 8193, 20000, 40000]), bytearray(), rnd.choice([2, 4, 16, 64, 256])
+        while len(out) < n:
+            k = rnd.random()
+            if k < 0.45 and len(out) > 8:
+                off = min(rnd.choice([1, 2, 3, 4, 13, rnd.randint(1, len(out))]), len(out))
+                for _ in range(rnd.choice([3, 4, 5, 8, 20, 300, rnd.randint(3, 2000)])):
+                    out.append(out[-off])
+            elif k < 0.55:
+                out += bytes([rnd.randrange(alpha)]) * rnd.randint(1, 50)
+            elif k < 0.65:
+                out += b"\0"
+            else:
+                out += bytes(rnd.randrange(alpha) for _ in range(rnd.randint(1, 30)))
+        other.append(bytes(out[:n]))
+    return text_like, other
+
+
+def test_column_finder_and_stream_tables(dec, libzstd, tmp_path):
+    """naf_b200/csrc/zstd_lzc_hd.cuh -- the data-parallel LZ stage (NAFGPU_LZ=shared): the column match finder as the phases one
+    CTA runs (thread = 32-byte chunk), per-stream Huffman / FSE tables from sampled blocks, blocks coded against them
+    (Treeless_Literals + Repeat_Mode).  tests/emu/emu_zlzc.cpp runs the phases thread by thread.  Every frame is decoded by the
+    oracle, libzstd 1.5.0 and our own decoder, and equals byte for byte what the serial restatement (lzcol.hpp + proto_shared.cpp)
+    writes; on the streams it is for the result stays within 1.4 x of per-block tables + the serial hash parse."""
+    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    proto = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    oracle = helpers.load_oracle()
+    text_like, other = _zlzc_cases()
+    streams, _ = oracle.split(synth.fastq(3000, 150, seed=3))
+    other += [s for s in streams[:4]]
+    streams, _ = oracle.split(synth.ont_fasta(40, 1000, 5000, seed=4))
+    other += [s for s in streams[:4]]
+    for data in text_like + other:
+        for bs in ("8192", "2048", "1000", "100", "33"):
+            inp, z, zp, zs, back = (str(tmp_path / x) for x in ("i.bin", "c.zst", "p.zst", "s.zst", "back.bin"))
+            with open(inp, "wb") as f:
+                f.write(data)
+            p = subprocess.run([exe, inp, z, bs], capture_output=True, text=True)
+            assert p.returncode == 0, p.stderr
+            frame = open(z, "rb").read()
+            assert oracle.zstd_decompress(frame) == data, (len(data), bs)
+            if libzstd is not None:
+                assert libzstd_decode(libzstd, frame, len(data)) == data, (len(data), bs)
+            q = subprocess.run([dec, z, back], capture_output=True)
+            assert q.returncode == 0 and open(back, "rb").read() == data, (len(data), bs, q.stderr)
+            if int(bs) >= 64:
+                assert subprocess.run([proto, inp, zp, bs, "col"], capture_output=True).returncode == 0
+                assert open(zp, "rb").read() == frame, ("serial restatement differs", len(data), bs)
+            if any(data is t for t in text_like) and bs == "8192":
+                assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
+                assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs))
