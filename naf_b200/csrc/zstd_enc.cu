@@ -25,6 +25,7 @@
 // compress/zstd_compress_literals.c:70 ZSTD_compressLiterals, zstd_compress.c:3967 ZSTD_writeFrameHeader.
 
 #include "zstd_enc_hd.cuh"
+#include "zstd_lzc_hd.cuh"
 
 namespace nafg {
 
@@ -35,7 +36,7 @@ static const u32 ZSLOT = ZBS + 512;          // bytes reserved per block for its
 static const u32 ZLB_MAX = 8 * 1024;         // uncompressed bytes per block of an LZ stream (one thread encodes a block)
 static u32 zlb_bytes()                       // NAFGPU_ZLB=1024..8192 (A/B measurements); a thread's latency is proportional to it
 {
-    static const u32 v = [] { const char *e = getenv("NAFGPU_ZLB"); const u32 x = e ? (u32)atoi(e) : 0u; return x >= 256 && x <= ZLB_MAX ? x : ZLB_MAX; }();
+    static const u32 v = [] { const char *e = getenv("NAFGPU_ZLB"); const u32 x = e ? (u32)atoi(e) : 0u; return x >= 256 && x <= ZLB_MAX ? (x & ~63u) : ZLB_MAX; }();
     return v;
 }
 static const int ZWINDOW_LOG = 17;
@@ -320,6 +321,114 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
     else { B.type = 0; B.csize = B.n; }
 }
 
+// ---- LZ streams, data-parallel (NAFGPU_LZ=shared; bodies: zstd_lzc_hd.cuh, emulated on the CPU by tests/emu/emu_zlzc.cpp):
+//   k_zlc_find    one CTA per block, thread = 32-byte chunk: column match finder (maps, neighbour walks over per-chunk summaries,
+//                 one block scan), sequences + compacted literals to the block's scratch; every 8th block of a stream also counts
+//                 its literal bytes and sequence codes into the stream's statistics
+//   k_zlc_define  one thread per stream: Huffman code + three FSE tables from the statistics; codes the block that carries them
+//   k_zlc_finish  one thread per block: serial coding against the stream's tables (Treeless_Literals + Repeat_Mode)
+static bool zlc_mode() { static const bool v = [] { const char *e = getenv("NAFGPU_LZ"); return e && e[0] == 's'; }(); return v; }
+struct ZlcArgs {
+    ZEncBlock *blk; nafz::ZlcBlk *info; u8 *slots; u8 *work; u32 *counts; nafz::ZlcTables *tables; u32 *def_size;
+    const u8 *src[8]; u64 n[8]; u64 slot_base[8];
+    u32 first[9]; u32 lzfirst[9]; u32 is_lz[8]; u32 ns; u32 nlz; u32 zlb;
+};
+__device__ __forceinline__ u32 zlc_stream_of(const ZlcArgs &A, u32 j) { u32 s = 0; while (s + 1 < A.ns && j >= A.lzfirst[s + 1]) s++; return s; }
+__device__ __forceinline__ nafz::ZlcStreamView zlc_view(const ZlcArgs &A, u32 s)
+{
+    nafz::ZlcStreamView V;
+    const u32 ws = nafz::zlc_work_bytes(A.zlb);
+    V.src = A.src[s]; V.n = A.n[s]; V.bs = A.zlb; V.nblk = A.first[s + 1] - A.first[s];
+    V.info = A.info + A.lzfirst[s]; V.work = A.work + (size_t)A.lzfirst[s] * ws; V.work_stride = ws;
+    V.slots = A.slots + A.slot_base[s]; V.slot_stride = A.zlb + 512;
+    return V;
+}
+
+__global__ void __launch_bounds__(256) k_zlc_find(const ZlcArgs A)
+{
+    extern __shared__ __align__(16) u8 zlc_smem[];
+    nafz::ZlcSh &sh = *reinterpret_cast<nafz::ZlcSh *>(zlc_smem);
+    __shared__ u64 smscan[33];
+    const u32 j = blockIdx.x, k = threadIdx.x;
+    const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
+    const ZEncBlock &B = A.blk[A.first[s] + bidx];
+    const u8 *src = B.src; const u32 n = B.n;
+    for (u32 i = k; i < n; i += 256) sh.src[i] = src[i];
+    if (k < 16) sh.src[n + k] = 0;
+    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) sh.hist[i] = 0;
+    if (k == 0) { sh.n = n; sh.nch = (n + nafz::ZLC_CH - 1) / nafz::ZLC_CH; sh.rle_break = 0; sh.lastend = 0; }
+    __syncthreads();
+    const bool act = k < sh.nch;
+    if (act) nafz::zlc_zeros(sh, k);
+    __syncthreads();
+    nafz::ZlcBlk &I = A.info[j];
+    if (n == 0 || !sh.rle_break || n < 16) {                   // empty, one repeated byte, or too small to parse: RLE / raw block
+        if (k == 0) { I.nseq = 0; I.nlit = 0; I.parsed = 0; I.rle = (n && !sh.rle_break) ? 1 : 0; I.conv = 0; I.pad = 0; }
+        return;
+    }
+    if (act) nafz::zlc_columns(sh, k);
+    __syncthreads();
+    if (act) nafz::zlc_breaks(sh, k);
+    __syncthreads();
+    if (act) nafz::zlc_choose(sh, k);
+    __syncthreads();
+    if (act) nafz::zlc_breaks_d(sh, k);
+    __syncthreads();
+    if (act) nafz::zlc_count(sh, k);
+    __syncthreads();
+    {
+        const u64 v = act ? ((u64)sh.cnt[k] | ((u64)sh.mls[k] << 32)) : 0;
+        u64 total; const u64 pre = block_excl_scan(v, &total, smscan);
+        if (act) { sh.ibase[k] = (u16)pre; sh.mbase[k] = (u16)(pre >> 32); }
+        if (k == 0) { sh.nseq = (u32)total; sh.mltot = (u32)(total >> 32); }
+    }
+    __syncthreads();
+    const bool sampled = bidx % nafz::ZLC_SAMPLE == 0;
+    nafz::ZlcWork K = nafz::zlc_work(A.work + (size_t)j * nafz::zlc_work_bytes(A.zlb), A.zlb);
+    if (act) nafz::zlc_emit_seqs(sh, k, K.S, K.lit, sampled);
+    nafz::zlc_emit_tail(sh, k, 256, K.lit, sampled);
+    if (k == 0) { I.nseq = sh.nseq; I.nlit = n - sh.mltot; I.parsed = 1; I.rle = 0; I.conv = 0; I.pad = 0; }
+    if (!sampled) return;
+    __syncthreads();
+    if (k == 0) nafz::zlc_count_offsets(sh);
+    __syncthreads();
+    u32 *acc = A.counts + s * nafz::ZLC_NBINS;
+    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) if (sh.hist[i]) atomicAdd(&acc[i], sh.hist[i]);
+}
+
+__global__ void __launch_bounds__(32) k_zlc_define(const ZlcArgs A)
+{
+    const u32 s = blockIdx.x;
+    if (threadIdx.x || s >= A.ns || !A.is_lz[s]) return;
+    const nafz::ZlcStreamView V = zlc_view(A, s);
+    u32 ds = 0;
+    nafz::zlc_define(V, A.counts + s * nafz::ZLC_NBINS, A.tables[s], &ds);
+    A.def_size[s] = ds;
+}
+
+__global__ void __launch_bounds__(64) k_zlc_finish(const ZlcArgs A)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.nlz) return;
+    const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
+    const nafz::ZlcStreamView V = zlc_view(A, s);
+    ZEncBlock &B = A.blk[A.first[s] + bidx];
+    u32 type = 0, csize = 0;
+    if (nafz::zlc_finish_block(V, bidx, A.tables[s], A.def_size[s], &type, &csize)) { B.type = type; B.csize = csize; }
+}
+// streams without tables of their own (no sequences at all, one literal symbol ...): every block builds its own, like k_zenc_lz
+__global__ void __launch_bounds__(64) k_zlc_finish_own(const ZlcArgs A)
+{
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= A.nlz) return;
+    const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
+    if (A.tables[s].ok) return;
+    const nafz::ZlcStreamView V = zlc_view(A, s);
+    ZEncBlock &B = A.blk[A.first[s] + bidx];
+    u32 type = 0, csize = 0;
+    if (nafz::zlc_finish_block_own(V, bidx, A.tables[s], &type, &csize)) { B.type = type; B.csize = csize; }
+}
+
 // ---- host-buffer encode: the big streams compressed behind the upload (Ctx::EarlyZ; called from split_streams_fused)
 static void zenc_early_begin(Ctx &ctx, CudaExec &ex, const u8 *seq, u64 seq_max_bytes, const u8 *qual, u64 qual_max_bytes)
 {
@@ -430,7 +539,35 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
             blk[i] = e;
         }, "zenc_init_blocks");
     }
-    if (nlz) {
+    if (nlz && zlc_mode()) {
+        ZlcArgs Z; memset(&Z, 0, sizeof Z);
+        Z.blk = b.d_blocks; Z.slots = b.d_slots; Z.ns = (u32)ns; Z.nlz = nlz; Z.zlb = ZLB;
+        for (size_t s = 0; s < ns; s++) { Z.src[s] = b.src[s]; Z.n[s] = b.n[s]; Z.slot_base[s] = tab.slot_base[s]; Z.is_lz[s] = (u32)b.lz[s]; }
+        for (size_t s = 0; s <= ns; s++) { Z.first[s] = L.first[s]; Z.lzfirst[s] = L.lzfirst[s]; }
+        Z.info = ex.alloc<nafz::ZlcBlk>(nlz);
+        Z.work = ex.alloc<u8>((size_t)nlz * nafz::zlc_work_bytes(ZLB));
+        Z.counts = ex.alloc<u32>(8 * nafz::ZLC_NBINS); ex.zero(Z.counts, 8 * nafz::ZLC_NBINS * 4);
+        Z.tables = ex.alloc<nafz::ZlcTables>(8); Z.def_size = ex.alloc<u32>(8);
+        CUDA_TRY(cudaFuncSetAttribute(k_zlc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nafz::ZlcSh)));
+        static const bool env_side = !(getenv("NAFGPU_SIDE") && getenv("NAFGPU_SIDE")[0] == '0');
+        side = env_side && ctx.side && !(ex.prof && ex.prof->on);
+        if (side) {
+            CUDA_TRY(cudaEventRecord(ctx.side_fork, ex.stream));
+            CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.side_fork, 0));
+            k_zlc_find<<<nlz, 256, sizeof(nafz::ZlcSh), ctx.side>>>(Z);
+            k_zlc_define<<<(unsigned)ns, 32, 0, ctx.side>>>(Z);
+            k_zlc_finish<<<(nlz + 63) / 64, 64, 0, ctx.side>>>(Z);
+            k_zlc_finish_own<<<(nlz + 63) / 64, 64, 0, ctx.side>>>(Z);
+            CUDA_TRY(cudaEventRecord(ctx.side_join, ctx.side));
+            ex.launches += 4;
+        } else {
+            KLAUNCH(ex, "k_zlc_find", k_zlc_find<<<nlz, 256, sizeof(nafz::ZlcSh), ex.stream>>>(Z));
+            KLAUNCH(ex, "k_zlc_define", k_zlc_define<<<(unsigned)ns, 32, 0, ex.stream>>>(Z));
+            KLAUNCH(ex, "k_zlc_finish", k_zlc_finish<<<(nlz + 63) / 64, 64, 0, ex.stream>>>(Z));
+            KLAUNCH(ex, "k_zlc_finish_own", k_zlc_finish_own<<<(nlz + 63) / 64, 64, 0, ex.stream>>>(Z));
+        }
+        CUDA_TRY(cudaGetLastError());
+    } else if (nlz) {
         L.blk = b.d_blocks; L.slots = b.d_slots; L.work = ex.alloc<u8>((size_t)nlz * zlz_work_bytes(ZLB));
         CUDA_TRY(cudaFuncSetAttribute(k_zenc_lz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ZLZ_SMEM));
         // next to the Huffman kernels of the big streams, not in front of them (when profiling: in line, so that its time is its own)

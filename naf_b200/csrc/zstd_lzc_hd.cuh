@@ -386,23 +386,42 @@ HDN inline void zlc_define(const ZlcStreamView &V, const u32 *cnt, ZlcTables &T,
     }
 }
 
-// One thread per block, after zlc_define: type (0 raw, 1 RLE, 2 compressed) and content size of block b
-HDN inline void zlc_finish_block(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 def_size, u32 *type, u32 *csize)
+// One thread per block, after zlc_define: type (0 raw, 1 RLE, 2 compressed) and content size of block b.  Two bodies, so that the
+// common one (coding against the stream's tables) does not carry the registers and the stack of a private Huffman / FSE build:
+// zlc_finish_block for streams whose tables are defined, zlc_finish_block_own for the others (each returns false when the block
+// belongs to the other one).
+HDN inline bool zlc_finish_block(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 def_size, u32 *type, u32 *csize)
 {
+    if (!T.ok) return false;
     const u32 n = V.len(b);
     ZlcBlk &I = V.info[b];
     u8 *slot = V.slots + (size_t)b * V.slot_stride;
-    if (I.rle) { slot[0] = V.src[(u64)b * V.bs]; *type = 1; *csize = 1; return; }
+    if (I.rle) { slot[0] = V.src[(u64)b * V.bs]; *type = 1; *csize = 1; return true; }
     *type = 0; *csize = n;
-    if (!I.parsed) return;
-    if (T.ok && b < T.fdef) return;                            // the tables are not defined yet: raw
-    if (T.ok && b == T.fdef) { *type = 2; *csize = def_size; return; }
+    if (!I.parsed || b < T.fdef) return true;                  // (before the defining block the tables are not there yet: raw)
+    if (b == T.fdef) { *type = 2; *csize = def_size; return true; }
     ZlcWork K = zlc_work(V.work + (size_t)b * V.work_stride, V.bs);
     K.S.n = I.nseq;
     zlc_offset_values(K.S, I);
-    const u32 cs = T.ok ? zlc_emit_shared(n, K.lit, I.nlit, K.S, T, false, slot, V.slot_stride)
-                        : zlz_emit_block(n, K.lit, I.nlit, K.S, V.bs / 4, K.W, slot, V.slot_stride);
+    const u32 cs = zlc_emit_shared(n, K.lit, I.nlit, K.S, T, false, slot, V.slot_stride);
     if (cs) { *type = 2; *csize = cs; }
+    return true;
+}
+HDN inline bool zlc_finish_block_own(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 *type, u32 *csize)
+{
+    if (T.ok) return false;
+    const u32 n = V.len(b);
+    ZlcBlk &I = V.info[b];
+    u8 *slot = V.slots + (size_t)b * V.slot_stride;
+    if (I.rle) { slot[0] = V.src[(u64)b * V.bs]; *type = 1; *csize = 1; return true; }
+    *type = 0; *csize = n;
+    if (!I.parsed) return true;
+    ZlcWork K = zlc_work(V.work + (size_t)b * V.work_stride, V.bs);
+    K.S.n = I.nseq;
+    zlc_offset_values(K.S, I);
+    const u32 cs = zlz_emit_block(n, K.lit, I.nlit, K.S, V.bs / 4, K.W, slot, V.slot_stride);
+    if (cs) { *type = 2; *csize = cs; }
+    return true;
 }
 
 }  // namespace nafz

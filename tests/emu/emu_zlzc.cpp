@@ -67,6 +67,7 @@ int main(int argc, char **argv)
     size_t n_comp = 0, n_rle = 0;
     std::vector<u32> types(nblk), sizes(nblk);
     for (size_t b = nblk; b-- > 0;) zlc_finish_block(V, (u32)b, *T, def_size, &types[b], &sizes[b]);
+    for (size_t b = 0; b < nblk; b++) zlc_finish_block_own(V, (u32)b, *T, &types[b], &sizes[b]);      // k_zlc_finish_own
     for (size_t b = 0; b < nblk; b++) {
         const u32 len = V.len((u32)b), last = b + 1 == nblk, type = types[b], size_field = type == 1 ? len : sizes[b];
         const u32 bh = last | (type << 1) | (size_field << 3);
