@@ -72,6 +72,10 @@ def main():
         ok_all &= o_ok and d_ok
         say(step="B", case=label, text=len(t), naf=len(naf), ratio=round(len(naf) / len(t), 4), oracle_decodes=o_ok, device_decodes=d_ok)
     say(step="verdict", all_ok=bool(ok_all))
+    if not ok_all:
+        sys.exit(1)
+    if n_time <= 0:
+        return
     big = synth.fastq(n_time, 150, seed=42)
     say(step="C", made_reads=n_time, text=len(big))
     naf = ctx.encode(big)
