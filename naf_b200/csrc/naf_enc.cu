@@ -637,7 +637,7 @@ namespace nafg {
 // overrides the level (A/B measurements).
 static bool lz_for_level(int level)
 {
-    static const char *env = getenv("NAFGPU_LZ");
+    const char *env = getenv("NAFGPU_LZ");
     if (env && (env[0] == '0' || env[0] == '1' || env[0] == 's')) return env[0] != '0';      // 's'hared: the data-parallel stage (zstd_enc.cu: zlc_mode)
     return level >= 2;
 }

@@ -325,11 +325,13 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
 //   k_zlc_find    one CTA per block, thread = 32-byte chunk: column match finder (maps, neighbour walks over per-chunk summaries,
 //                 one block scan), sequences + compacted literals to the block's scratch; every 8th block of a stream also counts
 //                 its literal bytes and sequence codes into the stream's statistics
-//   k_zlc_define  one thread per stream: Huffman code + three FSE tables from the statistics; codes the block that carries them
-//   k_zlc_finish  one thread per block: serial coding against the stream's tables (Treeless_Literals + Repeat_Mode)
-static bool zlc_mode() { static const bool v = [] { const char *e = getenv("NAFGPU_LZ"); return e && e[0] == 's'; }(); return v; }
+//   k_zlc_define  one thread per stream: Huffman code + three FSE tables from the statistics; which block will carry them
+//   k_zlc_finish  one thread per block: serial coding against the stream's tables (the defining block: Compressed_Literals +
+//                 FSE_Compressed; the ones behind it: Treeless_Literals + Repeat_Mode)
+//   k_zlc_finish_own  streams that got no tables (no sequences at all, one literal symbol ...): every block builds its own
+static bool zlc_mode() { const char *e = getenv("NAFGPU_LZ"); return e && e[0] == 's'; }      // (read per call: one process can A/B the modes)
 struct ZlcArgs {
-    ZEncBlock *blk; nafz::ZlcBlk *info; u8 *slots; u8 *work; u32 *counts; nafz::ZlcTables *tables; u32 *def_size;
+    ZEncBlock *blk; nafz::ZlcBlk *info; u8 *slots; u8 *work; u32 *counts; nafz::ZlcTables *tables; u32 *def_fail;
     const u8 *src[8]; u64 n[8]; u64 slot_base[8];
     u32 first[9]; u32 lzfirst[9]; u32 is_lz[8]; u32 ns; u32 nlz; u32 zlb;
 };
@@ -353,8 +355,7 @@ __global__ void __launch_bounds__(256) k_zlc_find(const ZlcArgs A)
     const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
     const ZEncBlock &B = A.blk[A.first[s] + bidx];
     const u8 *src = B.src; const u32 n = B.n;
-    for (u32 i = k; i < n; i += 256) sh.src[i] = src[i];
-    if (k < 16) sh.src[n + k] = 0;
+    for (u32 i = k; i < n; i += 256) sh.src_[nafz::zlc_ix(i)] = src[i];
     for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) sh.hist[i] = 0;
     if (k == 0) { sh.n = n; sh.nch = (n + nafz::ZLC_CH - 1) / nafz::ZLC_CH; sh.rle_break = 0; sh.lastend = 0; }
     __syncthreads();
@@ -401,20 +402,27 @@ __global__ void __launch_bounds__(32) k_zlc_define(const ZlcArgs A)
     const u32 s = blockIdx.x;
     if (threadIdx.x || s >= A.ns || !A.is_lz[s]) return;
     const nafz::ZlcStreamView V = zlc_view(A, s);
-    u32 ds = 0;
-    nafz::zlc_define(V, A.counts + s * nafz::ZLC_NBINS, A.tables[s], &ds);
-    A.def_size[s] = ds;
+    nafz::zlc_define(V, A.counts + s * nafz::ZLC_NBINS, A.tables[s]);
 }
 
 __global__ void __launch_bounds__(64) k_zlc_finish(const ZlcArgs A)
 {
-    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    // every symbol coded is two or three dependent table reads: the tables of the stream this CTA's first block belongs to are
+    // staged in shared memory (a CTA that straddles two streams reads the second one's from HBM / L1)
+    __shared__ __align__(16) nafz::ZlcTables Ts;
+    const u32 j0 = blockIdx.x * blockDim.x, j = j0 + threadIdx.x;
+    const u32 s0 = zlc_stream_of(A, j0);
+    {
+        const uint4 *g = (const uint4 *)(A.tables + s0); uint4 *d = (uint4 *)&Ts;
+        for (u32 i = threadIdx.x; i < sizeof(nafz::ZlcTables) / 16; i += blockDim.x) d[i] = g[i];
+    }
+    __syncthreads();
     if (j >= A.nlz) return;
     const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
     const nafz::ZlcStreamView V = zlc_view(A, s);
     ZEncBlock &B = A.blk[A.first[s] + bidx];
     u32 type = 0, csize = 0;
-    if (nafz::zlc_finish_block(V, bidx, A.tables[s], A.def_size[s], &type, &csize)) { B.type = type; B.csize = csize; }
+    if (nafz::zlc_finish_block(V, bidx, s == s0 ? Ts : A.tables[s], A.def_fail + s, &type, &csize)) { B.type = type; B.csize = csize; }
 }
 // streams without tables of their own (no sequences at all, one literal symbol ...): every block builds its own, like k_zenc_lz
 __global__ void __launch_bounds__(64) k_zlc_finish_own(const ZlcArgs A)
@@ -422,11 +430,12 @@ __global__ void __launch_bounds__(64) k_zlc_finish_own(const ZlcArgs A)
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= A.nlz) return;
     const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
-    if (A.tables[s].ok) return;
+    const u32 def_fail = A.def_fail[s];
+    if (A.tables[s].ok && !def_fail) return;
     const nafz::ZlcStreamView V = zlc_view(A, s);
     ZEncBlock &B = A.blk[A.first[s] + bidx];
     u32 type = 0, csize = 0;
-    if (nafz::zlc_finish_block_own(V, bidx, A.tables[s], &type, &csize)) { B.type = type; B.csize = csize; }
+    if (nafz::zlc_finish_block_own(V, bidx, A.tables[s], def_fail, &type, &csize)) { B.type = type; B.csize = csize; }
 }
 
 // ---- host-buffer encode: the big streams compressed behind the upload (Ctx::EarlyZ; called from split_streams_fused)
@@ -546,8 +555,10 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
         for (size_t s = 0; s <= ns; s++) { Z.first[s] = L.first[s]; Z.lzfirst[s] = L.lzfirst[s]; }
         Z.info = ex.alloc<nafz::ZlcBlk>(nlz);
         Z.work = ex.alloc<u8>((size_t)nlz * nafz::zlc_work_bytes(ZLB));
-        Z.counts = ex.alloc<u32>(8 * nafz::ZLC_NBINS); ex.zero(Z.counts, 8 * nafz::ZLC_NBINS * 4);
-        Z.tables = ex.alloc<nafz::ZlcTables>(8); Z.def_size = ex.alloc<u32>(8);
+        Z.counts = ex.alloc<u32>(8 * nafz::ZLC_NBINS + 8); ex.zero(Z.counts, (8 * nafz::ZLC_NBINS + 8) * 4);
+        Z.def_fail = Z.counts + 8 * nafz::ZLC_NBINS;
+        static_assert(sizeof(nafz::ZlcTables) % 16 == 0, "k_zlc_finish copies the tables in 16-byte pieces");
+        Z.tables = (nafz::ZlcTables *)ex.alloc<uint4>(8 * sizeof(nafz::ZlcTables) / 16);
         CUDA_TRY(cudaFuncSetAttribute(k_zlc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nafz::ZlcSh)));
         static const bool env_side = !(getenv("NAFGPU_SIDE") && getenv("NAFGPU_SIDE")[0] == '0');
         side = env_side && ctx.side && !(ex.prof && ex.prof->on);

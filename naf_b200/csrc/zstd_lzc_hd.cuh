@@ -31,10 +31,18 @@ static const u32 ZLC_LL0 = 256, ZLC_OF0 = 292, ZLC_ML0 = 324, ZLC_NBINS = 377;  
 #define ZLC_MAXU(x, v) ((x) = (x) > (v) ? (x) : (v))
 #endif
 
+// Thread k walks bytes 32 k .. 32 k + 31: with the arrays laid out plainly the 32 lanes of a warp would sit 32 bytes (8 banks) or
+// 32 u16 (16 banks) apart and every access would be an 8- or 16-way bank conflict.  One element of padding per chunk (33-element
+// pitch) puts the lanes of a warp into 32 different banks.
+static const u32 ZLC_PITCHED = ZLC_MAX + ZLC_NCH;
+HD u32 zlc_ix(u32 p) { return p + (p >> 5); }
 struct ZlcSh {                        // shared memory of one CTA = one block of at most ZLC_MAX bytes
-    u8  src[ZLC_MAX + 16];
-    u16 oc[ZLC_MAX];                  // column candidate: its offset where the byte matches there, else 0 (later: offsets / literal lengths of the sequences)
-    u16 d[ZLC_MAX];                   // chosen offset per byte, 0 = literal
+    u8  src_[ZLC_PITCHED + 24];
+    u16 oc_[ZLC_PITCHED];             // column candidate: its offset where the byte matches there, else 0 (later: offsets / literal lengths of the sequences)
+    u16 d_[ZLC_PITCHED];              // chosen offset per byte, 0 = literal
+    HD u8 src(u32 p) const { return src_[zlc_ix(p)]; }
+    HD u16 oc(u32 p) const { return oc_[zlc_ix(p)]; }
+    HD u16 d(u32 p) const { return d_[zlc_ix(p)]; }
     u16 z1[ZLC_NCH], z2[ZLC_NCH];     // last / second-last '\0' of a chunk
     u16 lbc[ZLC_NCH], fbc[ZLC_NCH];   // last / first position of a chunk at which a run of the column candidate does not continue
     u16 lbf[ZLC_NCH], fbf[ZLC_NCH];   // same, candidate 4
@@ -47,18 +55,18 @@ struct ZlcSh {                        // shared memory of one CTA = one block of
 
 struct ZlcBlk { u32 nseq, nlit; u8 parsed, rle, conv, pad; };      // what the finder leaves per block (conv: offsets already turned into Offset_Values)
 
-HD bool zlc_mf(const ZlcSh &sh, u32 p) { return p >= 4 && sh.src[p] == sh.src[p - 4]; }
-HD bool zlc_contc(const ZlcSh &sh, u32 p) { return sh.oc[p] && p > 0 && sh.oc[p - 1] == sh.oc[p]; }
+HD bool zlc_mf(const ZlcSh &sh, u32 p) { return p >= 4 && sh.src(p) == sh.src(p - 4); }
+HD bool zlc_contc(const ZlcSh &sh, u32 p) { return sh.oc(p) && p > 0 && sh.oc(p - 1) == sh.oc(p); }
 HD bool zlc_contf(const ZlcSh &sh, u32 p) { return p > 0 && zlc_mf(sh, p) && zlc_mf(sh, p - 1); }
-HD bool zlc_contd(const ZlcSh &sh, u32 p) { return sh.d[p] && p > 0 && sh.d[p - 1] == sh.d[p]; }
+HD bool zlc_contd(const ZlcSh &sh, u32 p) { return sh.d(p) && p > 0 && sh.d(p - 1) == sh.d(p); }
 HD u32 zlc_lo(u32 k) { return k * ZLC_CH; }
 HD u32 zlc_hi(const ZlcSh &sh, u32 k) { const u32 h = k * ZLC_CH + ZLC_CH; return h < sh.n ? h : sh.n; }
 
 // phase 1: where the chunk's last two terminators are; is the block one repeated byte
 HD void zlc_zeros(ZlcSh &sh, u32 k)
 {
-    u32 a = ZLC_NONE, b = ZLC_NONE; bool same = true; const u8 c0 = sh.src[0];
-    for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) { const u8 c = sh.src[p]; if (c == 0) { b = a; a = p; } if (c != c0) same = false; }
+    u32 a = ZLC_NONE, b = ZLC_NONE; bool same = true; const u8 c0 = sh.src(0);
+    for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) { const u8 c = sh.src(p); if (c == 0) { b = a; a = p; } if (c != c0) same = false; }
     sh.z1[k] = (u16)a; sh.z2[k] = (u16)b;
     if (!same) sh.rle_break = 1;
 }
@@ -75,9 +83,9 @@ HD void zlc_columns(ZlcSh &sh, u32 k)
     u32 cur = za == ZLC_NONE ? 0 : za + 1, prev = zb == ZLC_NONE ? 0 : zb + 1;
     for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) {
         u32 o = 0;
-        if (cur > 0) { const u32 dcol = cur - prev; if (sh.src[p] == sh.src[p - dcol]) o = dcol; }
-        sh.oc[p] = (u16)o;
-        if (sh.src[p] == 0) { prev = cur; cur = p + 1; }
+        if (cur > 0) { const u32 dcol = cur - prev; if (sh.src(p) == sh.src(p - dcol)) o = dcol; }
+        sh.oc_[zlc_ix(p)] = (u16)o;
+        if (sh.src(p) == 0) { prev = cur; cur = p + 1; }
     }
 }
 // phase 3: per chunk, where runs of either candidate break (so that a run's far ends are found chunk by chunk)
@@ -97,7 +105,7 @@ HD void zlc_choose(ZlcSh &sh, u32 k)
     u32 endc = 0, lenc = 0, endf = 0, lenf = 0;                  // the run p is in, per candidate (valid while p < end)
     for (u32 p = lo; p < hi; p++) {
         u32 lc = 0, lf = 0;
-        if (sh.oc[p]) {
+        if (sh.oc(p)) {
             if (p >= endc) {
                 u32 q = p; while (q > lo && zlc_contc(sh, q)) q--;
                 u32 start = q;
@@ -119,7 +127,7 @@ HD void zlc_choose(ZlcSh &sh, u32 k)
             }
             lf = lenf;
         }
-        sh.d[p] = lf > lc ? (u16)4 : sh.oc[p];
+        sh.d_[zlc_ix(p)] = lf > lc ? (u16)4 : sh.oc(p);
     }
 }
 // phase 5
@@ -135,7 +143,7 @@ template <class F> HD void zlc_each_match(const ZlcSh &sh, u32 k, F f)
     const u32 lo = zlc_lo(k), hi = zlc_hi(sh, k);
     u32 p = lo;
     while (p < hi) {
-        if (!sh.d[p] || zlc_contd(sh, p)) { p++; continue; }
+        if (!sh.d(p) || zlc_contd(sh, p)) { p++; continue; }
         u32 q = p + 1; while (q < hi && zlc_contd(sh, q)) q++;
         u32 end = q;
         if (q == hi && hi < sh.n && zlc_contd(sh, hi)) { u32 c = k + 1; while (c < sh.nch && sh.fbd[c] == ZLC_NONE) c++; end = c < sh.nch ? sh.fbd[c] : sh.n; }
@@ -167,12 +175,12 @@ HD void zlc_emit_seqs(ZlcSh &sh, u32 k, const ZLzSeqs &S, u8 *lit, bool sampled)
     u32 pe = 0;
     for (u32 c = k; c-- > 0;) if (sh.cnt[c]) { pe = sh.lend[c]; break; }
     u32 idx = sh.ibase[k], msum = sh.mbase[k];
-    u16 *so = sh.oc, *sl = sh.oc + ZLC_MAX / 2;
+    u16 *so = sh.oc_, *sl = sh.oc_ + ZLC_PITCHED / 2;
     zlc_each_match(sh, k, [&](u32 start, u32 end) {
-        const u32 ll = start - pe, ml = end - start, off = sh.d[start];
+        const u32 ll = start - pe, ml = end - start, off = sh.d(start);
         S.ll[idx] = (u16)ll; S.ml[idx] = (u16)ml; S.ov[idx] = (u16)off;
         u8 *dst = lit + (pe - msum);
-        for (u32 i = 0; i < ll; i++) { const u8 c = sh.src[pe + i]; dst[i] = c; if (sampled) ZLC_INC(sh.hist[c]); }
+        for (u32 i = 0; i < ll; i++) { const u8 c = sh.src(pe + i); dst[i] = c; if (sampled) ZLC_INC(sh.hist[c]); }
         if (sampled) { so[idx] = (u16)off; sl[idx] = (u16)ll; ZLC_INC(sh.hist[ZLC_LL0 + zlz_ll_code(ll)]); ZLC_INC(sh.hist[ZLC_ML0 + zlz_ml_code(ml)]); }
         msum += ml; pe = end; idx++;
     });
@@ -181,12 +189,12 @@ HD void zlc_emit_seqs(ZlcSh &sh, u32 k, const ZLzSeqs &S, u8 *lit, bool sampled)
 HD void zlc_emit_tail(ZlcSh &sh, u32 t, u32 nt, u8 *lit, bool sampled)
 {
     const u32 e = sh.lastend, base = e - sh.mltot;
-    for (u32 i = t; e + i < sh.n; i += nt) { const u8 c = sh.src[e + i]; lit[base + i] = c; if (sampled) ZLC_INC(sh.hist[c]); }
+    for (u32 i = t; e + i < sh.n; i += nt) { const u8 c = sh.src(e + i); lit[base + i] = c; if (sampled) ZLC_INC(sh.hist[c]); }
 }
 // phase 9 (sampled blocks, one thread): Offset_Value codes need the repeat-offset history, which is serial
 HD void zlc_count_offsets(ZlcSh &sh)
 {
-    const u16 *so = sh.oc, *sl = sh.oc + ZLC_MAX / 2;
+    const u16 *so = sh.oc_, *sl = sh.oc_ + ZLC_PITCHED / 2;
     ZLzRep rep; rep.r[0] = rep.r[1] = rep.r[2] = 0; rep.k = 0;
     for (u32 i = 0; i < sh.nseq; i++) sh.hist[ZLC_OF0 + (u32)hibit(rep.code(so[i], sl[i]))]++;
 }
@@ -200,6 +208,7 @@ struct ZlcTables {
     u8 desc[512]; u32 desc_len;                    // the three FSE table descriptions as the defining block writes them
     u32 ok;                                        // 0: this stream's blocks get their own tables (zlz_emit_block)
     u32 fdef;                                      // the block (index in the stream) that carries the tables
+    u32 pad[2];                                    // (size: a multiple of 16, the block coder's CTA copies it to shared memory in 16-byte pieces)
 };
 
 // Tables from the sampled statistics, smoothed: every sequence code a block of this size can produce keeps a probability
@@ -366,31 +375,35 @@ HD ZlcWork zlc_work(u8 *w, u32 bs)
     return R;
 }
 
-// One thread per stream, after the finder: tables from the sampled counts; the first block with literals and sequences is
-// coded here and carries them.  def_size: its Compressed_Block size.
-HDN inline void zlc_define(const ZlcStreamView &V, const u32 *cnt, ZlcTables &T, u32 *def_size)
+// One thread per stream, after the finder: which block will carry the tables -- the first one with literals and sequences (blocks
+// before it are stored raw or RLE, which leaves a decoder's entropy state alone) -- and the tables, from the sampled counts plus
+// that block's own when it is not a sampled one (so that each of its literal bytes has a code).
+HDN inline void zlc_define(const ZlcStreamView &V, u32 *cnt, ZlcTables &T)
 {
-    T.ok = 0; T.fdef = 0xFFFFFFFFu; *def_size = 0;
-    u8 tsym[512];
-    if (V.bs < 64 || !zlc_build_tables(cnt, V.bs, T, tsym)) return;
-    u32 tries = 0;
-    for (u32 b = 0; b < V.nblk && tries < 16; b++) {
-        ZlcBlk &I = V.info[b];
-        if (!I.parsed || !I.nlit || !I.nseq) continue;
-        tries++;
-        ZlcWork K = zlc_work(V.work + (size_t)b * V.work_stride, V.bs);
+    T.ok = 0; T.fdef = 0xFFFFFFFFu;
+    if (V.bs < 64) return;
+    u32 f = 0;
+    while (f < V.nblk && !(V.info[f].parsed && V.info[f].nlit && V.info[f].nseq)) f++;
+    if (f == V.nblk) return;
+    if (f % ZLC_SAMPLE) {
+        ZlcBlk &I = V.info[f];
+        ZlcWork K = zlc_work(V.work + (size_t)f * V.work_stride, V.bs);
         K.S.n = I.nseq;
         zlc_offset_values(K.S, I);
-        const u32 cs = zlc_emit_shared(V.len(b), K.lit, I.nlit, K.S, T, true, V.slots + (size_t)b * V.slot_stride, V.slot_stride);
-        if (cs) { T.ok = 1; T.fdef = b; *def_size = cs; return; }
+        for (u32 i = 0; i < I.nlit; i++) cnt[K.lit[i]]++;
+        for (u32 i = 0; i < I.nseq; i++) { cnt[ZLC_LL0 + zlz_ll_code(K.S.ll[i])]++; cnt[ZLC_OF0 + (u32)hibit(K.S.ov[i])]++; cnt[ZLC_ML0 + zlz_ml_code(K.S.ml[i])]++; }
     }
+    u8 tsym[512];
+    if (!zlc_build_tables(cnt, V.bs, T, tsym)) return;
+    T.ok = 1; T.fdef = f;
 }
 
 // One thread per block, after zlc_define: type (0 raw, 1 RLE, 2 compressed) and content size of block b.  Two bodies, so that the
 // common one (coding against the stream's tables) does not carry the registers and the stack of a private Huffman / FSE build:
 // zlc_finish_block for streams whose tables are defined, zlc_finish_block_own for the others (each returns false when the block
-// belongs to the other one).
-HDN inline bool zlc_finish_block(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 def_size, u32 *type, u32 *csize)
+// belongs to the other one).  *def_fail: the defining block could not be written (its literals, coded with the stream's code,
+// overflow the slot): zlc_finish_block_own then redoes the whole stream with private tables.
+HDN inline bool zlc_finish_block(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 *def_fail, u32 *type, u32 *csize)
 {
     if (!T.ok) return false;
     const u32 n = V.len(b);
@@ -399,17 +412,17 @@ HDN inline bool zlc_finish_block(const ZlcStreamView &V, u32 b, const ZlcTables 
     if (I.rle) { slot[0] = V.src[(u64)b * V.bs]; *type = 1; *csize = 1; return true; }
     *type = 0; *csize = n;
     if (!I.parsed || b < T.fdef) return true;                  // (before the defining block the tables are not there yet: raw)
-    if (b == T.fdef) { *type = 2; *csize = def_size; return true; }
     ZlcWork K = zlc_work(V.work + (size_t)b * V.work_stride, V.bs);
     K.S.n = I.nseq;
     zlc_offset_values(K.S, I);
-    const u32 cs = zlc_emit_shared(n, K.lit, I.nlit, K.S, T, false, slot, V.slot_stride);
+    const u32 cs = zlc_emit_shared(n, K.lit, I.nlit, K.S, T, b == T.fdef, slot, V.slot_stride);
     if (cs) { *type = 2; *csize = cs; }
+    else if (b == T.fdef) *def_fail = 1;
     return true;
 }
-HDN inline bool zlc_finish_block_own(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 *type, u32 *csize)
+HDN inline bool zlc_finish_block_own(const ZlcStreamView &V, u32 b, const ZlcTables &T, u32 def_fail, u32 *type, u32 *csize)
 {
-    if (T.ok) return false;
+    if (T.ok && !def_fail) return false;
     const u32 n = V.len(b);
     ZlcBlk &I = V.info[b];
     u8 *slot = V.slots + (size_t)b * V.slot_stride;

@@ -32,7 +32,7 @@ int main(int argc, char **argv)
         const u32 len = V.len((u32)b);
         const u8 *src = in.data() + b * bs;
         memset(&sh, 0xDD, sizeof sh);
-        memcpy(sh.src, src, len); memset(sh.src + len, 0, 16);
+        for (u32 i = 0; i < len; i++) sh.src_[zlc_ix(i)] = src[i];
         memset(sh.hist, 0, sizeof sh.hist);
         sh.n = len; sh.nch = (len + ZLC_CH - 1) / ZLC_CH; sh.rle_break = 0; sh.lastend = 0;
         const u32 nch = sh.nch;
@@ -60,14 +60,15 @@ int main(int argc, char **argv)
     }
     if (seqs) fclose(seqs);
     // ---- k_zlc_define: one thread per stream
-    ZlcTables *T = new ZlcTables; u32 def_size = 0;
-    zlc_define(V, counts.data(), *T, &def_size);
+    ZlcTables *T = new ZlcTables; u32 def_fail = 0;
+    static_assert(sizeof(ZlcTables) % 16 == 0, "k_zlc_finish copies the tables in 16-byte pieces");
+    zlc_define(V, counts.data(), *T);
     // ---- k_zlc_finish: one thread per block; then the frame as k_zenc_gather writes it
     std::vector<u8> out = { 0x28, 0xB5, 0x2F, 0xFD, 0x00, (u8)((17 - 10) << 3) };
     size_t n_comp = 0, n_rle = 0;
     std::vector<u32> types(nblk), sizes(nblk);
-    for (size_t b = nblk; b-- > 0;) zlc_finish_block(V, (u32)b, *T, def_size, &types[b], &sizes[b]);
-    for (size_t b = 0; b < nblk; b++) zlc_finish_block_own(V, (u32)b, *T, &types[b], &sizes[b]);      // k_zlc_finish_own
+    for (size_t b = nblk; b-- > 0;) zlc_finish_block(V, (u32)b, *T, &def_fail, &types[b], &sizes[b]);
+    for (size_t b = 0; b < nblk; b++) zlc_finish_block_own(V, (u32)b, *T, def_fail, &types[b], &sizes[b]);      // k_zlc_finish_own
     for (size_t b = 0; b < nblk; b++) {
         const u32 len = V.len((u32)b), last = b + 1 == nblk, type = types[b], size_field = type == 1 ? len : sizes[b];
         const u32 bh = last | (type << 1) | (size_field << 3);
@@ -78,6 +79,6 @@ int main(int argc, char **argv)
     }
     FILE *o = fopen(argv[2], "wb"); if (!o) return 2;
     fwrite(out.data(), 1, out.size(), o); fclose(o);
-    printf("in=%zu out=%zu blocks=%zu compressed=%zu rle=%zu shared=%u fdef=%d\n", n, out.size(), nblk, n_comp, n_rle, T->ok, (int)T->fdef);
+    printf("in=%zu out=%zu blocks=%zu compressed=%zu rle=%zu shared=%u fdef=%d def_fail=%u\n", n, out.size(), nblk, n_comp, n_rle, T->ok, (int)T->fdef, def_fail);
     return 0;
 }

@@ -185,30 +185,49 @@ int main(int argc, char **argv)
         P[b].parsed = true;
         if (b % SAMPLE == 0) count_block(C, lit.data(), nlit, S);
     }
-    Shared T; bool shared = build_shared(C, bs, T), defined = false;
+    // the block that will carry the tables: the first one with literals and sequences; its own statistics count too when it is
+    // not a sampled block (so that each of its literal bytes has a code)
+    size_t fdef = 0;
+    while (fdef < nblk && !(P[fdef].parsed && !P[fdef].lit.empty() && !P[fdef].ll.empty())) fdef++;
+    if (fdef < nblk && fdef % SAMPLE) {
+        ZLzSeqs S{P[fdef].ll.data(), P[fdef].ml.data(), P[fdef].ov.data(), (u32)P[fdef].ll.size()};
+        count_block(C, P[fdef].lit.data(), (u32)P[fdef].lit.size(), S);
+    }
+    Shared T; bool shared = bs >= 64 && fdef < nblk && build_shared(C, bs, T);
     size_t n_shared = 0, n_own = 0, n_raw = 0;
-    // pass 2: the first block with literals and sequences carries the tables; a raw / RLE block before it does not touch the
-    // decoder's entropy state, a compressed block before it would -- so until the tables are defined blocks are stored raw
+    // pass 2: raw / RLE blocks before the defining block do not touch the decoder's entropy state, a compressed block before it would
+    // -- so until the tables are defined blocks are stored raw.  Should the defining block not fit its slot when coded with the
+    // stream's tables, the whole stream gets per-block tables instead.
+    std::vector<std::vector<u8>> body(nblk); std::vector<u32> csz(nblk, 0);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        bool def_fail = false;
+        n_shared = n_own = n_raw = 0;
+        for (size_t b = 0; b < nblk; b++) {
+            const u32 len = (u32)(n - b * bs < bs ? n - b * bs : bs);
+            u32 cs = 0;
+            if (P[b].parsed) {
+                ZLzSeqs S{P[b].ll.data(), P[b].ml.data(), P[b].ov.data(), (u32)P[b].ll.size()};
+                ZLzWork W{spos.data(), tsym.data(), codes.data()};
+                const u32 nlit = (u32)P[b].lit.size();
+                if (shared) {
+                    if (b >= fdef) { cs = emit_shared(len, P[b].lit.data(), nlit, S, T, b == fdef, slot.data(), bs + 512); if (!cs && b == fdef) def_fail = true; }
+                    if (cs) n_shared++;
+                } else { cs = zlz_emit_block(len, P[b].lit.data(), nlit, S, max_seq, W, slot.data(), bs + 512); if (cs) n_own++; }
+            }
+            if (!cs) n_raw++;
+            csz[b] = cs; body[b].assign(slot.begin(), slot.begin() + cs);
+        }
+        if (!def_fail) break;
+        shared = false;
+    }
     for (size_t b = 0; b < nblk; b++) {
         const u32 len = (u32)(n - b * bs < bs ? n - b * bs : bs);
         const u8 *src = in.data() + b * bs;
-        const bool rle = P[b].rle; u32 cs = 0;
-        if (P[b].parsed) {
-            ZLzSeqs S{P[b].ll.data(), P[b].ml.data(), P[b].ov.data(), (u32)P[b].ll.size()};
-            ZLzWork W{spos.data(), tsym.data(), codes.data()};
-            const u32 nlit = (u32)P[b].lit.size();
-            if (shared) {
-                const bool first = !defined && nlit > 0 && S.n > 0;
-                if (defined || first) cs = emit_shared(len, P[b].lit.data(), nlit, S, T, first, slot.data(), bs + 1024);
-                if (first && cs) defined = true;
-                if (cs) n_shared++;
-            } else { cs = zlz_emit_block(len, P[b].lit.data(), nlit, S, max_seq, W, slot.data(), bs + 512); if (cs) n_own++; }
-        }
-        if (!cs) n_raw++;
+        const bool rle = P[b].rle; const u32 cs = csz[b];
         const u32 last = b + 1 == nblk, type = cs ? 2 : (rle ? 1 : 0), size_field = type == 2 ? cs : len;
         const u32 bh = last | (type << 1) | (size_field << 3);
         out.push_back((u8)bh); out.push_back((u8)(bh >> 8)); out.push_back((u8)(bh >> 16));
-        if (type == 2) out.insert(out.end(), slot.begin(), slot.begin() + cs);
+        if (type == 2) out.insert(out.end(), body[b].begin(), body[b].end());
         else if (type == 1) out.push_back(src[0]);
         else out.insert(out.end(), src, src + len);
     }

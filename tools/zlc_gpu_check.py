@@ -78,19 +78,24 @@ def main():
         return
     big = synth.fastq(n_time, 150, seed=42)
     say(step="C", made_reads=n_time, text=len(big))
-    naf = ctx.encode(big)
-    ctx.profile(True)
-    naf = ctx.encode(big)
-    rep = sorted(ctx.profile_report(), key=lambda x: -x[2])
-    ctx.profile(False)
-    say(step="C", naf=len(naf), ratio=round(len(naf) / len(big), 4), kernels={n: round(ms, 3) for n, c, ms in rep[:12]})
-    for _ in range(2):
+    for mode in ("0", "shared"):                               # "0": the level-1 parse (entropy only), same process, same box
+        os.environ["NAFGPU_LZ"] = mode
         naf = ctx.encode(big)
-        te = ctx.timing()
-        enc = (round(te.total_ms, 2), round(te.kernels_ms, 2))
+        ctx.profile(True)
+        naf = ctx.encode(big)
+        erep = sorted(ctx.profile_report(), key=lambda x: -x[2])
         out = ctx.decode(naf)
-        td = ctx.timing()
-        say(step="C", encode_ms=enc[0], encode_kernels_ms=enc[1], decode_ms=round(td.total_ms, 2), decode_kernels_ms=round(td.kernels_ms, 2), roundtrip_ok=out == big)
+        drep = sorted(ctx.profile_report(), key=lambda x: -x[2])
+        ctx.profile(False)
+        say(step="C", mode=mode, naf=len(naf), ratio=round(len(naf) / len(big), 4), roundtrip_ok=out == big,
+            encode_kernels={n: round(ms, 3) for n, c, ms in erep[:9]}, decode_kernels={n: round(ms, 3) for n, c, ms in drep[:9]})
+        enc, dec = [], []
+        for _ in range(4):
+            naf = ctx.encode(big)
+            enc.append(round(ctx.timing().kernels_ms, 2))
+            out = ctx.decode(naf)
+            dec.append(round(ctx.timing().kernels_ms, 2))
+        say(step="C", mode=mode, encode_kernels_ms=enc, decode_kernels_ms=dec)
 
 
 if __name__ == "__main__":
