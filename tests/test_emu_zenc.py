@@ -327,3 +327,77 @@ def test_column_finder_and_stream_tables(dec, libzstd, tmp_path):
             if any(data is t for t in text_like) and bs == "8192":
                 assert subprocess.run([enc, inp, zs, bs, "1"], capture_output=True).returncode == 0
                 assert len(frame) <= os.path.getsize(zs) * 1.4 + 64, (len(frame), os.path.getsize(zs))
+
+
+def _frame_blocks(frame):
+    """-> the block section of a single zstd frame written by our encoders (FHD 0x00 + window byte), as a list of (header int, content)"""
+    assert frame[:4] == b"\x28\xb5\x2f\xfd" and frame[4] == 0
+    at, out = 6, []
+    while True:
+        bh = frame[at] | (frame[at + 1] << 8) | (frame[at + 2] << 16)
+        size = 1 if (bh >> 1) & 3 == 1 else bh >> 3
+        out.append((bh, frame[at + 3:at + 3 + size]))
+        at += 3 + size
+        if bh & 1:
+            break
+    assert at == len(frame)
+    return out
+
+
+def test_stream_tables_survive_shard_concatenation(libzstd, tmp_path):
+    """N GPUs encode consecutive shards of a stream and the blocks are concatenated into ONE frame (sharded.py /
+    nafgpu_shard_finish).  With per-stream tables every shard's first coded block carries that shard's tables and the blocks behind
+    it inherit them (Treeless_Literals / Repeat_Mode) -- so the merged frame must decode whatever the neighbours are: shards with
+    tables, shards that fell back to per-block tables, raw / RLE-only shards, empty shards."""
+    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    oracle = helpers.load_oracle()
+    rng = np.random.default_rng(4)
+    ids = ids_stream(9000, 1)
+    parts_sets = [
+        [ids[:30000], ids[30000:61000], ids[61000:]],                                                   # three shards with tables of their own
+        [ids[:20000], bytes(rng.integers(0, 256, 20000, dtype=np.uint8)), ids[20000:50000]],            # raw-only shard in the middle
+        [b"x" * 20000, ids[:25000], b"", struct.pack("<I", 150) * 6000, ids[25000:40000]],               # RLE-only, empty, other statistics
+        [b"".join(struct.pack("<I", int(v)) for v in rng.integers(10000, 50000, 5000)), ids[:30000]],    # per-block tables first, then shared
+        [ids[:30000], b"".join(struct.pack("<I", int(v)) for v in rng.integers(10000, 50000, 5000)), ids[30000:45000]],
+    ]
+    for parts in parts_sets:
+        merged = bytearray(b"\x28\xb5\x2f\xfd\x00" + bytes([(17 - 10) << 3]))
+        for k, part in enumerate(parts):
+            inp, z = str(tmp_path / "i.bin"), str(tmp_path / "c.zst")
+            with open(inp, "wb") as f:
+                f.write(part)
+            assert subprocess.run([exe, inp, z, "8192"], capture_output=True).returncode == 0
+            blocks = _frame_blocks(open(z, "rb").read())
+            for j, (bh, content) in enumerate(blocks):
+                last = k == len(parts) - 1 and j == len(blocks) - 1
+                bh = (bh & ~1) | int(last)
+                merged += bytes([bh & 0xFF, (bh >> 8) & 0xFF, bh >> 16]) + content
+        data = b"".join(parts)
+        assert oracle.zstd_decompress(bytes(merged)) == data
+        if libzstd is not None:
+            assert libzstd_decode(libzstd, bytes(merged), len(data)) == data
+
+
+def test_defining_block_that_does_not_fit_gets_the_stream_private_tables(dec, libzstd, tmp_path):
+    """the first block with literals and sequences is mostly noise, the sample is dominated by 860 blocks of names: coded with the
+    stream's Huffman code the noise overflows the block's slot, the defining block cannot be written, and the whole stream falls
+    back to per-block tables (k_zlc_finish_own) -- still byte for byte the serial restatement, still valid for every decoder"""
+    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    proto = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    rng = np.random.default_rng(3)
+    b0 = bytearray(rng.integers(1, 256, 8192, dtype=np.uint8).tobytes())
+    for i in list(range(100, 130)) + list(range(5000, 5040)):
+        b0[i] = b0[i - 4]
+    data = bytes(b0) + ids_stream(600000, 1)
+    inp, z, zp, back = (str(tmp_path / x) for x in ("i.bin", "c.zst", "p.zst", "back.bin"))
+    with open(inp, "wb") as f:
+        f.write(data)
+    p = subprocess.run([exe, inp, z, "8192"], capture_output=True, text=True)
+    assert p.returncode == 0 and "def_fail=1" in p.stdout, p.stdout
+    frame = open(z, "rb").read()
+    assert helpers.load_oracle().zstd_decompress(frame) == data
+    if libzstd is not None:
+        assert libzstd_decode(libzstd, frame, len(data)) == data
+    assert subprocess.run([dec, z, back], capture_output=True).returncode == 0 and open(back, "rb").read() == data
+    assert subprocess.run([proto, inp, zp, "8192", "col"], capture_output=True).returncode == 0
+    assert open(zp, "rb").read() == frame
