@@ -47,7 +47,7 @@ static void show_help()
         "Options:\n"
         "  -o FILE            - Write compressed output to FILE\n"
         "  -c                 - Write to standard output\n"
-        "  -#, --level #      - 1 (default): fastest parse; 2 and above: also LZ77-match names, lengths and mask\n"
+        "  -#, --level #      - 1 (default): fastest parse; 2 and above: also LZ77-match names and lengths\n"
         "  --long N           - Accepted for compatibility (window of size 2^N for sequence stream)\n"
         "  --temp-dir DIR     - Accepted for compatibility (no temporary files are used)\n"
         "  --name NAME        - Accepted for compatibility\n"

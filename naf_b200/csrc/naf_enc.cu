@@ -632,15 +632,19 @@ namespace nafg {
 
 // ennaf -# (ennaf.c:222-223, compressor.c:7).  Level 1 -- the tools' default -- is the fastest parse: every stream entropy-coded
 // in independent 32 KB blocks.  Level >= 2 adds LZ77 matches and FSE-coded sequences to the text-like streams (ids, comments,
-// lengths, mask): the file shrinks to what `ennaf -1` writes, at (measured on B200, profiles/r1q_ab_level.json) about twice
-// the encode and decode time of level 1 while that path is one thread per 8 KB block.  NAFGPU_LZ=0/1 in the environment
-// overrides the level (A/B measurements).
+// lengths) in 8 KB blocks: the file shrinks to what `ennaf -1` writes (0.356 of the text on 150 bp FASTQ against 0.381; ennaf -1:
+// 0.358).  Two formulations (zstd_enc.cu): the data-parallel one (column match finder, one Huffman code and one set of FSE tables
+// per stream: + 2.1 ms encode, + 3.8 ms decode per million reads on a B200, profiles/r4b) is what a level selects; NAFGPU_LZ=1 in
+// the environment selects the first one (one thread per block, private tables: about twice that), NAFGPU_LZ=0 none, NAFGPU_LZ=s
+// the data-parallel one at any level.  The mask stream stays entropy-only in the data-parallel formulation: its run lengths
+// have no matches to find, and 8 KB blocks coded with a stream-wide Huffman code come out larger than 32 KB blocks with their own.
 static bool lz_for_level(int level)
 {
     const char *env = getenv("NAFGPU_LZ");
-    if (env && (env[0] == '0' || env[0] == '1' || env[0] == 's')) return env[0] != '0';      // 's'hared: the data-parallel stage (zstd_enc.cu: zlc_mode)
+    if (env && (env[0] == '0' || env[0] == '1' || env[0] == 's')) return env[0] != '0';
     return level >= 2;
 }
+static int lz_streams() { return zlc_mode() ? 3 : 4; }           // how many of ids, comments, lengths, mask take the LZ stage
 
 // ennaf.c:538-589: header, then per stream VLE(original size) VLE(compressed size - 4) frame-without-magic
 EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, const nafgpu_enc_opts &o, nafgpu_enc_info *info)
@@ -655,7 +659,7 @@ EncodeOut encode_on_device(Ctx &ctx, CudaExec &ex, const u8 *d_text, size_t n, c
     ZEncBatch batch;
     int which[6], ns = 0;
     const bool lz = lz_for_level(o.level);                     // ids, comments, lengths, mask: LZ77 + FSE-coded sequences
-    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(sp[k], ss[k], k == 4 ? o.window_log : 0, lz && k < 4); }
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(sp[k], ss[k], k == 4 ? o.window_log : 0, lz && k < lz_streams()); }
     zstd_compress_batch(ctx, ex, batch);                       // sizes known on the host afterwards
 
     // ---- block index: the compressed size of every block of the sequence / quality frames, as a skippable frame behind the
@@ -925,7 +929,7 @@ void shard_finish_on_device(Ctx &ctx, CudaExec &ex, const nafgpu_shard_link &lin
     const bool present[6] = { true, true, true, (bool)H.store_mask, true, (bool)(H.store_qual || link.store_qual) };
     int which[6], ns = 0;
     const bool lz = lz_for_level(H.opts.level);
-    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.stream[k] ? H.raw[k] : 0, 0, lz && k < 4); }
+    for (int k = 0; k < 6; k++) if (present[k]) { which[ns++] = k; batch.add(H.stream[k], H.stream[k] ? H.raw[k] : 0, 0, lz && k < lz_streams()); }
     zstd_compress_batch(ctx, ex, batch);
     u64 total = 0; std::vector<u64> at(ns);
     for (int j = 0; j < ns; j++) { at[j] = total; total += (batch.frame_size[j] + 63) & ~63ull; }

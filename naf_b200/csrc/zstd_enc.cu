@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
     else { B.type = 0; B.csize = B.n; }
 }
 
-// ---- LZ streams, data-parallel (NAFGPU_LZ=shared; bodies: zstd_lzc_hd.cuh, emulated on the CPU by tests/emu/emu_zlzc.cpp):
+// ---- LZ streams, data-parallel (level >= 2; bodies: zstd_lzc_hd.cuh, emulated on the CPU by tests/emu/emu_zlzc.cpp):
 //   k_zlc_find    one CTA per block, thread = 32-byte chunk: column match finder (maps, neighbour walks over per-chunk summaries,
 //                 one block scan), sequences + compacted literals to the block's scratch; every 8th block of a stream also counts
 //                 its literal bytes and sequence codes into the stream's statistics
@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
 //   k_zlc_finish  one thread per block: serial coding against the stream's tables (the defining block: Compressed_Literals +
 //                 FSE_Compressed; the ones behind it: Treeless_Literals + Repeat_Mode)
 //   k_zlc_finish_own  streams that got no tables (no sequences at all, one literal symbol ...): every block builds its own
-static bool zlc_mode() { const char *e = getenv("NAFGPU_LZ"); return e && e[0] == 's'; }      // (read per call: one process can A/B the modes)
+// NAFGPU_LZ=1 brings back the first formulation (k_zenc_lz: one thread per block does everything, private tables per block) for A/B
+// measurements; the switch is read per call, so one process can compare the two.
+static bool zlc_mode() { const char *e = getenv("NAFGPU_LZ"); return !(e && e[0] == '1'); }
 struct ZlcArgs {
     ZEncBlock *blk; nafz::ZlcBlk *info; u8 *slots; u8 *work; u32 *counts; nafz::ZlcTables *tables; u32 *def_fail;
     const u8 *src[8]; u64 n[8]; u64 slot_base[8];

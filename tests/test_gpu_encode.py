@@ -204,28 +204,43 @@ def test_zstd_compress_roundtrip(gpu, oracle):
 
 
 def test_lz_frames_equal_cpu_emulation(gpu, tmp_path):
-    """the GPU runs the same HD block encoder the not-gpu tests run on the CPU (tests/emu/emu_zenc.cpp): same bytes out"""
+    """the GPU runs the same HD bodies the not-gpu tests run on the CPU -- the data-parallel stage a level >= 2 selects
+    (tests/emu/emu_zlzc.cpp) and the thread-per-block one behind NAFGPU_LZ=1 (tests/emu/emu_zenc.cpp): same bytes out"""
     import shutil
     import subprocess
-    exe = os.path.join(helpers.ROOT, "tests", "_build", "emu_zenc")
-    if shutil.which("g++"):                                  # build from the sources of this snapshot; else the binary that travelled
-        exe = str(tmp_path / "emu_zenc")
-        subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(helpers.ROOT, "tests", "emu", "emu_zenc.cpp")], check=True)
-    elif not os.path.exists(exe):
-        pytest.skip("no emu_zenc binary and no g++ on this box")
+    exes = {}
+    for name in ("emu_zlzc", "emu_zenc"):
+        exe = os.path.join(helpers.ROOT, "tests", "_build", name)
+        if shutil.which("g++"):                              # build from the sources of this snapshot; else the binary that travelled
+            exe = str(tmp_path / name)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(helpers.ROOT, "tests", "emu", name + ".cpp")], check=True)
+        elif not os.path.exists(exe):
+            pytest.skip("no %s binary and no g++ on this box" % name)
+        exes[name] = exe
     rng = np.random.default_rng(9)
-    for d in [b"".join(b"SRR1.%d\0" % i for i in range(70000, 90000)), b"".join(b"%d/1\0" % i for i in range(1, 30000)),
-              np.tile(np.array([150, 0, 0, 0], dtype=np.uint8), 30000).tobytes(), bytes(rng.integers(0, 5, 100000, dtype=np.uint8)),
-              b"abcdefgh" * 9000 + b"tail", b"", b"q" * 20000]:
-        inp, z = str(tmp_path / "i.bin"), str(tmp_path / "o.zst")
-        with open(inp, "wb") as f:
-            f.write(d)
-        assert subprocess.run([exe, inp, z, "8192", "1", "32"], capture_output=True).returncode == 0
-        assert gpu.zstd_compress(d, level=3) == open(z, "rb").read(), len(d)
+    saved = os.environ.get("NAFGPU_LZ")
+    try:
+        for d in [b"".join(b"SRR1.%d\0" % i for i in range(70000, 90000)), b"".join(b"%d/1\0" % i for i in range(1, 30000)),
+                  np.tile(np.array([150, 0, 0, 0], dtype=np.uint8), 30000).tobytes(), bytes(rng.integers(0, 5, 100000, dtype=np.uint8)),
+                  b"abcdefgh" * 9000 + b"tail", b"", b"q" * 20000, b"r%d\0" % 7 * 5000 + bytes(rng.integers(0, 256, 9000, dtype=np.uint8))]:
+            inp, z = str(tmp_path / "i.bin"), str(tmp_path / "o.zst")
+            with open(inp, "wb") as f:
+                f.write(d)
+            os.environ.pop("NAFGPU_LZ", None)
+            assert subprocess.run([exes["emu_zlzc"], inp, z, "8192"], capture_output=True).returncode == 0
+            assert gpu.zstd_compress(d, level=3) == open(z, "rb").read(), ("data-parallel stage", len(d))
+            os.environ["NAFGPU_LZ"] = "1"                    # (the library reads the switch per call)
+            assert subprocess.run([exes["emu_zenc"], inp, z, "8192", "1", "32"], capture_output=True).returncode == 0
+            assert gpu.zstd_compress(d, level=3) == open(z, "rb").read(), ("thread-per-block stage", len(d))
+    finally:
+        if saved is None:
+            os.environ.pop("NAFGPU_LZ", None)
+        else:
+            os.environ["NAFGPU_LZ"] = saved
 
 
 def test_levels_lz_on_text_streams(gpu, oracle):
-    """ennaf -# : level >= 2 parses ids / comments / lengths / mask with matches, level 1 (the default) does not; both files
+    """ennaf -# : level >= 2 parses ids / comments / lengths with matches, level 1 (the default) does not; both files
     are valid for every decoder, and the sequence / quality streams do not depend on the level"""
     for text, kw in [(synth.fastq(60_000, 150, seed=11), {}), (synth.ont_fasta(200, 10000, 30000, seed=12), {}),
                      (synth.protein_fasta(30_000, 300, seed=13), {"seq_type": "protein"})]:
