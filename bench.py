@@ -19,6 +19,8 @@ naturally; no data-path collective) and `value` is all ranks' bases / max-over-r
           every piece compared with the text
   ref_made, ref_made_full, cli_wall_clock  (N = 1 only) the .naf the unmodified ennaf -1 makes of the 2 M-read sample / of the
           whole workload, decoded on the device and compared; wall clock of bin/ennaf, bin/unnaf against the reference's tools
+  level2  (N = 1 only, extra) the same workload at ennaf -2 (names and lengths LZ77-matched by the data-parallel stage), device-resident
+          encode / decode times, file size, verified; runs last, in a thread with a deadline
   single_file  (N > 1 only, extra to the contract) ONE .naf from all ranks' shards -- count all-gather, link, gather of zstd
           blocks over NCCL (naf_b200/sharded.py) -- and every rank decoding its record range of that one file; verified
 
@@ -51,6 +53,7 @@ def parse_args():
     ap.add_argument("--cpu-sample-records", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-level2", action="store_true", help="skip the level2 sub-record")
     ap.add_argument("--c5-gbp", type=float, default=3.0, help="size of the configs[4] FASTA for the c5_strong sub-record (0 = skip)")
     ap.add_argument("--level", type=int, default=1, help="ennaf -# (1 = the tools' default: every stream entropy-coded; >= 2: + LZ77 / FSE-coded sequences on ids, comments, lengths, mask)")
     return ap.parse_args()
@@ -658,7 +661,61 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": srec * READ_LEN / (te + td) / 1e9, "unit": UNIT, "cores": 1, "kind": "reference",
                                     "encode_gbases_s": srec * READ_LEN / te / 1e9, "decode_gbases_s": srec * READ_LEN / td / 1e9,
                                     "sample": f"first {srec} reads of the same workload, oracle/_ref ennaf -1 + unnaf (single-threaded tools), /dev/shm"}
-        print(json.dumps(line))
+        # ---- level 2 (extra to the contract, N = 1): the same workload with ids / comments / lengths LZ77-matched by the data-parallel
+        # stage (csrc/zstd_lzc_hd.cuh) -- device-resident encode and decode times next to the level-1 ones above, file size, verified.
+        # Runs last and in a thread of its own with a deadline: whatever happens here, the line above is printed.
+        hung = False
+        if world == 1 and not args.no_level2 and args.level == 1:
+            box = {}
+
+            def level2_record():
+                try:
+                    o2 = api.make_enc_opts(level=2)
+                    te2, td2, size2 = [], [], 0
+                    for rep in range(4):
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                        ev[0].record(stream)
+                        addr, size2, _info = ctx.encode_device(d_text.data_ptr(), n_text, o2)
+                        ev[1].record(stream)
+                        torch.cuda.synchronize()
+                        if size2 + 64 > naf_keep["d"].numel():
+                            raise RuntimeError("level-2 file larger than the level-1 buffers")
+                        ctx_copy_d2d(naf_keep["d"], addr, size2)
+                        naf_keep["h"][:size2].copy_(naf_keep["d"][:size2])
+                        torch.cuda.synchronize()
+                        ev[2].record(stream)
+                        ta, ts = ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
+                        ev[3].record(stream)
+                        torch.cuda.synchronize()
+                        te2.append(ev[0].elapsed_time(ev[1])); td2.append(ev[2].elapsed_time(ev[3]))
+                    got = torch.empty(ts, dtype=torch.uint8, device="cuda")
+                    ctx_copy_d2d(got, ta, ts)
+                    ok2 = ts == n_text and bool(torch.equal(got, d_text[:n_text]))
+                    del got
+                    ctx.profile(True)
+                    ctx.encode_device(d_text.data_ptr(), n_text, o2)
+                    p2 = {n: ms for n, c, ms in ctx.profile_report()}
+                    ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
+                    for n, c, ms in ctx.profile_report():
+                        p2[n] = p2.get(n, 0.0) + ms
+                    ctx.profile(False)
+                    e2m, d2m = min(te2[1:]), min(td2[1:])
+                    box["r"] = {"workload": "the same reads at ennaf -2: names and lengths LZ77-matched (k_zlc_find / _define / _finish), device-resident",
+                                "naf_bytes": int(size2), "naf_over_text": size2 / n_text, "level1_naf_over_text": int(naf_size) / n_text,
+                                "encode_ms": e2m, "decode_ms": d2m, "level1_encode_ms": enc_ms1, "level1_decode_ms": dec_ms1,
+                                "value": bases / ((e2m + d2m) * 1e-3) / 1e9, "unit": UNIT, "verified": ok2,
+                                "kernels_ms": {k: round(v, 4) for k, v in sorted(p2.items(), key=lambda kv: -kv[1])[:12]}}
+                except Exception as e:                        # noqa: BLE001
+                    box["r"] = {"error": repr(e)[:300]}
+
+            th = threading.Thread(target=level2_record, daemon=True)
+            th.start()
+            th.join(timeout=120)
+            hung = th.is_alive()
+            line["level2"] = {"error": "no result within 120 s"} if hung else box.get("r", {"error": "no result"})
+        print(json.dumps(line), flush=True)
+        if hung:
+            os._exit(0)                                       # a stuck call must not keep the process (and the printed line) from ending
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
