@@ -34,33 +34,51 @@ static const u32 ZLC_LL0 = 256, ZLC_OF0 = 292, ZLC_ML0 = 324, ZLC_NBINS = 377;  
 // Thread k walks bytes 32 k .. 32 k + 31: with the arrays laid out plainly the 32 lanes of a warp would sit 32 bytes (8 banks) or
 // 32 u16 (16 banks) apart and every access would be an 8- or 16-way bank conflict.  One element of padding per chunk (33-element
 // pitch) puts the lanes of a warp into 32 different banks.
+// Only the first three phases touch bytes; what they leave per chunk is a handful of 32-bit masks (one bit per byte: where each
+// candidate matches, where its run continues from the byte before), and everything after -- run lengths, the choice between the
+// candidates, the matches -- is bit scans over those masks plus per-chunk summaries for runs that leave the chunk.
 static const u32 ZLC_PITCHED = ZLC_MAX + ZLC_NCH;
 HD u32 zlc_ix(u32 p) { return p + (p >> 5); }
 struct ZlcSh {                        // shared memory of one CTA = one block of at most ZLC_MAX bytes
     u8  src_[ZLC_PITCHED + 24];
-    u16 oc_[ZLC_PITCHED];             // column candidate: its offset where the byte matches there, else 0 (later: offsets / literal lengths of the sequences)
-    u16 d_[ZLC_PITCHED];              // chosen offset per byte, 0 = literal
+    u16 oc_[ZLC_PITCHED];             // column candidate: its offset where the byte matches there, else 0
     HD u8 src(u32 p) const { return src_[zlc_ix(p)]; }
     HD u16 oc(u32 p) const { return oc_[zlc_ix(p)]; }
-    HD u16 d(u32 p) const { return d_[zlc_ix(p)]; }
+    // --- dead after phase 5, then reused for the sequences' offsets and literal lengths of a sampled block (zlc_seq_scratch) ---
+    u32 cm[ZLC_NCH], fm[ZLC_NCH];     // bit i: byte 32 k + i matches at the column candidate / at offset 4
+    u32 ccm[ZLC_NCH], ffm[ZLC_NCH];   // ... and so does the byte before it, at the same offset: the run continues
     u16 z1[ZLC_NCH], z2[ZLC_NCH];     // last / second-last '\0' of a chunk
     u16 lbc[ZLC_NCH], fbc[ZLC_NCH];   // last / first position of a chunk at which a run of the column candidate does not continue
     u16 lbf[ZLC_NCH], fbf[ZLC_NCH];   // same, candidate 4
-    u16 fbd[ZLC_NCH];                 // first position of a chunk at which a run of d does not continue
+    // --- live until the end ---
+    u32 d4m[ZLC_NCH], dcm[ZLC_NCH];   // the choice: offset 4 / the column offset (neither: literal)
+    u32 ddm[ZLC_NCH];                 // the chosen offset is the same as the byte before's: the match continues
+    u16 fbd[ZLC_NCH];                 // first position of a chunk at which a run of the chosen offset does not continue
     u16 cnt[ZLC_NCH], mls[ZLC_NCH], lend[ZLC_NCH];    // matches starting in a chunk: how many, their lengths added up, where the last one ends
     u16 ibase[ZLC_NCH], mbase[ZLC_NCH];               // exclusive prefix of cnt / mls over the chunks
     u32 n, nch, rle_break, lastend, nseq, mltot;
     u32 hist[ZLC_NBINS];
 };
 
+static const u32 ZLC_SEQCAP = 7 * ZLC_NCH;                      // u16 entries per array in the reused region (a block has at most ZLC_MAX / 5 matches)
+static_assert(ZLC_SEQCAP >= ZLC_MAX / ZLC_MINML + 1 && 2 * ZLC_SEQCAP * 2 <= 4 * ZLC_NCH * 4 + 6 * ZLC_NCH * 2, "sequence scratch does not fit the reused arrays");
+HD u16 *zlc_seq_scratch(ZlcSh &sh) { return (u16 *)sh.cm; }    // [0, SEQCAP): offsets, [SEQCAP, 2 SEQCAP): literal lengths
+
 struct ZlcBlk { u32 nseq, nlit; u8 parsed, rle, conv, pad; };      // what the finder leaves per block (conv: offsets already turned into Offset_Values)
 
-HD bool zlc_mf(const ZlcSh &sh, u32 p) { return p >= 4 && sh.src(p) == sh.src(p - 4); }
-HD bool zlc_contc(const ZlcSh &sh, u32 p) { return sh.oc(p) && p > 0 && sh.oc(p - 1) == sh.oc(p); }
-HD bool zlc_contf(const ZlcSh &sh, u32 p) { return p > 0 && zlc_mf(sh, p) && zlc_mf(sh, p - 1); }
-HD bool zlc_contd(const ZlcSh &sh, u32 p) { return sh.d(p) && p > 0 && sh.d(p - 1) == sh.d(p); }
 HD u32 zlc_lo(u32 k) { return k * ZLC_CH; }
 HD u32 zlc_hi(const ZlcSh &sh, u32 k) { const u32 h = k * ZLC_CH + ZLC_CH; return h < sh.n ? h : sh.n; }
+HD u32 zlc_below(u32 i) { return i >= 32 ? 0xFFFFFFFFu : ((1u << i) - 1); }          // bits 0 .. i-1
+HD u32 zlc_valid(const ZlcSh &sh, u32 k) { return zlc_below(zlc_hi(sh, k) - zlc_lo(k)); }
+HD u32 zlc_low(u32 m)                 // index of the lowest set bit (m != 0)
+{
+#ifdef __CUDA_ARCH__
+    return (u32)__ffs((int)m) - 1;
+#else
+    return (u32)__builtin_ctz(m);
+#endif
+}
+HD u32 zlc_top(u32 m) { return (u32)hibit(m); }                                     // index of the highest set bit (m != 0)
 
 // phase 1: where the chunk's last two terminators are; is the block one repeated byte
 HD void zlc_zeros(ZlcSh &sh, u32 k)
@@ -70,8 +88,8 @@ HD void zlc_zeros(ZlcSh &sh, u32 k)
     sh.z1[k] = (u16)a; sh.z2[k] = (u16)b;
     if (!same) sh.rle_break = 1;
 }
-// phase 2: the column candidate.  The record a byte is in starts behind the last terminator before it; the candidate offset is the
-// length of the record before that one.
+// phase 2: the two candidates, byte by byte.  The record a byte is in starts behind the last terminator before it; the column
+// candidate's offset is the length of the record before that one.
 HD void zlc_columns(ZlcSh &sh, u32 k)
 {
     u32 za = ZLC_NONE, zb = ZLC_NONE;
@@ -81,74 +99,100 @@ HD void zlc_columns(ZlcSh &sh, u32 k)
         else { zb = sh.z1[c]; break; }
     }
     u32 cur = za == ZLC_NONE ? 0 : za + 1, prev = zb == ZLC_NONE ? 0 : zb + 1;
-    for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) {
+    const u32 lo = zlc_lo(k), hi = zlc_hi(sh, k);
+    u32 cm = 0, fm = 0;
+    u32 w = 0;                                                  // the four bytes before p, oldest in the top byte
+    for (u32 i = lo >= 4 ? 4 : lo; i > 0; i--) w = (w << 8) | sh.src(lo - i);
+    for (u32 p = lo; p < hi; p++) {
+        const u32 c = sh.src(p), bit = 1u << (p - lo);
         u32 o = 0;
-        if (cur > 0) { const u32 dcol = cur - prev; if (sh.src(p) == sh.src(p - dcol)) o = dcol; }
+        if (cur > 0) { const u32 dcol = cur - prev; if (c == sh.src(p - dcol)) o = dcol; }
         sh.oc_[zlc_ix(p)] = (u16)o;
-        if (sh.src(p) == 0) { prev = cur; cur = p + 1; }
+        if (o) cm |= bit;
+        if (p >= 4 && c == (w >> 24)) fm |= bit;
+        w = (w << 8) | c;
+        if (c == 0) { prev = cur; cur = p + 1; }
     }
+    sh.cm[k] = cm; sh.fm[k] = fm;
 }
-// phase 3: per chunk, where runs of either candidate break (so that a run's far ends are found chunk by chunk)
+// phase 3: where runs continue, and per chunk where they break (so that a run's far ends are found chunk by chunk)
 HD void zlc_breaks(ZlcSh &sh, u32 k)
 {
-    u32 lc = ZLC_NONE, fc = ZLC_NONE, lf = ZLC_NONE, ff = ZLC_NONE;
-    for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) {
-        if (!zlc_contc(sh, p)) { if (fc == ZLC_NONE) fc = p; lc = p; }
-        if (!zlc_contf(sh, p)) { if (ff == ZLC_NONE) ff = p; lf = p; }
-    }
-    sh.lbc[k] = (u16)lc; sh.fbc[k] = (u16)fc; sh.lbf[k] = (u16)lf; sh.fbf[k] = (u16)ff;
+    const u32 lo = zlc_lo(k), hi = zlc_hi(sh, k), valid = zlc_valid(sh, k);
+    u32 ccm = 0, po = lo ? sh.oc(lo - 1) : 0;
+    for (u32 p = lo; p < hi; p++) { const u32 o = sh.oc(p); if (o && o == po) ccm |= 1u << (p - lo); po = o; }      // (p == 0: po = 0, no run continues)
+    const u32 fm = sh.fm[k], ffm = fm & ((fm << 1) | (k ? sh.fm[k - 1] >> 31 : 0));       // (chunk k - 1 is a full one)
+    sh.ccm[k] = ccm; sh.ffm[k] = ffm;
+    const u32 bc = ~ccm & valid, bf = ~ffm & valid;             // (never 0 for k == 0: nothing continues at byte 0)
+    sh.lbc[k] = (u16)(bc ? lo + zlc_top(bc) : ZLC_NONE); sh.fbc[k] = (u16)(bc ? lo + zlc_low(bc) : ZLC_NONE);
+    sh.lbf[k] = (u16)(bf ? lo + zlc_top(bf) : ZLC_NONE); sh.fbf[k] = (u16)(bf ? lo + zlc_low(bf) : ZLC_NONE);
 }
-// phase 4: a byte takes the candidate whose run around it is longer (ties: the column)
+// length of the run (of the candidate whose continue-mask is `cont`) that byte lo + a is in, and where it ends
+HD u32 zlc_run(const ZlcSh &sh, u32 k, u32 a, u32 cont, const u16 *lastbrk, const u16 *firstbrk, u32 *end)
+{
+    const u32 lo = zlc_lo(k), valid = zlc_valid(sh, k);
+    const u32 brk = ~cont & valid;
+    const u32 before = brk & zlc_below(a + 1), after = brk & ~zlc_below(a + 1);
+    u32 start, e;
+    if (before) start = lo + zlc_top(before);
+    else { u32 c = k; do c--; while (lastbrk[c] == ZLC_NONE); start = lastbrk[c]; }          // (k > 0: chunk 0 breaks at byte 0)
+    if (after) e = lo + zlc_low(after);
+    else if (valid != 0xFFFFFFFFu) e = sh.n;                                                 // the block's last, partial chunk
+    else { u32 c = k + 1; while (c < sh.nch && firstbrk[c] == ZLC_NONE) c++; e = c < sh.nch ? firstbrk[c] : sh.n; }
+    *end = e;
+    return e - start;
+}
+// phase 4: a byte takes the candidate whose run around it is longer (ties: the column).  Between two breaks of either candidate
+// both runs are the same for every byte, so the choice is made once per such piece.
 HD void zlc_choose(ZlcSh &sh, u32 k)
 {
-    const u32 lo = zlc_lo(k), hi = zlc_hi(sh, k), n = sh.n, nch = sh.nch;
-    u32 endc = 0, lenc = 0, endf = 0, lenf = 0;                  // the run p is in, per candidate (valid while p < end)
-    for (u32 p = lo; p < hi; p++) {
+    const u32 lo = zlc_lo(k), valid = zlc_valid(sh, k), nv = zlc_hi(sh, k) - lo;
+    const u32 cm = sh.cm[k], fm = sh.fm[k], ccm = sh.ccm[k], ffm = sh.ffm[k];
+    u32 pieces = ((~ccm | ~ffm) & valid) | 1u, d4 = 0, dc = 0;
+    u32 endc = 0, lenc = 0, endf = 0, lenf = 0;                 // the run the current piece is in, per candidate (valid while p < end)
+    while (pieces) {
+        const u32 a = zlc_low(pieces); pieces &= pieces - 1;
+        const u32 b = pieces ? zlc_low(pieces) : nv, p = lo + a;
+        if (!(((cm | fm) >> a) & 1)) continue;
         u32 lc = 0, lf = 0;
-        if (sh.oc(p)) {
-            if (p >= endc) {
-                u32 q = p; while (q > lo && zlc_contc(sh, q)) q--;
-                u32 start = q;
-                if (zlc_contc(sh, q)) { u32 c = k; do c--; while (sh.lbc[c] == ZLC_NONE); start = sh.lbc[c]; }     // (q == lo > 0: chunk 0 breaks at 0)
-                u32 e = p + 1; while (e < hi && zlc_contc(sh, e)) e++;
-                if (e == hi && hi < n && zlc_contc(sh, hi)) { u32 c = k + 1; while (c < nch && sh.fbc[c] == ZLC_NONE) c++; e = c < nch ? sh.fbc[c] : n; }
-                endc = e; lenc = e - start;
-            }
-            lc = lenc;
-        }
-        if (zlc_mf(sh, p)) {
-            if (p >= endf) {
-                u32 q = p; while (q > lo && zlc_contf(sh, q)) q--;
-                u32 start = q;
-                if (zlc_contf(sh, q)) { u32 c = k; do c--; while (sh.lbf[c] == ZLC_NONE); start = sh.lbf[c]; }
-                u32 e = p + 1; while (e < hi && zlc_contf(sh, e)) e++;
-                if (e == hi && hi < n && zlc_contf(sh, hi)) { u32 c = k + 1; while (c < nch && sh.fbf[c] == ZLC_NONE) c++; e = c < nch ? sh.fbf[c] : n; }
-                endf = e; lenf = e - start;
-            }
-            lf = lenf;
-        }
-        sh.d_[zlc_ix(p)] = lf > lc ? (u16)4 : sh.oc(p);
+        if ((cm >> a) & 1) { if (p >= endc) lenc = zlc_run(sh, k, a, ccm, sh.lbc, sh.fbc, &endc); lc = lenc; }
+        if ((fm >> a) & 1) { if (p >= endf) lenf = zlc_run(sh, k, a, ffm, sh.lbf, sh.fbf, &endf); lf = lenf; }
+        const u32 pm = zlc_below(b) & ~zlc_below(a);
+        if (lf > lc) d4 |= pm; else if (lc) dc |= pm;
     }
+    sh.d4m[k] = d4; sh.dcm[k] = dc;
 }
-// phase 5
+HD u32 zlc_dval(const ZlcSh &sh, u32 p) { const u32 k = p >> 5, bit = 1u << (p & 31); return (sh.d4m[k] & bit) ? 4u : ((sh.dcm[k] & bit) ? (u32)sh.oc(p) : 0u); }
+// phase 5: where the chosen offset continues.  Both bytes at offset 4: yes; both at the column offset: where the column run continues;
+// one of each: only if the column offset happens to be 4.
 HD void zlc_breaks_d(ZlcSh &sh, u32 k)
 {
-    u32 fd = ZLC_NONE;
-    for (u32 p = zlc_lo(k), hi = zlc_hi(sh, k); p < hi; p++) if (!zlc_contd(sh, p)) { fd = p; break; }
-    sh.fbd[k] = (u16)fd;
+    const u32 lo = zlc_lo(k), valid = zlc_valid(sh, k);
+    const u32 d4 = sh.d4m[k], dc = sh.dcm[k];
+    const u32 s4 = (d4 << 1) | (k ? sh.d4m[k - 1] >> 31 : 0), sc = (dc << 1) | (k ? sh.dcm[k - 1] >> 31 : 0);
+    u32 dd = (d4 & s4) | (dc & sc & sh.ccm[k]);
+    u32 mixed = (d4 & sc) | (dc & s4);
+    while (mixed) {
+        const u32 a = zlc_low(mixed); mixed &= mixed - 1;
+        if (zlc_dval(sh, lo + a) == zlc_dval(sh, lo + a - 1)) dd |= 1u << a;
+    }
+    sh.ddm[k] = dd;
+    const u32 bd = ~dd & valid;
+    sh.fbd[k] = (u16)(bd ? lo + zlc_low(bd) : ZLC_NONE);
 }
 // the matches that START in chunk k, in order: f(start, end)
 template <class F> HD void zlc_each_match(const ZlcSh &sh, u32 k, F f)
 {
-    const u32 lo = zlc_lo(k), hi = zlc_hi(sh, k);
-    u32 p = lo;
-    while (p < hi) {
-        if (!sh.d(p) || zlc_contd(sh, p)) { p++; continue; }
-        u32 q = p + 1; while (q < hi && zlc_contd(sh, q)) q++;
-        u32 end = q;
-        if (q == hi && hi < sh.n && zlc_contd(sh, hi)) { u32 c = k + 1; while (c < sh.nch && sh.fbd[c] == ZLC_NONE) c++; end = c < sh.nch ? sh.fbd[c] : sh.n; }
-        if (end - p >= ZLC_MINML) f(p, end);
-        p = q;
+    const u32 lo = zlc_lo(k), valid = zlc_valid(sh, k), dd = sh.ddm[k];
+    u32 starts = (sh.d4m[k] | sh.dcm[k]) & ~dd & valid;
+    while (starts) {
+        const u32 a = zlc_low(starts); starts &= starts - 1;
+        const u32 after = ~dd & valid & ~zlc_below(a + 1);
+        u32 end;
+        if (after) end = lo + zlc_low(after);
+        else if (valid != 0xFFFFFFFFu) end = sh.n;
+        else { u32 c = k + 1; while (c < sh.nch && sh.fbd[c] == ZLC_NONE) c++; end = c < sh.nch ? sh.fbd[c] : sh.n; }
+        if (end - (lo + a) >= ZLC_MINML) f(lo + a, end);
     }
 }
 // phase 6
@@ -175,9 +219,9 @@ HD void zlc_emit_seqs(ZlcSh &sh, u32 k, const ZLzSeqs &S, u8 *lit, bool sampled)
     u32 pe = 0;
     for (u32 c = k; c-- > 0;) if (sh.cnt[c]) { pe = sh.lend[c]; break; }
     u32 idx = sh.ibase[k], msum = sh.mbase[k];
-    u16 *so = sh.oc_, *sl = sh.oc_ + ZLC_PITCHED / 2;
+    u16 *so = zlc_seq_scratch(sh), *sl = so + ZLC_SEQCAP;
     zlc_each_match(sh, k, [&](u32 start, u32 end) {
-        const u32 ll = start - pe, ml = end - start, off = sh.d(start);
+        const u32 ll = start - pe, ml = end - start, off = zlc_dval(sh, start);
         S.ll[idx] = (u16)ll; S.ml[idx] = (u16)ml; S.ov[idx] = (u16)off;
         u8 *dst = lit + (pe - msum);
         for (u32 i = 0; i < ll; i++) { const u8 c = sh.src(pe + i); dst[i] = c; if (sampled) ZLC_INC(sh.hist[c]); }
@@ -194,7 +238,7 @@ HD void zlc_emit_tail(ZlcSh &sh, u32 t, u32 nt, u8 *lit, bool sampled)
 // phase 9 (sampled blocks, one thread): Offset_Value codes need the repeat-offset history, which is serial
 HD void zlc_count_offsets(ZlcSh &sh)
 {
-    const u16 *so = sh.oc_, *sl = sh.oc_ + ZLC_PITCHED / 2;
+    const u16 *so = zlc_seq_scratch(sh), *sl = so + ZLC_SEQCAP;
     ZLzRep rep; rep.r[0] = rep.r[1] = rep.r[2] = 0; rep.k = 0;
     for (u32 i = 0; i < sh.nseq; i++) sh.hist[ZLC_OF0 + (u32)hibit(rep.code(so[i], sl[i]))]++;
 }
@@ -250,7 +294,12 @@ HD void zlc_offset_values(const ZLzSeqs &S, ZlcBlk &I)
 {
     if (I.conv) return;
     ZLzRep rep; rep.r[0] = rep.r[1] = rep.r[2] = 0; rep.k = 0;
-    for (u32 i = 0; i < S.n; i++) S.ov[i] = (u16)rep.code(S.ov[i], S.ll[i]);
+    u32 i = 0;                                                  // (loads in groups: the history is a serial chain, the memory waits need not be)
+    for (; i + 4 <= S.n; i += 4) {
+        u16 o[4], l[4]; ld_group<4>(S.ov + i, o); ld_group<4>(S.ll + i, l);
+        for (int k = 0; k < 4; k++) S.ov[i + k] = (u16)rep.code(o[k], l[k]);
+    }
+    for (; i < S.n; i++) S.ov[i] = (u16)rep.code(S.ov[i], S.ll[i]);
     I.conv = 1;
 }
 
