@@ -33,8 +33,10 @@ def main():
     from naf_b200 import synth
     import helpers
     n_time = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+    import shutil
     emu = os.path.join(ROOT, "tests", "_build", "emu_zlzc")
-    if not os.path.exists(emu):
+    if shutil.which("g++"):                                   # from the sources of this snapshot; else the binary that travelled
+        emu = os.path.join(os.environ.get("TMPDIR", "/tmp"), "emu_zlzc_%d" % os.getpid())
         subprocess.run(["g++", "-std=c++17", "-O2", "-o", emu, os.path.join(ROOT, "tests", "emu", "emu_zlzc.cpp")], check=True)
     ctx = naf_b200.NafGpu(0)
     say(step="context")
