@@ -410,3 +410,40 @@ def test_defining_block_that_does_not_fit_gets_the_stream_private_tables(dec, li
     assert subprocess.run([dec, z, back], capture_output=True).returncode == 0 and open(back, "rb").read() == data
     assert subprocess.run([proto, inp, zp, "8192", "col"], capture_output=True).returncode == 0
     assert open(zp, "rb").read() == frame
+
+
+def test_reference_unnaf_decodes_files_with_stream_table_frames(tmp_path):
+    """a whole .naf whose ids / comments / lengths sections are the frames the data-parallel stage writes (emulation; the GPU writes
+    the same bytes), the other sections as the oracle's encoder makes them: the UNMODIFIED reference unnaf (input.c:211
+    ZSTD_decompress for these sections) prints the input back, and so does the oracle"""
+    from naf_b200 import container
+    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    oracle = helpers.load_oracle()
+    for text, kw in [(synth.fastq(30_000, 150, seed=21), {}), (synth.ont_fasta(60, 10000, 30000, seed=22), {}),
+                     (synth.protein_fasta(8000, 300, seed=23), {"seq_type": "protein"})]:
+        naf, _ = oracle.encode(text, **kw)
+        streams, info = oracle.split(text, **kw)
+        h = container.read_header(naf)
+        first = min(sec[2] for sec in h.sections if sec is not None)
+        out = bytearray()
+        for k in range(6):
+            sec = h.sections[k]
+            if sec is None:
+                continue
+            orig, comp, off = sec
+            body = naf[off:off + comp]
+            if k < 3:
+                inp, z = str(tmp_path / "i.bin"), str(tmp_path / "c.zst")
+                with open(inp, "wb") as f:
+                    f.write(streams[k])
+                assert subprocess.run([exe, inp, z, "8192"], capture_output=True).returncode == 0
+                body = open(z, "rb").read()[4:]                # sections are stored without the 4-byte magic (compressor.c:158)
+                assert orig == len(streams[k])
+            out += container.put_vle(orig) + container.put_vle(len(body)) + body
+        # header bytes up to the first section's two VLE numbers
+        hdr_end = first - len(container.put_vle(h.sections[0][0])) - len(container.put_vle(h.sections[0][1]))
+        mixed = bytes(naf[:hdr_end]) + bytes(out)
+        assert oracle.decode(mixed) == text
+        if helpers.have_ref():
+            rc, got, err = helpers.ref_run("unnaf", [], mixed)
+            assert rc == 0 and got == text, err[:300]
