@@ -78,8 +78,8 @@ typedef struct {
     int32_t  have_line_length;  /* ennaf --line-length N */
     uint64_t line_length;
     int32_t  level;             /* ennaf -# (default 1): <= 1 is the fastest parse (every stream entropy-coded); >= 2 adds LZ77
-                                   matches + FSE-coded sequences to the ids / comments / lengths / mask streams (file size of
-                                   `ennaf -1`, slower).  Sequence and quality are Huffman-coded at every level. */
+                                   matches + FSE-coded sequences to the ids / comments / lengths streams (file size of
+                                   `ennaf -1`, slower).  Sequence, quality and mask are Huffman-coded at every level. */
     int32_t  window_log;        /* ennaf --long N: declared window of the SEQ frame (0 = default) */
     const char *title;          /* ennaf --title, NULL = none */
     int32_t  general_parser;    /* 1: skip the canonical-input fast parser and use the general (process.c-exact FSM) one;
@@ -196,8 +196,8 @@ int nafgpu_zstd_decompress(nafgpu_ctx *ctx, const uint8_t *src, size_t n, size_t
 int nafgpu_zstd_compress(nafgpu_ctx *ctx, const uint8_t *src, size_t n, int window_log,
                          const uint8_t **out, size_t *out_size);
 /* The same with ennaf's -# (ZSTD_initCStream's level, compressor.c:17): level >= 2 parses the bytes with LZ77 matches and
- * FSE-coded sequences in independent 8 KB blocks (what nafgpu_encode does for ids / comments / lengths / mask at those
- * levels); level <= 1 is nafgpu_zstd_compress. */
+ * FSE-coded sequences in independent 8 KB blocks (what nafgpu_encode does for ids / comments / lengths at those
+ * levels: csrc/zstd_lzc_hd.cuh); level <= 1 is nafgpu_zstd_compress. */
 int nafgpu_zstd_compress_level(nafgpu_ctx *ctx, const uint8_t *src, size_t n, int window_log, int level,
                                const uint8_t **out, size_t *out_size);
 
