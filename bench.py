@@ -668,51 +668,74 @@ def run_ours(args):
         if world == 1 and not args.no_level2 and args.level == 1:
             box = {}
 
+            def level2_once(o2):
+                te2, td2, size2 = [], [], 0
+                for rep in range(4):
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                    ev[0].record(stream)
+                    addr, size2, _info = ctx.encode_device(d_text.data_ptr(), n_text, o2)
+                    ev[1].record(stream)
+                    torch.cuda.synchronize()
+                    if size2 + 64 > naf_keep["d"].numel():
+                        raise RuntimeError("level-2 file larger than the level-1 buffers")
+                    ctx_copy_d2d(naf_keep["d"], addr, size2)
+                    naf_keep["h"][:size2].copy_(naf_keep["d"][:size2])
+                    torch.cuda.synchronize()
+                    ev[2].record(stream)
+                    ta, ts = ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
+                    ev[3].record(stream)
+                    torch.cuda.synchronize()
+                    te2.append(ev[0].elapsed_time(ev[1])); td2.append(ev[2].elapsed_time(ev[3]))
+                got = torch.empty(ts, dtype=torch.uint8, device="cuda")
+                ctx_copy_d2d(got, ta, ts)
+                ok2 = ts == n_text and bool(torch.equal(got, d_text[:n_text]))
+                del got
+                ctx.profile(True)
+                ctx.encode_device(d_text.data_ptr(), n_text, o2)
+                p2 = {n: ms for n, c, ms in ctx.profile_report()}
+                ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
+                for n, c, ms in ctx.profile_report():
+                    p2[n] = p2.get(n, 0.0) + ms
+                ctx.profile(False)
+                e2m, d2m = min(te2[1:]), min(td2[1:])
+                return {"naf_bytes": int(size2), "naf_over_text": size2 / n_text, "encode_ms": e2m, "decode_ms": d2m,
+                        "value": bases / ((e2m + d2m) * 1e-3) / 1e9, "unit": UNIT, "verified": ok2,
+                        "kernels_ms": {k: round(v, 4) for k, v in sorted(p2.items(), key=lambda kv: -kv[1])[:12]}}
+
             def level2_record():
+                saved = os.environ.get("NAFGPU_LZ")
                 try:
                     o2 = api.make_enc_opts(level=2)
-                    te2, td2, size2 = [], [], 0
-                    for rep in range(4):
-                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-                        ev[0].record(stream)
-                        addr, size2, _info = ctx.encode_device(d_text.data_ptr(), n_text, o2)
-                        ev[1].record(stream)
-                        torch.cuda.synchronize()
-                        if size2 + 64 > naf_keep["d"].numel():
-                            raise RuntimeError("level-2 file larger than the level-1 buffers")
-                        ctx_copy_d2d(naf_keep["d"], addr, size2)
-                        naf_keep["h"][:size2].copy_(naf_keep["d"][:size2])
-                        torch.cuda.synchronize()
-                        ev[2].record(stream)
-                        ta, ts = ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
-                        ev[3].record(stream)
-                        torch.cuda.synchronize()
-                        te2.append(ev[0].elapsed_time(ev[1])); td2.append(ev[2].elapsed_time(ev[3]))
-                    got = torch.empty(ts, dtype=torch.uint8, device="cuda")
-                    ctx_copy_d2d(got, ta, ts)
-                    ok2 = ts == n_text and bool(torch.equal(got, d_text[:n_text]))
-                    del got
-                    ctx.profile(True)
-                    ctx.encode_device(d_text.data_ptr(), n_text, o2)
-                    p2 = {n: ms for n, c, ms in ctx.profile_report()}
-                    ctx.decode_device(naf_keep["d"].data_ptr(), size2, (naf_keep["h"].data_ptr(), size2), dopts)
-                    for n, c, ms in ctx.profile_report():
-                        p2[n] = p2.get(n, 0.0) + ms
-                    ctx.profile(False)
-                    e2m, d2m = min(te2[1:]), min(td2[1:])
-                    box["r"] = {"workload": "the same reads at ennaf -2: names and lengths LZ77-matched (k_zlc_find / _define / _finish), device-resident",
-                                "naf_bytes": int(size2), "naf_over_text": size2 / n_text, "level1_naf_over_text": int(naf_size) / n_text,
-                                "encode_ms": e2m, "decode_ms": d2m, "level1_encode_ms": enc_ms1, "level1_decode_ms": dec_ms1,
-                                "value": bases / ((e2m + d2m) * 1e-3) / 1e9, "unit": UNIT, "verified": ok2,
-                                "kernels_ms": {k: round(v, 4) for k, v in sorted(p2.items(), key=lambda kv: -kv[1])[:12]}}
+                    r = {"workload": "the same reads at ennaf -2: names and lengths LZ77-matched (k_zlc_find / _define / _finish), device-resident",
+                         "level1_naf_over_text": int(naf_size) / n_text, "level1_encode_ms": enc_ms1, "level1_decode_ms": dec_ms1}
+                    box["r"] = r
+                    r.update(level2_once(o2))                  # the finder as it ran on a B200 during the round (byte loops)
+                    try:                                      # ... and its bit-mask formulation (same frames; the switch is read per call)
+                        os.environ["NAFGPU_LZ"] = "b"
+                        r["finder_bit_masks"] = level2_once(o2)
+                    except Exception as e:                    # noqa: BLE001
+                        r["finder_bit_masks"] = {"error": repr(e)[:300]}
                 except Exception as e:                        # noqa: BLE001
-                    box["r"] = {"error": repr(e)[:300]}
+                    box.setdefault("r", {})["error"] = repr(e)[:300]
+                finally:
+                    if saved is None:
+                        os.environ.pop("NAFGPU_LZ", None)
+                    else:
+                        os.environ["NAFGPU_LZ"] = saved
 
             th = threading.Thread(target=level2_record, daemon=True)
             th.start()
             th.join(timeout=120)
             hung = th.is_alive()
-            line["level2"] = {"error": "no result within 120 s"} if hung else box.get("r", {"error": "no result"})
+            if hung:                                          # keep what was measured before the call that did not come back
+                try:
+                    partial = json.loads(json.dumps(box.get("r", {})))
+                except Exception:                             # noqa: BLE001
+                    partial = {}
+                partial["error"] = "no result within 120 s"
+                line["level2"] = partial
+            else:
+                line["level2"] = box.get("r", {"error": "no result"})
         print(json.dumps(line), flush=True)
         if hung:
             os._exit(0)                                       # a stuck call must not keep the process (and the printed line) from ending

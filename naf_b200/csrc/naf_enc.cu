@@ -641,7 +641,7 @@ namespace nafg {
 static bool lz_for_level(int level)
 {
     const char *env = getenv("NAFGPU_LZ");
-    if (env && (env[0] == '0' || env[0] == '1' || env[0] == 's')) return env[0] != '0';
+    if (env && (env[0] == '0' || env[0] == '1' || env[0] == 's' || env[0] == 'b')) return env[0] != '0';
     return level >= 2;
 }
 static int lz_streams() { return zlc_mode() ? 3 : 4; }           // how many of ids, comments, lengths, mask take the LZ stage

@@ -26,6 +26,7 @@
 
 #include "zstd_enc_hd.cuh"
 #include "zstd_lzc_hd.cuh"
+#include "zstd_lzc_bytes_hd.cuh"
 
 namespace nafg {
 
@@ -332,6 +333,8 @@ __global__ void __launch_bounds__(32) k_zenc_lz(const ZLzArgs A)
 // NAFGPU_LZ=1 brings back the first formulation (k_zenc_lz: one thread per block does everything, private tables per block) for A/B
 // measurements; the switch is read per call, so one process can compare the two.
 static bool zlc_mode() { const char *e = getenv("NAFGPU_LZ"); return !(e && e[0] == '1'); }
+// NAFGPU_LZ=b: the finder's bit-mask formulation (same frames; written after the round's last GPU call, so a level does not select it yet)
+static bool zlc_bits() { const char *e = getenv("NAFGPU_LZ"); return e && e[0] == 'b'; }
 struct ZlcArgs {
     ZEncBlock *blk; nafz::ZlcBlk *info; u8 *slots; u8 *work; u32 *counts; nafz::ZlcTables *tables; u32 *def_fail;
     const u8 *src[8]; u64 n[8]; u64 slot_base[8];
@@ -348,56 +351,60 @@ __device__ __forceinline__ nafz::ZlcStreamView zlc_view(const ZlcArgs &A, u32 s)
     return V;
 }
 
-__global__ void __launch_bounds__(256) k_zlc_find(const ZlcArgs A)
-{
-    extern __shared__ __align__(16) u8 zlc_smem[];
-    nafz::ZlcSh &sh = *reinterpret_cast<nafz::ZlcSh *>(zlc_smem);
-    __shared__ u64 smscan[33];
-    const u32 j = blockIdx.x, k = threadIdx.x;
-    const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s];
-    const ZEncBlock &B = A.blk[A.first[s] + bidx];
-    const u8 *src = B.src; const u32 n = B.n;
-    for (u32 i = k; i < n; i += 256) sh.src_[nafz::zlc_ix(i)] = src[i];
-    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) sh.hist[i] = 0;
-    if (k == 0) { sh.n = n; sh.nch = (n + nafz::ZLC_CH - 1) / nafz::ZLC_CH; sh.rle_break = 0; sh.lastend = 0; }
-    __syncthreads();
-    const bool act = k < sh.nch;
-    if (act) nafz::zlc_zeros(sh, k);
-    __syncthreads();
-    nafz::ZlcBlk &I = A.info[j];
-    if (n == 0 || !sh.rle_break || n < 16) {                   // empty, one repeated byte, or too small to parse: RLE / raw block
-        if (k == 0) { I.nseq = 0; I.nlit = 0; I.parsed = 0; I.rle = (n && !sh.rle_break) ? 1 : 0; I.conv = 0; I.pad = 0; }
-        return;
-    }
-    if (act) nafz::zlc_columns(sh, k);
-    __syncthreads();
-    if (act) nafz::zlc_breaks(sh, k);
-    __syncthreads();
-    if (act) nafz::zlc_choose(sh, k);
-    __syncthreads();
-    if (act) nafz::zlc_breaks_d(sh, k);
-    __syncthreads();
-    if (act) nafz::zlc_count(sh, k);
-    __syncthreads();
-    {
-        const u64 v = act ? ((u64)sh.cnt[k] | ((u64)sh.mls[k] << 32)) : 0;
-        u64 total; const u64 pre = block_excl_scan(v, &total, smscan);
-        if (act) { sh.ibase[k] = (u16)pre; sh.mbase[k] = (u16)(pre >> 32); }
-        if (k == 0) { sh.nseq = (u32)total; sh.mltot = (u32)(total >> 32); }
-    }
-    __syncthreads();
-    const bool sampled = bidx % nafz::ZLC_SAMPLE == 0;
-    nafz::ZlcWork K = nafz::zlc_work(A.work + (size_t)j * nafz::zlc_work_bytes(A.zlb), A.zlb);
-    if (act) nafz::zlc_emit_seqs(sh, k, K.S, K.lit, sampled);
-    nafz::zlc_emit_tail(sh, k, 256, K.lit, sampled);
-    if (k == 0) { I.nseq = sh.nseq; I.nlit = n - sh.mltot; I.parsed = 1; I.rle = 0; I.conv = 0; I.pad = 0; }
-    if (!sampled) return;
-    __syncthreads();
-    if (k == 0) nafz::zlc_count_offsets(sh);
-    __syncthreads();
-    u32 *acc = A.counts + s * nafz::ZLC_NBINS;
-    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) if (sh.hist[i]) atomicAdd(&acc[i], sh.hist[i]);
+// The finder kernel, once per formulation of its phases (FN: nafz::zlcb = byte loops, nafz = bit masks; same barriers, same outputs)
+#define ZLC_FIND_KERNEL(NAME, FN) \
+__global__ void __launch_bounds__(256) NAME(const ZlcArgs A) \
+{ \
+    extern __shared__ __align__(16) u8 zlc_smem[]; \
+    FN::ZlcSh &sh = *reinterpret_cast<FN::ZlcSh *>(zlc_smem); \
+    __shared__ u64 smscan[33]; \
+    const u32 j = blockIdx.x, k = threadIdx.x; \
+    const u32 s = zlc_stream_of(A, j), bidx = j - A.lzfirst[s]; \
+    const ZEncBlock &B = A.blk[A.first[s] + bidx]; \
+    const u8 *src = B.src; const u32 n = B.n; \
+    for (u32 i = k; i < n; i += 256) sh.src_[FN::zlc_ix(i)] = src[i]; \
+    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) sh.hist[i] = 0; \
+    if (k == 0) { sh.n = n; sh.nch = (n + nafz::ZLC_CH - 1) / nafz::ZLC_CH; sh.rle_break = 0; sh.lastend = 0; } \
+    __syncthreads(); \
+    const bool act = k < sh.nch; \
+    if (act) FN::zlc_zeros(sh, k); \
+    __syncthreads(); \
+    nafz::ZlcBlk &I = A.info[j]; \
+    if (n == 0 || !sh.rle_break || n < 16) {                   /* empty, one repeated byte, or too small to parse: RLE / raw block */ \
+        if (k == 0) { I.nseq = 0; I.nlit = 0; I.parsed = 0; I.rle = (n && !sh.rle_break) ? 1 : 0; I.conv = 0; I.pad = 0; } \
+        return; \
+    } \
+    if (act) FN::zlc_columns(sh, k); \
+    __syncthreads(); \
+    if (act) FN::zlc_breaks(sh, k); \
+    __syncthreads(); \
+    if (act) FN::zlc_choose(sh, k); \
+    __syncthreads(); \
+    if (act) FN::zlc_breaks_d(sh, k); \
+    __syncthreads(); \
+    if (act) FN::zlc_count(sh, k); \
+    __syncthreads(); \
+    { \
+        const u64 v = act ? ((u64)sh.cnt[k] | ((u64)sh.mls[k] << 32)) : 0; \
+        u64 total; const u64 pre = block_excl_scan(v, &total, smscan); \
+        if (act) { sh.ibase[k] = (u16)pre; sh.mbase[k] = (u16)(pre >> 32); } \
+        if (k == 0) { sh.nseq = (u32)total; sh.mltot = (u32)(total >> 32); } \
+    } \
+    __syncthreads(); \
+    const bool sampled = bidx % nafz::ZLC_SAMPLE == 0; \
+    nafz::ZlcWork K = nafz::zlc_work(A.work + (size_t)j * nafz::zlc_work_bytes(A.zlb), A.zlb); \
+    if (act) FN::zlc_emit_seqs(sh, k, K.S, K.lit, sampled); \
+    FN::zlc_emit_tail(sh, k, 256, K.lit, sampled); \
+    if (k == 0) { I.nseq = sh.nseq; I.nlit = n - sh.mltot; I.parsed = 1; I.rle = 0; I.conv = 0; I.pad = 0; } \
+    if (!sampled) return; \
+    __syncthreads(); \
+    if (k == 0) FN::zlc_count_offsets(sh); \
+    __syncthreads(); \
+    u32 *acc = A.counts + s * nafz::ZLC_NBINS; \
+    for (u32 i = k; i < nafz::ZLC_NBINS; i += 256) if (sh.hist[i]) atomicAdd(&acc[i], sh.hist[i]); \
 }
+ZLC_FIND_KERNEL(k_zlc_find, nafz::zlcb)
+ZLC_FIND_KERNEL(k_zlc_find_bits, nafz)
 
 __global__ void __launch_bounds__(32) k_zlc_define(const ZlcArgs A)
 {
@@ -561,20 +568,24 @@ static void zstd_compress_batch(Ctx &ctx, CudaExec &ex, ZEncBatch &b)
         Z.def_fail = Z.counts + 8 * nafz::ZLC_NBINS;
         static_assert(sizeof(nafz::ZlcTables) % 16 == 0, "k_zlc_finish copies the tables in 16-byte pieces");
         Z.tables = (nafz::ZlcTables *)ex.alloc<uint4>(8 * sizeof(nafz::ZlcTables) / 16);
-        CUDA_TRY(cudaFuncSetAttribute(k_zlc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nafz::ZlcSh)));
+        const bool bits = zlc_bits();
+        const size_t fsm = bits ? sizeof(nafz::ZlcSh) : sizeof(nafz::zlcb::ZlcSh);
+        CUDA_TRY(cudaFuncSetAttribute(k_zlc_find, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nafz::zlcb::ZlcSh)));
+        CUDA_TRY(cudaFuncSetAttribute(k_zlc_find_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nafz::ZlcSh)));
         static const bool env_side = !(getenv("NAFGPU_SIDE") && getenv("NAFGPU_SIDE")[0] == '0');
         side = env_side && ctx.side && !(ex.prof && ex.prof->on);
         if (side) {
             CUDA_TRY(cudaEventRecord(ctx.side_fork, ex.stream));
             CUDA_TRY(cudaStreamWaitEvent(ctx.side, ctx.side_fork, 0));
-            k_zlc_find<<<nlz, 256, sizeof(nafz::ZlcSh), ctx.side>>>(Z);
+            if (bits) k_zlc_find_bits<<<nlz, 256, fsm, ctx.side>>>(Z); else k_zlc_find<<<nlz, 256, fsm, ctx.side>>>(Z);
             k_zlc_define<<<(unsigned)ns, 32, 0, ctx.side>>>(Z);
             k_zlc_finish<<<(nlz + 63) / 64, 64, 0, ctx.side>>>(Z);
             k_zlc_finish_own<<<(nlz + 63) / 64, 64, 0, ctx.side>>>(Z);
             CUDA_TRY(cudaEventRecord(ctx.side_join, ctx.side));
             ex.launches += 4;
         } else {
-            KLAUNCH(ex, "k_zlc_find", k_zlc_find<<<nlz, 256, sizeof(nafz::ZlcSh), ex.stream>>>(Z));
+            if (bits) KLAUNCH(ex, "k_zlc_find_bits", k_zlc_find_bits<<<nlz, 256, fsm, ex.stream>>>(Z));
+            else KLAUNCH(ex, "k_zlc_find", k_zlc_find<<<nlz, 256, fsm, ex.stream>>>(Z));
             KLAUNCH(ex, "k_zlc_define", k_zlc_define<<<(unsigned)ns, 32, 0, ex.stream>>>(Z));
             KLAUNCH(ex, "k_zlc_finish", k_zlc_finish<<<(nlz + 63) / 64, 64, 0, ex.stream>>>(Z));
             KLAUNCH(ex, "k_zlc_finish_own", k_zlc_finish_own<<<(nlz + 63) / 64, 64, 0, ex.stream>>>(Z));

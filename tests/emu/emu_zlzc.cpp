@@ -2,12 +2,18 @@
 // block coder against them) on the CPU, thread after thread and phase after phase in the order k_zlc_find / k_zlc_define /
 // k_zlc_finish run them, and lays the blocks out as one frame like k_zenc_gather does.
 //   emu_zlzc IN OUT.zst BLOCK_SIZE [SEQS.txt]       (SEQS.txt: every block's sequences, for comparison with tests/emu/lzcol.hpp)
-#include "../../naf_b200/csrc/zstd_lzc_hd.cuh"
+#include "../../naf_b200/csrc/zstd_lzc_bytes_hd.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 using namespace nafz;
+// the finder's phases in one of their two formulations: -DZLC_BYTES = byte loops (nafz::zlcb, what a level selects), else bit masks
+#ifdef ZLC_BYTES
+namespace fin = nafz::zlcb;
+#else
+namespace fin = nafz;
+#endif
 
 int main(int argc, char **argv)
 {
@@ -25,33 +31,33 @@ int main(int argc, char **argv)
     std::vector<u8> work(nblk * (size_t)wstride + 64, 0xEE), slots(nblk * (size_t)sstride + 64, 0xEE);
     std::vector<u32> counts(ZLC_NBINS, 0);
     ZlcStreamView V{in.data(), n, bs, (u32)nblk, info.data(), work.data(), wstride, slots.data(), sstride};
-    ZlcSh *shp = new ZlcSh; ZlcSh &sh = *shp;
+    fin::ZlcSh *shp = new fin::ZlcSh; fin::ZlcSh &sh = *shp;
 
     // ---- k_zlc_find: one CTA per block, thread k = chunk k
     for (size_t b = 0; b < nblk; b++) {
         const u32 len = V.len((u32)b);
         const u8 *src = in.data() + b * bs;
         memset(&sh, 0xDD, sizeof sh);
-        for (u32 i = 0; i < len; i++) sh.src_[zlc_ix(i)] = src[i];
+        for (u32 i = 0; i < len; i++) sh.src_[fin::zlc_ix(i)] = src[i];
         memset(sh.hist, 0, sizeof sh.hist);
         sh.n = len; sh.nch = (len + ZLC_CH - 1) / ZLC_CH; sh.rle_break = 0; sh.lastend = 0;
         const u32 nch = sh.nch;
-        for (u32 t = 0; t < nch; t++) zlc_zeros(sh, t);
+        for (u32 t = 0; t < nch; t++) fin::zlc_zeros(sh, t);
         ZlcBlk &I = info[b];
         I.nseq = I.nlit = 0; I.parsed = I.rle = I.conv = I.pad = 0;
         if (len == 0 || !sh.rle_break || len < 16) { I.rle = len && !sh.rle_break; continue; }
-        for (u32 t = 0; t < nch; t++) zlc_columns(sh, t);
-        for (u32 t = 0; t < nch; t++) zlc_breaks(sh, t);
-        for (u32 t = nch; t-- > 0;) zlc_choose(sh, t);                 // (any thread order must give the same result)
-        for (u32 t = 0; t < nch; t++) zlc_breaks_d(sh, t);
-        for (u32 t = nch; t-- > 0;) zlc_count(sh, t);
-        zlc_scan_serial(sh);
+        for (u32 t = 0; t < nch; t++) fin::zlc_columns(sh, t);
+        for (u32 t = 0; t < nch; t++) fin::zlc_breaks(sh, t);
+        for (u32 t = nch; t-- > 0;) fin::zlc_choose(sh, t);                 // (any thread order must give the same result)
+        for (u32 t = 0; t < nch; t++) fin::zlc_breaks_d(sh, t);
+        for (u32 t = nch; t-- > 0;) fin::zlc_count(sh, t);
+        fin::zlc_scan_serial(sh);
         const bool sampled = b % ZLC_SAMPLE == 0;
         ZlcWork K = zlc_work(work.data() + b * wstride, bs);
-        for (u32 t = nch; t-- > 0;) zlc_emit_seqs(sh, t, K.S, K.lit, sampled);
-        for (u32 t = 0; t < 7; t++) zlc_emit_tail(sh, t, 7, K.lit, sampled);
+        for (u32 t = nch; t-- > 0;) fin::zlc_emit_seqs(sh, t, K.S, K.lit, sampled);
+        for (u32 t = 0; t < 7; t++) fin::zlc_emit_tail(sh, t, 7, K.lit, sampled);
         I.nseq = sh.nseq; I.nlit = len - sh.mltot; I.parsed = 1;
-        if (sampled) { zlc_count_offsets(sh); for (u32 i = 0; i < ZLC_NBINS; i++) counts[i] += sh.hist[i]; }
+        if (sampled) { fin::zlc_count_offsets(sh); for (u32 i = 0; i < ZLC_NBINS; i++) counts[i] += sh.hist[i]; }
         if (seqs) {
             fprintf(seqs, "block %zu nlit %u nseq %u\n", b, I.nlit, I.nseq);
             for (u32 i = 0; i < I.nseq; i++) fprintf(seqs, "%u %u %u\n", K.S.ll[i], K.S.ml[i], K.S.ov[i]);

@@ -20,13 +20,21 @@ BUILD = os.path.join(ROOT, "tests", "_build")
 CSRC = os.path.join(ROOT, "naf_b200", "csrc")
 
 
-def _build(name, deps):
+def _build(name, deps, source=None, flags=()):
     os.makedirs(BUILD, exist_ok=True)
-    exe, src = os.path.join(BUILD, name), os.path.join(ROOT, "tests", "emu", name + ".cpp")
+    exe, src = os.path.join(BUILD, name), os.path.join(ROOT, "tests", "emu", (source or name) + ".cpp")
     deps = [src, os.path.join(ROOT, "tests", "emu", "lzcol.hpp")] + [os.path.join(CSRC, d) for d in deps]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-        subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unused-function", "-o", exe, src], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-g", "-Wall", "-Wno-unused-function", *flags, "-o", exe, src], check=True)
     return exe
+
+
+ZLC_DEPS = ["zstd_lzc_hd.cuh", "zstd_lzc_bytes_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"]
+
+
+def _build_zlzc():
+    """tests/emu/emu_zlzc.cpp with the finder's phases as byte loops (what a level >= 2 runs on the GPU) and as bit masks (NAFGPU_LZ=b)"""
+    return [_build("emu_zlzc_bytes", ZLC_DEPS, source="emu_zlzc", flags=("-DZLC_BYTES",)), _build("emu_zlzc", ZLC_DEPS)]
 
 
 @pytest.fixture(scope="module")
@@ -308,7 +316,7 @@ def test_column_finder_and_stream_tables(dec, libzstd, tmp_path):
     (Treeless_Literals + Repeat_Mode).  tests/emu/emu_zlzc.cpp runs the phases thread by thread.  Every frame is decoded by the
     oracle, libzstd 1.5.0 and our own decoder, and equals byte for byte what the serial restatement (lzcol.hpp + proto_shared.cpp)
     writes; on the streams it is for the result stays within 1.4 x of per-block tables + the serial hash parse."""
-    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    exe, exe_bits = _build_zlzc()
     proto = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
     enc = _build("emu_zenc", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
     oracle = helpers.load_oracle()
@@ -325,6 +333,8 @@ def test_column_finder_and_stream_tables(dec, libzstd, tmp_path):
             p = subprocess.run([exe, inp, z, bs], capture_output=True, text=True)
             assert p.returncode == 0, p.stderr
             frame = open(z, "rb").read()
+            assert subprocess.run([exe_bits, inp, zp, bs], capture_output=True).returncode == 0
+            assert open(zp, "rb").read() == frame, ("the two formulations of the finder differ", len(data), bs)
             assert oracle.zstd_decompress(frame) == data, (len(data), bs)
             if libzstd is not None:
                 assert libzstd_decode(libzstd, frame, len(data)) == data, (len(data), bs)
@@ -358,7 +368,7 @@ def test_stream_tables_survive_shard_concatenation(libzstd, tmp_path):
     nafgpu_shard_finish).  With per-stream tables every shard's first coded block carries that shard's tables and the blocks behind
     it inherit them (Treeless_Literals / Repeat_Mode) -- so the merged frame must decode whatever the neighbours are: shards with
     tables, shards that fell back to per-block tables, raw / RLE-only shards, empty shards."""
-    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    exe = _build_zlzc()[0]
     oracle = helpers.load_oracle()
     rng = np.random.default_rng(4)
     ids = ids_stream(9000, 1)
@@ -391,7 +401,7 @@ def test_defining_block_that_does_not_fit_gets_the_stream_private_tables(dec, li
     """the first block with literals and sequences is mostly noise, the sample is dominated by 860 blocks of names: coded with the
     stream's Huffman code the noise overflows the block's slot, the defining block cannot be written, and the whole stream falls
     back to per-block tables (k_zlc_finish_own) -- still byte for byte the serial restatement, still valid for every decoder"""
-    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    exe, exe_bits = _build_zlzc()
     proto = _build("proto_shared", ["zstd_enc_hd.cuh", "zstd_hd.cuh"])
     rng = np.random.default_rng(3)
     b0 = bytearray(rng.integers(1, 256, 8192, dtype=np.uint8).tobytes())
@@ -410,6 +420,8 @@ def test_defining_block_that_does_not_fit_gets_the_stream_private_tables(dec, li
     assert subprocess.run([dec, z, back], capture_output=True).returncode == 0 and open(back, "rb").read() == data
     assert subprocess.run([proto, inp, zp, "8192", "col"], capture_output=True).returncode == 0
     assert open(zp, "rb").read() == frame
+    assert subprocess.run([exe_bits, inp, zp, "8192"], capture_output=True).returncode == 0
+    assert open(zp, "rb").read() == frame
 
 
 def test_reference_unnaf_decodes_files_with_stream_table_frames(tmp_path):
@@ -417,7 +429,7 @@ def test_reference_unnaf_decodes_files_with_stream_table_frames(tmp_path):
     the same bytes), the other sections as the oracle's encoder makes them: the UNMODIFIED reference unnaf (input.c:211
     ZSTD_decompress for these sections) prints the input back, and so does the oracle"""
     from naf_b200 import container
-    exe = _build("emu_zlzc", ["zstd_lzc_hd.cuh", "zstd_enc_hd.cuh", "zstd_hd.cuh"])
+    exe = _build_zlzc()[0]
     oracle = helpers.load_oracle()
     for text, kw in [(synth.fastq(30_000, 150, seed=21), {}), (synth.ont_fasta(60, 10000, 30000, seed=22), {}),
                      (synth.protein_fasta(8000, 300, seed=23), {"seq_type": "protein"})]:

@@ -210,10 +210,10 @@ def test_lz_frames_equal_cpu_emulation(gpu, tmp_path):
     import subprocess
     exes = {}
     for name in ("emu_zlzc", "emu_zenc"):
-        exe = os.path.join(helpers.ROOT, "tests", "_build", name)
+        exe = os.path.join(helpers.ROOT, "tests", "_build", name + ("_bytes" if name == "emu_zlzc" else ""))
         if shutil.which("g++"):                              # build from the sources of this snapshot; else the binary that travelled
             exe = str(tmp_path / name)
-            subprocess.run(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(helpers.ROOT, "tests", "emu", name + ".cpp")], check=True)
+            subprocess.run(["g++", "-std=c++17", "-O2", "-DZLC_BYTES", "-o", exe, os.path.join(helpers.ROOT, "tests", "emu", name + ".cpp")], check=True)
         elif not os.path.exists(exe):
             pytest.skip("no %s binary and no g++ on this box" % name)
         exes[name] = exe

@@ -3,7 +3,7 @@
      and decode back on the device
   B. a whole FASTQ / FASTA file: the oracle and the device decode the .naf back to the text; sizes next to level 1
   C. per-kernel times of one encode of N reads (CUDA events), and the encode / decode call times with and without the stage
-python tools/zlc_gpu_check.py [reads_for_timing] [log]      (no torch; every line is flushed, so a cut-off run still reports)"""
+python tools/zlc_gpu_check.py [reads_for_timing] [log] [NAFGPU_LZ for parts A and B: shared | b]      (no torch; every line is flushed, so a cut-off run still reports)"""
 import json
 import os
 import subprocess
@@ -13,7 +13,7 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["NAFGPU_LZ"] = "shared"
+os.environ["NAFGPU_LZ"] = sys.argv[3] if len(sys.argv) > 3 else "shared"      # "b": the finder's bit-mask formulation (same frames)
 T0 = time.time()
 LOG = open(sys.argv[2], "a") if len(sys.argv) > 2 else None
 
@@ -34,10 +34,10 @@ def main():
     import helpers
     n_time = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     import shutil
-    emu = os.path.join(ROOT, "tests", "_build", "emu_zlzc")
+    emu = os.path.join(ROOT, "tests", "_build", "emu_zlzc_bytes")
     if shutil.which("g++"):                                   # from the sources of this snapshot; else the binary that travelled
         emu = os.path.join(os.environ.get("TMPDIR", "/tmp"), "emu_zlzc_%d" % os.getpid())
-        subprocess.run(["g++", "-std=c++17", "-O2", "-o", emu, os.path.join(ROOT, "tests", "emu", "emu_zlzc.cpp")], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O2", "-DZLC_BYTES", "-o", emu, os.path.join(ROOT, "tests", "emu", "emu_zlzc.cpp")], check=True)
     ctx = naf_b200.NafGpu(0)
     say(step="context")
     oracle = helpers.load_oracle()
@@ -80,7 +80,7 @@ def main():
         return
     big = synth.fastq(n_time, 150, seed=42)
     say(step="C", made_reads=n_time, text=len(big))
-    for mode in ("0", "shared"):                               # "0": the level-1 parse (entropy only), same process, same box
+    for mode in ("0", "shared", "b"):                          # "b": the finder as bit masks;                               # "0": the level-1 parse (entropy only), same process, same box
         os.environ["NAFGPU_LZ"] = mode
         naf = ctx.encode(big)
         ctx.profile(True)
