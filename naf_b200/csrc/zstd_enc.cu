@@ -14,10 +14,14 @@
 // Per block: histogram -> code lengths -> tree description -> bit-exact sizes -> encode into a fixed slot
 // (k_zenc_hist / k_zenc_tables / k_zenc_encode); a scan over block sizes then lets k_zenc_gather lay the blocks
 // out as frames.
-//   * the small, text-like streams (ids, comments, lengths, mask) at level >= 2: 8 KB blocks with LZ77 matches
-//     (compress/zstd_fast.c:186 ZSTD_compressBlock_fast) and FSE-coded sequences (compress/zstd_compress_sequences.c:418),
-//     one thread per block (k_zenc_lz; the body is HD code in zstd_enc_hd.cuh, validated on the CPU against libzstd);
-//     still independent blocks — matches stay inside the block, repeat-offset codes only name offsets the block itself pushed
+//   * the small, text-like streams (ids, comments, lengths) at level >= 2: 8 KB blocks with LZ77 matches
+//     (compress/zstd_fast.c:186 ZSTD_compressBlock_fast's role) and FSE-coded sequences (compress/zstd_compress_sequences.c:418).
+//     Data-parallel stage (k_zlc_find / k_zlc_define / k_zlc_finish; bodies: zstd_lzc_hd.cuh, zstd_lzc_bytes_hd.cuh): a CTA per
+//     block finds the matches with maps and scans, the stream gets ONE Huffman code and ONE set of FSE tables, a thread per block
+//     codes against them (Treeless_Literals / Repeat_Mode).  NAFGPU_LZ=1: the first formulation, one thread per block doing
+//     everything with private tables (k_zenc_lz; body in zstd_enc_hd.cuh).  All of it is HD code validated on the CPU against
+//     libzstd.  Blocks stay independent in what they reference -- matches inside the block, repeat-offset codes only for offsets
+//     the block itself pushed -- and each shard of a multi-GPU encode defines its tables anew
 //
 // Format: zstd/doc/zstd_compression_format.md ("Huffman Tree Description", "Huffman-coded streams",
 // "FSE Table Description"); reference counterparts: compress/huf_compress.c:513 HUF_buildCTable_wksp,
