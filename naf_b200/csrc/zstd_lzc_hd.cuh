@@ -414,11 +414,11 @@ struct ZlcStreamView {
     HD u32 len(u32 b) const { const u64 off = (u64)b * bs, left = n > off ? n - off : 0; return (u32)(left < bs ? left : bs); }
 };
 struct ZlcWork { u8 *lit; ZLzSeqs S; ZLzWork W; };
-HD u32 zlc_work_bytes(u32 bs) { const u32 ms = bs / 4; return ((bs + 64) + 3 * ms * 2 + 1280 * 2 + 512 + 3 * ms + 15) & ~15u; }
+HD u32 zlc_work_bytes(u32 bs) { const u32 ms = bs / 4; return (((bs + 64 + 15) & ~15u) + 3 * ms * 2 + 1280 * 2 + 512 + 3 * ms + 15) & ~15u; }
 HD ZlcWork zlc_work(u8 *w, u32 bs)
 {
     const u32 ms = bs / 4; ZlcWork R;
-    R.lit = w; w += bs + 64;
+    R.lit = w; w += (bs + 64 + 15) & ~15u;                      // (the u16 arrays behind it stay aligned for any block size)
     R.S.ll = (u16 *)w; w += ms * 2; R.S.ml = (u16 *)w; w += ms * 2; R.S.ov = (u16 *)w; w += ms * 2; R.S.n = 0;
     R.W.spos = (u16 *)w; w += 1280 * 2; R.W.tsym = w; w += 512; R.W.codes = w;
     return R;
