@@ -737,8 +737,11 @@ def run_ours(args):
             else:
                 line["level2"] = box.get("r", {"error": "no result"})
         print(json.dumps(line), flush=True)
-        if hung:
-            os._exit(0)                                       # a stuck call must not keep the process (and the printed line) from ending
+        if hung or '"error"' in json.dumps(line.get("level2", {})):
+            # a stuck or failed extra call (a CUDA error is sticky: context teardown could then hang or abort) must not keep the
+            # process, whose line is printed, from ending normally
+            sys.stdout.flush()
+            os._exit(0)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
