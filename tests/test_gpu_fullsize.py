@@ -136,3 +136,28 @@ def test_one_record_beyond_4_gib(gpu, tmp_path):
         finally:
             if d != str(tmp_path):
                 shutil.rmtree(d, ignore_errors=True)
+
+
+def test_config2_level2_decoded_by_reference(gpu, tmp_path):
+    """ennaf -2 at the full size: names and lengths go through the data-parallel LZ stage (csrc/zstd_lzc_hd.cuh: 32 k blocks with
+    per-stream tables).  The file is smaller than level 1's, we decode it back, and so does the unmodified reference unnaf."""
+    text = synth.fastq(10_000_000, 150, seed=42)
+    naf1 = gpu.encode(text)
+    n1 = len(naf1)
+    del naf1
+    naf2, info = gpu.encode_with_info(text, level=2)
+    assert info.n_sequences == 10_000_000 and gpu.timing().parser_fallback == 0
+    assert len(naf2) < n1 and 0.34 < len(naf2) / len(text) < 0.37
+    assert gpu.decode(naf2) == text
+    if helpers.have_ref():
+        d = _workdir(tmp_path, len(text) + len(naf2))
+        try:
+            fnaf, fout = os.path.join(d, "l2.naf"), os.path.join(d, "l2.txt")
+            with open(fnaf, "wb") as f:
+                f.write(naf2)
+            subprocess.run([os.path.join(helpers.REF_BIN, "unnaf"), fnaf, "-o", fout], check=True, env=dict(os.environ, TMPDIR=d))
+            with open(fout, "rb") as f:
+                assert f.read() == text, "reference unnaf on our level-2 .naf differs from the input"
+        finally:
+            if d != str(tmp_path):
+                shutil.rmtree(d, ignore_errors=True)
