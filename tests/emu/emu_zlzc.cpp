@@ -33,7 +33,21 @@ int main(int argc, char **argv)
     ZlcStreamView V{in.data(), n, bs, (u32)nblk, info.data(), work.data(), wstride, slots.data(), sstride};
     fin::ZlcSh *shp = new fin::ZlcSh; fin::ZlcSh &sh = *shp;
 
-    // ---- k_zlc_find: one CTA per block, thread k = chunk k
+    // ---- k_zlc_find: one CTA per block, thread k = chunk k.  Between two barriers the threads of a CTA run in no particular order:
+    // ZLC_ORDER=<seed> in the environment shuffles the order of the threads of every phase (0 / unset: ascending or descending as
+    // written below); a phase in which one thread read what another one writes would then give different frames for different seeds.
+    const char *ord_env = getenv("ZLC_ORDER");
+    unsigned long long ord_state = ord_env ? strtoull(ord_env, nullptr, 10) : 0;
+    std::vector<u32> perm(ZLC_NCH);
+    auto order = [&](u32 count, bool descending) -> const std::vector<u32> & {
+        for (u32 i = 0; i < count; i++) perm[i] = descending ? count - 1 - i : i;
+        if (ord_state) for (u32 i = count; i > 1; i--) {
+            ord_state = ord_state * 6364136223846793005ull + 1442695040888963407ull;
+            const u32 j = (u32)((ord_state >> 33) % i);
+            const u32 t = perm[i - 1]; perm[i - 1] = perm[j]; perm[j] = t;
+        }
+        return perm;
+    };
     for (size_t b = 0; b < nblk; b++) {
         const u32 len = V.len((u32)b);
         const u8 *src = in.data() + b * bs;
@@ -42,19 +56,19 @@ int main(int argc, char **argv)
         memset(sh.hist, 0, sizeof sh.hist);
         sh.n = len; sh.nch = (len + ZLC_CH - 1) / ZLC_CH; sh.rle_break = 0; sh.lastend = 0;
         const u32 nch = sh.nch;
-        for (u32 t = 0; t < nch; t++) fin::zlc_zeros(sh, t);
+        { const std::vector<u32> P = order(nch, false); for (u32 i = 0; i < nch; i++) fin::zlc_zeros(sh, P[i]); }
         ZlcBlk &I = info[b];
         I.nseq = I.nlit = 0; I.parsed = I.rle = I.conv = I.pad = 0;
         if (len == 0 || !sh.rle_break || len < 16) { I.rle = len && !sh.rle_break; continue; }
-        for (u32 t = 0; t < nch; t++) fin::zlc_columns(sh, t);
-        for (u32 t = 0; t < nch; t++) fin::zlc_breaks(sh, t);
-        for (u32 t = nch; t-- > 0;) fin::zlc_choose(sh, t);                 // (any thread order must give the same result)
-        for (u32 t = 0; t < nch; t++) fin::zlc_breaks_d(sh, t);
-        for (u32 t = nch; t-- > 0;) fin::zlc_count(sh, t);
+        { const std::vector<u32> P = order(nch, false); for (u32 i = 0; i < nch; i++) fin::zlc_columns(sh, P[i]); }
+        { const std::vector<u32> P = order(nch, false); for (u32 i = 0; i < nch; i++) fin::zlc_breaks(sh, P[i]); }
+        { const std::vector<u32> P = order(nch, true); for (u32 i = 0; i < nch; i++) fin::zlc_choose(sh, P[i]); }
+        { const std::vector<u32> P = order(nch, false); for (u32 i = 0; i < nch; i++) fin::zlc_breaks_d(sh, P[i]); }
+        { const std::vector<u32> P = order(nch, true); for (u32 i = 0; i < nch; i++) fin::zlc_count(sh, P[i]); }
         fin::zlc_scan_serial(sh);
         const bool sampled = b % ZLC_SAMPLE == 0;
         ZlcWork K = zlc_work(work.data() + b * wstride, bs);
-        for (u32 t = nch; t-- > 0;) fin::zlc_emit_seqs(sh, t, K.S, K.lit, sampled);
+        { const std::vector<u32> P = order(nch, true); for (u32 i = 0; i < nch; i++) fin::zlc_emit_seqs(sh, P[i], K.S, K.lit, sampled); }
         for (u32 t = 0; t < 7; t++) fin::zlc_emit_tail(sh, t, 7, K.lit, sampled);
         I.nseq = sh.nseq; I.nlit = len - sh.mltot; I.parsed = 1;
         if (sampled) { fin::zlc_count_offsets(sh); for (u32 i = 0; i < ZLC_NBINS; i++) counts[i] += sh.hist[i]; }

@@ -459,3 +459,24 @@ def test_reference_unnaf_decodes_files_with_stream_table_frames(tmp_path):
         if helpers.have_ref():
             rc, got, err = helpers.ref_run("unnaf", [], mixed)
             assert rc == 0 and got == text, err[:300]
+
+
+def test_finder_phases_do_not_depend_on_thread_order(tmp_path):
+    """between two barriers the threads of a CTA run in no particular order: the emulation shuffles the order of the threads of every
+    phase (ZLC_ORDER=<seed>); a phase in which one thread read what another one writes would give different frames.  Both
+    formulations of the finder, several block sizes."""
+    exes = _build_zlzc()
+    text_like, other = _zlzc_cases()
+    picks = text_like[:3] + [d for d in other if 0 < len(d) <= 100000][:14]
+    for data in picks:
+        inp = str(tmp_path / "i.bin")
+        with open(inp, "wb") as f:
+            f.write(data[:200000])
+        for bs in ("8192", "1000", "100"):
+            for exe in exes:
+                frames = []
+                for seed in ("0", "1", "12345"):
+                    z = str(tmp_path / ("o%s.zst" % seed))
+                    assert subprocess.run([exe, inp, z, bs], capture_output=True, env=dict(os.environ, ZLC_ORDER=seed)).returncode == 0
+                    frames.append(open(z, "rb").read())
+                assert frames[0] == frames[1] == frames[2], (len(data), bs, os.path.basename(exe))
