@@ -1,7 +1,9 @@
 """A/B of the encoder's parse levels on one GPU, device-resident (CUDA events on the library's stream):
     python tools/ab_level.py RECORDS [OUT.json]
-level 1 = entropy-only parse of every stream; level 2 = LZ77 + FSE-coded sequences on ids / comments / lengths / mask.
-Each level: 2 warm-up + 3 timed round trips (bit-exact check on the device), then one profiled step (per-kernel ms)."""
+level 1 = entropy-only parse of every stream; level 2 = LZ77 + FSE-coded sequences on ids / comments / lengths, in each of its
+formulations (NAFGPU_LZ is read per call): "2" the data-parallel stage a level selects, "2b" the same with the finder's phases as
+bit masks, "2t" the thread-per-block stage of round 1 (also covers the mask).
+Each: 2 warm-up + 3 timed round trips (bit-exact check on the device), then one profiled step (per-kernel ms)."""
 import ctypes as C, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, naf_b200
@@ -16,8 +18,12 @@ stream = torch.cuda.ExternalStream(ctx.lib.nafgpu_stream(ctx.h))
 cudart = C.CDLL("libcudart.so"); cudart.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
 res = {"records": n, "text_bytes": n_text, "levels": {}}
 d_naf = torch.zeros(n_text // 2 + 4096, dtype=torch.uint8, device="cuda")
-for level in (1, 2):
-    eo, do = api.make_enc_opts(level=level), api.make_dec_opts()
+for level, env in ((1, None), ("2", None), ("2b", "b"), ("2t", "1")):
+    if env is None:
+        os.environ.pop("NAFGPU_LZ", None)
+    else:
+        os.environ["NAFGPU_LZ"] = env
+    eo, do = api.make_enc_opts(level=int(str(level)[0])), api.make_dec_opts()
     enc, dec = [], []
     for it in range(5):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
