@@ -752,8 +752,8 @@ def run_ours(args):
                 line["level2"] = partial
             else:
                 line["level2"] = box.get("r", {"error": "no result"})
-        print(json.dumps(line), flush=True)
-        if hung or '"error"' in json.dumps(line.get("level2", {})):
+        print(json.dumps(line, default=str), flush=True)
+        if hung or '"error"' in json.dumps(line.get("level2", {}), default=str):
             # a stuck or failed extra call (a CUDA error is sticky: context teardown could then hang or abort) must not keep the
             # process, whose line is printed, from ending normally
             sys.stdout.flush()
